@@ -1,0 +1,115 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference (/root/reference/fastgps)
+on top of the tests-only qmcpy stand-in (oracle/qmcpy_standin).  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The GPU box has neither /root/reference nor qmcpy: tests read the committed .npz files, never this script's imports.
+Every fixture stores the generator inputs (z / shift, gen matrices / digital shift / t), so the CUDA path and the
+oracle port are evaluated on IDENTICAL inputs.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "qmcpy_standin"))
+sys.path.insert(0, "/root/reference")
+
+torch.set_default_dtype(torch.float64)
+torch.set_num_threads(4)
+
+import fastgps  # noqa: E402  (the reference, unmodified)
+import qmcpy  # noqa: E402  (stand-in)
+
+
+def f_ackley(x, a=20, b=0.2, c=2 * np.pi, scaling=32.768):
+    # the reference doctests' test function (fast_gp_lattice.py:14-22)
+    x = 2 * scaling * x - scaling
+    t1 = a * torch.exp(-b * torch.sqrt(torch.mean(x ** 2, 1)))
+    t2 = torch.exp(torch.mean(torch.cos(c * x), 1))
+    return -t1 - t2 + a + np.exp(1)
+
+
+def f_smooth(x):
+    # smooth, periodic-friendly (multitask/fgp_lattice.ipynb cell 4 style)
+    j = torch.arange(1, x.shape[1] + 1)
+    return torch.cos(2 * np.pi * x).mul(1.0 / j).sum(1) + torch.sin(2 * np.pi * x[:, 0]) * torch.cos(2 * np.pi * x[:, -1])
+
+
+def run_case(name, family, d, n, m_test, alpha, f, scale=1.0, lengthscales=1.0, noise=None, fit_iterations=30, seed=7):
+    if family == "lattice":
+        seq = qmcpy.Lattice(dimension=d, seed=seed)
+        kw = {} if noise is None else {"noise": noise}
+        gp = fastgps.FastGPLattice(seq, alpha=alpha, scale=scale, lengthscales=lengthscales, **kw)
+        gen = {"z": seq.gen_vec.astype(np.uint64), "shift": seq.shift}
+    else:
+        seq = qmcpy.DigitalNetB2(dimension=d, seed=seed)
+        kw = {} if noise is None else {"noise": noise}
+        gp = fastgps.FastGPDigitalNetB2(seq, alpha=alpha, scale=scale, lengthscales=lengthscales, **kw)
+        gen = {"C": seq.gen_mats.astype(np.uint64), "dshift": seq.rshift.astype(np.uint64), "t": np.int64(seq.t)}
+    x = gp.get_x_next(n)
+    y = f(x)
+    gp.add_y_next(y)
+    rng = torch.Generator().manual_seed(17)
+    xt = torch.rand((m_test, d), generator=rng)
+    out = dict(gen)
+    out.update(family=family, d=d, n=n, alpha=alpha, x=x.numpy(), y=y.numpy(), xtest=xt.numpy(),
+               scale0=gp.scale.detach().numpy(), lengthscales0=gp.lengthscales.detach().numpy(), noise0=gp.noise.detach().numpy())
+    if family == "dnb2":
+        out["xb"] = gp.get_xb(0).numpy()
+    out["k1parts"] = gp.get_k1parts(0, 0).detach().numpy()[:, 0, 0, :]
+    # one MLL evaluation with autograd gradients at the initial hyperparameters (abstract_gp.py:239-260,294)
+    os.environ["FASTGP_FORCE_RECOMPILE"] = "True"
+    cache = gp.get_inv_log_det_cache()
+    norm_term, logdet = cache.get_norm_term_logdet_term()
+    loss = 0.5 * (norm_term.sum() + logdet.sum() + n * np.log(2 * np.pi))
+    loss.backward()
+    out.update(norm_term0=norm_term.detach().numpy(), logdet0=logdet.detach().numpy(), loss0=loss.item(),
+               grad_raw_scale0=gp.raw_scale.grad.numpy().copy(), grad_raw_lengthscales0=gp.raw_lengthscales.grad.numpy().copy())
+    gp.zero_grad()
+    del os.environ["FASTGP_FORCE_RECOMPILE"]
+    out["lam0"] = gp.get_lam(0, 0).detach().numpy()
+    out["ytilde"] = gp.get_ytilde(0).detach().numpy()
+    out["coeffs0"] = gp.coeffs.detach().numpy()
+    out["pmean0"] = gp.post_mean(xt).numpy()
+    out["pvar0"] = gp.post_var(xt).numpy()
+    mcov = min(m_test, 32)
+    out["pcov0"] = gp.post_cov(xt[:mcov], xt[:mcov // 2]).numpy()
+    out["pcmean0"] = gp.post_cubature_mean().numpy()
+    out["pcvar0"] = gp.post_cubature_var().numpy()
+    out["pvar0_future"] = gp.post_var(xt[:64], n=2 * n).numpy()
+    data = gp.fit(iterations=fit_iterations, verbose=0, store_hists=True)
+    out.update(fit_iterations=fit_iterations, fit_last_iteration=data["iterations"], loss_hist=data["loss_hist"].numpy(),
+               scale_hist=data["scale_hist"].numpy(), lengthscales_hist=data["lengthscales_hist"].numpy(),
+               scale1=gp.scale.detach().numpy(), lengthscales1=gp.lengthscales.detach().numpy())
+    out["coeffs1"] = gp.coeffs.detach().numpy()
+    out["pmean1"] = gp.post_mean(xt).numpy()
+    out["pvar1"] = gp.post_var(xt).numpy()
+    # incremental doubling (util.py:113-132,173-183): add the next n points and re-read lambda / posterior
+    x2 = gp.get_x_next(2 * n)
+    gp.add_y_next(f(x2))
+    out["lam_2n"] = gp.get_lam(0, 0).detach().numpy()
+    out["ytilde_2n"] = gp.get_ytilde(0).detach().numpy()
+    out["pmean_2n"] = gp.post_mean(xt[:64]).numpy()
+    out["pvar_2n"] = gp.post_var(xt[:64]).numpy()
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "loss0", out["loss0"], "its", data["iterations"], os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    # C1: FastGPLattice d=2 n=2^10 alpha=2, 2^12 test points (BASELINE.json configs[0])
+    run_case("lattice_d2_n1024_a2", "lattice", 2, 2 ** 10, 2 ** 12, 2, f_ackley, fit_iterations=40)
+    run_case("lattice_d3_n256_a3", "lattice", 3, 2 ** 8, 2 ** 8, 3, f_smooth, scale=2.5,
+             lengthscales=torch.tensor([0.2, 0.7, 1.3]), noise=1e-6, fit_iterations=15)
+    run_case("lattice_d8_n4096_a2", "lattice", 8, 2 ** 12, 2 ** 8, 2, f_smooth, scale=1.5, lengthscales=0.4, noise=1e-6, fit_iterations=12)
+    run_case("lattice_d2_n64_a1", "lattice", 2, 2 ** 6, 2 ** 6, 1, f_smooth, noise=1e-4, fit_iterations=8)
+    run_case("dnb2_d2_n1024_a2", "dnb2", 2, 2 ** 10, 2 ** 12, 2, f_ackley, fit_iterations=40)
+    run_case("dnb2_d4_n4096_a2", "dnb2", 4, 2 ** 12, 2 ** 8, 2, f_smooth, scale=2.0, lengthscales=0.6, noise=1e-8, fit_iterations=12)
+    run_case("dnb2_d3_n256_a3", "dnb2", 3, 2 ** 8, 2 ** 8, 3, f_smooth, scale=0.7, lengthscales=torch.tensor([0.3, 1.0, 1.9]), noise=1e-8, fit_iterations=10)
+    run_case("dnb2_d3_n256_a4", "dnb2", 3, 2 ** 8, 2 ** 8, 4, f_smooth, noise=1e-8, fit_iterations=10)
+    run_case("dnb2_d2_n128_a1", "dnb2", 2, 2 ** 7, 2 ** 7, 1, f_smooth, noise=1e-6, fit_iterations=10)

@@ -1,0 +1,4 @@
+"""fastgaussianprocesses_b200: B200-native structured-covariance hot path of FastGPs (drop-in API)."""
+from . import _lib  # noqa: F401
+
+__version__ = "0.1.0"

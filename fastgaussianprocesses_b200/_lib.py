@@ -1,0 +1,330 @@
+"""ctypes binding of libfgp_b200.so (include/fgp_b200.h).  No CPU fallback: every entry point needs the CUDA library
+and CUDA tensors, and fails loudly otherwise."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfgp_b200.so")
+
+MAX_D = 32
+MAX_ALPHA = 10
+
+_c = ctypes
+_vp, _i32, _i64, _u64, _f64, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint64, _c.c_double, _c.c_size_t
+
+# name -> (restype, argtypes); every symbol include/fgp_b200.h declares
+SIGNATURES = {
+    "fgp_version": (_i32, []),
+    "fgp_last_error": (_c.c_char_p, []),
+    "fgp_launch_count": (_u64, []),
+    "fgp_device_info": (_i32, [_vp, _vp, _vp, _vp]),
+    "fgp_lattice_points": (_i32, [_vp, _vp, _i32, _u64, _u64, _vp, _vp]),
+    "fgp_dnb2_points": (_i32, [_vp, _i32, _vp, _i32, _i32, _u64, _u64, _vp, _vp, _vp]),
+    "fgp_lattice_kernel_parts": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "fgp_dnb2_kernel_parts": (_i32, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "fgp_kernel_from_parts": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "fgp_fft_table_bytes": (_sz, [_i64]),
+    "fgp_fft_table_init": (_i32, [_i64, _vp, _vp]),
+    "fgp_fftbr_r2c": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "fgp_fftbr_c2c": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "fgp_ifftbr_c2c": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "fgp_fwht": (_i32, [_vp, _vp, _i64, _i64, _vp]),
+    "fgp_mll_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32]),
+    "fgp_lattice_mll_grad": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "fgp_dnb2_mll_grad": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "fgp_gram_solve": (_i32, [_i32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "fgp_post_mean_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "fgp_lattice_post_mean": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _f64, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "fgp_dnb2_post_mean": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "fgp_post_var_workspace_bytes": (_sz, [_i32, _i64, _i64]),
+    "fgp_lattice_post_var": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fgp_dnb2_post_var": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp, _vp, _vp]),
+    "fgp_lattice_cross_kernel": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _f64, _vp, _vp, _vp]),
+    "fgp_dnb2_cross_kernel": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp]),
+    "fgp_fp64_peak_probe": (_i32, [_i32, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+class FgpError(AssertionError):
+    """Raised when the native library reports an error (the reference raises AssertionError at the same places)."""
+
+
+def load():
+    """Load the C-ABI library (no GPU needed to load it; calls need one)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "fastgaussianprocesses_b200: %s is missing -- build it with `python -m fastgaussianprocesses_b200.build` "
+                "(there is deliberately no CPU fallback)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise FgpError("libfgp_b200: %s (code %d)" % (load().fgp_last_error().decode(), rc))
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("fastgaussianprocesses_b200 runs on CUDA tensors only (no CPU fallback); got %r" % (getattr(t, "device", type(t)),))
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("expected %s, got %s" % (dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def _harr(ctype, vals):
+    vals = list(vals)
+    return (ctype * max(1, len(vals)))(*vals)
+
+
+def launch_count():
+    return int(load().fgp_launch_count())
+
+
+def device_info():
+    sm, ma, mi, sh = _c.c_int(), _c.c_int(), _c.c_int(), _c.c_size_t()
+    _check(load().fgp_device_info(_c.byref(sm), _c.byref(ma), _c.byref(mi), _c.byref(sh)))
+    return {"sm_count": sm.value, "cc": (ma.value, mi.value), "smem_optin": sh.value}
+
+
+# --------------------------------------------------------------------------------------------- K1 points
+def lattice_points(z, shift, i0, i1, device):
+    d = len(z)
+    x = torch.empty((int(i1) - int(i0), d), dtype=torch.float64, device=device)
+    if x.numel() == 0:
+        return x
+    with torch.cuda.device(x.device):
+        _check(load().fgp_lattice_points(_harr(_u64, [int(v) for v in z]), _harr(_f64, [float(v) for v in shift]), d,
+                                         int(i0), int(i1), x.data_ptr(), _stream()))
+    return x
+
+
+def dnb2_points(C_dev, dshift, t, i0, i1, want_x=True):
+    d, mmax = C_dev.shape
+    _dev(C_dev, torch.int64)
+    xb = torch.empty((int(i1) - int(i0), d), dtype=torch.int64, device=C_dev.device)
+    x = torch.empty((int(i1) - int(i0), d), dtype=torch.float64, device=C_dev.device) if want_x else None
+    if xb.numel() == 0:
+        return xb, x
+    with torch.cuda.device(C_dev.device):
+        _check(load().fgp_dnb2_points(C_dev.data_ptr(), mmax, _harr(_u64, [int(v) for v in dshift]), d, int(t), int(i0), int(i1),
+                                      xb.data_ptr(), x.data_ptr() if want_x else None, _stream()))
+    return xb, x
+
+
+# --------------------------------------------------------------------------------------------- K2 kernels
+def lattice_kernel_parts(x, z, alpha):
+    n, d = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _check(load().fgp_lattice_kernel_parts(_dev(x, torch.float64), n, d, _harr(_f64, z), _harr(_i32, alpha), out.data_ptr(), _stream()))
+    return out
+
+
+def dnb2_kernel_parts(xb, zb, alpha, t):
+    n, d = xb.shape
+    out = torch.empty((n, d), dtype=torch.float64, device=xb.device)
+    with torch.cuda.device(xb.device):
+        _check(load().fgp_dnb2_kernel_parts(_dev(xb, torch.int64), n, d, _harr(_i64, zb), _harr(_i32, alpha), int(t), out.data_ptr(), _stream()))
+    return out
+
+
+def kernel_from_parts(parts, scale, ls):
+    """parts (n,d); scale (B,), ls (B,d) device tensors -> (B,n)."""
+    n, d = parts.shape
+    B = scale.numel()
+    out = torch.empty((B, n), dtype=torch.float64, device=parts.device)
+    with torch.cuda.device(parts.device):
+        _check(load().fgp_kernel_from_parts(_dev(parts, torch.float64), n, d, B, _dev(scale, torch.float64), _dev(ls, torch.float64),
+                                            out.data_ptr(), _stream()))
+    return out
+
+
+def cross_kernel(family, xs, xtrain, alpha, t, scale, ls):
+    m, d = xs.shape
+    n = xtrain.shape[0]
+    out = torch.empty((m, n), dtype=torch.float64, device=xs.device)
+    with torch.cuda.device(xs.device):
+        if family == 0:
+            _check(load().fgp_lattice_cross_kernel(_dev(xs, torch.float64), m, _dev(xtrain, torch.float64), n, d, _harr(_i32, alpha),
+                                                   float(scale), _harr(_f64, ls), out.data_ptr(), _stream()))
+        else:
+            _check(load().fgp_dnb2_cross_kernel(_dev(xs, torch.float64), m, _dev(xtrain, torch.int64), n, d, _harr(_i32, alpha), int(t),
+                                                float(scale), _harr(_f64, ls), out.data_ptr(), _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------------------------- K3 transforms
+_tables = {}
+
+
+def fft_table(n, device):
+    """Twiddle tables for length-n FFT-BRO on `device` (built once per (n, device) by a tiny kernel)."""
+    device = torch.device(device)
+    key = (int(n), device.index if device.index is not None else torch.cuda.current_device())
+    tab = _tables.get(key)
+    if tab is None:
+        nbytes = load().fgp_fft_table_bytes(int(n))
+        tab = torch.empty(nbytes // 8, dtype=torch.float64, device=device)
+        with torch.cuda.device(device):
+            _check(load().fgp_fft_table_init(int(n), tab.data_ptr(), _stream()))
+        _tables[key] = tab
+    return tab
+
+
+def _as2d(x):
+    _dev(x)
+    n = x.shape[-1]
+    return x.reshape(-1, n) if x.numel() else x.reshape(0, n), n
+
+
+def fftbr(x):
+    """Orthonormal FFT, bit-reversed-order input -> natural-order output, last dim.  Real or complex input."""
+    x2, n = _as2d(x.contiguous())
+    out = torch.empty(x2.shape, dtype=torch.complex128, device=x.device)
+    tab = fft_table(n, x.device)
+    with torch.cuda.device(x.device):
+        if x2.dtype == torch.float64:
+            _check(load().fgp_fftbr_r2c(_dev(x2), out.data_ptr(), x2.shape[0], n, tab.data_ptr(), _stream()))
+        elif x2.dtype == torch.complex128:
+            _check(load().fgp_fftbr_c2c(_dev(x2), out.data_ptr(), x2.shape[0], n, tab.data_ptr(), _stream()))
+        else:
+            raise TypeError("fftbr needs float64 or complex128")
+    return out.reshape(x.shape)
+
+
+def ifftbr(x):
+    x = x.contiguous()
+    if x.dtype == torch.float64:
+        x = x.to(torch.complex128)
+    x2, n = _as2d(x)
+    out = torch.empty_like(x2)
+    tab = fft_table(n, x.device)
+    with torch.cuda.device(x.device):
+        _check(load().fgp_ifftbr_c2c(_dev(x2, torch.complex128), out.data_ptr(), x2.shape[0], n, tab.data_ptr(), _stream()))
+    return out.reshape(x.shape)
+
+
+def fwht(x):
+    x2, n = _as2d(x.contiguous())
+    out = torch.empty_like(x2)
+    with torch.cuda.device(x.device):
+        _check(load().fgp_fwht(_dev(x2, torch.float64), out.data_ptr(), x2.shape[0], n, _stream()))
+    return out.reshape(x.shape)
+
+
+# --------------------------------------------------------------------------------------------- K4 MLL
+_workspaces = {}
+
+
+def _workspace(kind, nbytes, device):
+    device = torch.device(device)
+    key = (kind, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() * 8 < nbytes:
+        ws = torch.empty((max(nbytes, 256) + 7) // 8, dtype=torch.float64, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def mll_grad(family, xpts, alpha, t, ysq, scale, ls, noise, want_grad=True, want_lam=False):
+    """Fused MLL terms + gradients.  xpts: (n,d) float64 (lattice) / int64 (net); ysq (B,n); scale (B,), ls (B,d), noise (B,).
+    Returns out (B, d+4) = [norm, logdet, dL/dnoise, dL/dscale, dL/dls...] and lam (B,n) or None."""
+    n, d = xpts.shape
+    B = scale.numel()
+    dev = xpts.device
+    out = torch.zeros((B, d + 4), dtype=torch.float64, device=dev)
+    lam = torch.empty((B, n), dtype=torch.complex128 if family == 0 else torch.float64, device=dev) if want_lam else None
+    ws = _workspace("mll", load().fgp_mll_workspace_bytes(family, n, d, B), dev)
+    with torch.cuda.device(dev):
+        if family == 0:
+            tab = fft_table(n, dev)
+            _check(load().fgp_lattice_mll_grad(_dev(xpts, torch.float64), n, d, _harr(_i32, alpha), B, _dev(ysq, torch.float64),
+                                               _dev(scale, torch.float64), _dev(ls, torch.float64), _dev(noise, torch.float64),
+                                               tab.data_ptr(), ws.data_ptr(), lam.data_ptr() if want_lam else None, out.data_ptr(),
+                                               1 if want_grad else 0, _stream()))
+        else:
+            _check(load().fgp_dnb2_mll_grad(_dev(xpts, torch.int64), n, d, _harr(_i32, alpha), int(t), B, _dev(ysq, torch.float64),
+                                            _dev(scale, torch.float64), _dev(ls, torch.float64), _dev(noise, torch.float64),
+                                            ws.data_ptr(), lam.data_ptr() if want_lam else None, out.data_ptr(),
+                                            1 if want_grad else 0, _stream()))
+    return out, lam
+
+
+def gram_solve(family, y, lam):
+    """K^-1 y for y (..., n) with full eigenvalues lam (n,)."""
+    y2, n = _as2d(y.contiguous())
+    R = y2.shape[0]
+    out = torch.empty_like(y2)
+    with torch.cuda.device(y.device):
+        if family == 0:
+            tab = fft_table(n, y.device)
+            work = _workspace("solve", R * n * 16, y.device)
+            _check(load().fgp_gram_solve(0, _dev(y2, torch.float64), out.data_ptr(), R, n, _dev(lam, torch.complex128), tab.data_ptr(),
+                                         work.data_ptr(), _stream()))
+        else:
+            _check(load().fgp_gram_solve(1, _dev(y2, torch.float64), out.data_ptr(), R, n, _dev(lam, torch.float64), None, None, _stream()))
+    return out.reshape(y.shape)
+
+
+# --------------------------------------------------------------------------------------------- K5 posterior
+def post_mean(family, xs, xtrain, alpha, t, scale, ls, coeffs):
+    """xs (m,d); coeffs (B,n) -> (B,m)."""
+    m, d = xs.shape
+    n = xtrain.shape[0]
+    B = coeffs.shape[0]
+    out = torch.empty((B, m), dtype=torch.float64, device=xs.device)
+    ws = _workspace("pmean", load().fgp_post_mean_workspace_bytes(m, n, d, B), xs.device)
+    with torch.cuda.device(xs.device):
+        if family == 0:
+            _check(load().fgp_lattice_post_mean(_dev(xs, torch.float64), m, _dev(xtrain, torch.float64), n, d, _harr(_i32, alpha),
+                                                float(scale), _harr(_f64, ls), _dev(coeffs, torch.float64), B, ws.data_ptr(),
+                                                out.data_ptr(), _stream()))
+        else:
+            _check(load().fgp_dnb2_post_mean(_dev(xs, torch.float64), m, _dev(xtrain, torch.int64), n, d, _harr(_i32, alpha), int(t),
+                                             float(scale), _harr(_f64, ls), _dev(coeffs, torch.float64), B, ws.data_ptr(),
+                                             out.data_ptr(), _stream()))
+    return out
+
+
+def post_var(family, xs, xtrain, alpha, t, scale, ls, lam):
+    m, d = xs.shape
+    n = xtrain.shape[0]
+    out = torch.empty((m,), dtype=torch.float64, device=xs.device)
+    ws = _workspace("pvar", load().fgp_post_var_workspace_bytes(family, m, n), xs.device)
+    with torch.cuda.device(xs.device):
+        if family == 0:
+            tab = fft_table(n, xs.device)
+            _check(load().fgp_lattice_post_var(_dev(xs, torch.float64), m, _dev(xtrain, torch.float64), n, d, _harr(_i32, alpha),
+                                               float(scale), _harr(_f64, ls), _dev(lam, torch.complex128), tab.data_ptr(), ws.data_ptr(),
+                                               out.data_ptr(), _stream()))
+        else:
+            _check(load().fgp_dnb2_post_var(_dev(xs, torch.float64), m, _dev(xtrain, torch.int64), n, d, _harr(_i32, alpha), int(t),
+                                            float(scale), _harr(_f64, ls), _dev(lam, torch.float64), ws.data_ptr(), out.data_ptr(),
+                                            _stream()))
+    return out
+
+
+def fp64_peak_probe(iters, device):
+    sink = torch.zeros(8, dtype=torch.float64, device=device)
+    flops = _c.c_double()
+    with torch.cuda.device(device):
+        _check(load().fgp_fp64_peak_probe(int(iters), sink.data_ptr(), _c.byref(flops), _stream()))
+    return flops.value

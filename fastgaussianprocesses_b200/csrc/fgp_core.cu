@@ -1,0 +1,122 @@
+// Library plumbing: error state, launch counter, device probe, Bernoulli tables, FP64 peak probe.
+#include <stdarg.h>
+#include <atomic>
+#include "fgp_common.cuh"
+
+namespace fgp {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+static int g_sms = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int sm_count() {
+  if (g_sms == 0) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+      g_sms = sms;
+    else
+      g_sms = 148;
+  }
+  return g_sms;
+}
+
+// c_a B_{2a}(x) = sum_p q_p u^p, u = x(1-x).   B_{2a}(1/2 + y) = sum_p e_p y^{2p},
+// e_p = C(2a,2p) (2^{1-(2a-2p)} - 1) B_{2a-2p};  y^2 = 1/4 - u.
+int fill_lat_poly(const int* alpha_host, int d, LatPoly* out) {
+  static const long double BERN[11] = {1.0L,           1.0L / 6,        -1.0L / 30,      1.0L / 42,
+                                       -1.0L / 30,     5.0L / 66,       -691.0L / 2730,  7.0L / 6,
+                                       -3617.0L / 510, 43867.0L / 798,  -174611.0L / 330};  // B_0,B_2,...,B_20
+  memset(out, 0, sizeof(LatPoly));
+  for (int j = 0; j < d; ++j) {
+    const int a = alpha_host[j];
+    if (a < 1 || a > FGP_MAX_ALPHA) {
+      set_error("lattice alpha[%d]=%d outside 1..%d", j, a, FGP_MAX_ALPHA);
+      return FGP_EINVAL;
+    }
+    out->alpha[j] = a;
+    long double binom[2 * FGP_MAX_ALPHA + 1];
+    binom[0] = 1.0L;
+    for (int k = 1; k <= 2 * a; ++k) binom[k] = binom[k - 1] * (long double)(2 * a - k + 1) / (long double)k;
+    long double e[FGP_MAX_ALPHA + 1];
+    for (int p = 0; p <= a; ++p) {
+      const int k = 2 * a - 2 * p;  // Bernoulli index
+      e[p] = binom[2 * p] * (ldexpl(1.0L, 1 - k) - 1.0L) * BERN[k / 2];
+    }
+    // coefficient c_a
+    long double c = (a % 2 == 0) ? -1.0L : 1.0L;
+    const long double twopi = 6.283185307179586476925286766559L;
+    for (int k = 1; k <= 2 * a; ++k) c *= twopi / (long double)k;
+    for (int r = 0; r <= a; ++r) {
+      long double s = 0.0L;
+      for (int p = r; p <= a; ++p) {
+        long double cb = 1.0L;  // C(p,r)
+        for (int k = 1; k <= r; ++k) cb = cb * (long double)(p - k + 1) / (long double)k;
+        s += e[p] * cb * ldexpl(1.0L, -2 * (p - r));
+      }
+      out->q[j][r] = (double)(c * ((r % 2) ? -s : s));
+    }
+  }
+  return FGP_OK;
+}
+
+// dependent DFMA chains, 8 independent chains per thread
+__global__ void __launch_bounds__(256) fp64_probe_kernel(int iters, double* sink) {
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 1.0 + 1e-9 * (threadIdx.x + k);
+  const double m = 1.0000001, c = 1e-7;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = fma(a[k], m, c);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += a[k];
+  if (s == 12345.678) sink[0] = s;
+}
+
+}  // namespace fgp
+
+extern "C" {
+
+int fgp_version(void) { return FGP_VERSION; }
+const char* fgp_last_error(void) { return fgp::g_err; }
+uint64_t fgp_launch_count(void) { return fgp::g_launches.load(); }
+
+int fgp_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin) {
+  int dev = 0;
+  FGP_CUDA(cudaGetDevice(&dev));
+  int v = 0;
+  FGP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+  if (sm_count) *sm_count = v;
+  FGP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_major) *cc_major = v;
+  FGP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev));
+  if (cc_minor) *cc_minor = v;
+  FGP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (smem_optin) *smem_optin = (size_t)v;
+  return FGP_OK;
+}
+
+int fgp_fp64_peak_probe(int iters, double* sink_dev, double* flops, fgp_stream_t stream) {
+  FGP_REQUIRE(iters > 0 && sink_dev, "fp64 probe: bad arguments");
+  const int blocks = fgp::sm_count() * 8;
+  fgp::fp64_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink_dev);
+  FGP_LAUNCH_CHECK();
+  if (flops) *flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;
+  return FGP_OK;
+}
+
+}  // extern "C"

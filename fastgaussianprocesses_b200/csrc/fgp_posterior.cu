@@ -1,0 +1,360 @@
+// K5: posterior mean / variance as on-the-fly kernel-vector products (abstract_gp.py:352-380, :381-416).
+// The reference materialises parts of shape (m, n, 1, 1, d) (abstract_fast_gp.py:173-180) and then contracts with
+// coeffs; here the (m x n) cross-covariance only ever exists as one FP64 register per (test point, thread).
+//
+// post_mean is FP64-pipe bound.  Lattice alpha = 2 inner loop, per (test point, train point, dim):
+//     delta = xs' - X'          DADD      (coordinates pre-scaled by sigma_j = kappa_j^(1/2))
+//     v     = sigma_j - |delta| DADD
+//     h     = |delta| * v       DMUL      (= kappa_j a (1 - a),  a = |x - X| ; B_4(frac t) = B_4(|t|))
+//     f     = 1 - h*h           DFMA      (= (1 + ls_j c B_4(a)) / A_j)
+//     prod *= f                 DMUL
+// i.e. 5 FP64 issue slots per pair-dimension + 1 DFMA per pair for the coefficient: (5d + 1) slots / pair.
+#include "fgp_transform.cuh"
+
+namespace fgp {
+
+constexpr int kPT = 256;   // threads per CTA
+constexpr int kTN = 128;   // train points per shared-memory tile
+
+struct PostArgs {
+  const double* xs;   // (m,d) test points
+  int64_t m;
+  const void* x;      // (n,d) train points: double (lattice) / int64 (net)
+  int64_t n;
+  int d;
+  int t;
+  const double* coeffs;  // (B,n)
+  int B;
+  double* partial;    // (splits, B, m) or the output itself when splits == 1
+  int splits;
+  int64_t n_per_split;
+  // per-dimension polynomial in u = a(1-a):  f_j(u) = sum_p c[j][p] u^p  (ls and the "+1" folded in)
+  double c[FGP_MAX_D][FGP_MAX_ALPHA + 1];
+  int alpha[FGP_MAX_D];
+  double sig[FGP_MAX_D];  // alpha = 2 fast path: sigma_j
+  double ls[FGP_MAX_D];   // net: lengthscales
+  double pref;            // scale (times prod_j A_j on the fast path)
+};
+
+// MODE 0: lattice alpha=2 fast path; 1: lattice generic alpha; 2: net
+template <int DT, int R, int MODE>
+__global__ void __launch_bounds__(kPT) post_mean_kernel(const __grid_constant__ PostArgs a) {
+  constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
+  const int d = DT > 0 ? DT : a.d;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* sX = (double*)smraw;          // kTN * d   (lattice: scaled coords; net: int64 bit patterns)
+  double* sC = sX + (size_t)kTN * d;    // kTN coefficients
+  const int b = blockIdx.z;
+  const int64_t i0 = ((int64_t)blockIdx.x * kPT + threadIdx.x) * R;
+  double xr[R][DM];
+  uint64_t xbr[R][MODE == 2 ? DM : 1];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int64_t i = i0 + r < a.m ? i0 + r : a.m - 1;
+#pragma unroll
+    for (int j = 0; j < DM; ++j) {
+      if (j >= d) break;
+      const double v = a.xs[i * d + j];
+      if (MODE == 0) xr[r][j] = v * a.sig[j];
+      if (MODE == 1) xr[r][j] = v;
+      if (MODE == 2) xbr[r][j] = dnb2_to_b(v, a.t);
+    }
+  }
+  double acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.0;
+  const int64_t a0 = (int64_t)blockIdx.y * a.n_per_split;
+  const int64_t a1 = min(a.n, a0 + a.n_per_split);
+  const double* coef = a.coeffs + (int64_t)b * a.n;
+  for (int64_t base = a0; base < a1; base += kTN) {
+    const int cnt = (int)min((int64_t)kTN, a1 - base);
+    __syncthreads();
+    for (int e = threadIdx.x; e < cnt * d; e += kPT) {
+      if (MODE == 2) {
+        ((int64_t*)sX)[e] = ((const int64_t*)a.x)[base * d + e];
+      } else {
+        const double v = ((const double*)a.x)[base * d + e];
+        sX[e] = MODE == 0 ? v * a.sig[e % d] : v;
+      }
+    }
+    for (int e = threadIdx.x; e < cnt; e += kPT) sC[e] = coef[base + e];
+    __syncthreads();
+#pragma unroll 2
+    for (int k = 0; k < cnt; ++k) {
+      const double ck = sC[k];
+      double prod[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) prod[r] = 1.0;
+#pragma unroll
+      for (int j = 0; j < DM; ++j) {
+        if (j >= d) break;
+        if (MODE == 2) {
+          const uint64_t Xb = ((const uint64_t*)sX)[k * d + j];
+#pragma unroll
+          for (int r = 0; r < R; ++r) prod[r] *= fma(a.ls[j], dnb2_part(xbr[r][j] ^ Xb, a.alpha[j], a.t), 1.0);
+        } else {
+          const double X = sX[k * d + j];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const double ad = fabs(xr[r][j] - X);
+            if (MODE == 0) {
+              const double h = ad * (a.sig[j] - ad);
+              const double f = fma(-h, h, 1.0);
+              prod[r] = j == 0 ? f : prod[r] * f;
+            } else {
+              const double u = ad * (1.0 - ad);
+              double f = a.c[j][a.alpha[j]];
+              for (int p = a.alpha[j] - 1; p >= 0; --p) f = fma(f, u, a.c[j][p]);
+              prod[r] *= f;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = fma(prod[r], ck, acc[r]);
+    }
+  }
+  double* out = a.partial + ((int64_t)blockIdx.y * a.B + b) * a.m;
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (i0 + r < a.m) out[i0 + r] = acc[r] * a.pref;
+}
+
+__global__ void __launch_bounds__(256) post_mean_reduce_kernel(const double* __restrict__ partial, int splits,
+                                                               int64_t total, double* __restrict__ out) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < splits; ++k) s += partial[(int64_t)k * total + e];
+    out[e] = s;
+  }
+}
+
+// pvar_i = max(0, kxx - sum_k |kt_ik|^2 Re(1/lam_k))
+template <bool CPLX>
+__global__ void __launch_bounds__(256) post_var_reduce_kernel(const double* __restrict__ kt, const double* __restrict__ lam,
+                                                              int64_t n, double kxx, double* __restrict__ out) {
+  __shared__ double red[32 * 4];
+  const int64_t i = blockIdx.x;
+  double s[1] = {0.0};
+  if (CPLX) {
+    const double2* row = (const double2*)kt + i * n;
+    const double2* l = (const double2*)lam;
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
+      const double2 v = row[k], lk = l[k];
+      s[0] = fma(fma(v.x, v.x, v.y * v.y), lk.x / fma(lk.x, lk.x, lk.y * lk.y), s[0]);
+    }
+  } else {
+    const double* row = kt + i * n;
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
+      const double v = row[k];
+      s[0] = fma(v * v, 1.0 / lam[k], s[0]);
+    }
+  }
+  block_sum<1>(s, red);
+  if (threadIdx.x == 0) {
+    const double v = kxx - s[0];
+    out[i] = v < 0.0 ? 0.0 : v;
+  }
+}
+
+template <int DT, int R, int MODE>
+static int launch_post_mean(const PostArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+  post_mean_kernel<DT, R, MODE><<<grid, kPT, smem, st>>>(a);
+  FGP_LAUNCH_CHECK();
+  return FGP_OK;
+}
+
+template <int MODE>
+static int dispatch_post_mean(const PostArgs& a, cudaStream_t st) {
+  const int d = a.d;
+  const int R = d <= 8 ? 2 : 1;
+  const int64_t per_cta = (int64_t)kPT * R;
+  dim3 grid((unsigned)((a.m + per_cta - 1) / per_cta), (unsigned)a.splits, (unsigned)a.B);
+  const size_t smem = (size_t)kTN * (d + 1) * sizeof(double);
+  switch (d) {
+    case 2: return launch_post_mean<2, 2, MODE>(a, grid, smem, st);
+    case 3: return launch_post_mean<3, 2, MODE>(a, grid, smem, st);
+    case 4: return launch_post_mean<4, 2, MODE>(a, grid, smem, st);
+    case 8: return launch_post_mean<8, 2, MODE>(a, grid, smem, st);
+    case 16: return launch_post_mean<16, 1, MODE>(a, grid, smem, st);
+    default:
+      if (R == 2) return launch_post_mean<0, 2, MODE>(a, grid, smem, st);
+      return launch_post_mean<0, 1, MODE>(a, grid, smem, st);
+  }
+}
+
+static int choose_splits(int64_t m, int64_t n, int d, int B) {
+  const int R = d <= 8 ? 2 : 1;
+  const int64_t ctas = ((m + (int64_t)kPT * R - 1) / ((int64_t)kPT * R)) * B;
+  const int64_t want = (int64_t)sm_count() * 4;
+  int64_t s = 1;
+  if (ctas < want) s = (want + ctas - 1) / ctas;
+  const int64_t maxs = (n + kTN - 1) / kTN;
+  if (s > maxs) s = maxs;
+  if (s < 1) s = 1;
+  if (s > 1024) s = 1024;
+  return (int)s;
+}
+
+static int post_mean_common(int family, const double* xs, int64_t m, const void* x, int64_t n, int d,
+                            const int* alpha_host, int t, double scale, const double* ls_host, const double* coeffs, int B,
+                            void* partial, double* pmean, fgp_stream_t stream) {
+  FGP_REQUIRE(xs && x && alpha_host && ls_host && coeffs && pmean, "post_mean: null pointer");
+  FGP_REQUIRE(d >= 1 && d <= FGP_MAX_D && m >= 0 && n >= 1 && B >= 1 && B <= 65535, "post_mean: bad m/n/d/B");
+  if (m == 0) return FGP_OK;
+  PostArgs a;
+  memset(&a, 0, sizeof(a));
+  a.xs = xs;
+  a.m = m;
+  a.x = x;
+  a.n = n;
+  a.d = d;
+  a.t = t;
+  a.coeffs = coeffs;
+  a.B = B;
+  a.splits = choose_splits(m, n, d, B);
+  a.n_per_split = ((n + a.splits - 1) / a.splits + kTN - 1) / kTN * kTN;
+  a.splits = (int)((n + a.n_per_split - 1) / a.n_per_split);
+  FGP_REQUIRE(a.splits == 1 || partial, "post_mean: null workspace");
+  a.partial = a.splits == 1 ? pmean : (double*)partial;
+  a.pref = scale;
+  int mode;
+  if (family == 0) {
+    LatPoly P;
+    int rc = fill_lat_poly(alpha_host, d, &P);
+    if (rc) return rc;
+    bool all2 = true;
+    for (int j = 0; j < d; ++j) {
+      a.alpha[j] = alpha_host[j];
+      all2 = all2 && alpha_host[j] == 2;
+      for (int p = 0; p <= alpha_host[j]; ++p) a.c[j][p] = ls_host[j] * P.q[j][p];
+      a.c[j][0] += 1.0;
+    }
+    mode = all2 ? 0 : 1;
+    if (all2) {
+      for (int j = 0; j < d; ++j) {
+        const double A = a.c[j][0];  // 1 + ls q0 > 0
+        const double Bq = -a.c[j][2];  // ls |q2| > 0
+        FGP_REQUIRE(A > 0.0 && Bq >= 0.0, "post_mean: unexpected Bernoulli coefficients");
+        a.sig[j] = sqrt(sqrt(Bq / A));
+        a.pref *= A;
+      }
+    }
+  } else {
+    FGP_REQUIRE(t >= 1 && t < 64, "post_mean: t outside 1..63");
+    for (int j = 0; j < d; ++j) {
+      a.alpha[j] = alpha_host[j];
+      a.ls[j] = ls_host[j];
+      FGP_REQUIRE(alpha_host[j] >= 1 && alpha_host[j] <= 4, "post_mean: net alpha outside 1..4");
+    }
+    mode = 2;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = mode == 0 ? dispatch_post_mean<0>(a, st) : (mode == 1 ? dispatch_post_mean<1>(a, st) : dispatch_post_mean<2>(a, st));
+  if (rc) return rc;
+  if (a.splits > 1) {
+    const int64_t total = (int64_t)B * m;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    post_mean_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>((const double*)partial, a.splits, total, pmean);
+    FGP_LAUNCH_CHECK();
+  }
+  return FGP_OK;
+}
+
+static int64_t post_var_chunk(int64_t m, int64_t n) {
+  int64_t mc = (int64_t(1) << 27) / n;
+  if (mc < 1) mc = 1;
+  if (mc > m) mc = m;
+  return mc;
+}
+
+}  // namespace fgp
+
+extern "C" {
+
+size_t fgp_post_mean_workspace_bytes(int64_t m, int64_t n, int d, int B) {
+  if (m <= 0 || n <= 0 || d < 1 || B < 1) return 0;
+  const int s = fgp::choose_splits(m, n, d, B);
+  return s <= 1 ? 256 : (size_t)s * B * m * sizeof(double);
+}
+
+int fgp_lattice_post_mean(const double* xs_dev, int64_t m, const double* x_dev, int64_t n, int d, const int* alpha_host,
+                          double scale, const double* ls_host, const double* coeffs_dev, int B, void* partial_dev,
+                          double* pmean_dev, fgp_stream_t stream) {
+  return fgp::post_mean_common(0, xs_dev, m, x_dev, n, d, alpha_host, 0, scale, ls_host, coeffs_dev, B, partial_dev,
+                               pmean_dev, stream);
+}
+
+int fgp_dnb2_post_mean(const double* xs_dev, int64_t m, const int64_t* xb_dev, int64_t n, int d, const int* alpha_host,
+                       int t, double scale, const double* ls_host, const double* coeffs_dev, int B, void* partial_dev,
+                       double* pmean_dev, fgp_stream_t stream) {
+  return fgp::post_mean_common(1, xs_dev, m, xb_dev, n, d, alpha_host, t, scale, ls_host, coeffs_dev, B, partial_dev,
+                               pmean_dev, stream);
+}
+
+size_t fgp_post_var_workspace_bytes(int family, int64_t m, int64_t n) {
+  if (m <= 0 || n <= 0) return 0;
+  const int64_t mc = fgp::post_var_chunk(m, n);
+  return (size_t)mc * n * (family == 0 ? 3 : 1) * sizeof(double);
+}
+
+static int post_var_common(int family, const double* xs, int64_t m, const void* x, int64_t n, int d, const int* alpha_host,
+                           int t, double scale, const double* ls_host, const double* lam, const void* table, void* work,
+                           double* pvar, fgp_stream_t stream) {
+  using namespace fgp;
+  FGP_REQUIRE(xs && x && alpha_host && ls_host && lam && work && pvar, "post_var: null pointer");
+  FGP_REQUIRE(d >= 1 && d <= FGP_MAX_D && m >= 0 && is_pow2(n), "post_var: bad m/n/d (n must be a power of two)");
+  if (m == 0) return FGP_OK;
+  // k(x,x): delta = 0 in every dimension
+  double kxx = scale;
+  if (family == 0) {
+    FGP_REQUIRE(table, "post_var: null twiddle table");
+    LatPoly P;
+    int rc = fill_lat_poly(alpha_host, d, &P);
+    if (rc) return rc;
+    for (int j = 0; j < d; ++j) kxx *= 1.0 + ls_host[j] * P.q[j][0];
+  } else {
+    static const double w0[5] = {0.0, 1.0, 1.5, 43.0 / 18.0 - 1.0, 701.0 / 294.0 - 1.0};
+    for (int j = 0; j < d; ++j) {
+      FGP_REQUIRE(alpha_host[j] >= 1 && alpha_host[j] <= 4, "post_var: net alpha outside 1..4");
+      kxx *= 1.0 + ls_host[j] * w0[alpha_host[j]];
+    }
+  }
+  const int64_t mc = post_var_chunk(m, n);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* kreal = (double*)work;
+  double* kcplx = kreal + mc * n;
+  for (int64_t i0 = 0; i0 < m; i0 += mc) {
+    const int64_t cnt = m - i0 < mc ? m - i0 : mc;
+    int rc;
+    if (family == 0) {
+      if ((rc = fgp_lattice_cross_kernel(xs + i0 * d, cnt, (const double*)x, n, d, alpha_host, scale, ls_host, kreal, stream))) return rc;
+      if ((rc = fgp_fftbr_r2c(kreal, kcplx, cnt, n, table, stream))) return rc;
+      post_var_reduce_kernel<true><<<(unsigned)cnt, 256, 0, st>>>(kcplx, lam, n, kxx, pvar + i0);
+    } else {
+      if ((rc = fgp_dnb2_cross_kernel(xs + i0 * d, cnt, (const int64_t*)x, n, d, alpha_host, t, scale, ls_host, kreal, stream))) return rc;
+      if ((rc = fgp_fwht(kreal, kreal, cnt, n, stream))) return rc;
+      post_var_reduce_kernel<false><<<(unsigned)cnt, 256, 0, st>>>(kreal, lam, n, kxx, pvar + i0);
+    }
+    FGP_LAUNCH_CHECK();
+  }
+  return FGP_OK;
+}
+
+int fgp_lattice_post_var(const double* xs_dev, int64_t m, const double* x_dev, int64_t n, int d, const int* alpha_host,
+                         double scale, const double* ls_host, const double* lam_dev, const void* table_dev, void* work_dev,
+                         double* pvar_dev, fgp_stream_t stream) {
+  return post_var_common(0, xs_dev, m, x_dev, n, d, alpha_host, 0, scale, ls_host, lam_dev, table_dev, work_dev, pvar_dev,
+                         stream);
+}
+
+int fgp_dnb2_post_var(const double* xs_dev, int64_t m, const int64_t* xb_dev, int64_t n, int d, const int* alpha_host, int t,
+                      double scale, const double* ls_host, const double* lam_dev, void* work_dev, double* pvar_dev,
+                      fgp_stream_t stream) {
+  return post_var_common(1, xs_dev, m, xb_dev, n, d, alpha_host, t, scale, ls_host, lam_dev, nullptr, work_dev, pvar_dev,
+                         stream);
+}
+
+}  // extern "C"

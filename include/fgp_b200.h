@@ -1,0 +1,158 @@
+/*
+ * fgp_b200.h -- C ABI of libfgp_b200.so: the B200 (sm_100a) structured-covariance hot path of FastGPs.
+ *
+ * The reference (alegresor/FastGaussianProcesses, `fastgps` 0.0.4.1a) is pure Python and has NO FFI; the seams this
+ * library sits behind are Python call sites, cited per entry point as `file:line` into the reference tree.
+ * INTEGRATION.md shows the ctypes stubs a maintainer would add at each seam.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative FGP_E* code on failure; fgp_last_error() gives the message
+ *     (the reference raises AssertionError at the same places; the Python host layer turns codes into those).
+ *   - pointers named *_dev are device pointers owned by the caller (PyTorch); pointers named *_host are host arrays
+ *     of at most FGP_MAX_D entries that are copied into kernel parameters (no H2D copy, no allocation).
+ *   - no function allocates or frees memory; workspaces and twiddle tables are caller-provided
+ *     (sizes from the *_bytes functions).  All work is enqueued on `stream` (a cudaStream_t); nothing synchronises.
+ *   - all real data are IEEE float64, complex data are interleaved (re,im) float64 pairs, indices int64/uint64.
+ *   - "bit-reversed order" (BRO): the natural point order of an extensible lattice/net; transforms take BRO input
+ *     and give natural-order output (forward) or the converse (inverse) with no permutation pass.
+ */
+#ifndef FGP_B200_H
+#define FGP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGP_VERSION 100
+#define FGP_MAX_D 32          /* dimensions handled by the fused kernels */
+#define FGP_MAX_ALPHA 10      /* lattice smoothness (Bernoulli order 2*alpha <= 20) */
+#define FGP_MAX_LOG2N_FFT 24  /* two-pass FFT-BRO: n <= 2^24 */
+#define FGP_MAX_LOG2N_WHT 26  /* two-pass FWHT:    n <= 2^26 */
+
+#define FGP_OK 0
+#define FGP_EINVAL (-1)   /* bad argument (size not a power of two, d > FGP_MAX_D, null pointer, ...) */
+#define FGP_ECUDA (-2)    /* a CUDA runtime call or launch failed */
+#define FGP_ENODEV (-3)   /* no sm_100 device */
+
+typedef void* fgp_stream_t; /* cudaStream_t */
+
+int fgp_version(void);
+const char* fgp_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t fgp_launch_count(void);
+int fgp_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K1  point generation      (replaces qmcpy generator calls at abstract_gp.py:307-309 and
+ *                            fast_gp_digital_net_b2.py:266-269, cached by util.py:24-38)
+ * ------------------------------------------------------------------------------------------------------------- */
+/* x[i-i0, j] = ( frac(phi2(i) * z_j) + shift_j ) mod 1 for i in [i0,i1), row-major (i1-i0, d).  Bit-exact integer
+ * radical inverse; one IEEE add for the shift. */
+int fgp_lattice_points(const uint64_t* z_host, const double* shift_host, int d, uint64_t i0, uint64_t i1,
+                       double* x_dev, fgp_stream_t stream);
+/* xb[i-i0, j] = XOR_{k: bit k of i} C[j*mmax+k] ^ dshift_j ; x = (double)xb * 2^-t.  C_dev: device (d, mmax). */
+int fgp_dnb2_points(const uint64_t* C_dev, int mmax, const uint64_t* dshift_host, int d, int t, uint64_t i0,
+                    uint64_t i1, int64_t* xb_dev, double* x_dev, fgp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K2  kernel parts and product kernel   (fast_gp_lattice.py:263-273, fast_gp_digital_net_b2.py:270-301,
+ *                                        abstract_fast_gp.py:173-196; first column cached by util.py:50-62)
+ * ------------------------------------------------------------------------------------------------------------- */
+/* parts[i,j] = c_j * B_{2 alpha_j}((x[i,j]-z[j]) mod 1), c_j = (-1)^(alpha_j+1) (2 pi)^(2 alpha_j)/(2 alpha_j)!  */
+int fgp_lattice_kernel_parts(const double* x_dev, int64_t n, int d, const double* z_host, const int* alpha_host,
+                             double* parts_dev, fgp_stream_t stream);
+/* parts[i,j] = W_{alpha_j}(xb[i,j] ^ zb[j]) - 1  (alpha_j = 1: 1 - 3*2^-beta), beta = t - floor(log2 delta) */
+int fgp_dnb2_kernel_parts(const int64_t* xb_dev, int64_t n, int d, const int64_t* zb_host, const int* alpha_host,
+                          int t, double* parts_dev, fgp_stream_t stream);
+/* k[b,i] = scale[b] * prod_j (1 + ls[b,j] * parts[i,j]);  scale_dev (B), ls_dev (B,d) on the device. */
+int fgp_kernel_from_parts(const double* parts_dev, int64_t n, int d, int B, const double* scale_dev,
+                          const double* ls_dev, double* k_dev, fgp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K3  fast transforms    (qmcpy.fftbr_torch / ifftbr_torch / fwht_torch injected at fast_gp_lattice.py:224-225 and
+ *                         fast_gp_digital_net_b2.py:226; wrapped by abstract_fast_gp.py:197-228)
+ *     Orthonormal, along the last dim of a (batch, n) row-major array, n = 2^m.  In-place (in == out) is allowed
+ *     when input and output element types match.
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t fgp_fft_table_bytes(int64_t n);
+int fgp_fft_table_init(int64_t n, void* table_dev, fgp_stream_t stream);
+/* real BRO input -> complex natural-order output */
+int fgp_fftbr_r2c(const double* in_dev, double* out_dev, int64_t batch, int64_t n, const void* table_dev,
+                  fgp_stream_t stream);
+int fgp_fftbr_c2c(const double* in_dev, double* out_dev, int64_t batch, int64_t n, const void* table_dev,
+                  fgp_stream_t stream);
+/* complex natural-order input -> complex BRO output (inverse of fgp_fftbr_c2c) */
+int fgp_ifftbr_c2c(const double* in_dev, double* out_dev, int64_t batch, int64_t n, const void* table_dev,
+                   fgp_stream_t stream);
+/* Sylvester-ordered Walsh-Hadamard transform (self-inverse) */
+int fgp_fwht(const double* in_dev, double* out_dev, int64_t batch, int64_t n, fgp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K4  fused eigen-solve + marginal log-likelihood + gradients
+ *     (util.py:95-141 _LamCaches, :275-300 __call__ single task, :354-370 norm/logdet; autograd of
+ *      abstract_gp.py:253-260,294 replaced by the analytic gradient)
+ *
+ *     For each of B independent hyperparameter sets b (shared points, per-b data):
+ *       k1_i   = scale_b prod_j (1 + ls_bj P_ij)          P from x (lattice) or xb (net), never stored
+ *       lam_k  = sum_i T_ki k1_i + noise_b                (unnormalised FFT-BRO / FWHT  ==  sqrt(n) ft(k1) + noise)
+ *       norm   = sum_k ysq_bk Re(1/lam_k),  logdet = sum_k log|lam_k|
+ *       out[b] = { norm, logdet, dL/dnoise, dL/dscale, dL/dls_0 .. dL/dls_{d-1} },  L = (norm + logdet)/2
+ *     ysq_dev (B,n): sum over the reference's batch dims of |ytilde_k|^2 (natural transform order).
+ *     lam_dev: optional (B,n) complex (lattice) / real (net) output of lam (may be NULL).
+ *     want_grad = 0 skips the backward transform.
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t fgp_mll_workspace_bytes(int family /*0 lattice, 1 net*/, int64_t n, int d, int B);
+int fgp_lattice_mll_grad(const double* x_dev, int64_t n, int d, const int* alpha_host, int B, const double* ysq_dev,
+                         const double* scale_dev, const double* ls_dev, const double* noise_dev,
+                         const void* table_dev, void* workspace_dev, double* lam_dev, double* out_dev, int want_grad,
+                         fgp_stream_t stream);
+int fgp_dnb2_mll_grad(const int64_t* xb_dev, int64_t n, int d, const int* alpha_host, int t, int B,
+                      const double* ysq_dev, const double* scale_dev, const double* ls_dev, const double* noise_dev,
+                      void* workspace_dev, double* lam_dev, double* out_dev, int want_grad, fgp_stream_t stream);
+
+/* K^-1 y for R right-hand sides sharing one spectrum: out = T^-1( T(y) / lam ), util.py:338-344 (single task).
+ * lam_dev: (n) complex (family 0) or real (family 1) full eigenvalues sqrt(n) ft(k1)+noise.  y,out: (R,n) real.
+ * work_dev: R*n complex (family 0) / unused (family 1, may be NULL). */
+int fgp_gram_solve(int family, const double* y_dev, double* out_dev, int64_t R, int64_t n, const double* lam_dev,
+                   const void* table_dev, void* work_dev, fgp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K5  posterior mean / variance as on-the-fly kernel-vector products   (abstract_gp.py:352-380, :381-416)
+ * ------------------------------------------------------------------------------------------------------------- */
+/* pmean[b,i] = sum_a k_b(xs_i, X_a) coeffs[b,a];  xs (m,d), X (n,d), coeffs (B,n), scale/ls host arrays of one
+ * hyperparameter set shared by the B data columns.  partial_dev: workspace of fgp_post_mean_workspace_bytes. */
+size_t fgp_post_mean_workspace_bytes(int64_t m, int64_t n, int d, int B);
+int fgp_lattice_post_mean(const double* xs_dev, int64_t m, const double* x_dev, int64_t n, int d,
+                          const int* alpha_host, double scale, const double* ls_host, const double* coeffs_dev,
+                          int B, void* partial_dev, double* pmean_dev, fgp_stream_t stream);
+int fgp_dnb2_post_mean(const double* xs_dev, int64_t m, const int64_t* xb_dev, int64_t n, int d,
+                       const int* alpha_host, int t, double scale, const double* ls_host, const double* coeffs_dev,
+                       int B, void* partial_dev, double* pmean_dev, fgp_stream_t stream);
+/* pvar[i] = max(0, k(xs_i,xs_i) - sum_k |T k(xs_i, X)|_k^2 / lam_k).  lam_dev as in fgp_gram_solve.
+ * work_dev: fgp_post_var_workspace_bytes. */
+size_t fgp_post_var_workspace_bytes(int family, int64_t m, int64_t n);
+int fgp_lattice_post_var(const double* xs_dev, int64_t m, const double* x_dev, int64_t n, int d,
+                         const int* alpha_host, double scale, const double* ls_host, const double* lam_dev,
+                         const void* table_dev, void* work_dev, double* pvar_dev, fgp_stream_t stream);
+int fgp_dnb2_post_var(const double* xs_dev, int64_t m, const int64_t* xb_dev, int64_t n, int d,
+                      const int* alpha_host, int t, double scale, const double* ls_host, const double* lam_dev,
+                      void* work_dev, double* pvar_dev, fgp_stream_t stream);
+/* dense cross-kernel tile K[i,a] = k(xs_i, X_a) (m,n) for post_cov / user-facing kernel() calls */
+int fgp_lattice_cross_kernel(const double* xs_dev, int64_t m, const double* x_dev, int64_t n, int d,
+                             const int* alpha_host, double scale, const double* ls_host, double* k_dev,
+                             fgp_stream_t stream);
+int fgp_dnb2_cross_kernel(const double* xs_dev, int64_t m, const int64_t* xb_dev, int64_t n, int d,
+                          const int* alpha_host, int t, double scale, const double* ls_host, double* k_dev,
+                          fgp_stream_t stream);
+
+/* FP64 FMA-chain peak probe used by bench.py for the FP64 roofline denominator: runs `iters` dependent-chain
+ * DFMA blocks on every SM and returns the flop count in *flops (time it with events on `stream`). */
+int fgp_fp64_peak_probe(int iters, double* sink_dev, double* flops, fgp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGP_B200_H */

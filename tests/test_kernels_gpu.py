@@ -1,0 +1,238 @@
+"""GPU parity tests of the CUDA kernels, called through the C ABI (ctypes), against the CPU oracle and the golden
+fixtures produced by the unmodified reference.  Tolerance: north_star's 1e-10 relative (norm-wise for vectors);
+points are bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().cpu()
+    b = torch.as_tensor(b).detach().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from fastgaussianprocesses_b200 import _lib
+    _lib.load()
+    return _lib
+
+
+@pytest.fixture(scope="module")
+def P():
+    from oracle import primitives
+    return primitives
+
+
+dev = "cuda:0"
+
+
+@pytest.mark.parametrize("d,i0,i1", [(1, 0, 1), (2, 0, 1024), (8, 1024, 5000), (3, 0, 0), (16, 2 ** 20 - 7, 2 ** 20 + 300), (32, 5, 77)])
+def test_lattice_points_bit_exact(L, P, d, i0, i1):
+    rng = np.random.default_rng(3)
+    z = (rng.integers(0, 2 ** 31, size=d, dtype=np.uint64) * 2 + 1).astype(np.uint64)
+    shift = rng.random(d)
+    x = L.lattice_points(z, shift, i0, i1, dev).cpu().numpy()
+    ref = P.lattice_points(z, shift, i0, i1)
+    assert x.shape == ref.shape
+    assert np.array_equal(x, ref)
+
+
+@pytest.mark.parametrize("d,t,i0,i1", [(1, 32, 0, 1), (2, 63, 0, 1024), (4, 52, 1000, 70000), (16, 40, 2 ** 20, 2 ** 20 + 99), (3, 63, 0, 0)])
+def test_dnb2_points_bit_exact(L, P, d, t, i0, i1):
+    rng = np.random.default_rng(4)
+    C = P.default_dnb2_gen_mats(d, t)
+    ds = rng.integers(0, 2 ** t, size=d, dtype=np.uint64)
+    xb, x = L.dnb2_points(torch.from_numpy(C.astype(np.int64)).to(dev), ds, t, i0, i1)
+    rb, rx = P.dnb2_points(C, ds, t, i0, i1)
+    assert np.array_equal(xb.cpu().numpy(), rb)
+    assert np.array_equal(x.cpu().numpy(), rx)
+
+
+@pytest.mark.parametrize("m", list(range(0, 15)) + [16, 20])
+def test_fftbr_matches_oracle(L, P, m):
+    n = 1 << m
+    batch = 3 if m <= 14 else 1
+    g = torch.Generator().manual_seed(m)
+    x = torch.randn(batch, n, generator=g)
+    z = torch.randn(batch, n, generator=g) + 1j * torch.randn(batch, n, generator=g)
+    if m <= 14:
+        ref_r, ref_c, ref_i = P.fftbr_torch(x), P.fftbr_torch(z), P.ifftbr_torch(z)
+    else:  # definition check at sizes where the staged oracle is slow
+        br = bitrev_perm(m)
+        ref_r = torch.fft.fft(x[..., br].to(torch.complex128), norm="ortho")
+        ref_c = torch.fft.fft(z[..., br], norm="ortho")
+        ref_i = torch.fft.ifft(z, norm="ortho")[..., br]
+    assert rel(L.fftbr(x.to(dev)), ref_r) < 1e-13
+    assert rel(L.fftbr(z.to(dev)), ref_c) < 1e-13
+    assert rel(L.ifftbr(z.to(dev)), ref_i) < 1e-13
+    # round trip
+    zz = z.to(dev)
+    assert rel(L.ifftbr(L.fftbr(zz)), z) < 1e-13
+
+
+def bitrev_perm(m):
+    n = 1 << m
+    i = np.arange(n, dtype=np.uint64)
+    r = np.zeros(n, dtype=np.uint64)
+    for k in range(m):
+        r |= ((i >> np.uint64(k)) & np.uint64(1)) << np.uint64(m - 1 - k)
+    return torch.from_numpy(r.astype(np.int64))
+
+
+@pytest.mark.parametrize("m", list(range(0, 16)) + [18, 22])
+def test_fwht_matches_oracle(L, P, m):
+    n = 1 << m
+    batch = 3 if m <= 15 else 1
+    g = torch.Generator().manual_seed(100 + m)
+    x = torch.randn(batch, n, generator=g)
+    y = L.fwht(x.to(dev))
+    assert rel(y, P.fwht_torch(x)) < 1e-13
+    assert rel(L.fwht(y), x) < 1e-13  # self-inverse
+
+
+def test_fft_linearity_and_parseval_large(L):
+    n = 1 << 22
+    g = torch.Generator(device=dev).manual_seed(5)
+    a = torch.randn(n, generator=g, device=dev)
+    b = torch.randn(n, generator=g, device=dev)
+    fa, fb, fab = L.fftbr(a), L.fftbr(b), L.fftbr(2.0 * a - 3.0 * b)
+    assert rel(fab, 2.0 * fa - 3.0 * fb) < 1e-12
+    assert abs(float((fa.abs() ** 2).sum() / (a ** 2).sum()) - 1.0) < 1e-12
+    assert rel(L.ifftbr(fa).real, a) < 1e-12
+
+
+def test_fwht_parseval_large(L):
+    n = 1 << 24
+    g = torch.Generator(device=dev).manual_seed(6)
+    a = torch.randn(n, generator=g, device=dev)
+    fa = L.fwht(a)
+    assert abs(float((fa ** 2).sum() / (a ** 2).sum()) - 1.0) < 1e-12
+    assert rel(L.fwht(fa), a) < 1e-12
+
+
+def _setup(g):
+    fam = 0 if str(g["family"]) == "lattice" else 1
+    d, n, alpha = int(g["d"]), int(g["n"]), int(g["alpha"])
+    t = int(g["t"]) if fam else 0
+    x = torch.from_numpy(g["x"]).to(dev)
+    xpts = x if fam == 0 else torch.from_numpy(g["xb"]).to(dev)
+    return fam, d, n, alpha, t, x, xpts
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_kernel_parts_and_k1_vs_reference_fixture(L, case):
+    g = load_golden(case)
+    fam, d, n, alpha, t, x, xpts = _setup(g)
+    if fam == 0:
+        parts = L.lattice_kernel_parts(x, g["x"][0], [alpha] * d)
+    else:
+        parts = L.dnb2_kernel_parts(xpts, g["xb"][0], [alpha] * d, t)
+    assert rel(parts, g["k1parts"]) < 1e-13
+    scale = torch.from_numpy(g["scale0"]).to(dev)
+    ls = torch.from_numpy(g["lengthscales0"]).to(dev).reshape(1, d)
+    k1 = L.kernel_from_parts(parts, scale, ls)
+    ref = g["scale0"] * np.prod(1 + g["lengthscales0"] * g["k1parts"], axis=-1)
+    assert rel(k1[0], ref) < 1e-14
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_mll_grad_vs_reference_fixture(L, case):
+    g = load_golden(case)
+    fam, d, n, alpha, t, x, xpts = _setup(g)
+    yt = torch.from_numpy(g["ytilde"]).to(dev)
+    ysq = (yt.abs() ** 2).reshape(1, n).contiguous()
+    scale = torch.from_numpy(g["scale0"]).to(dev)
+    ls = torch.from_numpy(g["lengthscales0"]).to(dev).reshape(1, d).contiguous()
+    noise = torch.from_numpy(g["noise0"]).to(dev)
+    out, lam = L.mll_grad(fam, xpts, [alpha] * d, t, ysq, scale, ls, noise, want_grad=True, want_lam=True)
+    out = out.cpu().numpy()[0]
+    lam_ref = np.sqrt(n) * g["lam0"] + g["noise0"]
+    assert rel(lam[0], lam_ref) < TOL
+    assert abs(out[0] - g["norm_term0"].item()) <= TOL * abs(g["norm_term0"].item())
+    assert abs(out[1] - g["logdet0"].item()) <= TOL * abs(g["logdet0"].item())
+    loss = 0.5 * (out[0] + out[1] + n * np.log(2 * np.pi))
+    assert abs(loss - float(g["loss0"])) <= TOL * abs(float(g["loss0"]))
+    # raw parameters are log-transformed: dL/draw = theta * dL/dtheta
+    gs = out[3] * g["scale0"]
+    gl = out[4:4 + d] * g["lengthscales0"]
+    assert rel(gs, g["grad_raw_scale0"]) < 1e-8
+    assert rel(gl, g["grad_raw_lengthscales0"]) < 1e-8
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_posterior_vs_reference_fixture(L, case):
+    g = load_golden(case)
+    fam, d, n, alpha, t, x, xpts = _setup(g)
+    lam = torch.from_numpy(np.sqrt(n) * g["lam0"] + g["noise0"]).to(dev)
+    y = torch.from_numpy(g["y"]).to(dev)
+    coeffs = L.gram_solve(fam, y, lam)
+    assert rel(coeffs, g["coeffs0"]) < 1e-9
+    xt = torch.from_numpy(g["xtest"]).to(dev)
+    sc, ls = float(g["scale0"][0]), g["lengthscales0"]
+    # feed the REFERENCE's coeffs so the product kernel itself is compared at 1e-10
+    cref = torch.from_numpy(g["coeffs0"]).to(dev).reshape(1, n)
+    pm = L.post_mean(fam, xt, xpts, [alpha] * d, t, sc, ls, cref)
+    assert rel(pm[0], g["pmean0"]) < TOL
+    pv = L.post_var(fam, xt, xpts, [alpha] * d, t, sc, ls, lam)
+    scale_v = max(float(np.abs(g["pvar0"]).max()), sc * 1e-6)
+    assert float((pv.cpu() - torch.from_numpy(g["pvar0"])).abs().max()) < 1e-8 * scale_v + 1e-9 * sc
+    K = L.cross_kernel(fam, xt[:16], xpts, [alpha] * d, t, sc, ls)
+    assert rel((K * cref).sum(-1), g["pmean0"][:16]) < 1e-9
+
+
+@pytest.mark.parametrize("fam,d,m,alpha", [(0, 8, 14, 2), (0, 2, 13, 3), (1, 4, 14, 2), (1, 16, 13, 2), (0, 5, 15, 2), (1, 3, 16, 3), (1, 2, 14, 4), (1, 2, 14, 1), (0, 2, 13, 1)])
+def test_mll_two_pass_vs_oracle(L, P, fam, d, m, alpha):
+    """Sizes that take the two-pass (global workspace) path, checked against the CPU oracle port."""
+    from oracle.fgp_oracle import OracleFastGP
+    n = 1 << m
+    rng = np.random.default_rng(10 + m)
+    ls0 = rng.uniform(0.2, 1.3, size=d)
+    # eigenvalues below ~1e-12 * n * scale are pure transform round-off in ANY float64 implementation (the reference
+    # included), so log|lam| is only reproducible to 1e-10 when the nugget keeps lam well above that floor
+    nz = 1e-6 if alpha <= 2 else 1e-3
+    if fam == 0:
+        z = P.default_lattice_gen_vec(d)
+        xh = P.lattice_points(z, rng.random(d), 0, n)
+        o = OracleFastGP("lattice", xh, alpha=alpha, scale=2.5, lengthscales=ls0, noise=nz)
+        xpts = torch.from_numpy(xh).to(dev)
+        t = 0
+    else:
+        t = 52
+        xbh, xh = P.dnb2_points(P.default_dnb2_gen_mats(d, t), rng.integers(0, 2 ** t, size=d, dtype=np.uint64), t, 0, n)
+        o = OracleFastGP("dnb2", xh, xb=xbh, t=t, alpha=alpha, scale=2.5, lengthscales=ls0, noise=nz)
+        xpts = torch.from_numpy(xbh).to(dev)
+    y = torch.cos(2 * np.pi * o.x).sum(1) + 0.3 * torch.sin(2 * np.pi * o.x[:, 0] * 3)
+    o.add_y(y)
+    loss, norm, logdet = o.mll_loss()
+    loss.backward()
+    ysq = (o.ytilde.abs() ** 2).reshape(1, n).to(dev)
+    scale = torch.tensor([2.5], device=dev)
+    ls = torch.from_numpy(ls0).to(dev).reshape(1, d)
+    noise = torch.tensor([nz], device=dev)
+    out, lam = L.mll_grad(fam, xpts, [alpha] * d, t, ysq, scale, ls, noise, want_grad=True, want_lam=True)
+    out = out.cpu().numpy()[0]
+    assert rel(lam[0], o.full_lam().detach()) < TOL
+    assert abs(out[0] - norm.item()) <= 1e-9 * abs(norm.item())
+    assert abs(out[1] - logdet.item()) <= TOL * abs(logdet.item())
+    assert rel(out[3] * 2.5, o.raw_scale.grad) < 1e-8
+    assert rel(out[4:4 + d] * ls0, o.raw_lengthscales.grad) < 1e-8
+    # batched hyperparameter sets give the same answer per set
+    B = 3
+    out3, _ = L.mll_grad(fam, xpts, [alpha] * d, t, ysq.repeat(B, 1), scale.repeat(B), ls.repeat(B, 1).contiguous(), noise.repeat(B))
+    assert np.array_equal(out3.cpu().numpy()[1], out) and np.array_equal(out3.cpu().numpy()[2], out)
+
+
+def test_error_codes(L):
+    x = torch.zeros(6, dtype=torch.float64, device=dev)
+    with pytest.raises(AssertionError):
+        L.fwht(x)  # not a power of two
+    with pytest.raises(RuntimeError):
+        L.fwht(torch.zeros(8))  # CPU tensor: no fallback

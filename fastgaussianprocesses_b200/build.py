@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfgp_b200.so")
-SOURCES = ["fgp_core.cu", "fgp_points.cu", "fgp_kernel_eval.cu", "fgp_transform.cu", "fgp_mll.cu", "fgp_posterior.cu"]
+SOURCES = ["fgp_core.cu", "fgp_points.cu", "fgp_kernel_eval.cu", "fgp_transform.cu", "fgp_mll_lat.cu", "fgp_mll_net.cu", "fgp_solve.cu", "fgp_posterior.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--fmad=true", "-Xptxas", "-v"]
@@ -44,8 +44,8 @@ def build(force=False, verbose=False):
     if verbose:
         for l in logs:
             sys.stderr.write(l)
-    with open(os.path.join(LIBDIR, "ptxas.log"), "a" if not force else "w") as fh:
-        for l in logs:
+    for cmd, l in zip(jobs, logs):
+        with open(cmd[-1].replace(".o", ".ptxas.log"), "w") as fh:
             fh.write(l)
     if jobs or not os.path.exists(LIB):
         run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"])

@@ -10,11 +10,11 @@
 // which immediately starts the backward transform on the same tile, and the last pass contracts the back-transformed
 // dL/dk1 with the leave-one-out kernel products.  Global traffic per iteration: 16n B written + 16n B read between
 // the passes twice (complex workspace, L2-resident up to n = 2^21), 8n B of |y~|^2, and the points twice.
+#pragma once
 #include "fgp_transform.cuh"
 
 namespace fgp {
 
-constexpr int kT = 256;
 constexpr int kRed = 32 * (FGP_MAX_D + 4);  // doubles of reduction scratch
 
 struct MllArgs {
@@ -22,6 +22,7 @@ struct MllArgs {
   int64_t n;
   int d;
   int t;          // net only
+  double tscale;  // net only: 2^-t
   LatPoly P;      // lattice only
   IVec alpha;     // net only
   const double* ysq;    // (B,n)
@@ -61,33 +62,74 @@ __device__ __forceinline__ void load_hyp(Hyp& H, const MllArgs& a, int b) {
   }
 }
 
-// parts of point i against the first point
-template <int DT, bool NET>
+// net alpha = 2 without branches on alpha: W_2(delta) - 1 = 3/2 - (5/2) 2^-beta - beta x_f, beta = t - floor(log2 delta)
+__device__ __forceinline__ double dnb2_part_a2(uint64_t delta, int t, double tscale) {
+  const int fl = 63 - __clzll((long long)delta);  // -1 when delta == 0
+  const int beta = t - fl;
+  const double xf = __ull2double_rn(delta) * tscale;
+  const double pw = __longlong_as_double((long long)(1023 - beta) << 52);  // 2^-beta
+  const double r = fma(-(double)beta, xf, fma(-2.5, pw, 1.5));
+  return delta ? r : 1.5;
+}
+
+// parts of point i against the first point.  A2: every alpha_j == 2 (straight-line code, no per-dimension loop on alpha)
+template <int DT, bool NET, bool A2>
 __device__ __forceinline__ void point_parts(const MllArgs& a, const Hyp& H, int64_t i, double* p) {
+  constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
   const int d = DT > 0 ? DT : a.d;
   if (NET) {
     const int64_t* row = (const int64_t*)a.x + i * d;
+    uint64_t xr[DM];
+    if (DT > 0 && DT % 2 == 0) {
 #pragma unroll
-    for (int j = 0; j < (DT > 0 ? DT : FGP_MAX_D); ++j) {
+      for (int j = 0; j < DM; j += 2) {
+        const longlong2 v = __ldg((const longlong2*)(row + j));
+        xr[j] = (uint64_t)v.x;
+        xr[j + 1] = (uint64_t)v.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < DM; ++j) {
+        if (j >= d) break;
+        xr[j] = (uint64_t)__ldg(row + j);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < DM; ++j) {
       if (j >= d) break;
-      p[j] = dnb2_part((uint64_t)__ldg(row + j) ^ H.xb0[j], a.alpha.v[j], a.t);
+      p[j] = A2 ? dnb2_part_a2(xr[j] ^ H.xb0[j], a.t, a.tscale) : dnb2_part(xr[j] ^ H.xb0[j], a.alpha.v[j], a.t);
     }
   } else {
     const double* row = (const double*)a.x + i * d;
+    double xr[DM];
+    if (DT > 0 && DT % 2 == 0) {
 #pragma unroll
-    for (int j = 0; j < (DT > 0 ? DT : FGP_MAX_D); ++j) {
+      for (int j = 0; j < DM; j += 2) {
+        const double2 v = __ldg((const double2*)(row + j));
+        xr[j] = v.x;
+        xr[j + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < DM; ++j) {
+        if (j >= d) break;
+        xr[j] = __ldg(row + j);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < DM; ++j) {
       if (j >= d) break;
-      p[j] = lat_part(__ldg(row + j) - H.x0[j], a.P.q[j], a.P.alpha[j]);
+      p[j] = A2 ? lat_part_a2(xr[j] - H.x0[j], a.P.q[j][0], a.P.q[j][2]) : lat_part(xr[j] - H.x0[j], a.P.q[j], a.P.alpha[j]);
     }
   }
 }
 
-template <int DT, bool NET>
+template <int DT, bool NET, bool A2>
 __device__ __forceinline__ double point_k1(const MllArgs& a, const Hyp& H, int64_t i) {
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
   const int d = DT > 0 ? DT : a.d;
   double p[DM];
-  point_parts<DT, NET>(a, H, i, p);
+  point_parts<DT, NET, A2>(a, H, i, p);
   double k = H.scale;
 #pragma unroll
   for (int j = 0; j < DM; ++j) {
@@ -98,12 +140,12 @@ __device__ __forceinline__ double point_k1(const MllArgs& a, const Hyp& H, int64
 }
 
 // acc[0] += w*k1 ; acc[1+j] += w * dk1/dls_j   (leave-one-out products: factors may cross zero)
-template <int DT, bool NET>
+template <int DT, bool NET, bool A2>
 __device__ __forceinline__ void point_grad(const MllArgs& a, const Hyp& H, int64_t i, double w, double* acc) {
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
   const int d = DT > 0 ? DT : a.d;
   double p[DM], left[DM];
-  point_parts<DT, NET>(a, H, i, p);
+  point_parts<DT, NET, A2>(a, H, i, p);
   double pre = H.scale;
 #pragma unroll
   for (int j = 0; j < DM; ++j) {
@@ -162,8 +204,8 @@ __device__ __forceinline__ void reduce_store(double* v, int nv, double* red, dou
 // ------------------------------------------------------------------------------------------------------------
 // single-pass kernel: one CTA per hyperparameter set, n <= block capacity
 // ------------------------------------------------------------------------------------------------------------
-template <int DT, bool NET>
-__global__ void __launch_bounds__(kT) mll_single_kernel(MllArgs a) {
+template <int DT, bool NET, bool A2>
+__global__ void __launch_bounds__(256, 2) mll_single_kernel(MllArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
   __shared__ double red[kRed];
@@ -177,8 +219,8 @@ __global__ void __launch_bounds__(kT) mll_single_kernel(MllArgs a) {
   double2* smc = (double2*)smraw;
   double* smr = (double*)smraw;
   const double c = H.scale;  // DC guess removed before the transform (role of abstract_fast_gp.py:209-211)
-  for (int i = threadIdx.x; i < n; i += kT) {
-    const double k1 = point_k1<DT, NET>(a, H, i) - c;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double k1 = point_k1<DT, NET, A2>(a, H, i) - c;
     if (NET)
       smr[padidx(i)] = k1;
     else
@@ -191,7 +233,7 @@ __global__ void __launch_bounds__(kT) mll_single_kernel(MllArgs a) {
     block_fft_fwd(smc, l, 1, LP, a.T.stage);
   double s[3] = {0.0, 0.0, 0.0};
   const double* ysq = a.ysq + (int64_t)b * n;
-  for (int k = threadIdx.x; k < n; k += kT) {
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
     if (NET) {
       double lam = smr[padidx(k)] + H.noise;
       if (k == 0) lam += c * (double)n;
@@ -217,9 +259,9 @@ __global__ void __launch_bounds__(kT) mll_single_kernel(MllArgs a) {
   double acc[DM + 1];
 #pragma unroll
   for (int j = 0; j <= DM; ++j) acc[j] = 0.0;
-  for (int i = threadIdx.x; i < n; i += kT) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double w = NET ? smr[padidx(i)] : smc[padidx(i)].x;
-    point_grad<DT, NET>(a, H, i, w, acc);
+    point_grad<DT, NET, A2>(a, H, i, w, acc);
   }
   acc[0] /= H.scale;
   reduce_store<DM + 1>(acc, d + 1, red, out + 3);
@@ -229,8 +271,8 @@ __global__ void __launch_bounds__(kT) mll_single_kernel(MllArgs a) {
 // two-pass kernels
 // ------------------------------------------------------------------------------------------------------------
 // pass A: k1 on the fly -> contiguous block transform -> inter-pass twiddle -> workspace
-template <int DT, bool NET>
-__global__ void __launch_bounds__(kT) mll_passA_kernel(MllArgs a) {
+template <int DT, bool NET, bool A2>
+__global__ void __launch_bounds__(256, 2) mll_passA_kernel(MllArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
   const int b = blockIdx.y;
@@ -244,8 +286,8 @@ __global__ void __launch_bounds__(kT) mll_passA_kernel(MllArgs a) {
   const int64_t g0 = blk0 << l1;
   const int qmask = (1 << l1) - 1;
   const double c = H.scale;
-  for (int e = threadIdx.x; e < cnt; e += kT) {
-    const double k1 = point_k1<DT, NET>(a, H, g0 + e) - c;
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+    const double k1 = point_k1<DT, NET, A2>(a, H, g0 + e) - c;
     const int si = (e >> l1) * LP + padidx(e & qmask);
     if (NET)
       smr[si] = k1;
@@ -256,11 +298,11 @@ __global__ void __launch_bounds__(kT) mll_passA_kernel(MllArgs a) {
   if (NET) {
     block_wht(smr, l1, ntr, LP);
     double* W = (double*)a.W + (int64_t)b * a.n;
-    for (int e = threadIdx.x; e < cnt; e += kT) W[g0 + e] = smr[(e >> l1) * LP + padidx(e & qmask)];
+    for (int e = threadIdx.x; e < cnt; e += blockDim.x) W[g0 + e] = smr[(e >> l1) * LP + padidx(e & qmask)];
   } else {
     block_fft_fwd(smc, l1, ntr, LP, a.T.stage);
     double2* W = (double2*)a.W + (int64_t)b * a.n;
-    for (int e = threadIdx.x; e < cnt; e += kT) {
+    for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
       const int tr = e >> l1, q = e & qmask;
       const uint32_t bb = (uint32_t)((blk0 + tr) & ((1 << l2) - 1));
       W[g0 + e] = cmul(smc[tr * LP + padidx(q)], twiddle_n(a.T, brev_bits(bb, l2) * (uint32_t)q));
@@ -270,7 +312,7 @@ __global__ void __launch_bounds__(kT) mll_passA_kernel(MllArgs a) {
 
 // pass B: strided columns -> forward transform -> spectral epilogue -> backward transform of dL/dlam -> workspace
 template <bool NET>
-__global__ void __launch_bounds__(kT) mll_passB_kernel(MllArgs a) {
+__global__ void __launch_bounds__(256, 2) mll_passB_kernel(MllArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ double red[kRed];
   __shared__ double s_noise, s_scale;
@@ -288,13 +330,13 @@ __global__ void __launch_bounds__(kT) mll_passB_kernel(MllArgs a) {
   const int64_t boff = (int64_t)b * a.n;
   if (NET) {
     const double* W = (const double*)a.W + boff + q0;
-    for (int e = threadIdx.x; e < cnt; e += kT) {
+    for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
       const int cc = e & (ntr - 1), r = e >> lntr;
       smr[cc * LP + padidx(r)] = W[((int64_t)r << l1) + cc];
     }
   } else {
     const double2* W = (const double2*)a.W + boff + q0;
-    for (int e = threadIdx.x; e < cnt; e += kT) {
+    for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
       const int cc = e & (ntr - 1), r = e >> lntr;
       smc[cc * LP + padidx(r)] = W[((int64_t)r << l1) + cc];
     }
@@ -307,7 +349,7 @@ __global__ void __launch_bounds__(kT) mll_passB_kernel(MllArgs a) {
   double s[3] = {0.0, 0.0, 0.0};
   const double* ysq = a.ysq + boff + q0;
   const double noise = s_noise;
-  for (int e = threadIdx.x; e < cnt; e += kT) {
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
     const int cc = e & (ntr - 1), r = e >> lntr;
     const int64_t k = ((int64_t)r << l1) + cc;  // + q0
     const int si = cc * LP + padidx(r);
@@ -330,14 +372,14 @@ __global__ void __launch_bounds__(kT) mll_passB_kernel(MllArgs a) {
   if (NET) {
     block_wht(smr, l2, ntr, LP);
     double* W = (double*)a.W + boff + q0;
-    for (int e = threadIdx.x; e < cnt; e += kT) {
+    for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
       const int cc = e & (ntr - 1), r = e >> lntr;
       W[((int64_t)r << l1) + cc] = smr[cc * LP + padidx(r)];
     }
   } else {
     block_fft_inv(smc, l2, ntr, LP, a.T.stage);
     double2* W = (double2*)a.W + boff + q0;
-    for (int e = threadIdx.x; e < cnt; e += kT) {
+    for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
       const int cc = e & (ntr - 1), r = e >> lntr;
       const double2 w = twiddle_n(a.T, brev_bits((uint32_t)r, l2) * (uint32_t)(q0 + cc));
       W[((int64_t)r << l1) + cc] = cmulc(w, smc[cc * LP + padidx(r)]);
@@ -346,8 +388,8 @@ __global__ void __launch_bounds__(kT) mll_passB_kernel(MllArgs a) {
 }
 
 // pass C: contiguous blocks of the back-transformed dL/dlam -> inverse block transform -> contraction with dk1/dtheta
-template <int DT, bool NET>
-__global__ void __launch_bounds__(kT) mll_passC_kernel(MllArgs a) {
+template <int DT, bool NET, bool A2>
+__global__ void __launch_bounds__(256, 2) mll_passC_kernel(MllArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
   __shared__ double red[kRed];
@@ -363,10 +405,10 @@ __global__ void __launch_bounds__(kT) mll_passC_kernel(MllArgs a) {
   const int qmask = (1 << l1) - 1;
   if (NET) {
     const double* W = (const double*)a.W + (int64_t)b * a.n;
-    for (int e = threadIdx.x; e < cnt; e += kT) smr[(e >> l1) * LP + padidx(e & qmask)] = W[g0 + e];
+    for (int e = threadIdx.x; e < cnt; e += blockDim.x) smr[(e >> l1) * LP + padidx(e & qmask)] = W[g0 + e];
   } else {
     const double2* W = (const double2*)a.W + (int64_t)b * a.n;
-    for (int e = threadIdx.x; e < cnt; e += kT) smc[(e >> l1) * LP + padidx(e & qmask)] = W[g0 + e];
+    for (int e = threadIdx.x; e < cnt; e += blockDim.x) smc[(e >> l1) * LP + padidx(e & qmask)] = W[g0 + e];
   }
   __syncthreads();
   if (NET)
@@ -377,16 +419,16 @@ __global__ void __launch_bounds__(kT) mll_passC_kernel(MllArgs a) {
   double acc[DM + 1];
 #pragma unroll
   for (int j = 0; j <= DM; ++j) acc[j] = 0.0;
-  for (int e = threadIdx.x; e < cnt; e += kT) {
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
     const int si = (e >> l1) * LP + padidx(e & qmask);
     const double w = NET ? smr[si] : smc[si].x;
-    point_grad<DT, NET>(a, H, g0 + e, w, acc);
+    point_grad<DT, NET, A2>(a, H, g0 + e, w, acc);
   }
   reduce_store<DM + 1>(acc, d + 1, red, a.partC + ((int64_t)b * a.ctasA + blockIdx.x) * (d + 1));
 }
 
 // finalize: deterministic reduction of the per-CTA partial sums
-__global__ void __launch_bounds__(kT) mll_finalize_kernel(MllArgs a) {
+static __global__ void __launch_bounds__(256, 2) mll_finalize_kernel(MllArgs a) {
   __shared__ double red[kRed];
   const int b = blockIdx.x;
   const int d = a.d;
@@ -394,7 +436,7 @@ __global__ void __launch_bounds__(kT) mll_finalize_kernel(MllArgs a) {
   {
     double s[3] = {0.0, 0.0, 0.0};
     const double* p = a.partB + (int64_t)b * a.ctasB * 3;
-    for (int c = threadIdx.x; c < a.ctasB; c += kT) {
+    for (int c = threadIdx.x; c < a.ctasB; c += blockDim.x) {
       s[0] += p[c * 3 + 0];
       s[1] += p[c * 3 + 1];
       s[2] += p[c * 3 + 2];
@@ -406,41 +448,16 @@ __global__ void __launch_bounds__(kT) mll_finalize_kernel(MllArgs a) {
   const double inv_scale = 1.0 / a.scale[b];
   for (int j = 0; j <= d; ++j) {
     double v[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int c = threadIdx.x; c < a.ctasA; c += kT) v[0] += p[(int64_t)c * (d + 1) + j];
+    for (int c = threadIdx.x; c < a.ctasA; c += blockDim.x) v[0] += p[(int64_t)c * (d + 1) + j];
     block_sum<4>(v, red);
     if (threadIdx.x == 0) out[3 + j] = j == 0 ? v[0] * inv_scale : v[0];
     __syncthreads();
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// K^-1 y: spectral division kernels used between the stand-alone transforms
-// ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) divide_c_kernel(double2* __restrict__ v, const double2* __restrict__ lam,
-                                                       int64_t R, int64_t n) {
-  const int64_t total = R * n;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const double2 l = lam[e % n];
-    const double inv = 1.0 / fma(l.x, l.x, l.y * l.y);
-    const double2 x = v[e];
-    v[e] = make_double2(fma(x.x, l.x, x.y * l.y) * inv, fma(x.y, l.x, -x.x * l.y) * inv);  // x * conj(l) / |l|^2
-  }
-}
-__global__ void __launch_bounds__(256) divide_r_kernel(double* __restrict__ v, const double* __restrict__ lam, int64_t R,
-                                                       int64_t n) {
-  const int64_t total = R * n;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
-    v[e] = v[e] / lam[e % n];
-}
-__global__ void __launch_bounds__(256) real_part_kernel(const double2* __restrict__ v, double* __restrict__ out,
-                                                        int64_t total) {
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
-    out[e] = v[e].x;
-}
-
 template <typename K>
 static int set_smem_attr(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) {
+  if (bytes > 24 * 1024) {  // static shared memory counts towards the 48 KiB default limit
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(%zu bytes): %s", bytes, cudaGetErrorString(e));
@@ -450,47 +467,57 @@ static int set_smem_attr(K kernel, size_t bytes) {
   return FGP_OK;
 }
 
-template <int DT, bool NET>
+template <int DT, bool NET, bool A2>
 static int launch_mll(const MllArgs& a, const PassGeom& g, int B, cudaStream_t st) {
   int rc;
   if (g.l2 == 0) {
-    if ((rc = set_smem_attr(mll_single_kernel<DT, NET>, g.smemA))) return rc;
-    mll_single_kernel<DT, NET><<<B, kT, g.smemA, st>>>(a);
+    if ((rc = set_smem_attr(mll_single_kernel<DT, NET, A2>, g.smemA))) return rc;
+    mll_single_kernel<DT, NET, A2><<<B, g.threads, g.smemA, st>>>(a);
     FGP_LAUNCH_CHECK();
     return FGP_OK;
   }
-  if ((rc = set_smem_attr(mll_passA_kernel<DT, NET>, g.smemA))) return rc;
-  mll_passA_kernel<DT, NET><<<dim3(a.ctasA, B), kT, g.smemA, st>>>(a);
+  if ((rc = set_smem_attr(mll_passA_kernel<DT, NET, A2>, g.smemA))) return rc;
+  mll_passA_kernel<DT, NET, A2><<<dim3(a.ctasA, B), g.threads, g.smemA, st>>>(a);
   FGP_LAUNCH_CHECK();
   if ((rc = set_smem_attr(mll_passB_kernel<NET>, g.smemB))) return rc;
-  mll_passB_kernel<NET><<<dim3(a.ctasB, B), kT, g.smemB, st>>>(a);
+  mll_passB_kernel<NET><<<dim3(a.ctasB, B), g.threads, g.smemB, st>>>(a);
   FGP_LAUNCH_CHECK();
   if (a.want_grad) {
-    if ((rc = set_smem_attr(mll_passC_kernel<DT, NET>, g.smemA))) return rc;
-    mll_passC_kernel<DT, NET><<<dim3(a.ctasA, B), kT, g.smemA, st>>>(a);
+    if ((rc = set_smem_attr(mll_passC_kernel<DT, NET, A2>, g.smemA))) return rc;
+    mll_passC_kernel<DT, NET, A2><<<dim3(a.ctasA, B), g.threads, g.smemA, st>>>(a);
     FGP_LAUNCH_CHECK();
   }
-  mll_finalize_kernel<<<B, kT, 0, st>>>(a);
+  mll_finalize_kernel<<<B, 256, 0, st>>>(a);
   FGP_LAUNCH_CHECK();
   return FGP_OK;
 }
 
 template <bool NET>
-static int dispatch_mll(const MllArgs& a, const PassGeom& g, int B, cudaStream_t st) {
+static int dispatch_mll(const MllArgs& a, const PassGeom& g, int B, bool all2, cudaStream_t st) {
+  if (all2) {
+    switch (a.d) {
+      case 2: return launch_mll<2, NET, true>(a, g, B, st);
+      case 4: return launch_mll<4, NET, true>(a, g, B, st);
+      case 8: return launch_mll<8, NET, true>(a, g, B, st);
+      case 16: return launch_mll<16, NET, true>(a, g, B, st);
+      default: break;
+    }
+  }
   switch (a.d) {
-    case 2: return launch_mll<2, NET>(a, g, B, st);
-    case 4: return launch_mll<4, NET>(a, g, B, st);
-    case 8: return launch_mll<8, NET>(a, g, B, st);
-    case 16: return launch_mll<16, NET>(a, g, B, st);
-    default: return launch_mll<0, NET>(a, g, B, st);
+    case 2: return launch_mll<2, NET, false>(a, g, B, st);
+    case 4: return launch_mll<4, NET, false>(a, g, B, st);
+    case 8: return launch_mll<8, NET, false>(a, g, B, st);
+    default: return launch_mll<0, NET, false>(a, g, B, st);
   }
 }
 
-static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-static int mll_common(bool net, const void* x, int64_t n, int d, const int* alpha_host, int t, int B, const double* ysq,
+template <bool NET>
+static int mll_common( const void* x, int64_t n, int d, const int* alpha_host, int t, int B, const double* ysq,
                       const double* scale, const double* ls, const double* noise, const void* table, void* workspace,
                       double* lam, double* out, int want_grad, fgp_stream_t stream) {
+  const bool net = NET;
   FGP_REQUIRE(x && alpha_host && ysq && scale && ls && noise && out, "mll_grad: null pointer");
   FGP_REQUIRE(d >= 1 && d <= FGP_MAX_D, "mll_grad: d=%d outside 1..%d", d, FGP_MAX_D);
   FGP_REQUIRE(B >= 1 && B <= 65535, "mll_grad: B=%d outside 1..65535", B);
@@ -502,6 +529,7 @@ static int mll_common(bool net, const void* x, int64_t n, int d, const int* alph
   a.n = n;
   a.d = d;
   a.t = t;
+  a.tscale = ldexp(1.0, -t);
   if (net) {
     FGP_REQUIRE(t >= 1 && t < 64, "mll_grad: t outside 1..63");
     for (int j = 0; j < d; ++j) {
@@ -514,7 +542,7 @@ static int mll_common(bool net, const void* x, int64_t n, int d, const int* alph
     if (rc) return rc;
     a.T = make_tables(table);
   }
-  const PassGeom g = make_geom(n, net ? kBlkLogR : kBlkLogC, net ? sizeof(double) : sizeof(double2));
+  const PassGeom g = make_geom(n, !net);
   a.ysq = ysq;
   a.scale = scale;
   a.ls = ls;
@@ -538,64 +566,9 @@ static int mll_common(bool net, const void* x, int64_t n, int d, const int* alph
     a.partB = (double*)((char*)workspace + wbytes);
     a.partC = (double*)((char*)workspace + wbytes + pb);
   }
-  return net ? dispatch_mll<true>(a, g, B, (cudaStream_t)stream) : dispatch_mll<false>(a, g, B, (cudaStream_t)stream);
+  bool all2 = true;
+  for (int j = 0; j < d; ++j) all2 = all2 && alpha_host[j] == 2;
+  return dispatch_mll<NET>(a, g, B, all2, (cudaStream_t)stream);
 }
 
 }  // namespace fgp
-
-extern "C" {
-
-size_t fgp_mll_workspace_bytes(int family, int64_t n, int d, int B) {
-  using namespace fgp;
-  if (!is_pow2(n) || B < 1 || d < 1) return 0;
-  const bool net = family != 0;
-  const PassGeom g = make_geom(n, net ? kBlkLogR : kBlkLogC, net ? sizeof(double) : sizeof(double2));
-  if (g.l2 == 0) return 256;
-  return align256((size_t)B * n * (net ? sizeof(double) : sizeof(double2))) +
-         align256((size_t)B * g.ctasB * 3 * sizeof(double)) + align256((size_t)B * g.ctasA * (d + 1) * sizeof(double));
-}
-
-int fgp_lattice_mll_grad(const double* x_dev, int64_t n, int d, const int* alpha_host, int B, const double* ysq_dev,
-                         const double* scale_dev, const double* ls_dev, const double* noise_dev, const void* table_dev,
-                         void* workspace_dev, double* lam_dev, double* out_dev, int want_grad, fgp_stream_t stream) {
-  return fgp::mll_common(false, x_dev, n, d, alpha_host, 0, B, ysq_dev, scale_dev, ls_dev, noise_dev, table_dev,
-                         workspace_dev, lam_dev, out_dev, want_grad, stream);
-}
-
-int fgp_dnb2_mll_grad(const int64_t* xb_dev, int64_t n, int d, const int* alpha_host, int t, int B, const double* ysq_dev,
-                      const double* scale_dev, const double* ls_dev, const double* noise_dev, void* workspace_dev,
-                      double* lam_dev, double* out_dev, int want_grad, fgp_stream_t stream) {
-  return fgp::mll_common(true, xb_dev, n, d, alpha_host, t, B, ysq_dev, scale_dev, ls_dev, noise_dev, nullptr,
-                         workspace_dev, lam_dev, out_dev, want_grad, stream);
-}
-
-int fgp_gram_solve(int family, const double* y_dev, double* out_dev, int64_t R, int64_t n, const double* lam_dev,
-                   const void* table_dev, void* work_dev, fgp_stream_t stream) {
-  using namespace fgp;
-  FGP_REQUIRE(y_dev && out_dev && lam_dev, "gram_solve: null pointer");
-  FGP_REQUIRE(R >= 0 && is_pow2(n), "gram_solve: bad R/n");
-  if (R == 0) return FGP_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int64_t total = R * n;
-  int64_t blocks = (total + 255) / 256;
-  const int64_t cap = (int64_t)sm_count() * 16;
-  if (blocks > cap) blocks = cap;
-  int rc;
-  if (family == 0) {
-    FGP_REQUIRE(table_dev && work_dev, "gram_solve: lattice needs a twiddle table and a complex workspace");
-    if ((rc = fgp_fftbr_r2c(y_dev, (double*)work_dev, R, n, table_dev, stream))) return rc;
-    divide_c_kernel<<<(unsigned)blocks, 256, 0, st>>>((double2*)work_dev, (const double2*)lam_dev, R, n);
-    FGP_LAUNCH_CHECK();
-    if ((rc = fgp_ifftbr_c2c((const double*)work_dev, (double*)work_dev, R, n, table_dev, stream))) return rc;
-    real_part_kernel<<<(unsigned)blocks, 256, 0, st>>>((const double2*)work_dev, out_dev, total);
-    FGP_LAUNCH_CHECK();
-  } else {
-    if ((rc = fgp_fwht(y_dev, out_dev, R, n, stream))) return rc;
-    divide_r_kernel<<<(unsigned)blocks, 256, 0, st>>>(out_dev, lam_dev, R, n);
-    FGP_LAUNCH_CHECK();
-    if ((rc = fgp_fwht(out_dev, out_dev, R, n, stream))) return rc;
-  }
-  return FGP_OK;
-}
-
-}  // extern "C"

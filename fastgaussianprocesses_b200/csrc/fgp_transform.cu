@@ -4,7 +4,6 @@
 
 namespace fgp {
 
-constexpr int kThreads = 256;
 
 __global__ void fft_table_kernel(double2* stage, double2* lo, double2* hi, double n) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -32,7 +31,7 @@ __global__ void fft_table_kernel(double2* stage, double2* lo, double2* hi, doubl
 
 // ---- forward -------------------------------------------------------------------------------------------------
 template <bool REAL_IN>
-__global__ void __launch_bounds__(kThreads) fft_passA_fwd(const double* __restrict__ in, double2* __restrict__ out,
+__global__ void __launch_bounds__(256, 2) fft_passA_fwd(const double* __restrict__ in, double2* __restrict__ out,
                                                          int64_t total_blocks, int l1, int l2, int ntr, int LP,
                                                          double scale, FftTables T) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -42,7 +41,7 @@ __global__ void __launch_bounds__(kThreads) fft_passA_fwd(const double* __restri
   const int cnt = nb << l1;
   const int64_t g0 = blk0 << l1;
   const int qmask = (1 << l1) - 1;
-  for (int e = threadIdx.x; e < cnt; e += kThreads) {
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
     double2 v;
     if (REAL_IN) {
       v = make_double2(in[g0 + e] * scale, 0.0);
@@ -55,7 +54,7 @@ __global__ void __launch_bounds__(kThreads) fft_passA_fwd(const double* __restri
   }
   __syncthreads();
   block_fft_fwd(sm, l1, nb, LP, T.stage);
-  for (int e = threadIdx.x; e < cnt; e += kThreads) {
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
     const int tr = e >> l1, q = e & qmask;
     double2 v = sm[tr * LP + padidx(q)];
     if (l2) {
@@ -67,7 +66,7 @@ __global__ void __launch_bounds__(kThreads) fft_passA_fwd(const double* __restri
 }
 
 template <bool INV>
-__global__ void __launch_bounds__(kThreads) fft_passB(const double2* __restrict__ in, double2* __restrict__ out, int l1,
+__global__ void __launch_bounds__(256, 2) fft_passB(const double2* __restrict__ in, double2* __restrict__ out, int l1,
                                                      int l2, int lntr, int LP, FftTables T) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double2* sm = (double2*)smraw;
@@ -77,7 +76,7 @@ __global__ void __launch_bounds__(kThreads) fft_passB(const double2* __restrict_
   const int q0 = (int)(col0 & ((1 << l1) - 1));
   const int64_t base = (item << (l1 + l2)) + q0;
   const int cnt = ntr << l2;
-  for (int e = threadIdx.x; e < cnt; e += kThreads) {
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
     const int cc = e & (ntr - 1), b = e >> lntr;
     sm[cc * LP + padidx(b)] = in[base + ((int64_t)b << l1) + cc];
   }
@@ -86,7 +85,7 @@ __global__ void __launch_bounds__(kThreads) fft_passB(const double2* __restrict_
     block_fft_fwd(sm, l2, ntr, LP, T.stage);
   else
     block_fft_inv(sm, l2, ntr, LP, T.stage);
-  for (int e = threadIdx.x; e < cnt; e += kThreads) {
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
     const int cc = e & (ntr - 1), b = e >> lntr;
     double2 v = sm[cc * LP + padidx(b)];
     if (INV) {
@@ -97,7 +96,7 @@ __global__ void __launch_bounds__(kThreads) fft_passB(const double2* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(kThreads) fft_passA_inv(const double2* __restrict__ in, double2* __restrict__ out,
+__global__ void __launch_bounds__(256, 2) fft_passA_inv(const double2* __restrict__ in, double2* __restrict__ out,
                                                          int64_t total_blocks, int l1, int ntr, int LP, double scale,
                                                          FftTables T) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -107,10 +106,10 @@ __global__ void __launch_bounds__(kThreads) fft_passA_inv(const double2* __restr
   const int cnt = nb << l1;
   const int64_t g0 = blk0 << l1;
   const int qmask = (1 << l1) - 1;
-  for (int e = threadIdx.x; e < cnt; e += kThreads) sm[(e >> l1) * LP + padidx(e & qmask)] = in[g0 + e];
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) sm[(e >> l1) * LP + padidx(e & qmask)] = in[g0 + e];
   __syncthreads();
   block_fft_inv(sm, l1, nb, LP, T.stage);
-  for (int e = threadIdx.x; e < cnt; e += kThreads) {
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
     double2 v = sm[(e >> l1) * LP + padidx(e & qmask)];
     v.x *= scale;
     v.y *= scale;
@@ -119,7 +118,7 @@ __global__ void __launch_bounds__(kThreads) fft_passA_inv(const double2* __restr
 }
 
 // ---- FWHT ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) wht_passA(const double* __restrict__ in, double* __restrict__ out,
+__global__ void __launch_bounds__(1024, 1) wht_passA(const double* __restrict__ in, double* __restrict__ out,
                                                      int64_t total_blocks, int l1, int ntr, int LP, double scale) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double* sm = (double*)smraw;
@@ -128,13 +127,13 @@ __global__ void __launch_bounds__(kThreads) wht_passA(const double* __restrict__
   const int cnt = nb << l1;
   const int64_t g0 = blk0 << l1;
   const int qmask = (1 << l1) - 1;
-  for (int e = threadIdx.x; e < cnt; e += kThreads) sm[(e >> l1) * LP + padidx(e & qmask)] = in[g0 + e] * scale;
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) sm[(e >> l1) * LP + padidx(e & qmask)] = in[g0 + e] * scale;
   __syncthreads();
   block_wht(sm, l1, nb, LP);
-  for (int e = threadIdx.x; e < cnt; e += kThreads) out[g0 + e] = sm[(e >> l1) * LP + padidx(e & qmask)];
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) out[g0 + e] = sm[(e >> l1) * LP + padidx(e & qmask)];
 }
 
-__global__ void __launch_bounds__(kThreads) wht_passB(double* __restrict__ data, int l1, int l2, int lntr, int LP) {
+__global__ void __launch_bounds__(1024, 1) wht_passB(double* __restrict__ data, int l1, int l2, int lntr, int LP) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double* sm = (double*)smraw;
   const int ntr = 1 << lntr;
@@ -143,13 +142,13 @@ __global__ void __launch_bounds__(kThreads) wht_passB(double* __restrict__ data,
   const int q0 = (int)(col0 & ((1 << l1) - 1));
   double* base = data + (item << (l1 + l2)) + q0;
   const int cnt = ntr << l2;
-  for (int e = threadIdx.x; e < cnt; e += kThreads) {
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
     const int cc = e & (ntr - 1), b = e >> lntr;
     sm[cc * LP + padidx(b)] = base[((int64_t)b << l1) + cc];
   }
   __syncthreads();
   block_wht(sm, l2, ntr, LP);
-  for (int e = threadIdx.x; e < cnt; e += kThreads) {
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
     const int cc = e & (ntr - 1), b = e >> lntr;
     base[((int64_t)b << l1) + cc] = sm[cc * LP + padidx(b)];
   }
@@ -157,7 +156,7 @@ __global__ void __launch_bounds__(kThreads) wht_passB(double* __restrict__ data,
 
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) {
+  if (bytes > 24 * 1024) {  // static shared memory counts towards the 48 KiB default limit
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(%zu bytes): %s", bytes, cudaGetErrorString(e));
@@ -182,7 +181,7 @@ static int check_transform_args(const void* in, const void* out, int64_t batch, 
 
 static int fft_forward(const double* in, double* out, int64_t batch, int64_t n, const void* table, bool real_in,
                        cudaStream_t st) {
-  const PassGeom g = make_geom(n, kBlkLogC, sizeof(double2));
+  const PassGeom g = make_geom(n, true);
   const FftTables T = make_tables(table);
   const int64_t total_blocks = batch * (n >> g.l1);
   const int64_t ctas = (total_blocks + g.ntrA - 1) / g.ntrA;
@@ -190,18 +189,18 @@ static int fft_forward(const double* in, double* out, int64_t batch, int64_t n, 
   int rc;
   if (real_in) {
     if ((rc = set_smem(fft_passA_fwd<true>, g.smemA))) return rc;
-    fft_passA_fwd<true><<<(unsigned)ctas, kThreads, g.smemA, st>>>(in, (double2*)out, total_blocks, g.l1, g.l2, g.ntrA,
+    fft_passA_fwd<true><<<(unsigned)ctas, g.threads, g.smemA, st>>>(in, (double2*)out, total_blocks, g.l1, g.l2, g.ntrA,
                                                                   g.LPA, scale, T);
   } else {
     if ((rc = set_smem(fft_passA_fwd<false>, g.smemA))) return rc;
-    fft_passA_fwd<false><<<(unsigned)ctas, kThreads, g.smemA, st>>>(in, (double2*)out, total_blocks, g.l1, g.l2, g.ntrA,
+    fft_passA_fwd<false><<<(unsigned)ctas, g.threads, g.smemA, st>>>(in, (double2*)out, total_blocks, g.l1, g.l2, g.ntrA,
                                                                    g.LPA, scale, T);
   }
   FGP_LAUNCH_CHECK();
   if (g.l2) {
     if ((rc = set_smem(fft_passB<false>, g.smemB))) return rc;
     const int64_t ctasB = (batch << g.l1) / g.ntrB;
-    fft_passB<false><<<(unsigned)ctasB, kThreads, g.smemB, st>>>((const double2*)out, (double2*)out, g.l1, g.l2,
+    fft_passB<false><<<(unsigned)ctasB, g.threads, g.smemB, st>>>((const double2*)out, (double2*)out, g.l1, g.l2,
                                                                 ilog2(g.ntrB), g.LPB, T);
     FGP_LAUNCH_CHECK();
   }
@@ -255,20 +254,20 @@ int fgp_ifftbr_c2c(const double* in_dev, double* out_dev, int64_t batch, int64_t
   FGP_REQUIRE(table_dev, "ifftbr_c2c: null table");
   if (batch == 0) return FGP_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const PassGeom g = make_geom(n, kBlkLogC, sizeof(double2));
+  const PassGeom g = make_geom(n, true);
   const FftTables T = make_tables(table_dev);
   const double2* src = (const double2*)in_dev;
   if (g.l2) {
     if ((rc = set_smem(fft_passB<true>, g.smemB))) return rc;
     const int64_t ctasB = (batch << g.l1) / g.ntrB;
-    fft_passB<true><<<(unsigned)ctasB, kThreads, g.smemB, st>>>(src, (double2*)out_dev, g.l1, g.l2, ilog2(g.ntrB), g.LPB, T);
+    fft_passB<true><<<(unsigned)ctasB, g.threads, g.smemB, st>>>(src, (double2*)out_dev, g.l1, g.l2, ilog2(g.ntrB), g.LPB, T);
     FGP_LAUNCH_CHECK();
     src = (const double2*)out_dev;
   }
   if ((rc = set_smem(fft_passA_inv, g.smemA))) return rc;
   const int64_t total_blocks = batch * (n >> g.l1);
   const int64_t ctas = (total_blocks + g.ntrA - 1) / g.ntrA;
-  fft_passA_inv<<<(unsigned)ctas, kThreads, g.smemA, st>>>(src, (double2*)out_dev, total_blocks, g.l1, g.ntrA, g.LPA,
+  fft_passA_inv<<<(unsigned)ctas, g.threads, g.smemA, st>>>(src, (double2*)out_dev, total_blocks, g.l1, g.ntrA, g.LPA,
                                                           1.0 / sqrt((double)n), T);
   FGP_LAUNCH_CHECK();
   return FGP_OK;
@@ -280,17 +279,17 @@ int fgp_fwht(const double* in_dev, double* out_dev, int64_t batch, int64_t n, fg
   if (rc) return rc;
   if (batch == 0) return FGP_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const PassGeom g = make_geom(n, kBlkLogR, sizeof(double));
+  const PassGeom g = make_geom(n, false, 1024);
   if ((rc = set_smem(wht_passA, g.smemA))) return rc;
   const int64_t total_blocks = batch * (n >> g.l1);
   const int64_t ctas = (total_blocks + g.ntrA - 1) / g.ntrA;
-  wht_passA<<<(unsigned)ctas, kThreads, g.smemA, st>>>(in_dev, out_dev, total_blocks, g.l1, g.ntrA, g.LPA,
+  wht_passA<<<(unsigned)ctas, g.threads, g.smemA, st>>>(in_dev, out_dev, total_blocks, g.l1, g.ntrA, g.LPA,
                                                       1.0 / sqrt((double)n));
   FGP_LAUNCH_CHECK();
   if (g.l2) {
     if ((rc = set_smem(wht_passB, g.smemB))) return rc;
     const int64_t ctasB = (batch << g.l1) / g.ntrB;
-    wht_passB<<<(unsigned)ctasB, kThreads, g.smemB, st>>>(out_dev, g.l1, g.l2, ilog2(g.ntrB), g.LPB);
+    wht_passB<<<(unsigned)ctasB, g.threads, g.smemB, st>>>(out_dev, g.l1, g.l2, ilog2(g.ntrB), g.LPB);
     FGP_LAUNCH_CHECK();
   }
   return FGP_OK;

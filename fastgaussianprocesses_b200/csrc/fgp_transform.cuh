@@ -190,21 +190,27 @@ struct PassGeom {
   int ntrA; // transforms per CTA in pass A
   int ntrB; // columns per CTA in pass B
   int LPA, LPB;
+  int threads;  // CTA size: one radix-16 butterfly group per thread per round
   int64_t ctasA, ctasB;  // per batch item
   size_t smemA, smemB;
 };
-static inline PassGeom make_geom(int64_t n, int blklog, size_t elem) {
+// Tile capacity (elements per CTA) is chosen by problem size: small tiles (128 threads, 4 CTAs/SM) keep several CTAs in
+// different phases (global load / butterflies / store) resident per SM; the largest sizes need the full-size tile so
+// that two passes suffice.  l1 is taken as large as the tile allows so that pass B's column tiles are as wide as possible.
+static inline int tile_log(int m, bool cplx) {
+  if (cplx) return m <= 22 ? 11 : 12;
+  return m <= 22 ? 12 : (m == 23 ? 13 : 14);  // >= 64-byte column segments once the data no longer fits L2
+}
+static inline PassGeom make_geom(int64_t n, bool cplx, int max_threads = 256) {
   PassGeom g;
+  const size_t elem = cplx ? sizeof(double2) : sizeof(double);
   g.m = ilog2(n);
-  if (g.m <= blklog) {
-    g.l1 = g.m;
-    g.l2 = 0;
-  } else {
-    g.l1 = (g.m + 1) / 2;
-    if (g.l1 > blklog) g.l1 = blklog;
-    g.l2 = g.m - g.l1;
-  }
+  const int blklog = tile_log(g.m, cplx);
+  g.l1 = g.m <= blklog ? g.m : blklog;
+  g.l2 = g.m - g.l1;
   const int cap = 1 << blklog;
+  g.threads = cap / 16 < max_threads ? cap / 16 : max_threads;
+  if (g.threads < 32) g.threads = 32;
   g.ntrA = cap >> g.l1;
   if (g.ntrA < 1) g.ntrA = 1;
   g.ntrB = g.l2 ? (cap >> g.l2) : 1;

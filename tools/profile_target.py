@@ -1,0 +1,40 @@
+"""Small driver for ncu: runs each hot kernel a few times at the C3/C4 sizes."""
+import os
+import sys
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fastgaussianprocesses_b200 import _lib as L
+
+dev = "cuda:0"
+torch.set_default_dtype(torch.float64)
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+d, n = 8, 1 << 20
+z = [1, 182667, 469891, 498753, 110745, 446247, 250185, 118627]
+xp = L.lattice_points(z, np.linspace(0.1, 0.9, d), 0, n, dev)
+if which in ("all", "fft"):
+    x = torch.randn(n, device=dev)
+    for _ in range(reps):
+        y = L.fftbr(x)
+        x2 = L.ifftbr(y)
+if which in ("all", "fwht"):
+    x = torch.randn(1 << 24, device=dev)
+    for _ in range(reps):
+        y = L.fwht(x)
+    x = torch.randn(1 << 20, device=dev)
+    for _ in range(reps):
+        y = L.fwht(x)
+if which in ("all", "mll"):
+    ysq = torch.rand(1, n, device=dev)
+    scale = torch.ones(1, device=dev); ls = torch.full((1, d), 0.5, device=dev); noise = torch.full((1,), 1e-6, device=dev)
+    for _ in range(reps):
+        L.mll_grad(0, xp, [2] * d, 0, ysq, scale, ls, noise)
+if which in ("all", "pmean"):
+    xs = torch.rand(1 << 13, d, device=dev)
+    co = torch.randn(1, n, device=dev)
+    for _ in range(reps):
+        L.post_mean(0, xs, xp, [2] * d, 0, 1.0, [0.5] * d, co)
+torch.cuda.synchronize()
+print("ok")

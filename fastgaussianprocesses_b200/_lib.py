@@ -32,8 +32,8 @@ SIGNATURES = {
     "fgp_ifftbr_c2c": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "fgp_fwht": (_i32, [_vp, _vp, _i64, _i64, _vp]),
     "fgp_mll_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32]),
-    "fgp_lattice_mll_grad": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
-    "fgp_dnb2_mll_grad": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "fgp_lattice_mll_grad": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "fgp_dnb2_mll_grad": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "fgp_gram_solve": (_i32, [_i32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "fgp_post_mean_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "fgp_lattice_post_mean": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _f64, _vp, _vp, _i32, _vp, _vp, _vp]),
@@ -244,7 +244,7 @@ def _workspace(kind, nbytes, device):
     return ws
 
 
-def mll_grad(family, xpts, alpha, t, ysq, scale, ls, noise, want_grad=True, want_lam=False):
+def mll_grad(family, xpts, alpha, t, ysq, scale, ls, noise, want_grad=True, want_lam=False, weights=None):
     """Fused MLL terms + gradients.  xpts: (n,d) float64 (lattice) / int64 (net); ysq (B,n); scale (B,), ls (B,d), noise (B,).
     Returns out (B, d+4) = [norm, logdet, dL/dnoise, dL/dscale, dL/dls...] and lam (B,n) or None."""
     n, d = xpts.shape
@@ -253,16 +253,17 @@ def mll_grad(family, xpts, alpha, t, ysq, scale, ls, noise, want_grad=True, want
     out = torch.zeros((B, d + 4), dtype=torch.float64, device=dev)
     lam = torch.empty((B, n), dtype=torch.complex128 if family == 0 else torch.float64, device=dev) if want_lam else None
     ws = _workspace("mll", load().fgp_mll_workspace_bytes(family, n, d, B), dev)
+    wptr = None if weights is None else _dev(weights, torch.float64)
     with torch.cuda.device(dev):
         if family == 0:
             tab = fft_table(n, dev)
             _check(load().fgp_lattice_mll_grad(_dev(xpts, torch.float64), n, d, _harr(_i32, alpha), B, _dev(ysq, torch.float64),
-                                               _dev(scale, torch.float64), _dev(ls, torch.float64), _dev(noise, torch.float64),
+                                               _dev(scale, torch.float64), _dev(ls, torch.float64), _dev(noise, torch.float64), wptr,
                                                tab.data_ptr(), ws.data_ptr(), lam.data_ptr() if want_lam else None, out.data_ptr(),
                                                1 if want_grad else 0, _stream()))
         else:
             _check(load().fgp_dnb2_mll_grad(_dev(xpts, torch.int64), n, d, _harr(_i32, alpha), int(t), B, _dev(ysq, torch.float64),
-                                            _dev(scale, torch.float64), _dev(ls, torch.float64), _dev(noise, torch.float64),
+                                            _dev(scale, torch.float64), _dev(ls, torch.float64), _dev(noise, torch.float64), wptr,
                                             ws.data_ptr(), lam.data_ptr() if want_lam else None, out.data_ptr(),
                                             1 if want_grad else 0, _stream()))
     return out, lam

@@ -29,6 +29,7 @@ struct MllArgs {
   const double* scale;  // (B)
   const double* ls;     // (B,d)
   const double* noise;  // (B)
+  const double* weights;  // (B,2) (wn, wl) or NULL for (1/2, 1/2): gradients are those of wn*norm + wl*logdet
   void* W;              // workspace: (B,n) complex (lattice) / real (net)
   double* lam;          // optional (B,n) complex / real
   double* partB;        // (B, ctasB, 3)
@@ -164,23 +165,24 @@ __device__ __forceinline__ void point_grad(const MllArgs& a, const Hyp& H, int64
 }
 
 // spectral epilogue: lam -> (norm, logdet, dnoise) partial sums and G = dL/dlam (stored in place of lam)
-__device__ __forceinline__ double2 spectral_c(double2 lam, double ysq, double* s) {
+__device__ __forceinline__ double2 spectral_c(double2 lam, double ysq, double wn, double wl, double* s) {
   const double a = lam.x, b = lam.y;
   const double m2 = fma(a, a, b * b);
   const double inv = 1.0 / m2;
   s[0] = fma(ysq, a * inv, s[0]);
   s[1] += 0.5 * log(m2);
-  const double yi2 = ysq * inv * inv;
-  const double ga = 0.5 * fma(yi2, fma(b, b, -a * a), a * inv);
-  const double gb = 0.5 * fma(-2.0 * a * b, yi2, b * inv);
+  const double yi2 = wn * ysq * inv * inv;
+  const double li = wl * inv;
+  const double ga = fma(yi2, fma(b, b, -a * a), a * li);
+  const double gb = fma(-2.0 * a * b, yi2, b * li);
   s[2] += ga;
   return make_double2(ga, gb);
 }
-__device__ __forceinline__ double spectral_r(double lam, double ysq, double* s) {
+__device__ __forceinline__ double spectral_r(double lam, double ysq, double wn, double wl, double* s) {
   const double inv = 1.0 / lam;
   s[0] = fma(ysq, inv, s[0]);
   s[1] += log(fabs(lam));
-  const double g = 0.5 * (inv - ysq * inv * inv);
+  const double g = inv * (wl - wn * ysq * inv);
   s[2] += g;
   return g;
 }
@@ -233,18 +235,19 @@ __global__ void __launch_bounds__(256, 2) mll_single_kernel(MllArgs a) {
     block_fft_fwd(smc, l, 1, LP, a.T.stage);
   double s[3] = {0.0, 0.0, 0.0};
   const double* ysq = a.ysq + (int64_t)b * n;
+  const double wn = a.weights ? a.weights[2 * b] : 0.5, wl = a.weights ? a.weights[2 * b + 1] : 0.5;
   for (int k = threadIdx.x; k < n; k += blockDim.x) {
     if (NET) {
       double lam = smr[padidx(k)] + H.noise;
       if (k == 0) lam += c * (double)n;
       if (a.lam) a.lam[(int64_t)b * n + k] = lam;
-      smr[padidx(k)] = spectral_r(lam, ysq[k], s);
+      smr[padidx(k)] = spectral_r(lam, ysq[k], wn, wl, s);
     } else {
       double2 lam = smc[padidx(k)];
       lam.x += H.noise;
       if (k == 0) lam.x += c * (double)n;
       if (a.lam) ((double2*)a.lam)[(int64_t)b * n + k] = lam;
-      smc[padidx(k)] = spectral_c(lam, ysq[k], s);
+      smc[padidx(k)] = spectral_c(lam, ysq[k], wn, wl, s);
     }
   }
   double* out = a.out + (int64_t)b * (d + 4);
@@ -349,6 +352,7 @@ __global__ void __launch_bounds__(256, 2) mll_passB_kernel(MllArgs a) {
   double s[3] = {0.0, 0.0, 0.0};
   const double* ysq = a.ysq + boff + q0;
   const double noise = s_noise;
+  const double wn = a.weights ? a.weights[2 * b] : 0.5, wl = a.weights ? a.weights[2 * b + 1] : 0.5;
   for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
     const int cc = e & (ntr - 1), r = e >> lntr;
     const int64_t k = ((int64_t)r << l1) + cc;  // + q0
@@ -357,13 +361,13 @@ __global__ void __launch_bounds__(256, 2) mll_passB_kernel(MllArgs a) {
       double lam = smr[si] + noise;
       if (k + q0 == 0) lam += s_scale * (double)a.n;
       if (a.lam) a.lam[boff + q0 + k] = lam;
-      smr[si] = spectral_r(lam, ysq[k], s);
+      smr[si] = spectral_r(lam, ysq[k], wn, wl, s);
     } else {
       double2 lam = smc[si];
       lam.x += noise;
       if (k + q0 == 0) lam.x += s_scale * (double)a.n;
       if (a.lam) ((double2*)a.lam)[boff + q0 + k] = lam;
-      smc[si] = spectral_c(lam, ysq[k], s);
+      smc[si] = spectral_c(lam, ysq[k], wn, wl, s);
     }
   }
   reduce_store<3>(s, 3, red, a.partB + ((int64_t)b * a.ctasB + blockIdx.x) * 3);
@@ -515,7 +519,7 @@ static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 template <bool NET>
 static int mll_common( const void* x, int64_t n, int d, const int* alpha_host, int t, int B, const double* ysq,
-                      const double* scale, const double* ls, const double* noise, const void* table, void* workspace,
+                      const double* scale, const double* ls, const double* noise, const double* weights, const void* table, void* workspace,
                       double* lam, double* out, int want_grad, fgp_stream_t stream) {
   const bool net = NET;
   FGP_REQUIRE(x && alpha_host && ysq && scale && ls && noise && out, "mll_grad: null pointer");
@@ -547,6 +551,7 @@ static int mll_common( const void* x, int64_t n, int d, const int* alpha_host, i
   a.scale = scale;
   a.ls = ls;
   a.noise = noise;
+  a.weights = weights;
   a.lam = lam;
   a.out = out;
   a.want_grad = want_grad;

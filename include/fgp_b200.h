@@ -99,7 +99,9 @@ int fgp_fwht(const double* in_dev, double* out_dev, int64_t batch, int64_t n, fg
  *       k1_i   = scale_b prod_j (1 + ls_bj P_ij)          P from x (lattice) or xb (net), never stored
  *       lam_k  = sum_i T_ki k1_i + noise_b                (unnormalised FFT-BRO / FWHT  ==  sqrt(n) ft(k1) + noise)
  *       norm   = sum_k ysq_bk Re(1/lam_k),  logdet = sum_k log|lam_k|
- *       out[b] = { norm, logdet, dL/dnoise, dL/dscale, dL/dls_0 .. dL/dls_{d-1} },  L = (norm + logdet)/2
+ *       out[b] = { norm, logdet, dL/dnoise, dL/dscale, dL/dls_0 .. dL/dls_{d-1} },  L = wn_b norm + wl_b logdet
+ *     weights_dev (B,2) = (wn_b, wl_b), NULL for (1/2, 1/2): the reference weighs logdet by the number of batch
+ *     columns sharing a hyperparameter set (abstract_gp.py:255-256), so the weights are inputs.
  *     ysq_dev (B,n): sum over the reference's batch dims of |ytilde_k|^2 (natural transform order).
  *     lam_dev: optional (B,n) complex (lattice) / real (net) output of lam (may be NULL).
  *     want_grad = 0 skips the backward transform.
@@ -107,11 +109,11 @@ int fgp_fwht(const double* in_dev, double* out_dev, int64_t batch, int64_t n, fg
 size_t fgp_mll_workspace_bytes(int family /*0 lattice, 1 net*/, int64_t n, int d, int B);
 int fgp_lattice_mll_grad(const double* x_dev, int64_t n, int d, const int* alpha_host, int B, const double* ysq_dev,
                          const double* scale_dev, const double* ls_dev, const double* noise_dev,
-                         const void* table_dev, void* workspace_dev, double* lam_dev, double* out_dev, int want_grad,
+                         const double* weights_dev, const void* table_dev, void* workspace_dev, double* lam_dev, double* out_dev, int want_grad,
                          fgp_stream_t stream);
 int fgp_dnb2_mll_grad(const int64_t* xb_dev, int64_t n, int d, const int* alpha_host, int t, int B,
                       const double* ysq_dev, const double* scale_dev, const double* ls_dev, const double* noise_dev,
-                      void* workspace_dev, double* lam_dev, double* out_dev, int want_grad, fgp_stream_t stream);
+                      const double* weights_dev, void* workspace_dev, double* lam_dev, double* out_dev, int want_grad, fgp_stream_t stream);
 
 /* K^-1 y for R right-hand sides sharing one spectrum: out = T^-1( T(y) / lam ), util.py:338-344 (single task).
  * lam_dev: (n) complex (family 0) or real (family 1) full eigenvalues sqrt(n) ft(k1)+noise.  y,out: (R,n) real.

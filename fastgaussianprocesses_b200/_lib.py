@@ -14,6 +14,23 @@ MAX_ALPHA = 10
 _c = ctypes
 _vp, _i32, _i64, _u64, _f64, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint64, _c.c_double, _c.c_size_t
 
+_dp = _c.POINTER(_c.c_double)
+
+
+class FitLayout(_c.Structure):
+    """fgp_fit_layout (include/fgp_b200.h)."""
+    _fields_ = [("B", _i32), ("d", _i32), ("n_scale", _i32), ("n_ls_b", _i32), ("n_ls_d", _i32), ("n_noise", _i32),
+                ("req_scale", _i32), ("req_ls", _i32), ("req_noise", _i32), ("tau", _f64),
+                ("raw_scale", _vp), ("raw_ls", _vp), ("raw_noise", _vp), ("scale_B", _vp), ("ls_B", _vp), ("noise_B", _vp),
+                ("state", _vp), ("loss_hist", _vp), ("scale_hist", _vp), ("ls_hist", _vp), ("noise_hist", _vp)]
+
+
+class FitOptions(_c.Structure):
+    """fgp_fit_options (include/fgp_b200.h)."""
+    _fields_ = [("iterations", _i32), ("stop_wait", _i32), ("hist_capacity", _i32), ("logtol", _f64), ("half_const", _f64),
+                ("wn", _f64), ("wl", _f64), ("lr", _f64), ("etaminus", _f64), ("etaplus", _f64), ("step_min", _f64), ("step_max", _f64)]
+
+
 # name -> (restype, argtypes); every symbol include/fgp_b200.h declares
 SIGNATURES = {
     "fgp_version": (_i32, []),
@@ -34,6 +51,12 @@ SIGNATURES = {
     "fgp_mll_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32]),
     "fgp_lattice_mll_grad": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "fgp_dnb2_mll_grad": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "fgp_fit_state_doubles": (_sz, [_i32]),
+    "fgp_fit_init": (_i32, [_c.POINTER(FitLayout), _c.POINTER(FitOptions), _vp]),
+    "fgp_fit_step": (_i32, [_c.POINTER(FitLayout), _vp, _vp]),
+    "fgp_fit_finish": (_i32, [_c.POINTER(FitLayout), _vp]),
+    "fgp_profile_begin": (_i32, [_vp]),
+    "fgp_profile_end": (_i32, [_vp, _i32, _c.POINTER(_c.c_char_p), _c.POINTER(_c.c_float)]),
     "fgp_gram_solve": (_i32, [_i32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "fgp_post_mean_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "fgp_lattice_post_mean": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _f64, _vp, _vp, _i32, _vp, _vp, _vp]),
@@ -43,6 +66,7 @@ SIGNATURES = {
     "fgp_dnb2_post_var": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp, _vp, _vp]),
     "fgp_lattice_cross_kernel": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _f64, _vp, _vp, _vp]),
     "fgp_dnb2_cross_kernel": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp]),
+    "fgp_kernel_pairs": (_i32, [_i32, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp]),
     "fgp_fp64_peak_probe": (_i32, [_i32, _vp, _vp, _vp]),
 }
 
@@ -171,6 +195,17 @@ def cross_kernel(family, xs, xtrain, alpha, t, scale, ls):
     return out
 
 
+def kernel_pairs(family, x, z, alpha, t, scale, ls):
+    """k(x_i, z_i) for row pairs: x (N,d) float64, z (N,d) float64 (or int64 net integers) -> (N,)."""
+    N, d = x.shape
+    out = torch.empty((N,), dtype=torch.float64, device=x.device)
+    z_is_int = z.dtype == torch.int64
+    with torch.cuda.device(x.device):
+        _check(load().fgp_kernel_pairs(int(family), _dev(x, torch.float64), _dev(z, torch.int64 if z_is_int else torch.float64), int(z_is_int),
+                                       N, d, _harr(_i32, alpha), int(t), float(scale), _harr(_f64, ls), out.data_ptr(), _stream()))
+    return out
+
+
 # --------------------------------------------------------------------------------------------- K3 transforms
 _tables = {}
 
@@ -267,6 +302,54 @@ def mll_grad(family, xpts, alpha, t, ysq, scale, ls, noise, want_grad=True, want
                                             ws.data_ptr(), lam.data_ptr() if want_lam else None, out.data_ptr(),
                                             1 if want_grad else 0, _stream()))
     return out, lam
+
+
+def mll_grad_into(family, xpts, alpha, t, ysq, scale, ls, noise, weights, ws, lam, out, want_grad=True):
+    """Allocation-free form of `mll_grad` (all buffers caller-provided) -- safe inside CUDA graph capture."""
+    n, d = xpts.shape
+    B = scale.numel()
+    wptr = None if weights is None else weights.data_ptr()
+    lptr = None if lam is None else lam.data_ptr()
+    if family == 0:
+        tab = fft_table(n, xpts.device)
+        _check(load().fgp_lattice_mll_grad(xpts.data_ptr(), n, d, _harr(_i32, alpha), B, ysq.data_ptr(), scale.data_ptr(), ls.data_ptr(),
+                                           noise.data_ptr(), wptr, tab.data_ptr(), ws.data_ptr(), lptr, out.data_ptr(), 1 if want_grad else 0, _stream()))
+    else:
+        _check(load().fgp_dnb2_mll_grad(xpts.data_ptr(), n, d, _harr(_i32, alpha), int(t), B, ysq.data_ptr(), scale.data_ptr(), ls.data_ptr(),
+                                        noise.data_ptr(), wptr, ws.data_ptr(), lptr, out.data_ptr(), 1 if want_grad else 0, _stream()))
+
+
+def mll_workspace(family, n, d, B, device):
+    return torch.empty((max(load().fgp_mll_workspace_bytes(family, n, d, B), 256) + 7) // 8, dtype=torch.float64, device=device)
+
+
+def fit_state_doubles(P):
+    return int(load().fgp_fit_state_doubles(int(P)))
+
+
+def fit_init(layout, options):
+    _check(load().fgp_fit_init(_c.byref(layout), _c.byref(options), _stream()))
+
+
+def fit_step(layout, out):
+    _check(load().fgp_fit_step(_c.byref(layout), out.data_ptr(), _stream()))
+
+
+def fit_finish(layout):
+    _check(load().fgp_fit_finish(_c.byref(layout), _stream()))
+
+
+def profile_begin():
+    _check(load().fgp_profile_begin(_stream()))
+
+
+def profile_end(max_entries=256):
+    names = (_c.c_char_p * max_entries)()
+    ms = (_c.c_float * max_entries)()
+    cnt = load().fgp_profile_end(_stream(), max_entries, names, ms)
+    if cnt < 0:
+        _check(cnt)
+    return [(names[i].decode(), float(ms[i])) for i in range(cnt)]
 
 
 def gram_solve(family, y, lam):

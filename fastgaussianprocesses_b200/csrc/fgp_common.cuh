@@ -11,6 +11,7 @@ namespace fgp {
 
 void set_error(const char* fmt, ...);
 void count_launch();
+void prof_mark(const char* name, cudaStream_t st);  // no-op unless fgp_profile_begin() armed it
 int sm_count();
 
 #define FGP_REQUIRE(cond, ...)                    \
@@ -38,6 +39,13 @@ int sm_count();
       fgp::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
       return FGP_ECUDA;                                                                  \
     }                                                                                    \
+  } while (0)
+
+// launch check that also drops a timing mark (per-kernel durations for bench.py's roofline block)
+#define FGP_LAUNCH_NAMED(name, st)       \
+  do {                                   \
+    FGP_LAUNCH_CHECK();                  \
+    fgp::prof_mark(name, st);            \
   } while (0)
 
 static inline bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }

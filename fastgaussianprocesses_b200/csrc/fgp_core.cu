@@ -17,6 +17,19 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// ---- optional per-kernel timing marks (armed by fgp_profile_begin; never active inside graph capture)
+constexpr int kMaxMarks = 256;
+static bool g_prof = false;
+static int g_nmarks = 0;
+static cudaEvent_t g_ev[kMaxMarks];
+static const char* g_names[kMaxMarks];
+void prof_mark(const char* name, cudaStream_t st) {
+  if (!g_prof || g_nmarks >= kMaxMarks) return;
+  if (cudaEventCreate(&g_ev[g_nmarks]) != cudaSuccess) return;
+  cudaEventRecord(g_ev[g_nmarks], st);
+  g_names[g_nmarks++] = name;
+}
+
 int sm_count() {
   if (g_sms == 0) {
     int dev = 0, sms = 0;
@@ -94,6 +107,29 @@ extern "C" {
 int fgp_version(void) { return FGP_VERSION; }
 const char* fgp_last_error(void) { return fgp::g_err; }
 uint64_t fgp_launch_count(void) { return fgp::g_launches.load(); }
+
+int fgp_profile_begin(fgp_stream_t stream) {
+  for (int i = 0; i < fgp::g_nmarks; ++i) cudaEventDestroy(fgp::g_ev[i]);
+  fgp::g_nmarks = 0;
+  fgp::g_prof = true;
+  fgp::prof_mark("begin", (cudaStream_t)stream);
+  return FGP_OK;
+}
+
+int fgp_profile_end(fgp_stream_t stream, int max_entries, const char** names, float* ms) {
+  fgp::g_prof = false;
+  FGP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  int cnt = 0;
+  for (int i = 1; i < fgp::g_nmarks && cnt < max_entries; ++i, ++cnt) {
+    float t = 0.f;
+    FGP_CUDA(cudaEventElapsedTime(&t, fgp::g_ev[i - 1], fgp::g_ev[i]));
+    if (names) names[cnt] = fgp::g_names[i];
+    if (ms) ms[cnt] = t;
+  }
+  for (int i = 0; i < fgp::g_nmarks; ++i) cudaEventDestroy(fgp::g_ev[i]);
+  fgp::g_nmarks = 0;
+  return cnt;
+}
 
 int fgp_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin) {
   int dev = 0;

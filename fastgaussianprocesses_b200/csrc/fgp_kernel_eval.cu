@@ -59,6 +59,29 @@ __global__ void __launch_bounds__(256) cross_kernel_kernel(const double* __restr
   }
 }
 
+
+// k[i] = scale prod_j (1 + ls_j part(x_ij, z_ij)) for N row pairs (diagonal terms k(x,x) and elementwise kernel() calls)
+template <bool NET>
+__global__ void __launch_bounds__(256) pair_kernel_kernel(const double* __restrict__ x, const void* __restrict__ z,
+                                                          int z_is_int, int64_t N, int d, LatPoly P, IVec alpha, int t,
+                                                          double scale, DVec ls, double* __restrict__ k) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    double prod = scale;
+    for (int j = 0; j < d; ++j) {
+      double part;
+      if (NET) {
+        const uint64_t xb = dnb2_to_b(x[i * d + j], t);
+        const uint64_t zb = z_is_int ? (uint64_t)((const int64_t*)z)[i * d + j] : dnb2_to_b(((const double*)z)[i * d + j], t);
+        part = dnb2_part(xb ^ zb, alpha.v[j], t);
+      } else {
+        part = lat_part(x[i * d + j] - ((const double*)z)[i * d + j], P.q[j], P.alpha[j]);
+      }
+      prod *= fma(ls.v[j], part, 1.0);
+    }
+    k[i] = prod;
+  }
+}
+
 static inline unsigned grid_for(int64_t total) {
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
@@ -150,6 +173,33 @@ int fgp_lattice_cross_kernel(const double* xs_dev, int64_t m, const double* x_de
 int fgp_dnb2_cross_kernel(const double* xs_dev, int64_t m, const int64_t* xb_dev, int64_t n, int d, const int* alpha_host,
                           int t, double scale, const double* ls_host, double* k_dev, fgp_stream_t stream) {
   return cross_common(true, xs_dev, m, xb_dev, n, d, alpha_host, t, scale, ls_host, k_dev, stream);
+}
+
+int fgp_kernel_pairs(int family, const double* x_dev, const void* z_dev, int z_is_int, int64_t N, int d,
+                     const int* alpha_host, int t, double scale, const double* ls_host, double* k_dev, fgp_stream_t stream) {
+  FGP_REQUIRE(x_dev && z_dev && alpha_host && ls_host && k_dev, "kernel_pairs: null pointer");
+  FGP_REQUIRE(d >= 1 && d <= FGP_MAX_D && N >= 0, "kernel_pairs: bad N/d");
+  if (N == 0) return FGP_OK;
+  fgp::LatPoly P;
+  memset(&P, 0, sizeof(P));
+  fgp::IVec al;
+  fgp::DVec ls;
+  for (int j = 0; j < d; ++j) {
+    al.v[j] = alpha_host[j];
+    ls.v[j] = ls_host[j];
+  }
+  if (family == 0) {
+    FGP_REQUIRE(!z_is_int, "kernel_pairs: lattice points are float64");
+    int rc = fgp::fill_lat_poly(alpha_host, d, &P);
+    if (rc) return rc;
+    fgp::pair_kernel_kernel<false><<<fgp::grid_for(N), 256, 0, (cudaStream_t)stream>>>(x_dev, z_dev, 0, N, d, P, al, t, scale, ls, k_dev);
+  } else {
+    FGP_REQUIRE(t >= 1 && t < 64, "kernel_pairs: t outside 1..63");
+    for (int j = 0; j < d; ++j) FGP_REQUIRE(al.v[j] >= 1 && al.v[j] <= 4, "kernel_pairs: net alpha outside 1..4");
+    fgp::pair_kernel_kernel<true><<<fgp::grid_for(N), 256, 0, (cudaStream_t)stream>>>(x_dev, z_dev, z_is_int, N, d, P, al, t, scale, ls, k_dev);
+  }
+  FGP_LAUNCH_CHECK();
+  return FGP_OK;
 }
 
 }  // extern "C"

@@ -477,22 +477,22 @@ static int launch_mll(const MllArgs& a, const PassGeom& g, int B, cudaStream_t s
   if (g.l2 == 0) {
     if ((rc = set_smem_attr(mll_single_kernel<DT, NET, A2>, g.smemA))) return rc;
     mll_single_kernel<DT, NET, A2><<<B, g.threads, g.smemA, st>>>(a);
-    FGP_LAUNCH_CHECK();
+    FGP_LAUNCH_NAMED("mll_single", st);
     return FGP_OK;
   }
   if ((rc = set_smem_attr(mll_passA_kernel<DT, NET, A2>, g.smemA))) return rc;
   mll_passA_kernel<DT, NET, A2><<<dim3(a.ctasA, B), g.threads, g.smemA, st>>>(a);
-  FGP_LAUNCH_CHECK();
+  FGP_LAUNCH_NAMED("mll_passA", st);
   if ((rc = set_smem_attr(mll_passB_kernel<NET>, g.smemB))) return rc;
   mll_passB_kernel<NET><<<dim3(a.ctasB, B), g.threads, g.smemB, st>>>(a);
-  FGP_LAUNCH_CHECK();
+  FGP_LAUNCH_NAMED("mll_passB", st);
   if (a.want_grad) {
     if ((rc = set_smem_attr(mll_passC_kernel<DT, NET, A2>, g.smemA))) return rc;
     mll_passC_kernel<DT, NET, A2><<<dim3(a.ctasA, B), g.threads, g.smemA, st>>>(a);
-    FGP_LAUNCH_CHECK();
+    FGP_LAUNCH_NAMED("mll_passC", st);
   }
   mll_finalize_kernel<<<B, 256, 0, st>>>(a);
-  FGP_LAUNCH_CHECK();
+  FGP_LAUNCH_NAMED("mll_finalize", st);
   return FGP_OK;
 }
 

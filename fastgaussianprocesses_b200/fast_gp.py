@@ -1,0 +1,1324 @@
+"""Host-side mirror of the reference's fast GP classes for the structured-covariance hot path.
+
+Reference surface being mirrored (same names, argument meaning, shapes and assertion behaviour):
+    fastgps/abstract_gp.py      AbstractGP      (ctor :13-150, fit :152-306, get_x_next/add_y_next :310-351,
+                                                  post_mean :352-380, post_var :381-416, post_cov :417-474,
+                                                  post_error/post_ci :475-526, properties :610-706)
+    fastgps/abstract_fast_gp.py AbstractFastGP  (ctor :12-31, power-of-two guards :32-52, default optimizer :53-57,
+                                                  get_inv_log_det_cache :58-64, cubature :65-154, get_* :155-172,
+                                                  _kernel* :173-196, ft/ift :197-228)
+    fastgps/util.py             _XXbSeq :16-38, _K1PartsSeq :40-62, _LamCaches :64-141, _YtildeCache :164-183,
+                                _FastInverseLogDetCache :275-394 (single-task branch), _CoeffsCache :396-425
+
+Everything numerical is done by libfgp_b200.so (include/fgp_b200.h) on CUDA tensors; torch is used for memory,
+streams, the tiny hyperparameter transforms and (outside the fast path) the optimizer.  There is no CPU fallback.
+
+Scope: single task (num_tasks None or 1), no derivative information, no adaptive nugget.
+Those options raise NotImplementedError -- they are rows (f)2-(f)3 of the scope table, not silently approximated.
+"""
+import os
+from typing import List, Tuple, Union
+
+import numpy as np
+import scipy.stats
+import torch
+
+from . import _lib
+from . import sequences
+
+
+def _tf_log(x):
+    return torch.log(x)
+
+
+def _tf_exp(x):
+    return torch.exp(x)
+
+
+def _tf_id(x):
+    return x
+
+
+DEFAULT_TFS_LOG_EXP = (_tf_log, _tf_exp)
+DEFAULT_TFS_ID = (_tf_id, _tf_id)
+
+
+def _prod(shape):
+    out = 1
+    for s in shape:
+        out *= int(s)
+    return out
+
+
+class _XXbSeq(object):
+    """Growing cache of the points of one sequence, generated on the GPU (util.py:16-38)."""
+
+    def __init__(self, fgp, seq):
+        self.fgp = fgp
+        self.seq = seq
+        self.n = 0
+        self.x = torch.empty((0, seq.d), device=fgp.device)
+        self.xb = torch.empty((0, seq.d), dtype=fgp._XBDTYPE, device=fgp.device)
+
+    def __getitem__(self, i):
+        if isinstance(i, (int, np.integer)):
+            i = slice(None, int(i), None)
+        if isinstance(i, torch.Tensor):
+            assert i.numel() == 1
+            i = slice(None, int(i.item()), None)
+        assert isinstance(i, slice)
+        stop = int(i.stop)
+        if stop > self.n:
+            x_next, xb_next = self.fgp._sample(self.seq, self.n, stop)
+            if x_next.data_ptr() == xb_next.data_ptr():
+                self.x = self.xb = torch.vstack([self.x, x_next])
+            else:
+                self.x = torch.vstack([self.x, x_next])
+                self.xb = torch.vstack([self.xb, xb_next])
+            self.n = stop
+        i = slice(None if i.start is None else int(i.start), stop, None)
+        return self.x[i], self.xb[i]
+
+
+class _MLLFunction(torch.autograd.Function):
+    """loss_b = wn_b*norm_b + wl_b*logdet_b of B hyperparameter sets with the analytic gradient of the fused kernel
+    (replaces autograd through util.py:285-300,354-370 and the transform)."""
+
+    @staticmethod
+    def forward(ctx, scale_B, ls_B, noise_B, fgp, n, ysq, weights, want_grad):
+        xpts = fgp._xpts(n)
+        out, _ = _lib.mll_grad(fgp._FAMILY, xpts, fgp._alpha_list, fgp._t, ysq, scale_B.detach().contiguous(),
+                               ls_B.detach().contiguous(), noise_B.detach().contiguous(), want_grad=want_grad,
+                               weights=weights)
+        ctx.save_for_backward(out)
+        ctx.d = fgp.d
+        ctx.have_grad = want_grad
+        lossb = weights[:, 0] * out[:, 0] + weights[:, 1] * out[:, 1]
+        norm, logdet = out[:, 0].clone(), out[:, 1].clone()
+        ctx.mark_non_differentiable(norm, logdet)
+        return lossb, norm, logdet
+
+    @staticmethod
+    def backward(ctx, g, _gn, _gl):
+        (out,) = ctx.saved_tensors
+        assert ctx.have_grad, "gradients were not requested in the forward pass"
+        d = ctx.d
+        return g * out[:, 3], g[:, None] * out[:, 4:4 + d], g * out[:, 2], None, None, None, None, None
+
+
+class _FusedFitLoop(object):
+    """Device-side fit() loop (the product's fast path): every iteration is [fgp_*_mll_grad, fgp_fit_step] and runs
+    from a CUDA graph; the host only polls the `stopped` flag between graph replays (include/fgp_b200.h, K4/K4b).
+    Used when the loss is MLL, the optimiser is the default Rprop and the transforms are the default (log, exp)."""
+    GRAPH_ITERS = 16
+    ST_STOPPED, ST_LAST_ITER, ST_HEADER = 4, 5, 32
+
+    @staticmethod
+    def eligible(fgp):
+        if not fgp._default_tfs:
+            return False
+        if fgp.raw_factor_task_kernel.requires_grad or fgp.raw_noise_task_kernel.requires_grad:
+            return False
+        if fgp.raw_factor_task_kernel.numel() != 0 or fgp.raw_noise_task_kernel.numel() != 1:
+            return False
+        B = _prod(torch.broadcast_shapes(fgp.raw_scale.shape[:-1], fgp.raw_lengthscales.shape[:-1], fgp.raw_noise.shape[:-1]))
+        ok = lambda p: _prod(p.shape[:-1]) in (1, B) and p.is_contiguous()
+        return ok(fgp.raw_scale) and ok(fgp.raw_lengthscales) and ok(fgp.raw_noise) and B <= 65535
+
+    def __init__(self, fgp, hist_flags=(False, False, False), hist_capacity=0):
+        self.fgp = fgp
+        dev = fgp.device
+        with torch.no_grad():
+            scale_B, ls_B, noise_B, pshape = fgp._hyper()
+            self.tau = float(fgp.gram_matrix_tasks.reshape(-1)[0])
+        self.pshape = pshape
+        self.B, self.d, self.n = scale_B.numel(), fgp.d, fgp._nint
+        self.raw = (fgp.raw_scale.data, fgp.raw_lengthscales.data, fgp.raw_noise.data)
+        self.req = (fgp.raw_scale.requires_grad, fgp.raw_lengthscales.requires_grad, fgp.raw_noise.requires_grad)
+        self.scale_B = scale_B.clone().contiguous()
+        self.ls_B = ls_B.clone().contiguous()
+        self.noise_B = noise_B.clone().contiguous()
+        self.xpts = fgp._xpts(self.n).contiguous()
+        self.ysq = fgp._get_ysq(pshape)
+        self.d_out = _prod(fgp.shape_batch)
+        self.out = torch.zeros((self.B, self.d + 4), dtype=torch.float64, device=dev)
+        self.ws = _lib.mll_workspace(fgp._FAMILY, self.n, self.d, self.B, dev)
+        self.weights = torch.tensor([0.5, 0.5 * self.d_out / self.B], device=dev).expand(self.B, 2).contiguous()
+        self.P = sum(r.numel() for r in self.raw)
+        self.state = torch.zeros(_lib.fit_state_doubles(self.P), dtype=torch.float64, device=dev)
+        self.state_host = torch.zeros(self.ST_HEADER, dtype=torch.float64).pin_memory()
+        self.hist_flags = tuple(bool(f) for f in hist_flags)
+        self.hist_capacity = int(hist_capacity)
+        cap = max(self.hist_capacity, 1)
+        self.loss_hist = torch.zeros((cap, 3), dtype=torch.float64, device=dev)
+        mk = lambda flag, r: torch.zeros((cap, r.numel()), dtype=torch.float64, device=dev) if flag else None
+        self.scale_hist, self.ls_hist, self.noise_hist = (mk(f, r) for f, r in zip(self.hist_flags, self.raw))
+        L = _lib.FitLayout()
+        L.B, L.d = self.B, self.d
+        L.n_scale = _prod(self.raw[0].shape[:-1])
+        L.n_ls_b, L.n_ls_d = _prod(self.raw[1].shape[:-1]), int(self.raw[1].shape[-1])
+        L.n_noise = _prod(self.raw[2].shape[:-1])
+        L.req_scale, L.req_ls, L.req_noise = (int(r) for r in self.req)
+        L.tau = self.tau
+        L.raw_scale, L.raw_ls, L.raw_noise = (r.data_ptr() for r in self.raw)
+        L.scale_B, L.ls_B, L.noise_B = self.scale_B.data_ptr(), self.ls_B.data_ptr(), self.noise_B.data_ptr()
+        L.state = self.state.data_ptr()
+        L.loss_hist = self.loss_hist.data_ptr()
+        L.scale_hist = None if self.scale_hist is None else self.scale_hist.data_ptr()
+        L.ls_hist = None if self.ls_hist is None else self.ls_hist.data_ptr()
+        L.noise_hist = None if self.noise_hist is None else self.noise_hist.data_ptr()
+        self.layout = L
+        self.graphs = {}
+        self.launches = 0
+        self.kernels_per_iteration = None
+        # eager warm-up of every kernel before any capture; `stopped` is raised so that fit_step changes nothing
+        with torch.cuda.device(dev):
+            self.state[self.ST_STOPPED] = 1.0
+            c0 = _lib.launch_count()
+            self._iteration()
+            self.kernels_per_iteration = _lib.launch_count() - c0
+            torch.cuda.synchronize(dev)
+
+    def matches(self, fgp, hist_flags, hist_capacity):
+        return (fgp._nint == self.n and tuple(p.data_ptr() for p in (fgp.raw_scale, fgp.raw_lengthscales, fgp.raw_noise)) == tuple(r.data_ptr() for r in self.raw)
+                and (fgp.raw_scale.requires_grad, fgp.raw_lengthscales.requires_grad, fgp.raw_noise.requires_grad) == self.req
+                and fgp._ysq is self.ysq and tuple(bool(f) for f in hist_flags) == self.hist_flags and hist_capacity <= self.hist_capacity
+                and float(fgp.gram_matrix_tasks.reshape(-1)[0]) == self.tau)
+
+    # algorithmic bytes of one iteration: points read by the first and last pass, workspace written and
+    # read twice, |ytilde|^2 read once
+    @property
+    def algorithmic_bytes(self):
+        e = 16 if self.fgp._FAMILY == 0 else 8
+        return self.B * (2 * 8 * self.n * self.d + 4 * e * self.n + 8 * self.n)
+
+    def kernel_algorithmic_bytes(self, name):
+        e = 16 if self.fgp._FAMILY == 0 else 8
+        n, d, B = self.n, self.d, self.B
+        return {"mll_passA": B * (8 * n * d + e * n), "mll_passB": B * (2 * e * n + 8 * n), "mll_passC": B * (8 * n * d + e * n),
+                "mll_single": B * (16 * n * d + 8 * n)}.get(name, 0)
+
+    def _iteration(self):
+        f = self.fgp
+        _lib.mll_grad_into(f._FAMILY, self.xpts, f._alpha_list, f._t, self.ysq, self.scale_B, self.ls_B, self.noise_B, self.weights,
+                           self.ws, None, self.out, want_grad=any(self.req))
+        _lib.fit_step(self.layout, self.out)
+
+    def begin(self, iterations, stop_wait, logtol, lr):
+        o = _lib.FitOptions()
+        o.iterations, o.stop_wait, o.hist_capacity = int(iterations), int(stop_wait), int(self.hist_capacity)
+        o.logtol = float(logtol)
+        o.half_const = 0.5 * self.d_out * self.n * float(np.log(2 * np.pi))
+        o.wn, o.wl = 0.5, 0.5 * self.d_out / self.B
+        o.lr, o.etaminus, o.etaplus, o.step_min, o.step_max = float(lr), 0.5, 1.2, 1e-6, 50.0
+        with torch.cuda.device(self.fgp.device):
+            _lib.fit_init(self.layout, o)
+
+    def _graph(self, k):
+        g = self.graphs.get(k)
+        if g is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.device(self.fgp.device):
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    for _ in range(k):
+                        self._iteration()
+            self.graphs[k] = g
+        return g
+
+    def replay(self, k):
+        self._graph(k).replay()
+        self.launches += k * self.kernels_per_iteration
+
+    def step(self):
+        self.replay(1)
+
+    def read_state(self):
+        self.state_host.copy_(self.state[:self.ST_HEADER], non_blocking=True)
+        torch.cuda.current_stream(self.fgp.device).synchronize()
+        return self.state_host
+
+    def finish(self):
+        with torch.cuda.device(self.fgp.device):
+            _lib.fit_finish(self.layout)
+
+    def kernel_times(self, reps=10, flush=None):
+        """Per-kernel device time of one iteration (eager launches, CUDA events between kernels; L2 flushed first)."""
+        acc = {}
+        with torch.cuda.device(self.fgp.device):
+            for _ in range(reps):
+                if flush is not None:
+                    flush.zero_()
+                _lib.profile_begin()
+                self._iteration()
+                for name, ms in _lib.profile_end():
+                    acc.setdefault(name, []).append(ms)
+        return [{"name": k, "ms": float(np.mean(v)), "alg_bytes": self.kernel_algorithmic_bytes(k)} for k, v in acc.items()]
+
+    def close(self):
+        self.graphs = {}
+
+
+class _FastInverseLogDetCache(object):
+    """Strategy object handed out by `get_inv_log_det_cache` (util.py:275-394, single-task branch)."""
+
+    def __init__(self, fgp, n):
+        self.fgp = fgp
+        self.n = n
+        self.nint = int(n[0])
+        self.task_order = torch.zeros(1, dtype=int, device=fgp.device)
+        self.inv_task_order = torch.zeros(1, dtype=int, device=fgp.device)
+        self._key = None
+
+    def _lam_full(self):
+        """(B,n) eigenvalues sqrt(n)*ft(k1)+noise (times the task kernel), cached on the hyperparameter state."""
+        key = self.fgp._param_key()
+        if self._key != key or os.environ.get("FASTGP_FORCE_RECOMPILE") == "True":
+            with torch.no_grad():
+                scale_B, ls_B, noise_B, pshape = self.fgp._hyper()
+                B = scale_B.numel()
+                ysq = torch.zeros((B, self.nint), dtype=torch.float64, device=self.fgp.device)
+                _, lam = _lib.mll_grad(self.fgp._FAMILY, self.fgp._xpts(self.nint), self.fgp._alpha_list, self.fgp._t, ysq,
+                                       scale_B.contiguous(), ls_B.contiguous(), noise_B.contiguous(), want_grad=False,
+                                       want_lam=True)
+            self.lam = lam
+            self.pshape = pshape
+            self._key = key
+        return self.lam
+
+    def __call__(self):
+        lam = self._lam_full()
+        lamp = lam.reshape(tuple(self.pshape) + (self.nint,))
+        self.logdet = torch.log(torch.abs(lamp)).sum(-1)
+        self.inv = (1 / lamp)[..., None, None, :]
+        return self.inv, self.logdet
+
+    def gram_matrix_solve(self, y):
+        """K^-1 y along the last dim; batch dims of y broadcast against the hyperparameter batch shape."""
+        assert y.size(-1) == self.nint
+        lam = self._lam_full()
+        B = lam.shape[0]
+        y = y.to(self.fgp.device)
+        if B == 1:
+            return _lib.gram_solve(self.fgp._FAMILY, y.contiguous(), lam[0])
+        k = len(self.pshape)
+        assert tuple(y.shape[-1 - k:-1]) == tuple(self.pshape), "y batch dims must end with the hyperparameter batch shape %s" % (tuple(self.pshape),)
+        lead = y.shape[:-1 - k]
+        yb = y.reshape((_prod(lead), B, self.nint))
+        out = torch.empty_like(yb)
+        for b in range(B):
+            out[:, b, :] = _lib.gram_solve(self.fgp._FAMILY, yb[:, b, :].contiguous(), lam[b])
+        return out.reshape(y.shape)
+
+    def get_norm_term_logdet_term(self):
+        """(norm_term[...,1], logdet[...,1]); differentiable w.r.t. the raw hyperparameters when grad mode is on."""
+        fgp = self.fgp
+        assert self.nint == fgp._nint, "norm term needs the current data size"
+        ytilde = fgp.get_ytilde(0)
+        scale_B, ls_B, noise_B, pshape = fgp._hyper()
+        B = scale_B.numel()
+        k = len(pshape)
+        sb = tuple(fgp.shape_batch)
+        lead = _prod(sb[:len(sb) - k])
+        want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in (scale_B, ls_B, noise_B))
+        # one "hyperparameter set" per y column so the norm term keeps the reference's per-column shape
+        ysq_cols = (ytilde.abs() ** 2).reshape(lead * B, self.nint).contiguous()
+        w_norm = torch.tensor([1.0, 0.0], device=fgp.device).expand(lead * B, 2).contiguous()
+        rep = lambda v: v.expand((lead,) + tuple(v.shape)).reshape((lead * B,) + tuple(v.shape[1:]))
+        norm_cols, _, _ = _MLLFunction.apply(rep(scale_B), rep(ls_B), rep(noise_B), fgp, self.nint, ysq_cols, w_norm, want_grad)
+        w_ld = torch.tensor([0.0, 1.0], device=fgp.device).expand(B, 2).contiguous()
+        ld, _, _ = _MLLFunction.apply(scale_B, ls_B, noise_B, fgp, self.nint, torch.zeros((B, self.nint), device=fgp.device), w_ld, want_grad)
+        return norm_cols.reshape(sb + (1,)), ld.reshape(tuple(pshape) + (1,))
+
+    def get_gcv_numer_denom(self):
+        fgp = self.fgp
+        ytilde = fgp.get_ytilde(0)
+        inv, _ = self()
+        ztilde = ytilde * inv[..., 0, 0, :]
+        numer = (ztilde.conj() * ztilde).real.sum(-1, keepdim=True)
+        tr_k_inv = inv[..., 0, 0, :].real.sum(-1, keepdim=True)
+        denom = ((tr_k_inv / self.nint) ** 2).real
+        return numer, denom
+
+    def get_inv_diag(self):
+        lam = self._lam_full().reshape(tuple(self.pshape) + (self.nint,))
+        return (1 / lam).mean(-1, keepdim=True)
+
+
+class AbstractFastGP(torch.nn.Module):
+    _FAMILY = None  # 0 lattice, 1 digital net
+    _XBDTYPE = None
+    _FTOUTDTYPE = None
+    _DEFAULT_NOISE = None
+
+    def __init__(self, seqs, num_tasks, seed_for_seq, alpha, scale, lengthscales, noise, factor_task_kernel,
+                 rank_factor_task_kernel, noise_task_kernel, device, tfs_scale, tfs_lengthscales, tfs_noise,
+                 tfs_factor_task_kernel, tfs_noise_task_kernel, requires_grad_scale, requires_grad_lengthscales,
+                 requires_grad_noise, requires_grad_factor_task_kernel, requires_grad_noise_task_kernel, shape_batch,
+                 shape_scale, shape_lengthscales, shape_noise, shape_factor_task_kernel, shape_noise_task_kernel,
+                 derivatives, derivatives_coeffs, compile_fts, compile_fts_kwargs, adaptive_nugget):
+        super().__init__()
+        assert torch.get_default_dtype() == torch.float64, "fast transforms do not work without torch.float64 precision"
+        _lib.load()  # fail loudly when the CUDA library is missing: there is no CPU path
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("fastgaussianprocesses_b200 computes on a CUDA device only (got device=%r); there is no CPU fallback" % (device,))
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if num_tasks is None:
+            solo_task, default_task, num_tasks = True, 0, 1
+        else:
+            assert isinstance(num_tasks, int) and num_tasks > 0
+            solo_task, default_task = False, torch.arange(num_tasks)
+        if num_tasks != 1:
+            raise NotImplementedError("multi-task GPs (num_tasks>1) are outside the B200 hot path built so far (SURVEY.md section 8(f) row 2)")
+        if derivatives is not None or derivatives_coeffs is not None:
+            raise NotImplementedError("derivative-informed kernels are outside the B200 hot path built so far (SURVEY.md section 8(f) row 3)")
+        if adaptive_nugget:
+            raise NotImplementedError("adaptive_nugget is not supported by the B200 hot path")
+        self.num_tasks = num_tasks
+        self.default_task = default_task
+        self.solo_task = solo_task
+        # sequences
+        if isinstance(seqs, (int, np.integer)):
+            seqs = np.array([self._default_sequence(int(seqs), seed) for seed in np.random.SeedSequence(seed_for_seq).spawn(num_tasks)], dtype=object)
+        elif isinstance(seqs, (list, tuple)):
+            seqs = np.array(list(seqs), dtype=object)
+        elif not isinstance(seqs, np.ndarray):
+            seqs = np.array([seqs], dtype=object)
+        assert seqs.shape == (num_tasks,), "seqs should be a length num_tasks=%d list" % num_tasks
+        seqs = np.array([self._adopt_sequence(s) for s in seqs], dtype=object)
+        assert all(seqs[i].order == "NATURAL" for i in range(num_tasks)), "each seq should be in 'NATURAL' order "
+        assert all(seqs[i].replications == 1 for i in range(num_tasks)), "each seq should have only 1 replication"
+        self.d = seqs[0].d
+        assert self.d <= _lib.MAX_D, "dimension %d exceeds the fused-kernel limit %d" % (self.d, _lib.MAX_D)
+        self.seqs = seqs
+        self.n = torch.zeros(self.num_tasks, dtype=int, device=self.device)
+        self.m = -1 * torch.ones(self.num_tasks, dtype=int, device=self.device)
+        self._nint = 0
+        self.derivatives = [torch.zeros((1, self.d), dtype=torch.int64, device=self.device)]
+        self.derivatives_coeffs = [torch.ones(1, device=self.device)]
+        # alpha
+        assert (np.isscalar(alpha) and alpha % 1 == 0) or (isinstance(alpha, torch.Tensor) and alpha.shape == (self.d,)), "alpha should be an int or a torch.Tensor of length d"
+        if np.isscalar(alpha):
+            alpha = int(alpha) * torch.ones(self.d, dtype=int, device=self.device)
+        self.alpha = alpha.to(self.device)
+        self._alpha_list = [int(a) for a in self.alpha.tolist()]
+        # shape_batch
+        if isinstance(shape_batch, (list, tuple)):
+            shape_batch = torch.Size(shape_batch)
+        assert isinstance(shape_batch, torch.Size)
+        self.shape_batch = shape_batch
+        self.ndim_batch = len(self.shape_batch)
+        # scale (abstract_gp.py:77-88)
+        assert np.isscalar(scale) or isinstance(scale, torch.Tensor), "scale must be a scalar or torch.Tensor"
+        if isinstance(scale, torch.Tensor):
+            shape_scale = scale.shape
+        if isinstance(shape_scale, (list, tuple)):
+            shape_scale = torch.Size(shape_scale)
+        assert isinstance(shape_scale, torch.Size) and shape_scale[-1] == 1
+        if len(shape_scale) > 1:
+            assert shape_scale[:-1] == shape_batch[-(len(shape_scale) - 1):]
+        if np.isscalar(scale):
+            scale = scale * torch.ones(shape_scale, device=self.device)
+        scale = scale.to(self.device)
+        assert (scale > 0).all(), "scale must be positive"
+        assert len(tfs_scale) == 2 and callable(tfs_scale[0]) and callable(tfs_scale[1]), "tfs_scale should be a tuple of two callables, the transform and inverse transform"
+        self.tf_scale = tfs_scale[1]
+        self.raw_scale = torch.nn.Parameter(tfs_scale[0](scale), requires_grad=requires_grad_scale)
+        # lengthscales (abstract_gp.py:89-100)
+        assert np.isscalar(lengthscales) or isinstance(lengthscales, torch.Tensor), "lengthscales must be a scalar or torch.Tensor"
+        if isinstance(lengthscales, torch.Tensor):
+            shape_lengthscales = lengthscales.shape
+        if shape_lengthscales is None:
+            shape_lengthscales = torch.Size([self.d])
+        if isinstance(shape_lengthscales, (list, tuple)):
+            shape_lengthscales = torch.Size(shape_lengthscales)
+        assert isinstance(shape_lengthscales, torch.Size) and (shape_lengthscales[-1] == self.d or shape_lengthscales[-1] == 1)
+        if len(shape_lengthscales) > 1:
+            assert shape_lengthscales[:-1] == shape_batch[-(len(shape_lengthscales) - 1):]
+        if np.isscalar(lengthscales):
+            lengthscales = lengthscales * torch.ones(shape_lengthscales, device=self.device)
+        lengthscales = lengthscales.to(self.device)
+        assert (lengthscales > 0).all(), "lengthscales must be positive"
+        assert len(tfs_lengthscales) == 2 and callable(tfs_lengthscales[0]) and callable(tfs_lengthscales[1]), "tfs_lengthscales should be a tuple of two callables, the transform and inverse transform"
+        self.tf_lengthscales = tfs_lengthscales[1]
+        self.raw_lengthscales = torch.nn.Parameter(tfs_lengthscales[0](lengthscales), requires_grad=requires_grad_lengthscales)
+        # noise (abstract_gp.py:101-111)
+        assert np.isscalar(noise) or isinstance(noise, torch.Tensor), "noise must be a scalar or torch.Tensor"
+        if isinstance(noise, torch.Tensor):
+            shape_noise = noise.shape
+        if isinstance(shape_noise, (list, tuple)):
+            shape_noise = torch.Size(shape_noise)
+        assert isinstance(shape_noise, torch.Size) and shape_noise[-1] == 1
+        if len(shape_noise) > 1:
+            assert shape_noise[:-1] == shape_batch[-(len(shape_noise) - 1):]
+        if np.isscalar(noise):
+            noise = noise * torch.ones(shape_noise, device=self.device)
+        noise = noise.to(self.device)
+        assert (noise > 0).all(), "noise must be positive"
+        assert len(tfs_noise) == 2 and callable(tfs_noise[0]) and callable(tfs_noise[1]), "tfs_scale should be a tuple of two callables, the transform and inverse transform"
+        self.tf_noise = tfs_noise[1]
+        self.raw_noise = torch.nn.Parameter(tfs_noise[0](noise), requires_grad=requires_grad_noise)
+        # task kernel of a single task: F F^T + diag(v) with F of rank 0 (abstract_gp.py:112-139)
+        assert np.isscalar(factor_task_kernel) or isinstance(factor_task_kernel, torch.Tensor), "factor_task_kernel must be a scalar or torch.Tensor"
+        if isinstance(factor_task_kernel, torch.Tensor):
+            shape_factor_task_kernel = factor_task_kernel.shape
+        if shape_factor_task_kernel is None:
+            if rank_factor_task_kernel is None:
+                rank_factor_task_kernel = 0
+            assert isinstance(rank_factor_task_kernel, int) and 0 <= rank_factor_task_kernel <= self.num_tasks
+            shape_factor_task_kernel = torch.Size([self.num_tasks, rank_factor_task_kernel])
+        if isinstance(shape_factor_task_kernel, (list, tuple)):
+            shape_factor_task_kernel = torch.Size(shape_factor_task_kernel)
+        assert isinstance(shape_factor_task_kernel, torch.Size) and 0 <= shape_factor_task_kernel[-1] <= self.num_tasks and shape_factor_task_kernel[-2] == self.num_tasks
+        if len(shape_factor_task_kernel) > 2:
+            assert shape_factor_task_kernel[:-2] == shape_batch[-(len(shape_factor_task_kernel) - 2):]
+        if np.isscalar(factor_task_kernel):
+            factor_task_kernel = factor_task_kernel * torch.ones(shape_factor_task_kernel, device=self.device)
+        factor_task_kernel = factor_task_kernel.to(self.device)
+        assert len(tfs_factor_task_kernel) == 2 and callable(tfs_factor_task_kernel[0]) and callable(tfs_factor_task_kernel[1])
+        self.tf_factor_task_kernel = tfs_factor_task_kernel[1]
+        if requires_grad_factor_task_kernel is None:
+            requires_grad_factor_task_kernel = self.num_tasks > 1
+        self.raw_factor_task_kernel = torch.nn.Parameter(tfs_factor_task_kernel[0](factor_task_kernel), requires_grad=requires_grad_factor_task_kernel)
+        assert np.isscalar(noise_task_kernel) or isinstance(noise_task_kernel, torch.Tensor), "noise_task_kernel must be a scalar or torch.Tensor"
+        if isinstance(noise_task_kernel, torch.Tensor):
+            shape_noise_task_kernel = noise_task_kernel.shape
+        if shape_noise_task_kernel is None:
+            shape_noise_task_kernel = torch.Size([self.num_tasks])
+        if isinstance(shape_noise_task_kernel, (list, tuple)):
+            shape_noise_task_kernel = torch.Size(shape_noise_task_kernel)
+        assert isinstance(shape_noise_task_kernel, torch.Size) and (shape_noise_task_kernel[-1] == self.num_tasks or shape_noise_task_kernel[-1] == 1)
+        if len(shape_noise_task_kernel) > 1:
+            assert shape_noise_task_kernel[:-1] == shape_batch[-(len(shape_noise_task_kernel) - 1):]
+        if np.isscalar(noise_task_kernel):
+            noise_task_kernel = noise_task_kernel * torch.ones(shape_noise_task_kernel, device=self.device)
+        noise_task_kernel = noise_task_kernel.to(self.device)
+        assert (noise_task_kernel >= 0).all(), "noise_task_kernel must be positive"
+        assert len(tfs_noise_task_kernel) == 2 and callable(tfs_noise_task_kernel[0]) and callable(tfs_noise_task_kernel[1])
+        self.tf_noise_task_kernel = tfs_noise_task_kernel[1]
+        if requires_grad_noise_task_kernel is None:
+            requires_grad_noise_task_kernel = self.num_tasks > 1
+        self.raw_noise_task_kernel = torch.nn.Parameter(tfs_noise_task_kernel[0](noise_task_kernel), requires_grad=requires_grad_noise_task_kernel)
+        self._default_tfs = (tuple(tfs_scale) == DEFAULT_TFS_LOG_EXP and tuple(tfs_lengthscales) == DEFAULT_TFS_LOG_EXP and
+                             tuple(tfs_noise) == DEFAULT_TFS_LOG_EXP)
+        # storage and caches
+        self._y = [torch.empty(0, device=self.device) for _ in range(self.num_tasks)]
+        self.xxb_seqs = np.array([_XXbSeq(self, self.seqs[i]) for i in range(self.num_tasks)], dtype=object)
+        self.inv_log_det_cache_dict = {}
+        self.adaptive_nugget = False
+        self._epoch = 0
+        self._coeffs = None
+        self._coeffs_key = None
+        self._ytilde = None
+        self._ytilde_n = -1
+        self._ysq = None
+        # the injected transforms of the reference (abstract_fast_gp.py:26-27)
+        self.ft_unstable = self._ft_unstable
+        self.ift_unstable = self._ift_unstable
+
+    # ------------------------------------------------------------------------------------------------ state keys
+    def _param_key(self):
+        ps = (self.raw_scale, self.raw_lengthscales, self.raw_noise, self.raw_factor_task_kernel, self.raw_noise_task_kernel)
+        return (self._epoch,) + tuple((id(p), p._version, p.data_ptr()) for p in ps)
+
+    def _hyper(self):
+        """Effective per-set hyperparameters (scale_B (B,), ls_B (B,d), noise_B (B,), batch shape), autograd-connected.
+        The 1x1 task kernel multiplies lam after the noise is added (util.py:293,298), so it folds into scale and noise."""
+        scale, ls, noise = self.scale, self.lengthscales, self.noise
+        tau = self.gram_matrix_tasks[..., 0, 0]
+        pshape = torch.broadcast_shapes(scale.shape[:-1], ls.shape[:-1], noise.shape[:-1], tau.shape)
+        B = _prod(pshape)
+        scale_B = (scale[..., 0] * tau).expand(pshape).reshape(B)
+        noise_B = (noise[..., 0] * tau).expand(pshape).reshape(B)
+        ls_B = ls.expand(tuple(pshape) + (self.d,)).reshape(B, self.d)
+        return scale_B, ls_B, noise_B, pshape
+
+    def _hyper_host(self):
+        with torch.no_grad():
+            scale_B, ls_B, noise_B, pshape = self._hyper()
+            return scale_B.cpu().numpy(), ls_B.cpu().numpy(), noise_B.cpu().numpy(), pshape
+
+    def _xpts(self, n):
+        x, xb = self.xxb_seqs[0][:int(n)]
+        return xb if self._FAMILY == 1 else x
+
+    # ------------------------------------------------------------------------------------------------ data
+    def _sample(self, seq, n_min, n_max):
+        return seq.generate(int(n_min), int(n_max), self.device)
+
+    def get_x_next(self, n: Union[int, torch.Tensor], task: Union[int, torch.Tensor] = None):
+        n_og = n
+        if isinstance(n, (int, np.integer)):
+            n = torch.tensor([n], dtype=int, device=self.device)
+        if isinstance(n, list):
+            n = torch.tensor(n, dtype=int, device=self.device)
+        assert isinstance(n, torch.Tensor) and torch.logical_or(n == 0, n & (n - 1) == 0).all(), "maximum sequence index must be a power of 2"
+        if task is None:
+            task = self.default_task
+        inttask = isinstance(task, int)
+        if inttask:
+            task = torch.tensor([task], dtype=int)
+        if isinstance(task, list):
+            task = torch.tensor(task, dtype=int)
+        assert isinstance(n, torch.Tensor) and isinstance(task, torch.Tensor) and n.ndim == task.ndim == 1 and len(n) == len(task)
+        assert (n >= self.n[task]).all(), "maximum sequence index must be greater than the current number of samples"
+        x_next = [self.xxb_seqs[int(l)][int(self.n[l]):int(n[i])][0] for i, l in enumerate(task)]
+        return x_next[0] if inttask else x_next
+
+    def add_y_next(self, y_next: Union[torch.Tensor, List], task: Union[int, torch.Tensor] = None):
+        if isinstance(y_next, torch.Tensor):
+            y_next = [y_next]
+        if task is None:
+            task = self.default_task
+        if isinstance(task, int):
+            task = torch.tensor([task], dtype=int)
+        if isinstance(task, list):
+            task = torch.tensor(task, dtype=int)
+        assert isinstance(y_next, list) and isinstance(task, torch.Tensor) and task.ndim == 1 and len(y_next) == len(task)
+        assert all(y_next[i].shape[:-1] == self.shape_batch for i in range(len(y_next)))
+        for i, l in enumerate(task):
+            self._y[int(l)] = torch.cat([self._y[int(l)], y_next[i].to(self.device)], -1)
+        self._nint = int(self._y[0].size(-1))
+        self.n = torch.tensor([self._y[i].size(-1) for i in range(self.num_tasks)], dtype=int, device=self.device)
+        self.m = torch.where(self.n == 0, -1, torch.log2(self.n)).to(int)
+        assert self._nint == 0 or (self._nint & (self._nint - 1)) == 0, "total samples must be power of 2"
+        for key in list(self.inv_log_det_cache_dict.keys()):
+            if key[0] < self._nint:
+                del self.inv_log_det_cache_dict[key]
+        self._epoch += 1
+
+    # ------------------------------------------------------------------------------------------------ properties
+    @property
+    def total_parameters(self):
+        return sum(p.numel() for p in self.parameters())
+
+    @property
+    def total_tuneable_parameters(self):
+        return sum((p.numel() if p.requires_grad else 0) for p in self.parameters())
+
+    @property
+    def scale(self):
+        return self.tf_scale(self.raw_scale)
+
+    @property
+    def lengthscales(self):
+        return self.tf_lengthscales(self.raw_lengthscales)
+
+    @property
+    def noise(self):
+        return self.tf_noise(self.raw_noise)
+
+    @property
+    def factor_task_kernel(self):
+        return self.tf_factor_task_kernel(self.raw_factor_task_kernel)
+
+    @property
+    def noise_task_kernel(self):
+        return self.tf_noise_task_kernel(self.raw_noise_task_kernel)
+
+    @property
+    def gram_matrix_tasks(self):
+        f = self.factor_task_kernel
+        kmat = torch.einsum("...il,...kl->...ik", f, f)
+        return kmat + self.noise_task_kernel[..., None] * torch.eye(self.num_tasks, device=self.device)
+
+    @property
+    def coeffs(self):
+        r"""Coefficients $\mathsf{K}^{-1} \boldsymbol{y}$ (util.py:419-425)."""
+        key = (self._nint,) + self._param_key()
+        if self._coeffs is None or self._coeffs_key != key or os.environ.get("FASTGP_FORCE_RECOMPILE") == "True":
+            with torch.no_grad():
+                self._coeffs = self.get_inv_log_det_cache().gram_matrix_solve(self._y[0])
+            self._coeffs_key = key
+        return self._coeffs
+
+    @property
+    def x(self):
+        xs = [self.get_x(l) for l in range(self.num_tasks)]
+        return xs[0] if self.solo_task else xs
+
+    @property
+    def y(self):
+        return self._y[0] if self.solo_task else self._y
+
+    def get_x(self, task, n=None):
+        assert 0 <= task < self.num_tasks
+        if n is None:
+            n = self._nint
+        assert n >= 0
+        return self.xxb_seqs[task][:int(n)][0]
+
+    def get_xb(self, task, n=None):
+        assert 0 <= task < self.num_tasks
+        if n is None:
+            n = self._nint
+        assert n >= 0
+        return self.xxb_seqs[task][:int(n)][1]
+
+    # ------------------------------------------------------------------------------------------------ transforms
+    def ft(self, x):
+        """Mean-stabilised orthonormal fast transform along the last dim (abstract_fast_gp.py:197-212)."""
+        x = x.to(self.device)
+        xmean = x.mean(-1)
+        y = self.ft_unstable(x - xmean[..., None])
+        y[..., 0] += xmean * np.sqrt(x.size(-1))
+        return y
+
+    def ift(self, x):
+        """Mean-stabilised orthonormal inverse fast transform along the last dim (abstract_fast_gp.py:213-228)."""
+        x = x.to(self.device)
+        xmean = x.mean(-1)
+        y = self.ift_unstable(x - xmean[..., None])
+        y[..., 0] += xmean * np.sqrt(x.size(-1))
+        return y
+
+    def get_ytilde(self, task):
+        assert 0 <= task < self.num_tasks
+        if self._ytilde is None or self._ytilde_n != self._nint:
+            y = self._y[task]
+            self._ytilde = self.ft(y) if self._nint > 1 else y.clone().to(self._FTOUTDTYPE)
+            self._ytilde_n = self._nint
+            self._ysq = None
+        return self._ytilde
+
+    def _get_ysq(self, pshape):
+        """(B,n) sums of |ytilde|^2 over the leading batch dims that share one hyperparameter set."""
+        ytilde = self.get_ytilde(0)
+        B = _prod(pshape)
+        if self._ysq is None or self._ysq.shape[0] != B:
+            sb = tuple(self.shape_batch)
+            lead = _prod(sb[:len(sb) - len(pshape)])
+            a = ytilde.abs() ** 2 if ytilde.is_complex() else ytilde ** 2
+            self._ysq = a.reshape(lead, B, self._nint).sum(0).contiguous()
+        return self._ysq
+
+    def get_k1parts(self, task0, task1, n=None):
+        assert 0 <= task0 < self.num_tasks and 0 <= task1 < self.num_tasks
+        if n is None:
+            n = self._nint
+        assert n >= 0
+        x, xb = self.xxb_seqs[0][:int(n)]
+        if self._FAMILY == 0:
+            parts = _lib.lattice_kernel_parts(x.contiguous(), x[0].cpu().numpy(), self._alpha_list)
+        else:
+            parts = _lib.dnb2_kernel_parts(xb.contiguous(), xb[0].cpu().numpy(), self._alpha_list, self._t)
+        return parts[:, None, None, :]
+
+    def get_lam(self, task0, task1, n=None):
+        """lam~ = ft(k1) in the reference's normalisation (util.py:95-141)."""
+        assert 0 <= task0 < self.num_tasks and 0 <= task1 < self.num_tasks
+        if n is None:
+            n = self._nint
+        n = int(n)
+        with torch.no_grad():
+            parts = self.get_k1parts(task0, task1, n)[:, 0, 0, :].contiguous()
+            scale, ls = self.scale, self.lengthscales
+            pshape = torch.broadcast_shapes(scale.shape[:-1], ls.shape[:-1])
+            B = _prod(pshape)
+            k1 = _lib.kernel_from_parts(parts, scale[..., 0].expand(pshape).reshape(B).contiguous(),
+                                        ls.expand(tuple(pshape) + (self.d,)).reshape(B, self.d).contiguous())
+            lam = self.ft(k1)
+        return lam.reshape(tuple(pshape) + (n,))
+
+    def get_inv_log_det_cache(self, n=None):
+        if n is None:
+            n = self.n
+        if isinstance(n, (int, np.integer)):
+            n = torch.tensor([int(n)], dtype=int, device=self.device)
+        assert isinstance(n, torch.Tensor) and n.shape == (self.num_tasks,) and (n >= self.n).all()
+        ntup = tuple(n.tolist())
+        if ntup not in self.inv_log_det_cache_dict.keys():
+            self.inv_log_det_cache_dict[ntup] = _FastInverseLogDetCache(self, n)
+        return self.inv_log_det_cache_dict[ntup]
+
+    def get_inv_log_det(self, n=None):
+        return self.get_inv_log_det_cache(n)()
+
+    def get_default_optimizer(self, lr):
+        if lr is None:
+            lr = 1e-1
+        return torch.optim.Rprop(self.parameters(), lr=lr)
+
+    # ------------------------------------------------------------------------------------------------ kernel
+    def kernel(self, x: torch.Tensor, z: torch.Tensor, beta0: torch.Tensor = None, beta1: torch.Tensor = None,
+               c0: torch.Tensor = None, c1: torch.Tensor = None):
+        assert isinstance(x, torch.Tensor) and x.size(-1) == self.d
+        assert isinstance(z, torch.Tensor) and z.size(-1) == self.d
+        for b in (beta0, beta1):
+            if b is not None and (b != 0).any():
+                raise NotImplementedError("derivative-informed kernels are outside the B200 hot path built so far")
+        for c in (c0, c1):
+            if c is not None:
+                assert c.numel() == 1, "without derivatives there is one coefficient"
+        k = self._kernel(x, z)
+        for c in (c0, c1):
+            if c is not None:
+                k = k * c.to(self.device).reshape(())
+        return k
+
+    def _kernel(self, x, z, *unused):
+        """k(x,z) with numpy-style broadcasting of the leading dims; hyperparameter batch dims come first
+        (abstract_fast_gp.py:181-196)."""
+        x = x.to(self.device)
+        z = z.to(self.device)
+        scale_B, ls_B, _, pshape = self._hyper_host()
+        B = len(scale_B)
+        lead = torch.broadcast_shapes(x.shape[:-1], z.shape[:-1])
+        outs = []
+        cross = x.ndim == 3 and z.ndim == 3 and x.shape[1] == 1 and z.shape[0] == 1 and torch.is_floating_point(x)
+        for b in range(B):
+            if cross:
+                k = _lib.cross_kernel(self._FAMILY, x[:, 0, :].contiguous(), z[0].contiguous() if self._FAMILY == 0 or not torch.is_floating_point(z) else self._convert_to_b(z[0]).contiguous(),
+                                      self._alpha_list, self._t, scale_B[b], ls_B[b])
+            else:
+                xe = x.expand(tuple(lead) + (self.d,)).reshape(-1, self.d)
+                ze = z.expand(tuple(lead) + (self.d,)).reshape(-1, self.d)
+                if not torch.is_floating_point(xe):
+                    xe = self._convert_from_b(xe)
+                k = _lib.kernel_pairs(self._FAMILY, xe.contiguous(), ze.contiguous(), self._alpha_list, self._t, scale_B[b], ls_B[b]).reshape(lead)
+            outs.append(k)
+        if len(pshape) == 0:
+            return outs[0]
+        return torch.stack(outs, 0).reshape(tuple(pshape) + tuple(outs[0].shape))
+
+    # ------------------------------------------------------------------------------------------------ fit
+    def _mll_terms(self, want_grad):
+        """Weighted MLL per hyperparameter set through the fused kernel; returns (loss, term1, term2) tensors."""
+        scale_B, ls_B, noise_B, pshape = self._hyper()
+        B = scale_B.numel()
+        d_out = _prod(self.shape_batch)
+        ysq = self._get_ysq(pshape)
+        if getattr(self, "_mllw", None) is None or self._mllw.shape[0] != B or self._mllw_dout != d_out:
+            self._mllw = torch.tensor([0.5, 0.5 * d_out / B], device=self.device).expand(B, 2).contiguous()
+            self._mllw_dout = d_out
+        lossb, norm, logdet = _MLLFunction.apply(scale_B, ls_B, noise_B, self, self._nint, ysq, self._mllw, want_grad)
+        return lossb.sum(), norm.sum(), d_out / B * logdet.sum()
+
+    def fit(self,
+            loss_metric: str = "MLL",
+            iterations: int = 5000,
+            lr: float = None,
+            optimizer: torch.optim.Optimizer = None,
+            stop_crit_improvement_threshold: float = 5e-2,
+            stop_crit_wait_iterations: int = 10,
+            store_hists: bool = False,
+            store_loss_hist: bool = False,
+            store_scale_hist: bool = False,
+            store_lengthscales_hist: bool = False,
+            store_noise_hist: bool = False,
+            store_task_kernel_hist: bool = False,
+            verbose: int = 5,
+            verbose_indent: int = 4,
+            masks: torch.Tensor = None,
+            cv_weights: torch.Tensor = 1,
+            ):
+        """Hyperparameter optimisation; arguments and return value as the reference (abstract_gp.py:152-306).
+        The MLL value and its gradient come from the fused CUDA eigen-solve (one call per iteration) instead of an
+        autograd tape through log2(n) transform passes."""
+        assert isinstance(loss_metric, str) and loss_metric.upper() in ["MLL", "GCV", "CV"]
+        assert self._nint > 0, "cannot fit without data"
+        assert isinstance(iterations, int) and iterations >= 0
+        assert isinstance(store_hists, bool), "require bool store_mll_hist"
+        assert isinstance(store_loss_hist, bool), "require bool store_loss_hist"
+        assert isinstance(store_scale_hist, bool), "require bool store_scale_hist"
+        assert isinstance(store_lengthscales_hist, bool), "require bool store_lengthscales_hist"
+        assert isinstance(store_noise_hist, bool), "require bool store_noise_hist"
+        assert isinstance(store_task_kernel_hist, bool), "require bool store_task_kernel_hist"
+        assert (isinstance(verbose, int) or isinstance(verbose, bool)) and verbose >= 0, "require verbose is a non-negative int"
+        assert isinstance(verbose_indent, int) and verbose_indent >= 0, "require verbose_indent is a non-negative int"
+        assert np.isscalar(stop_crit_improvement_threshold) and 0 < stop_crit_improvement_threshold, "require stop_crit_improvement_threshold is a positive float"
+        assert isinstance(stop_crit_wait_iterations, int) and stop_crit_wait_iterations > 0
+        assert masks is None or (isinstance(masks, torch.Tensor))
+        loss_metric = loss_metric.upper()
+        if loss_metric != "MLL":
+            raise NotImplementedError("loss_metric=%r: only the MLL loss is on the B200 hot path built so far (SURVEY.md section 8(f) row 4)" % loss_metric)
+        if masks is not None:
+            raise NotImplementedError("fit(masks=...) is not supported by the B200 hot path built so far")
+        fused = optimizer is None and _FusedFitLoop.eligible(self) and os.environ.get("FGP_B200_GENERIC_FIT") != "1"
+        if optimizer is None:
+            optimizer = self.get_default_optimizer(lr)
+        assert isinstance(optimizer, torch.optim.Optimizer)
+        logtol = np.log(1 + stop_crit_improvement_threshold)
+        store_loss_hist = store_hists or store_loss_hist
+        store_scale_hist = store_hists or (store_scale_hist and self.raw_scale.requires_grad)
+        store_lengthscales_hist = store_hists or (store_lengthscales_hist and self.raw_lengthscales.requires_grad)
+        store_noise_hist = store_hists or (store_noise_hist and self.raw_noise.requires_grad)
+        store_task_kernel_hist = store_hists or (store_task_kernel_hist and (self.raw_factor_task_kernel.requires_grad or self.raw_noise_task_kernel.requires_grad))
+        if fused:
+            return self._fit_fused(iterations, 1e-1 if lr is None else lr, logtol, stop_crit_wait_iterations, store_loss_hist, store_scale_hist,
+                                   store_lengthscales_hist, store_noise_hist, store_task_kernel_hist, verbose, verbose_indent)
+        if store_loss_hist:
+            loss_hist = torch.empty(iterations + 1)
+        if store_scale_hist:
+            scale_hist = torch.empty(torch.Size([iterations + 1]) + self.raw_scale.shape)
+        if store_lengthscales_hist:
+            lengthscales_hist = torch.empty(torch.Size([iterations + 1]) + self.raw_lengthscales.shape)
+        if store_noise_hist:
+            noise_hist = torch.empty(torch.Size([iterations + 1]) + self.raw_noise.shape)
+        if store_task_kernel_hist:
+            task_kernel_hist = torch.empty(torch.Size([iterations + 1]) + self.gram_matrix_tasks.shape)
+        d_out = _prod(self.shape_batch)
+        if verbose:
+            _s = "%16s | %-10s | %-10s | %-10s" % ("iter of %.1e" % iterations, "loss", "term1", "term2")
+            print(" " * verbose_indent + _s)
+            print(" " * verbose_indent + "~" * len(_s))
+        mll_const = d_out * self._nint * np.log(2 * np.pi)
+        stop_crit_best_loss = torch.inf
+        stop_crit_save_loss = torch.inf
+        stop_crit_iterations_without_improvement_loss = 0
+        want_grad = any(p.requires_grad for p in self.parameters())
+        self.get_ytilde(0)
+        for i in range(iterations + 1):
+            wsum, term1, term2 = self._mll_terms(want_grad)
+            loss = wsum + 0.5 * mll_const
+            metric_val = -loss
+            lossv = loss.item()
+            if lossv < stop_crit_best_loss:
+                stop_crit_best_loss = lossv
+                best_params = {param[0]: param[1].data.clone() for param in self.named_parameters()}
+            if (stop_crit_save_loss - lossv) > logtol:
+                stop_crit_iterations_without_improvement_loss = 0
+                stop_crit_save_loss = stop_crit_best_loss
+            else:
+                stop_crit_iterations_without_improvement_loss += 1
+            break_condition = i == iterations or stop_crit_iterations_without_improvement_loss == stop_crit_wait_iterations
+            if store_loss_hist:
+                loss_hist[i] = -lossv
+            if store_scale_hist:
+                scale_hist[i] = self.scale.detach().to(scale_hist.device)
+            if store_lengthscales_hist:
+                lengthscales_hist[i] = self.lengthscales.detach().to(lengthscales_hist.device)
+            if store_noise_hist:
+                noise_hist[i] = self.noise.detach().to(noise_hist.device)
+            if store_task_kernel_hist:
+                task_kernel_hist[i] = self.gram_matrix_tasks.detach().to(task_kernel_hist.device)
+            if verbose and (i % verbose == 0 or break_condition):
+                _s = "%16.2e | %-10.2e | %-10.2e | %-10.2e" % (i, lossv, term1.item(), term2.item())
+                print(" " * verbose_indent + _s)
+            if break_condition:
+                break
+            if want_grad:
+                loss.backward()
+            optimizer.step()
+            optimizer.zero_grad()
+        for pname, pdata in best_params.items():
+            setattr(self, pname, torch.nn.Parameter(pdata, requires_grad=getattr(self, pname).requires_grad))
+        self._epoch += 1
+        data = {"iterations": i}
+        if store_loss_hist:
+            data["loss_hist"] = loss_hist[:(i + 1)]
+        if store_scale_hist:
+            data["scale_hist"] = scale_hist[:(i + 1)]
+        if store_lengthscales_hist:
+            data["lengthscales_hist"] = lengthscales_hist[:(i + 1)]
+        if store_noise_hist:
+            data["noise_hist"] = noise_hist[:(i + 1)]
+        if store_task_kernel_hist:
+            data["task_kernel_hist"] = task_kernel_hist[:(i + 1)]
+        return data
+
+    def _get_fused_loop(self, hist_flags=(False, False, False), hist_capacity=0):
+        loop = getattr(self, "_fused_loop", None)
+        self.get_ytilde(0)
+        if loop is None or not loop.matches(self, hist_flags, hist_capacity):
+            if loop is not None:
+                loop.close()
+            with torch.no_grad():
+                _, _, _, pshape = self._hyper()
+            self._get_ysq(pshape)
+            loop = _FusedFitLoop(self, hist_flags, max(hist_capacity, 1))
+            self._fused_loop = loop
+        return loop
+
+    def fit_stepper(self):
+        """The fused device-side fit loop armed for an open-ended run: `.step()` = one MLL+gradient+Rprop iteration."""
+        assert self._nint > 0, "cannot fit without data"
+        assert _FusedFitLoop.eligible(self), "fit_stepper needs the default transforms and parameter layouts"
+        loop = self._get_fused_loop()
+        loop.begin(2 ** 30, 2 ** 30, np.log(1.05), 1e-1)
+        self._epoch += 1
+        return loop
+
+    def _fit_fused(self, iterations, lr, logtol, stop_wait, store_loss_hist, store_scale_hist, store_lengthscales_hist, store_noise_hist,
+                   store_task_kernel_hist, verbose, verbose_indent):
+        """fit() on the device: same state machine and outputs as the generic loop below (abstract_gp.py:236-306)."""
+        flags = (store_scale_hist, store_lengthscales_hist, store_noise_hist)
+        loop = self._get_fused_loop(flags, iterations + 1)
+        if verbose:
+            _s = "%16s | %-10s | %-10s | %-10s" % ("iter of %.1e" % iterations, "loss", "term1", "term2")
+            print(" " * verbose_indent + _s)
+            print(" " * verbose_indent + "~" * len(_s))
+        loop.begin(iterations, stop_wait, logtol, lr)
+        printed = 0
+        while True:
+            if iterations + 1 >= loop.GRAPH_ITERS:
+                loop.replay(loop.GRAPH_ITERS)
+            else:
+                for _ in range(iterations + 1):
+                    loop.replay(1)
+            st = loop.read_state()
+            last, stopped = int(st[loop.ST_LAST_ITER]), bool(st[loop.ST_STOPPED] != 0)
+            if verbose:
+                rows = loop.loss_hist[printed:last + 1].cpu().numpy()
+                for r, row in enumerate(rows):
+                    it = printed + r
+                    if it % verbose == 0 or (stopped and it == last):
+                        print(" " * verbose_indent + "%16.2e | %-10.2e | %-10.2e | %-10.2e" % (it, row[0], row[1], row[2]))
+                printed = last + 1
+            if stopped:
+                break
+        loop.finish()
+        i = last
+        for pname in ("raw_scale", "raw_lengthscales", "raw_noise", "raw_factor_task_kernel", "raw_noise_task_kernel"):
+            p = getattr(self, pname)
+            setattr(self, pname, torch.nn.Parameter(p.data, requires_grad=p.requires_grad))
+        self._epoch += 1
+        data = {"iterations": i}
+        if store_loss_hist:
+            data["loss_hist"] = -loop.loss_hist[:(i + 1), 0].cpu()
+        if store_scale_hist:
+            data["scale_hist"] = loop.scale_hist[:(i + 1)].reshape((i + 1,) + tuple(self.raw_scale.shape)).cpu()
+        if store_lengthscales_hist:
+            data["lengthscales_hist"] = loop.ls_hist[:(i + 1)].reshape((i + 1,) + tuple(self.raw_lengthscales.shape)).cpu()
+        if store_noise_hist:
+            data["noise_hist"] = loop.noise_hist[:(i + 1)].reshape((i + 1,) + tuple(self.raw_noise.shape)).cpu()
+        if store_task_kernel_hist:
+            data["task_kernel_hist"] = self.gram_matrix_tasks.detach().cpu()[None].expand((i + 1,) + tuple(self.gram_matrix_tasks.shape)).clone()
+        return data
+
+    # ------------------------------------------------------------------------------------------------ posterior
+    def _parse_task(self, task):
+        if task is None:
+            task = self.default_task
+        inttask = isinstance(task, int)
+        if inttask:
+            task = torch.tensor([task], dtype=int)
+        if isinstance(task, list):
+            task = torch.tensor(task, dtype=int)
+        assert task.ndim == 1 and (task >= 0).all() and (task < self.num_tasks).all()
+        return inttask, task
+
+    def _parse_n(self, n):
+        if n is None:
+            return self._nint
+        if isinstance(n, torch.Tensor):
+            assert n.numel() == 1
+            n = int(n.item())
+        n = int(n)
+        assert (n & (n - 1)) == 0 and n >= self._nint, "require n are all power of two greater than or equal to self.n"
+        return n
+
+    def post_mean(self, x: torch.Tensor, task: Union[int, torch.Tensor] = None, eval: bool = True):
+        """Posterior mean (abstract_gp.py:352-380) as an on-the-fly kernel-vector product: the (N,n) cross-covariance
+        is never materialised."""
+        assert x.ndim == 2 and x.size(1) == self.d, "x must a torch.Tensor with shape (-1,d)"
+        inttask, task = self._parse_task(task)
+        coeffs = self.coeffs
+        x = x.to(self.device).contiguous()
+        scale_B, ls_B, _, pshape = self._hyper_host()
+        B = len(scale_B)
+        sb = tuple(self.shape_batch)
+        N = x.shape[0]
+        xpts = self._xpts(self._nint)
+        c = coeffs.reshape(-1, B, self._nint)
+        if B == 1:
+            pm = _lib.post_mean(self._FAMILY, x, xpts, self._alpha_list, self._t, scale_B[0], ls_B[0], c[:, 0, :].contiguous())
+        else:
+            pm = torch.empty((c.shape[0], B, N), dtype=torch.float64, device=self.device)
+            for b in range(B):
+                pm[:, b, :] = _lib.post_mean(self._FAMILY, x, xpts, self._alpha_list, self._t, scale_B[b], ls_B[b], c[:, b, :].contiguous())
+        pmean = pm.reshape(sb + (1, N))
+        return pmean[..., 0, :] if inttask else pmean
+
+    def post_var(self, x: torch.Tensor, task: Union[int, torch.Tensor] = None, n: Union[int, torch.Tensor] = None, eval: bool = True):
+        """Posterior variance (abstract_gp.py:381-416 with the guard of abstract_fast_gp.py:41-46)."""
+        n = self._parse_n(n)
+        assert x.ndim == 2 and x.size(1) == self.d, "x must a torch.Tensor with shape (-1,d)"
+        inttask, task = self._parse_task(task)
+        x = x.to(self.device).contiguous()
+        scale_B, ls_B, _, pshape = self._hyper_host()
+        B = len(scale_B)
+        lam = self.get_inv_log_det_cache(n)._lam_full()
+        xpts = self._xpts(n)
+        outs = [_lib.post_var(self._FAMILY, x, xpts, self._alpha_list, self._t, scale_B[b], ls_B[b], lam[b]) for b in range(B)]
+        pvar = torch.stack(outs, 0).reshape(tuple(pshape) + (1, x.shape[0]))
+        return pvar[..., 0, :] if inttask else pvar
+
+    def post_cov(self, x0: torch.Tensor, x1: torch.Tensor, task0: Union[int, torch.Tensor] = None, task1: Union[int, torch.Tensor] = None,
+                 n: Union[int, torch.Tensor] = None, eval: bool = True):
+        """Posterior covariance matrix (abstract_gp.py:417-474)."""
+        n = self._parse_n(n)
+        assert x0.ndim == 2 and x0.size(1) == self.d, "x must a torch.Tensor with shape (-1,d)"
+        assert x1.ndim == 2 and x1.size(1) == self.d, "z must a torch.Tensor with shape (-1,d)"
+        inttask0, task0 = self._parse_task(task0)
+        inttask1, task1 = self._parse_task(task1)
+        x0 = x0.to(self.device).contiguous()
+        x1 = x1.to(self.device).contiguous()
+        equal = torch.equal(x0, x1) and torch.equal(task0, task1)
+        scale_B, ls_B, _, pshape = self._hyper_host()
+        B = len(scale_B)
+        cache = self.get_inv_log_det_cache(n)
+        lam = cache._lam_full()
+        xpts = self._xpts(n)
+        fam, al, t = self._FAMILY, self._alpha_list, self._t
+        outs = []
+        with torch.no_grad():
+            for b in range(B):
+                knew = _lib.cross_kernel(fam, x0, x1 if fam == 0 else self._convert_to_b(x1), al, t, scale_B[b], ls_B[b])
+                k1 = _lib.cross_kernel(fam, x0, xpts, al, t, scale_B[b], ls_B[b])
+                k2 = k1 if equal else _lib.cross_kernel(fam, x1, xpts, al, t, scale_B[b], ls_B[b])
+                tm = _lib.gram_solve(fam, k2, lam[b])
+                kmat = knew - k1 @ tm.T
+                if equal:
+                    dg = kmat.diagonal()
+                    dg.clamp_(min=0)
+                outs.append(kmat)
+        kmat = torch.stack(outs, 0).reshape(tuple(pshape) + (1, 1) + tuple(outs[0].shape))
+        if inttask0 and inttask1:
+            return kmat[..., 0, 0, :, :]
+        elif inttask0 and not inttask1:
+            return kmat[..., 0, :, :, :]
+        elif not inttask0 and inttask1:
+            return kmat[..., :, 0, :, :]
+        return kmat
+
+    def post_error(self, x: torch.Tensor, task: Union[int, torch.Tensor] = None, n: Union[int, torch.Tensor] = None, confidence: float = 0.99, eval: bool = True):
+        assert np.isscalar(confidence) and 0 < confidence < 1, "confidence must be between 0 and 1"
+        q = scipy.stats.norm.ppf(1 - (1 - confidence) / 2)
+        pvar = self.post_var(x, task=task, n=n, eval=eval)
+        pstd = torch.sqrt(pvar)
+        perror = q * pstd
+        return pvar, q, perror
+
+    def post_ci(self, x: torch.Tensor, task: Union[int, torch.Tensor] = None, confidence: float = 0.99, eval: bool = True):
+        # the reference multiplies by the quantile twice (abstract_gp.py:498,523-525); kept for drop-in parity
+        assert np.isscalar(confidence) and 0 < confidence < 1, "confidence must be between 0 and 1"
+        q = scipy.stats.norm.ppf(1 - (1 - confidence) / 2)
+        pmean = self.post_mean(x, task=task, eval=eval)
+        pvar, q, perror = self.post_error(x, task=task, confidence=confidence)
+        pci_low = pmean - q * perror
+        pci_high = pmean + q * perror
+        return pmean, pvar, q, pci_low, pci_high
+
+    def post_cubature_mean(self, task: Union[int, torch.Tensor] = None, eval: bool = True):
+        """abstract_fast_gp.py:65-81 for one task: scale * sum(coeffs) * K_task."""
+        inttask, task = self._parse_task(task)
+        with torch.no_grad():
+            scale_B, _, _, pshape = self._hyper()
+            coeffs = self.coeffs
+            pcmean = (scale_B.reshape(tuple(pshape) + (1,)) * coeffs).sum(-1)[..., None]
+        return pcmean[..., 0] if inttask else pcmean
+
+    def post_cubature_var(self, task: Union[int, torch.Tensor] = None, n: Union[int, torch.Tensor] = None, eval: bool = True):
+        """abstract_fast_gp.py:82-109 for one task: s - s^2 n / lam_0 (clamped at 0), s = scale*K_task."""
+        n = self._parse_n(n)
+        inttask, task = self._parse_task(task)
+        with torch.no_grad():
+            scale_B, _, _, pshape = self._hyper()
+            lam = self.get_inv_log_det_cache(n)._lam_full()
+            term = (n / lam[:, 0]).real
+            pcvar = (scale_B - scale_B ** 2 * term).clamp_(min=0).reshape(tuple(pshape) + (1,))
+        return pcvar[..., 0] if inttask else pcvar
+
+    def post_cubature_cov(self, task0: Union[int, torch.Tensor] = None, task1: Union[int, torch.Tensor] = None, n: Union[int, torch.Tensor] = None, eval: bool = True):
+        n = self._parse_n(n)
+        inttask0, task0 = self._parse_task(task0)
+        inttask1, task1 = self._parse_task(task1)
+        pcvar = self.post_cubature_var(task=[0], n=n)[..., None]
+        if inttask0 and inttask1:
+            return pcvar[..., 0, 0]
+        elif inttask0 and not inttask1:
+            return pcvar[..., 0, :]
+        elif not inttask0 and inttask1:
+            return pcvar[..., :, 0]
+        return pcvar
+
+    def post_cubature_error(self, task: Union[int, torch.Tensor] = None, n: Union[int, torch.Tensor] = None, confidence: float = 0.99, eval: bool = True):
+        assert np.isscalar(confidence) and 0 < confidence < 1, "confidence must be between 0 and 1"
+        q = scipy.stats.norm.ppf(1 - (1 - confidence) / 2)
+        pcvar = self.post_cubature_var(task=task, n=n, eval=eval)
+        pcstd = torch.sqrt(pcvar)
+        pcerror = q * pcstd
+        return pcvar, q, pcerror
+
+    def post_cubature_ci(self, task: Union[int, torch.Tensor] = None, confidence: float = 0.99, eval: bool = True):
+        assert np.isscalar(confidence) and 0 < confidence < 1, "confidence must be between 0 and 1"
+        q = scipy.stats.norm.ppf(1 - (1 - confidence) / 2)
+        pcmean = self.post_cubature_mean(task=task, eval=eval)
+        pcvar, q, pcerror = self.post_cubature_error(task=task, confidence=confidence, eval=eval)
+        pcci_low = pcmean - pcerror
+        pcci_high = pcmean + pcerror
+        return pcmean, pcvar, q, pcci_low, pcci_high
+
+
+_CTOR_DOC = """
+    Args mirror the reference constructor (fast_gp_lattice.py:125-158 / fast_gp_digital_net_b2.py:120-153).  Differences:
+    `device` defaults to "cuda" and must be a CUDA device; `seqs` may be an int (dimension), one of this package's
+    GPU-side sequence specs (`sequences.Lattice` / `sequences.DigitalNetB2`) or any qmcpy-style sequence object, whose
+    points are then taken from its own host generator; `compile_fts*` are accepted and ignored (the transforms are
+    hand-written CUDA kernels); `num_tasks>1`, `derivatives` and `adaptive_nugget` raise NotImplementedError.
+"""
+
+
+class FastGPLattice(AbstractFastGP):
+    """Fast GP regression on rank-1 lattice points with shift-invariant (Bernoulli-polynomial) kernels.
+    Drop-in for fastgps.FastGPLattice (fast_gp_lattice.py:7-273) on the single-task path.""" + _CTOR_DOC
+    _FAMILY = 0
+    _XBDTYPE = torch.float64
+    _FTOUTDTYPE = torch.complex128
+    _t = 0
+
+    def __init__(self,
+                 seqs,
+                 num_tasks: int = None,
+                 seed_for_seq: int = None,
+                 alpha: int = 2,
+                 scale: float = 1.,
+                 lengthscales: Union[torch.Tensor, float] = 1.,
+                 noise: float = 1e-8,
+                 factor_task_kernel: Union[torch.Tensor, int] = 1.,
+                 rank_factor_task_kernel: int = None,
+                 noise_task_kernel: Union[torch.Tensor, float] = 1.,
+                 device: torch.device = "cuda",
+                 tfs_scale: Tuple[callable, callable] = DEFAULT_TFS_LOG_EXP,
+                 tfs_lengthscales: Tuple[callable, callable] = DEFAULT_TFS_LOG_EXP,
+                 tfs_noise: Tuple[callable, callable] = DEFAULT_TFS_LOG_EXP,
+                 tfs_factor_task_kernel: Tuple[callable, callable] = DEFAULT_TFS_ID,
+                 tfs_noise_task_kernel: Tuple[callable, callable] = DEFAULT_TFS_LOG_EXP,
+                 requires_grad_scale: bool = True,
+                 requires_grad_lengthscales: bool = True,
+                 requires_grad_noise: bool = False,
+                 requires_grad_factor_task_kernel: bool = None,
+                 requires_grad_noise_task_kernel: bool = None,
+                 shape_batch: torch.Size = torch.Size([]),
+                 shape_scale: torch.Size = torch.Size([1]),
+                 shape_lengthscales: torch.Size = None,
+                 shape_noise: torch.Size = torch.Size([1]),
+                 shape_factor_task_kernel: torch.Size = None,
+                 shape_noise_task_kernel: torch.Size = None,
+                 derivatives: list = None,
+                 derivatives_coeffs: list = None,
+                 compile_fts: bool = False,
+                 compile_fts_kwargs: dict = {},
+                 adaptive_nugget: bool = False,
+                 ):
+        assert isinstance(alpha, int) and 1 <= alpha <= _lib.MAX_ALPHA, "alpha must be in %s" % list(range(1, _lib.MAX_ALPHA + 1))
+        super().__init__(seqs, num_tasks, seed_for_seq, alpha, scale, lengthscales, noise, factor_task_kernel,
+                         rank_factor_task_kernel, noise_task_kernel, device, tfs_scale, tfs_lengthscales, tfs_noise,
+                         tfs_factor_task_kernel, tfs_noise_task_kernel, requires_grad_scale, requires_grad_lengthscales,
+                         requires_grad_noise, requires_grad_factor_task_kernel, requires_grad_noise_task_kernel, shape_batch,
+                         shape_scale, shape_lengthscales, shape_noise, shape_factor_task_kernel, shape_noise_task_kernel,
+                         derivatives, derivatives_coeffs, compile_fts, compile_fts_kwargs, adaptive_nugget)
+        assert all(self.seqs[i].randomize in ['FALSE', 'SHIFT'] for i in range(self.num_tasks)), "each seq should have randomize in ['FALSE','SHIFT']"
+
+    @staticmethod
+    def _default_sequence(d, seed):
+        return sequences.Lattice(d, seed=seed, randomize="SHIFT")
+
+    @staticmethod
+    def _adopt_sequence(seq):
+        if isinstance(seq, sequences.Lattice):
+            return seq
+        assert not isinstance(seq, sequences.DigitalNetB2), "each seq should be a lattice sequence"
+        return sequences.HostSequence(seq, family=0)
+
+    def get_omega(self, m):
+        return torch.exp(-torch.pi * 1j * torch.arange(2 ** m, device=self.device) / 2 ** m)
+
+    def _ft_unstable(self, x):
+        return _lib.fftbr(x)
+
+    def _ift_unstable(self, x):
+        return _lib.ifftbr(x)
+
+    def _ominus(self, x, z):
+        return (x - z) % 1
+
+
+class FastGPDigitalNetB2(AbstractFastGP):
+    """Fast GP regression on base-2 digital nets with digitally-shift-invariant (Walsh) kernels.
+    Drop-in for fastgps.FastGPDigitalNetB2 (fast_gp_digital_net_b2.py:7-301) on the single-task path.""" + _CTOR_DOC
+    _FAMILY = 1
+    _XBDTYPE = torch.int64
+    _FTOUTDTYPE = torch.float64
+
+    def __init__(self,
+                 seqs,
+                 num_tasks: int = None,
+                 seed_for_seq: int = None,
+                 alpha: int = 2,
+                 scale: float = 1.,
+                 lengthscales: Union[torch.Tensor, float] = 1.,
+                 noise: float = 1e-16,
+                 factor_task_kernel: Union[torch.Tensor, int] = 1.,
+                 rank_factor_task_kernel: int = None,
+                 noise_task_kernel: Union[torch.Tensor, float] = 1.,
+                 device: torch.device = "cuda",
+                 tfs_scale: Tuple[callable, callable] = DEFAULT_TFS_LOG_EXP,
+                 tfs_lengthscales: Tuple[callable, callable] = DEFAULT_TFS_LOG_EXP,
+                 tfs_noise: Tuple[callable, callable] = DEFAULT_TFS_LOG_EXP,
+                 tfs_factor_task_kernel: Tuple[callable, callable] = DEFAULT_TFS_ID,
+                 tfs_noise_task_kernel: Tuple[callable, callable] = DEFAULT_TFS_LOG_EXP,
+                 requires_grad_scale: bool = True,
+                 requires_grad_lengthscales: bool = True,
+                 requires_grad_noise: bool = False,
+                 requires_grad_factor_task_kernel: bool = None,
+                 requires_grad_noise_task_kernel: bool = None,
+                 shape_batch: torch.Size = torch.Size([]),
+                 shape_scale: torch.Size = torch.Size([1]),
+                 shape_lengthscales: torch.Size = None,
+                 shape_noise: torch.Size = torch.Size([1]),
+                 shape_factor_task_kernel: torch.Size = None,
+                 shape_noise_task_kernel: torch.Size = None,
+                 derivatives: list = None,
+                 derivatives_coeffs: list = None,
+                 compile_fts: bool = False,
+                 compile_fts_kwargs: dict = {},
+                 adaptive_nugget: bool = False,
+                 ):
+        super().__init__(seqs, num_tasks, seed_for_seq, alpha, scale, lengthscales, noise, factor_task_kernel,
+                         rank_factor_task_kernel, noise_task_kernel, device, tfs_scale, tfs_lengthscales, tfs_noise,
+                         tfs_factor_task_kernel, tfs_noise_task_kernel, requires_grad_scale, requires_grad_lengthscales,
+                         requires_grad_noise, requires_grad_factor_task_kernel, requires_grad_noise_task_kernel, shape_batch,
+                         shape_scale, shape_lengthscales, shape_noise, shape_factor_task_kernel, shape_noise_task_kernel,
+                         derivatives, derivatives_coeffs, compile_fts, compile_fts_kwargs, adaptive_nugget)
+        assert self.seqs[0].randomize in ['FALSE', 'DS', 'LMS', 'LMS_DS'], "seq should have randomize in ['FALSE','DS','LMS','LMS_DS']"
+        ts = [int(self.seqs[i].t) for i in range(self.num_tasks)]
+        assert all(t < 64 for t in ts), "each seq must have t<64"
+        assert all(t == ts[0] for t in ts), "all seqs should have the same t"
+        self.t = self._t = ts[0]
+        assert (1 <= self.alpha).all() and (self.alpha <= 4).all()
+
+    @staticmethod
+    def _default_sequence(d, seed):
+        return sequences.DigitalNetB2(d, seed=seed, randomize="DS")
+
+    @staticmethod
+    def _adopt_sequence(seq):
+        if isinstance(seq, sequences.DigitalNetB2):
+            return seq
+        assert not isinstance(seq, sequences.Lattice), "each seq should be a digital net sequence"
+        return sequences.HostSequence(seq, family=1)
+
+    def get_omega(self, m):
+        return 1
+
+    def _ft_unstable(self, x):
+        return _lib.fwht(x)
+
+    _ift_unstable = _ft_unstable
+
+    def _convert_to_b(self, x):
+        return torch.floor((x % 1) * 2 ** (self.t)).to(self._XBDTYPE)
+
+    def _convert_from_b(self, xb):
+        return xb * 2 ** (-self.t)
+
+    def _ominus(self, x_or_xb, z_or_zb):
+        fp_x = torch.is_floating_point(x_or_xb)
+        fp_z = torch.is_floating_point(z_or_zb)
+        xb = self._convert_to_b(x_or_xb) if fp_x else x_or_xb
+        zb = self._convert_to_b(z_or_zb) if fp_z else z_or_zb
+        return xb ^ zb

@@ -113,3 +113,27 @@ class DigitalNetB2(_SequenceBase):
             self._C_dev[device] = C
         xb, x = _lib.dnb2_points(C, self.rshift, self.t, n_min, n_max)
         return x, xb
+
+
+class HostSequence(object):
+    """Adapter for a user-supplied qmcpy-style sequence object (the reference's `seqs` argument, fast_gp_lattice.py:219-223,
+    fast_gp_digital_net_b2.py:214-225).  Its points are an INPUT: they come from the user's own host generator exactly as
+    in the reference (abstract_gp.py:307-309, fast_gp_digital_net_b2.py:266-269) and are copied to the GPU once."""
+
+    def __init__(self, seq, family):
+        self.seq = seq
+        self.family = int(family)
+        self.d = int(seq.d)
+        self.order = str(seq.order).upper()
+        rep = getattr(seq, "replications", 1)
+        self.replications = 1 if rep is None else int(rep)
+        self.randomize = str(seq.randomize).upper()
+        if self.family == 1:
+            self.t = int(seq.t)
+
+    def generate(self, n_min, n_max, device):
+        if self.family == 0:
+            x = torch.from_numpy(np.ascontiguousarray(self.seq(n_min=int(n_min), n_max=int(n_max)), dtype=np.float64)).to(device)
+            return x, x
+        xb = torch.from_numpy(np.ascontiguousarray(self.seq(n_min=int(n_min), n_max=int(n_max), return_binary=True)).astype(np.int64)).to(device)
+        return xb * 2 ** (-self.t), xb

@@ -43,6 +43,10 @@ int fgp_version(void);
 const char* fgp_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t fgp_launch_count(void);
+/* per-kernel device timings for bench.py: begin arms event marks after every named launch on `stream`; end synchronises,
+ * disarms and returns the number of (name, milliseconds) pairs written (each = time since the previous mark). */
+int fgp_profile_begin(fgp_stream_t stream);
+int fgp_profile_end(fgp_stream_t stream, int max_entries, const char** names, float* ms);
 int fgp_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin);
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -115,6 +119,40 @@ int fgp_dnb2_mll_grad(const int64_t* xb_dev, int64_t n, int d, const int* alpha_
                       const double* ysq_dev, const double* scale_dev, const double* ls_dev, const double* noise_dev,
                       const double* weights_dev, void* workspace_dev, double* lam_dev, double* out_dev, int want_grad, fgp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * K4b device-side fit() loop bookkeeping   (abstract_gp.py:236-298 with the default Rprop optimiser of
+ *     abstract_fast_gp.py:53-57 and the default (log, exp) transforms of fast_gp_lattice.py:137-139)
+ *     One single-CTA kernel per iteration consumes the (B, d+4) output of fgp_*_mll_grad, assembles the loss, runs the
+ *     reference's best/save/wait early-stop state machine, snapshots the best iterate, records history rows, applies
+ *     torch.optim.Rprop's update to the raw (log) parameters IN PLACE and rewrites the effective hyperparameters
+ *     (scale_B, ls_B, noise_B) that the next fgp_*_mll_grad call reads.  Nothing returns to the host, so
+ *     [mll_grad, fit_step] x k can be captured in a CUDA graph; the host polls state[4] (stopped) now and then.
+ *     state block (doubles): [0] best loss [1] save loss [2] wait [3] next iteration index [4] stopped [5] last
+ *     evaluated iteration [6] its loss [7] term1 [8] term2; [9..] options; then prev-grad, step-size, best-raw (P each).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, d;                            /* hyperparameter sets, dimension */
+  int n_scale, n_ls_b, n_ls_d, n_noise; /* raw parameter layouts: n_scale,n_ls_b,n_noise in {1,B}; n_ls_d in {1,d} */
+  int req_scale, req_ls, req_noise;    /* requires_grad flags */
+  double tau;                          /* 1x1 task-kernel value folded into scale and noise (util.py:293,298) */
+  double *raw_scale, *raw_ls, *raw_noise; /* device: the nn.Parameter storages, updated in place */
+  double *scale_B, *ls_B, *noise_B;    /* device: (B), (B,d), (B) effective values for fgp_*_mll_grad */
+  double *state;                       /* device: fgp_fit_state_doubles(P) doubles, P = n_scale+n_ls_b*n_ls_d+n_noise */
+  double *loss_hist;                   /* device (hist_capacity,3) rows {loss, term1, term2}, or NULL */
+  double *scale_hist, *ls_hist, *noise_hist; /* device (hist_capacity, numel) rows of exp(raw), or NULL */
+} fgp_fit_layout;
+typedef struct {
+  int iterations, stop_wait, hist_capacity;
+  double logtol;      /* log(1 + stop_crit_improvement_threshold) */
+  double half_const;  /* d_out * n * log(2 pi) / 2 */
+  double wn, wl;      /* loss = sum_b (wn norm_b + wl logdet_b) + half_const; MLL: wn = 1/2, wl = d_out/(2B) */
+  double lr, etaminus, etaplus, step_min, step_max; /* torch.optim.Rprop: 0.1, 0.5, 1.2, 1e-6, 50 */
+} fgp_fit_options;
+size_t fgp_fit_state_doubles(int n_raw_params);
+int fgp_fit_init(const fgp_fit_layout* layout, const fgp_fit_options* opt, fgp_stream_t stream); /* synchronises `stream` once */
+int fgp_fit_step(const fgp_fit_layout* layout, const double* mll_out_dev, fgp_stream_t stream);
+int fgp_fit_finish(const fgp_fit_layout* layout, fgp_stream_t stream); /* best iterate -> parameters */
+
 /* K^-1 y for R right-hand sides sharing one spectrum: out = T^-1( T(y) / lam ), util.py:338-344 (single task).
  * lam_dev: (n) complex (family 0) or real (family 1) full eigenvalues sqrt(n) ft(k1)+noise.  y,out: (R,n) real.
  * work_dev: R*n complex (family 0) / unused (family 1, may be NULL). */
@@ -149,6 +187,11 @@ int fgp_lattice_cross_kernel(const double* xs_dev, int64_t m, const double* x_de
 int fgp_dnb2_cross_kernel(const double* xs_dev, int64_t m, const int64_t* xb_dev, int64_t n, int d,
                           const int* alpha_host, int t, double scale, const double* ls_host, double* k_dev,
                           fgp_stream_t stream);
+
+/* k[i] = k(x_i, z_i) for N row pairs (the k(x,x) term of abstract_gp.py:407 and elementwise kernel() calls,
+ * abstract_gp.py:693-706).  x (N,d) float64; z (N,d) float64, or int64 net integers when z_is_int. */
+int fgp_kernel_pairs(int family, const double* x_dev, const void* z_dev, int z_is_int, int64_t N, int d,
+                     const int* alpha_host, int t, double scale, const double* ls_host, double* k_dev, fgp_stream_t stream);
 
 /* FP64 FMA-chain peak probe used by bench.py for the FP64 roofline denominator: runs `iters` dependent-chain
  * DFMA blocks on every SM and returns the flop count in *flops (time it with events on `stream`). */

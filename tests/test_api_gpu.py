@@ -1,0 +1,171 @@
+"""GPU parity tests of the drop-in Python API (FastGPLattice / FastGPDigitalNetB2) against the fixtures written by the
+UNMODIFIED reference (tests/golden/make_golden.py).  The test bodies follow the reference's own doctests
+(fast_gp_lattice.py:24-121, fast_gp_digital_net_b2.py:24-116): get_x_next -> add_y_next -> posterior -> fit -> doubling.
+Tolerances: points bit-exact; 1e-10 relative (norm-wise) unless a looser one is stated with its reason."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden
+
+pytestmark = pytest.mark.gpu
+dev = "cuda:0"
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().cpu()
+    b = torch.as_tensor(b).detach().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+
+
+def make_gp(g, **kw):
+    import fastgaussianprocesses_b200 as fgp
+    fam = str(g["family"])
+    d, alpha = int(g["d"]), int(g["alpha"])
+    args = dict(alpha=alpha, scale=float(g["scale0"][0]), lengthscales=torch.from_numpy(g["lengthscales0"]).clone(), noise=float(g["noise0"][0]), device=dev)
+    args.update(kw)
+    if fam == "lattice":
+        seq = fgp.Lattice(d, generating_vector=g["z"], shift=g["shift"])
+        return fgp.FastGPLattice(seq, **args)
+    seq = fgp.DigitalNetB2(d, generating_matrices=g["C"], dshift=g["dshift"], t=int(g["t"]))
+    return fgp.FastGPDigitalNetB2(seq, **args)
+
+
+@pytest.mark.parametrize("path", ["fused", "generic"])
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_api_matches_reference_fixture(case, path, monkeypatch):
+    """path: "fused" = device-side CUDA-graph fit loop; "generic" = Python loop with torch.optim.Rprop (the route taken for
+    user optimisers / transforms).  Both must reproduce the reference's trajectory."""
+    if path == "generic":
+        monkeypatch.setenv("FGP_B200_GENERIC_FIT", "1")
+    g = load_golden(case)
+    n, d = int(g["n"]), int(g["d"])
+    gp = make_gp(g)
+    x = gp.get_x_next(n)
+    assert x.is_cuda and np.array_equal(x.cpu().numpy(), g["x"])  # bit-exact points
+    if "xb" in g:
+        assert np.array_equal(gp.get_xb(0, n).cpu().numpy(), g["xb"])
+    gp.add_y_next(torch.from_numpy(g["y"]))  # host buffer in, as a reference user would pass it
+    assert rel(gp.get_k1parts(0, 0)[:, 0, 0, :], g["k1parts"]) < 1e-13
+    assert rel(gp.get_lam(0, 0), g["lam0"]) < 1e-10
+    assert rel(gp.get_ytilde(0), g["ytilde"]) < 1e-12
+    # coefficients K^-1 y are conditioned like 1/noise: 1e-9 norm-wise
+    assert rel(gp.coeffs, g["coeffs0"]) < 1e-9
+    xt = torch.from_numpy(g["xtest"])
+    pm = gp.post_mean(xt)
+    assert pm.shape == (xt.shape[0],)
+    ymax = float(np.abs(g["y"]).max())
+    # pmean = sum of n terms of size |coeffs| ~ |y|/noise cancelling down to |y|: compare on the scale of y
+    assert float((pm.cpu() - torch.from_numpy(g["pmean0"])).abs().max()) < 1e-8 * ymax
+    pv = gp.post_var(xt)
+    sc = float(g["scale0"][0])
+    assert float((pv.cpu() - torch.from_numpy(g["pvar0"])).abs().max()) < 1e-8 * max(float(np.abs(g["pvar0"]).max()), sc * 1e-6) + 1e-9 * sc
+    mcov = g["pcov0"].shape[0]
+    pc = gp.post_cov(xt[:mcov], xt[:mcov // 2])
+    assert pc.shape == g["pcov0"].shape
+    assert float((pc.cpu() - torch.from_numpy(g["pcov0"])).abs().max()) < 1e-7 * sc
+    pcs = gp.post_cov(xt[:mcov], xt[:mcov])
+    assert (pcs.diagonal() >= 0).all()
+    assert torch.allclose(pcs.diagonal(), pv[:mcov], atol=1e-7 * sc)
+    assert abs(float(gp.post_cubature_mean()) - float(g["pcmean0"])) < 1e-8 * ymax
+    assert abs(float(gp.post_cubature_var()) - float(g["pcvar0"])) < 1e-8 * sc
+    pvf = gp.post_var(xt[:64], n=2 * n)
+    assert float((pvf.cpu() - torch.from_numpy(g["pvar0_future"])).abs().max()) < 1e-8 * sc
+    # fit: same loss trajectory, same stopping iteration, same hyperparameters
+    data = gp.fit(iterations=int(g["fit_iterations"]), verbose=0, store_hists=True)
+    assert data["iterations"] == int(g["fit_last_iteration"])
+    assert np.allclose(data["loss_hist"].numpy(), g["loss_hist"], rtol=1e-8, atol=0)
+    assert rel(data["scale_hist"], g["scale_hist"]) < 1e-8
+    assert rel(data["lengthscales_hist"], g["lengthscales_hist"]) < 1e-8
+    assert rel(gp.scale, g["scale1"]) < 1e-8
+    assert rel(gp.lengthscales, g["lengthscales1"]) < 1e-8
+    assert float((gp.post_mean(xt).cpu() - torch.from_numpy(g["pmean1"])).abs().max()) < 1e-6 * ymax
+    pv1 = gp.post_var(xt)
+    sc1 = float(g["scale1"][0])
+    assert float((pv1.cpu() - torch.from_numpy(g["pvar1"])).abs().max()) < 1e-6 * max(float(np.abs(g["pvar1"]).max()), sc1 * 1e-6) + 1e-8 * sc1
+
+
+@pytest.mark.parametrize("case", ["lattice_d2_n1024_a2", "dnb2_d2_n1024_a2"])
+def test_api_doubling_matches_reference_fixture(case):
+    """Incremental doubling (util.py:113-132,173-183): after fit, add the next n points and re-read the spectrum."""
+    g = load_golden(case)
+    n = int(g["n"])
+    gp = make_gp(g, scale=float(g["scale1"][0]), lengthscales=torch.from_numpy(g["lengthscales1"]).clone())
+    gp.add_y_next(_f_ackley(gp.get_x_next(n)))
+    assert rel(gp.y, g["y"]) < 1e-13
+    x2 = gp.get_x_next(2 * n)
+    assert x2.shape == (n, int(g["d"]))
+    gp.add_y_next(_f_ackley(x2))
+    assert rel(gp.get_lam(0, 0), g["lam_2n"]) < 1e-9
+    assert rel(gp.get_ytilde(0), g["ytilde_2n"]) < 1e-10
+    xt = torch.from_numpy(g["xtest"])[:64]
+    ymax = float(np.abs(g["y"]).max())
+    assert float((gp.post_mean(xt).cpu() - torch.from_numpy(g["pmean_2n"])).abs().max()) < 1e-6 * ymax
+    sc1 = float(g["scale1"][0])
+    assert float((gp.post_var(xt).cpu() - torch.from_numpy(g["pvar_2n"])).abs().max()) < 1e-6 * max(float(np.abs(g["pvar_2n"]).max()), sc1 * 1e-6) + 1e-8 * sc1
+
+
+def _f_ackley(x, a=20, b=0.2, c=2 * np.pi, scaling=32.768):
+    x = 2 * scaling * x - scaling
+    t1 = a * torch.exp(-b * torch.sqrt(torch.mean(x ** 2, 1)))
+    t2 = torch.exp(torch.mean(torch.cos(c * x), 1))
+    return -t1 - t2 + a + np.exp(1)
+
+
+def test_api_guards_and_errors():
+    import fastgaussianprocesses_b200 as fgp
+    gp = fgp.FastGPLattice(3, seed_for_seq=7, device=dev)
+    with pytest.raises(AssertionError):
+        gp.get_x_next(100)  # not a power of two (abstract_fast_gp.py:36)
+    x = gp.get_x_next(64)
+    with pytest.raises(AssertionError):
+        gp.add_y_next(torch.zeros(48))  # total samples must be a power of two (abstract_fast_gp.py:40)
+    gp = fgp.FastGPLattice(3, seed_for_seq=7, device=dev)
+    with pytest.raises(AssertionError):
+        gp.fit()  # cannot fit without data
+    gp.add_y_next(torch.sin(x.sum(1)))
+    with pytest.raises(AssertionError):
+        gp.post_var(x[:4], n=96)
+    with pytest.raises(AssertionError):
+        gp.post_mean(torch.zeros(4, 2))
+    with pytest.raises(RuntimeError):
+        fgp.FastGPLattice(3, device="cpu")
+    with pytest.raises(NotImplementedError):
+        fgp.FastGPLattice(3, num_tasks=2, device=dev)
+    assert gp.post_mean(torch.rand(5, 3)).shape == (5,)
+    assert gp.post_mean(torch.rand(5, 3), task=[0]).shape == (1, 5)
+    assert gp.post_mean(torch.zeros(0, 3)).shape == (0,)
+
+
+@pytest.mark.parametrize("family", ["lattice", "dnb2"])
+def test_api_batched_outputs_and_hyperparameters(family):
+    """shape_batch with per-batch hyperparameters: every batch element must equal an independent single GP."""
+    import fastgaussianprocesses_b200 as fgp
+    d, n, Bt = 3, 256, 4
+    mk = (lambda **kw: fgp.FastGPLattice(fgp.Lattice(d, seed=11), device=dev, **kw)) if family == "lattice" else \
+         (lambda **kw: fgp.FastGPDigitalNetB2(fgp.DigitalNetB2(d, seed=11), device=dev, **kw))
+    scale = torch.tensor([[0.5], [1.0], [2.0], [3.0]])
+    ls = torch.rand(Bt, d, generator=torch.Generator().manual_seed(3)) + 0.2
+    noise = torch.full((Bt, 1), 1e-6)
+    gpb = mk(scale=scale, lengthscales=ls, noise=noise, shape_batch=[Bt])
+    x = gpb.get_x_next(n)
+    freqs = torch.arange(1, Bt + 1, device=x.device, dtype=torch.float64)
+    yb = torch.cos(2 * np.pi * x.sum(1)[None, :] * freqs[:, None])
+    gpb.add_y_next(yb)
+    xt = torch.rand(33, d, generator=torch.Generator().manual_seed(4))
+    pmb, pvb = gpb.post_mean(xt), gpb.post_var(xt)
+    assert pmb.shape == (Bt, 33) and pvb.shape == (Bt, 33)
+    datab = gpb.fit(iterations=6, verbose=0, store_hists=True, stop_crit_wait_iterations=100)
+    losses = []
+    for b in range(Bt):
+        gp1 = mk(scale=float(scale[b, 0]), lengthscales=ls[b].clone(), noise=1e-6)
+        gp1.get_x_next(n)
+        gp1.add_y_next(yb[b])
+        assert rel(gp1.post_mean(xt), pmb[b]) < 1e-9
+        assert float((gp1.post_var(xt) - pvb[b]).abs().max()) < 1e-9 * float(scale[b, 0])
+        d1 = gp1.fit(iterations=6, verbose=0, store_hists=True, stop_crit_wait_iterations=100)
+        losses.append(d1["loss_hist"])
+        assert rel(d1["lengthscales_hist"], datab["lengthscales_hist"][:, b]) < 1e-9
+        assert rel(d1["scale_hist"], datab["scale_hist"][:, b]) < 1e-9
+    # the batched loss is the sum of the independent losses (abstract_gp.py:253-260)
+    assert np.allclose(torch.stack(losses).sum(0).numpy(), datab["loss_hist"].numpy(), rtol=1e-9)

@@ -18,7 +18,8 @@ namespace fgp {
 constexpr int kRed = 32 * (FGP_MAX_D + 4);  // doubles of reduction scratch
 
 struct MllArgs {
-  const void* x;  // lattice: double (n,d); net: int64 (n,d)
+  const void* x;  // lattice: double (n,d); net: int64 (n,d); NULL in generator mode
+  UVec z;         // generator mode (lattice): generating vector, delta_ij = frac(phi2(i) z_j) regenerated from the index
   int64_t n;
   int d;
   int t;          // net only
@@ -56,11 +57,19 @@ __device__ __forceinline__ void load_hyp(Hyp& H, const MllArgs& a, int b) {
   }
   for (int j = threadIdx.x; j < a.d; j += blockDim.x) {
     H.ls[j] = a.ls[(int64_t)b * a.d + j];
-    if (NET)
-      H.xb0[j] = (uint64_t)((const int64_t*)a.x)[j];
-    else
-      H.x0[j] = ((const double*)a.x)[j];
+    if (a.x) {
+      if (NET)
+        H.xb0[j] = (uint64_t)((const int64_t*)a.x)[j];
+      else
+        H.x0[j] = ((const double*)a.x)[j];
+    }
   }
+}
+
+// generator mode, lattice: x_i - x_0 = frac(phi2(i) z_j) exactly (the shift cancels), phi2(i) = brev64(i) / 2^64.
+// The wrap-around product keeps its ceil(log2 n) <= 32 significant bits at the top of the word.
+__device__ __forceinline__ double lat_delta_gen(uint64_t rev, uint64_t zj) {
+  return (double)(uint32_t)((rev * zj) >> 32) * 0x1.0p-32;
 }
 
 // net alpha = 2 without branches on alpha: W_2(delta) - 1 = 3/2 - (5/2) 2^-beta - beta x_f, beta = t - floor(log2 delta)
@@ -74,10 +83,25 @@ __device__ __forceinline__ double dnb2_part_a2(uint64_t delta, int t, double tsc
 }
 
 // parts of point i against the first point.  A2: every alpha_j == 2 (straight-line code, no per-dimension loop on alpha)
-template <int DT, bool NET, bool A2>
+template <int DT, bool NET, bool A2, bool GEN>
 __device__ __forceinline__ void point_parts(const MllArgs& a, const Hyp& H, int64_t i, double* p) {
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
   const int d = DT > 0 ? DT : a.d;
+  if (GEN && !NET) {
+    const uint64_t rev = __brevll((unsigned long long)i);
+#pragma unroll
+    for (int j = 0; j < DM; ++j) {
+      if (j >= d) break;
+      const double delta = lat_delta_gen(rev, a.z.v[j]);
+      if (A2) {
+        const double u = delta * (1.0 - delta);
+        p[j] = fma(a.P.q[j][2] * u, u, a.P.q[j][0]);
+      } else {
+        p[j] = lat_part(delta, a.P.q[j], a.P.alpha[j]);
+      }
+    }
+    return;
+  }
   if (NET) {
     const int64_t* row = (const int64_t*)a.x + i * d;
     uint64_t xr[DM];
@@ -125,12 +149,12 @@ __device__ __forceinline__ void point_parts(const MllArgs& a, const Hyp& H, int6
   }
 }
 
-template <int DT, bool NET, bool A2>
+template <int DT, bool NET, bool A2, bool GEN>
 __device__ __forceinline__ double point_k1(const MllArgs& a, const Hyp& H, int64_t i) {
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
   const int d = DT > 0 ? DT : a.d;
   double p[DM];
-  point_parts<DT, NET, A2>(a, H, i, p);
+  point_parts<DT, NET, A2, GEN>(a, H, i, p);
   double k = H.scale;
 #pragma unroll
   for (int j = 0; j < DM; ++j) {
@@ -141,12 +165,12 @@ __device__ __forceinline__ double point_k1(const MllArgs& a, const Hyp& H, int64
 }
 
 // acc[0] += w*k1 ; acc[1+j] += w * dk1/dls_j   (leave-one-out products: factors may cross zero)
-template <int DT, bool NET, bool A2>
+template <int DT, bool NET, bool A2, bool GEN>
 __device__ __forceinline__ void point_grad(const MllArgs& a, const Hyp& H, int64_t i, double w, double* acc) {
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
   const int d = DT > 0 ? DT : a.d;
   double p[DM], left[DM];
-  point_parts<DT, NET, A2>(a, H, i, p);
+  point_parts<DT, NET, A2, GEN>(a, H, i, p);
   double pre = H.scale;
 #pragma unroll
   for (int j = 0; j < DM; ++j) {
@@ -206,7 +230,7 @@ __device__ __forceinline__ void reduce_store(double* v, int nv, double* red, dou
 // ------------------------------------------------------------------------------------------------------------
 // single-pass kernel: one CTA per hyperparameter set, n <= block capacity
 // ------------------------------------------------------------------------------------------------------------
-template <int DT, bool NET, bool A2>
+template <int DT, bool NET, bool A2, bool GEN>
 __global__ void __launch_bounds__(256, 2) mll_single_kernel(MllArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
@@ -222,7 +246,7 @@ __global__ void __launch_bounds__(256, 2) mll_single_kernel(MllArgs a) {
   double* smr = (double*)smraw;
   const double c = H.scale;  // DC guess removed before the transform (role of abstract_fast_gp.py:209-211)
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double k1 = point_k1<DT, NET, A2>(a, H, i) - c;
+    const double k1 = point_k1<DT, NET, A2, GEN>(a, H, i) - c;
     if (NET)
       smr[padidx(i)] = k1;
     else
@@ -264,7 +288,7 @@ __global__ void __launch_bounds__(256, 2) mll_single_kernel(MllArgs a) {
   for (int j = 0; j <= DM; ++j) acc[j] = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double w = NET ? smr[padidx(i)] : smc[padidx(i)].x;
-    point_grad<DT, NET, A2>(a, H, i, w, acc);
+    point_grad<DT, NET, A2, GEN>(a, H, i, w, acc);
   }
   acc[0] /= H.scale;
   reduce_store<DM + 1>(acc, d + 1, red, out + 3);
@@ -274,7 +298,7 @@ __global__ void __launch_bounds__(256, 2) mll_single_kernel(MllArgs a) {
 // two-pass kernels
 // ------------------------------------------------------------------------------------------------------------
 // pass A: k1 on the fly -> contiguous block transform -> inter-pass twiddle -> workspace
-template <int DT, bool NET, bool A2>
+template <int DT, bool NET, bool A2, bool GEN>
 __global__ void __launch_bounds__(256, 2) mll_passA_kernel(MllArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
@@ -290,7 +314,7 @@ __global__ void __launch_bounds__(256, 2) mll_passA_kernel(MllArgs a) {
   const int qmask = (1 << l1) - 1;
   const double c = H.scale;
   for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
-    const double k1 = point_k1<DT, NET, A2>(a, H, g0 + e) - c;
+    const double k1 = point_k1<DT, NET, A2, GEN>(a, H, g0 + e) - c;
     const int si = (e >> l1) * LP + padidx(e & qmask);
     if (NET)
       smr[si] = k1;
@@ -392,7 +416,7 @@ __global__ void __launch_bounds__(256, 2) mll_passB_kernel(MllArgs a) {
 }
 
 // pass C: contiguous blocks of the back-transformed dL/dlam -> inverse block transform -> contraction with dk1/dtheta
-template <int DT, bool NET, bool A2>
+template <int DT, bool NET, bool A2, bool GEN>
 __global__ void __launch_bounds__(256, 2) mll_passC_kernel(MllArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
@@ -426,7 +450,7 @@ __global__ void __launch_bounds__(256, 2) mll_passC_kernel(MllArgs a) {
   for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
     const int si = (e >> l1) * LP + padidx(e & qmask);
     const double w = NET ? smr[si] : smc[si].x;
-    point_grad<DT, NET, A2>(a, H, g0 + e, w, acc);
+    point_grad<DT, NET, A2, GEN>(a, H, g0 + e, w, acc);
   }
   reduce_store<DM + 1>(acc, d + 1, red, a.partC + ((int64_t)b * a.ctasA + blockIdx.x) * (d + 1));
 }
@@ -471,24 +495,24 @@ static int set_smem_attr(K kernel, size_t bytes) {
   return FGP_OK;
 }
 
-template <int DT, bool NET, bool A2>
+template <int DT, bool NET, bool A2, bool GEN>
 static int launch_mll(const MllArgs& a, const PassGeom& g, int B, cudaStream_t st) {
   int rc;
   if (g.l2 == 0) {
-    if ((rc = set_smem_attr(mll_single_kernel<DT, NET, A2>, g.smemA))) return rc;
-    mll_single_kernel<DT, NET, A2><<<B, g.threads, g.smemA, st>>>(a);
+    if ((rc = set_smem_attr(mll_single_kernel<DT, NET, A2, GEN>, g.smemA))) return rc;
+    mll_single_kernel<DT, NET, A2, GEN><<<B, g.threads, g.smemA, st>>>(a);
     FGP_LAUNCH_NAMED("mll_single", st);
     return FGP_OK;
   }
-  if ((rc = set_smem_attr(mll_passA_kernel<DT, NET, A2>, g.smemA))) return rc;
-  mll_passA_kernel<DT, NET, A2><<<dim3(a.ctasA, B), g.threads, g.smemA, st>>>(a);
+  if ((rc = set_smem_attr(mll_passA_kernel<DT, NET, A2, GEN>, g.smemA))) return rc;
+  mll_passA_kernel<DT, NET, A2, GEN><<<dim3(a.ctasA, B), g.threads, g.smemA, st>>>(a);
   FGP_LAUNCH_NAMED("mll_passA", st);
   if ((rc = set_smem_attr(mll_passB_kernel<NET>, g.smemB))) return rc;
   mll_passB_kernel<NET><<<dim3(a.ctasB, B), g.threads, g.smemB, st>>>(a);
   FGP_LAUNCH_NAMED("mll_passB", st);
   if (a.want_grad) {
-    if ((rc = set_smem_attr(mll_passC_kernel<DT, NET, A2>, g.smemA))) return rc;
-    mll_passC_kernel<DT, NET, A2><<<dim3(a.ctasA, B), g.threads, g.smemA, st>>>(a);
+    if ((rc = set_smem_attr(mll_passC_kernel<DT, NET, A2, GEN>, g.smemA))) return rc;
+    mll_passC_kernel<DT, NET, A2, GEN><<<dim3(a.ctasA, B), g.threads, g.smemA, st>>>(a);
     FGP_LAUNCH_NAMED("mll_passC", st);
   }
   mll_finalize_kernel<<<B, 256, 0, st>>>(a);
@@ -496,40 +520,46 @@ static int launch_mll(const MllArgs& a, const PassGeom& g, int B, cudaStream_t s
   return FGP_OK;
 }
 
-template <bool NET>
+template <bool NET, bool GEN>
 static int dispatch_mll(const MllArgs& a, const PassGeom& g, int B, bool all2, cudaStream_t st) {
   if (all2) {
     switch (a.d) {
-      case 2: return launch_mll<2, NET, true>(a, g, B, st);
-      case 4: return launch_mll<4, NET, true>(a, g, B, st);
-      case 8: return launch_mll<8, NET, true>(a, g, B, st);
-      case 16: return launch_mll<16, NET, true>(a, g, B, st);
+      case 2: return launch_mll<2, NET, true, GEN>(a, g, B, st);
+      case 4: return launch_mll<4, NET, true, GEN>(a, g, B, st);
+      case 8: return launch_mll<8, NET, true, GEN>(a, g, B, st);
+      case 16: return launch_mll<16, NET, true, GEN>(a, g, B, st);
       default: break;
     }
   }
+  if (GEN) return launch_mll<0, NET, false, GEN>(a, g, B, st);
   switch (a.d) {
-    case 2: return launch_mll<2, NET, false>(a, g, B, st);
-    case 4: return launch_mll<4, NET, false>(a, g, B, st);
-    case 8: return launch_mll<8, NET, false>(a, g, B, st);
-    default: return launch_mll<0, NET, false>(a, g, B, st);
+    case 2: return launch_mll<2, NET, false, GEN>(a, g, B, st);
+    case 4: return launch_mll<4, NET, false, GEN>(a, g, B, st);
+    case 8: return launch_mll<8, NET, false, GEN>(a, g, B, st);
+    default: return launch_mll<0, NET, false, GEN>(a, g, B, st);
   }
 }
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 template <bool NET>
-static int mll_common( const void* x, int64_t n, int d, const int* alpha_host, int t, int B, const double* ysq,
+static int mll_common(const uint64_t* z_host, const void* x, int64_t n, int d, const int* alpha_host, int t, int B, const double* ysq,
                       const double* scale, const double* ls, const double* noise, const double* weights, const void* table, void* workspace,
                       double* lam, double* out, int want_grad, fgp_stream_t stream) {
   const bool net = NET;
-  FGP_REQUIRE(x && alpha_host && ysq && scale && ls && noise && out, "mll_grad: null pointer");
+  FGP_REQUIRE((x || z_host) && alpha_host && ysq && scale && ls && noise && out, "mll_grad: null pointer");
+  FGP_REQUIRE(!(NET && z_host), "mll_grad: generator mode is lattice-only");
   FGP_REQUIRE(d >= 1 && d <= FGP_MAX_D, "mll_grad: d=%d outside 1..%d", d, FGP_MAX_D);
   FGP_REQUIRE(B >= 1 && B <= 65535, "mll_grad: B=%d outside 1..65535", B);
   FGP_REQUIRE(is_pow2(n) && ilog2(n) <= (net ? FGP_MAX_LOG2N_WHT : FGP_MAX_LOG2N_FFT),
               "mll_grad: n=%lld must be a power of two <= 2^%d", (long long)n, net ? FGP_MAX_LOG2N_WHT : FGP_MAX_LOG2N_FFT);
   MllArgs a;
   memset(&a, 0, sizeof(a));
-  a.x = x;
+  a.x = z_host ? nullptr : x;
+  if (z_host) {
+    FGP_REQUIRE(ilog2(n) <= 32, "mll_grad: generator mode needs n <= 2^32");
+    for (int j = 0; j < d; ++j) a.z.v[j] = z_host[j];
+  }
   a.n = n;
   a.d = d;
   a.t = t;
@@ -573,7 +603,8 @@ static int mll_common( const void* x, int64_t n, int d, const int* alpha_host, i
   }
   bool all2 = true;
   for (int j = 0; j < d; ++j) all2 = all2 && alpha_host[j] == 2;
-  return dispatch_mll<NET>(a, g, B, all2, (cudaStream_t)stream);
+  if (!NET && z_host) return dispatch_mll<false, true>(a, g, B, all2, (cudaStream_t)stream);
+  return dispatch_mll<NET, false>(a, g, B, all2, (cudaStream_t)stream);
 }
 
 }  // namespace fgp

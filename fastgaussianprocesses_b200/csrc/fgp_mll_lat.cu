@@ -16,7 +16,15 @@ size_t fgp_mll_workspace_bytes(int family, int64_t n, int d, int B) {
 int fgp_lattice_mll_grad(const double* x_dev, int64_t n, int d, const int* alpha_host, int B, const double* ysq_dev,
                          const double* scale_dev, const double* ls_dev, const double* noise_dev, const double* weights_dev, const void* table_dev,
                          void* workspace_dev, double* lam_dev, double* out_dev, int want_grad, fgp_stream_t stream) {
-  return fgp::mll_common<false>(x_dev, n, d, alpha_host, 0, B, ysq_dev, scale_dev, ls_dev, noise_dev, weights_dev, table_dev,
+  return fgp::mll_common<false>(nullptr, x_dev, n, d, alpha_host, 0, B, ysq_dev, scale_dev, ls_dev, noise_dev, weights_dev, table_dev,
+                                workspace_dev, lam_dev, out_dev, want_grad, stream);
+}
+
+int fgp_lattice_mll_grad_z(const uint64_t* z_host, int64_t n, int d, const int* alpha_host, int B, const double* ysq_dev,
+                           const double* scale_dev, const double* ls_dev, const double* noise_dev, const double* weights_dev, const void* table_dev,
+                           void* workspace_dev, double* lam_dev, double* out_dev, int want_grad, fgp_stream_t stream) {
+  FGP_REQUIRE(z_host, "mll_grad_z: null generating vector");
+  return fgp::mll_common<false>(z_host, nullptr, n, d, alpha_host, 0, B, ysq_dev, scale_dev, ls_dev, noise_dev, weights_dev, table_dev,
                                 workspace_dev, lam_dev, out_dev, want_grad, stream);
 }
 

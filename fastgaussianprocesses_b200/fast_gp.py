@@ -1023,7 +1023,9 @@ class AbstractFastGP(torch.nn.Module):
         N = x.shape[0]
         xpts = self._xpts(self._nint)
         c = coeffs.reshape(-1, B, self._nint)
-        if B == 1:
+        if N == 0:
+            pm = torch.empty((c.shape[0], B, 0), dtype=torch.float64, device=self.device)
+        elif B == 1:
             pm = _lib.post_mean(self._FAMILY, x, xpts, self._alpha_list, self._t, scale_B[0], ls_B[0], c[:, 0, :].contiguous())
         else:
             pm = torch.empty((c.shape[0], B, N), dtype=torch.float64, device=self.device)
@@ -1042,7 +1044,10 @@ class AbstractFastGP(torch.nn.Module):
         B = len(scale_B)
         lam = self.get_inv_log_det_cache(n)._lam_full()
         xpts = self._xpts(n)
-        outs = [_lib.post_var(self._FAMILY, x, xpts, self._alpha_list, self._t, scale_B[b], ls_B[b], lam[b]) for b in range(B)]
+        if x.shape[0] == 0:
+            outs = [torch.empty((0,), dtype=torch.float64, device=self.device) for b in range(B)]
+        else:
+            outs = [_lib.post_var(self._FAMILY, x, xpts, self._alpha_list, self._t, scale_B[b], ls_B[b], lam[b]) for b in range(B)]
         pvar = torch.stack(outs, 0).reshape(tuple(pshape) + (1, x.shape[0]))
         return pvar[..., 0, :] if inttask else pvar
 

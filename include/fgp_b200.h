@@ -115,6 +115,13 @@ int fgp_lattice_mll_grad(const double* x_dev, int64_t n, int d, const int* alpha
                          const double* scale_dev, const double* ls_dev, const double* noise_dev,
                          const double* weights_dev, const void* table_dev, void* workspace_dev, double* lam_dev, double* out_dev, int want_grad,
                          fgp_stream_t stream);
+/* Generator form for a rank-1 lattice in natural order: the points are never read.  x_i - x_0 = frac(phi2(i) z_j) exactly
+ * (the random shift cancels in the first kernel column), so delta is regenerated from the index and z_host[d] inside
+ * the first and last pass; this removes the 16*n*d bytes of point traffic per iteration.  n <= 2^24. */
+int fgp_lattice_mll_grad_z(const uint64_t* z_host, int64_t n, int d, const int* alpha_host, int B, const double* ysq_dev,
+                           const double* scale_dev, const double* ls_dev, const double* noise_dev,
+                           const double* weights_dev, const void* table_dev, void* workspace_dev, double* lam_dev, double* out_dev, int want_grad,
+                           fgp_stream_t stream);
 int fgp_dnb2_mll_grad(const int64_t* xb_dev, int64_t n, int d, const int* alpha_host, int t, int B,
                       const double* ysq_dev, const double* scale_dev, const double* ls_dev, const double* noise_dev,
                       const double* weights_dev, void* workspace_dev, double* lam_dev, double* out_dev, int want_grad, fgp_stream_t stream);

@@ -50,6 +50,7 @@ SIGNATURES = {
     "fgp_fwht": (_i32, [_vp, _vp, _i64, _i64, _vp]),
     "fgp_mll_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32]),
     "fgp_lattice_mll_grad": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "fgp_lattice_mll_grad_z": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "fgp_dnb2_mll_grad": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "fgp_fit_state_doubles": (_sz, [_i32]),
     "fgp_fit_init": (_i32, [_c.POINTER(FitLayout), _c.POINTER(FitOptions), _vp]),
@@ -279,8 +280,9 @@ def _workspace(kind, nbytes, device):
     return ws
 
 
-def mll_grad(family, xpts, alpha, t, ysq, scale, ls, noise, want_grad=True, want_lam=False, weights=None):
+def mll_grad(family, xpts, alpha, t, ysq, scale, ls, noise, want_grad=True, want_lam=False, weights=None, z=None):
     """Fused MLL terms + gradients.  xpts: (n,d) float64 (lattice) / int64 (net); ysq (B,n); scale (B,), ls (B,d), noise (B,).
+    z: lattice generating vector -> generator mode (the points are regenerated from the index, xpts only gives n, d, device).
     Returns out (B, d+4) = [norm, logdet, dL/dnoise, dL/dscale, dL/dls...] and lam (B,n) or None."""
     n, d = xpts.shape
     B = scale.numel()
@@ -290,7 +292,13 @@ def mll_grad(family, xpts, alpha, t, ysq, scale, ls, noise, want_grad=True, want
     ws = _workspace("mll", load().fgp_mll_workspace_bytes(family, n, d, B), dev)
     wptr = None if weights is None else _dev(weights, torch.float64)
     with torch.cuda.device(dev):
-        if family == 0:
+        if family == 0 and z is not None:
+            tab = fft_table(n, dev)
+            _check(load().fgp_lattice_mll_grad_z(_harr(_u64, [int(v) for v in z]), n, d, _harr(_i32, alpha), B, _dev(ysq, torch.float64),
+                                                 _dev(scale, torch.float64), _dev(ls, torch.float64), _dev(noise, torch.float64), wptr,
+                                                 tab.data_ptr(), ws.data_ptr(), lam.data_ptr() if want_lam else None, out.data_ptr(),
+                                                 1 if want_grad else 0, _stream()))
+        elif family == 0:
             tab = fft_table(n, dev)
             _check(load().fgp_lattice_mll_grad(_dev(xpts, torch.float64), n, d, _harr(_i32, alpha), B, _dev(ysq, torch.float64),
                                                _dev(scale, torch.float64), _dev(ls, torch.float64), _dev(noise, torch.float64), wptr,
@@ -304,13 +312,17 @@ def mll_grad(family, xpts, alpha, t, ysq, scale, ls, noise, want_grad=True, want
     return out, lam
 
 
-def mll_grad_into(family, xpts, alpha, t, ysq, scale, ls, noise, weights, ws, lam, out, want_grad=True):
+def mll_grad_into(family, xpts, alpha, t, ysq, scale, ls, noise, weights, ws, lam, out, want_grad=True, z=None):
     """Allocation-free form of `mll_grad` (all buffers caller-provided) -- safe inside CUDA graph capture."""
     n, d = xpts.shape
     B = scale.numel()
     wptr = None if weights is None else weights.data_ptr()
     lptr = None if lam is None else lam.data_ptr()
-    if family == 0:
+    if family == 0 and z is not None:
+        tab = fft_table(n, xpts.device)
+        _check(load().fgp_lattice_mll_grad_z(_harr(_u64, [int(v) for v in z]), n, d, _harr(_i32, alpha), B, ysq.data_ptr(), scale.data_ptr(), ls.data_ptr(),
+                                             noise.data_ptr(), wptr, tab.data_ptr(), ws.data_ptr(), lptr, out.data_ptr(), 1 if want_grad else 0, _stream()))
+    elif family == 0:
         tab = fft_table(n, xpts.device)
         _check(load().fgp_lattice_mll_grad(xpts.data_ptr(), n, d, _harr(_i32, alpha), B, ysq.data_ptr(), scale.data_ptr(), ls.data_ptr(),
                                            noise.data_ptr(), wptr, tab.data_ptr(), ws.data_ptr(), lptr, out.data_ptr(), 1 if want_grad else 0, _stream()))

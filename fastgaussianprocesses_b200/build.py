@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfgp_b200.so")
-SOURCES = ["fgp_core.cu", "fgp_points.cu", "fgp_kernel_eval.cu", "fgp_transform.cu", "fgp_mll_lat.cu", "fgp_mll_net.cu", "fgp_fit.cu", "fgp_solve.cu", "fgp_posterior.cu"]
+SOURCES = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--fmad=true", "-Xptxas", "-v"]

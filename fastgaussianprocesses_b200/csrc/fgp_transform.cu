@@ -30,128 +30,100 @@ __global__ void fft_table_kernel(double2* stage, double2* lo, double2* hi, doubl
 }
 
 // ---- forward -------------------------------------------------------------------------------------------------
+// pass A: 2^lntr contiguous length-2^l1 blocks per CTA; the first round reads global memory straight into registers,
+// the last round applies the inter-pass twiddle and writes global memory (coalesced: its elements are 2^(l1-4) apart).
 template <bool REAL_IN>
-__global__ void __launch_bounds__(256, 2) fft_passA_fwd(const double* __restrict__ in, double2* __restrict__ out,
-                                                         int64_t total_blocks, int l1, int l2, int ntr, int LP,
-                                                         double scale, FftTables T) {
+__global__ void __launch_bounds__(512, 1) fft_passA_fwd(const double* __restrict__ in, double2* __restrict__ out, int64_t total_blocks,
+                                                         int l1, int l2, int lntr, int LP, double scale, FftTables T) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double2* sm = (double2*)smraw;
-  const int64_t blk0 = (int64_t)blockIdx.x * ntr;
-  const int nb = (int)min((int64_t)ntr, total_blocks - blk0);
-  const int cnt = nb << l1;
+  const int64_t blk0 = (int64_t)blockIdx.x << lntr;
+  const int nb = (int)min((int64_t)1 << lntr, total_blocks - blk0);
   const int64_t g0 = blk0 << l1;
-  const int qmask = (1 << l1) - 1;
-  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
-    double2 v;
-    if (REAL_IN) {
-      v = make_double2(in[g0 + e] * scale, 0.0);
-    } else {
-      v = ((const double2*)in)[g0 + e];
-      v.x *= scale;
-      v.y *= scale;
-    }
-    sm[(e >> l1) * LP + padidx(e & qmask)] = v;
-  }
-  __syncthreads();
-  block_fft_fwd(sm, l1, nb, LP, T.stage);
-  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
-    const int tr = e >> l1, q = e & qmask;
-    double2 v = sm[tr * LP + padidx(q)];
+  auto gld = [&](int tr, int idx) -> double2 {
+    if (tr >= nb) return make_double2(0.0, 0.0);
+    const int64_t e = g0 + ((int64_t)tr << l1) + idx;
+    if (REAL_IN) return make_double2(in[e] * scale, 0.0);
+    const double2 v = ((const double2*)in)[e];
+    return make_double2(v.x * scale, v.y * scale);
+  };
+  auto gst = [&](int tr, int idx, double2 v) {
+    if (tr >= nb) return;
     if (l2) {
       const uint32_t b = (uint32_t)((blk0 + tr) & ((1 << l2) - 1));
-      v = cmul(v, twiddle_n(T, brev_bits(b, l2) * (uint32_t)q));
+      v = cmul(v, twiddle_n(T, brev_bits(b, l2) * (uint32_t)idx));
     }
-    out[g0 + e] = v;
-  }
+    out[g0 + ((int64_t)tr << l1) + idx] = v;
+  };
+  block_fft_fwd_io<false>(sm, l1, lntr, LP, T.stage, gld, gst);
 }
 
+// pass B: 2^lntr adjacent stride-2^l1 columns per CTA, in place; consecutive threads take consecutive columns.
 template <bool INV>
-__global__ void __launch_bounds__(256, 2) fft_passB(const double2* __restrict__ in, double2* __restrict__ out, int l1,
-                                                     int l2, int lntr, int LP, FftTables T) {
+__global__ void __launch_bounds__(512, 1) fft_passB(const double2* __restrict__ in, double2* __restrict__ out, int l1, int l2, int lntr,
+                                                     int LP, FftTables T) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double2* sm = (double2*)smraw;
-  const int ntr = 1 << lntr;
   const int64_t col0 = (int64_t)blockIdx.x << lntr;
   const int64_t item = col0 >> l1;
   const int q0 = (int)(col0 & ((1 << l1) - 1));
   const int64_t base = (item << (l1 + l2)) + q0;
-  const int cnt = ntr << l2;
-  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
-    const int cc = e & (ntr - 1), b = e >> lntr;
-    sm[cc * LP + padidx(b)] = in[base + ((int64_t)b << l1) + cc];
-  }
-  __syncthreads();
-  if (!INV)
-    block_fft_fwd(sm, l2, ntr, LP, T.stage);
-  else
-    block_fft_inv(sm, l2, ntr, LP, T.stage);
-  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
-    const int cc = e & (ntr - 1), b = e >> lntr;
-    double2 v = sm[cc * LP + padidx(b)];
-    if (INV) {
-      const double2 w = twiddle_n(T, brev_bits((uint32_t)b, l2) * (uint32_t)(q0 + cc));
-      v = cmulc(w, v);
-    }
-    out[base + ((int64_t)b << l1) + cc] = v;
+  auto gld = [&](int tr, int idx) -> double2 { return in[base + ((int64_t)idx << l1) + tr]; };
+  if (!INV) {
+    auto gst = [&](int tr, int idx, double2 v) { out[base + ((int64_t)idx << l1) + tr] = v; };
+    block_fft_fwd_io<true>(sm, l2, lntr, LP, T.stage, gld, gst);
+  } else {
+    auto gst = [&](int tr, int idx, double2 v) {
+      const double2 w = twiddle_n(T, brev_bits((uint32_t)idx, l2) * (uint32_t)(q0 + tr));
+      out[base + ((int64_t)idx << l1) + tr] = cmulc(w, v);
+    };
+    block_fft_inv_io<true>(sm, l2, lntr, LP, T.stage, gld, gst);
   }
 }
 
-__global__ void __launch_bounds__(256, 2) fft_passA_inv(const double2* __restrict__ in, double2* __restrict__ out,
-                                                         int64_t total_blocks, int l1, int ntr, int LP, double scale,
-                                                         FftTables T) {
+__global__ void __launch_bounds__(512, 1) fft_passA_inv(const double2* __restrict__ in, double2* __restrict__ out, int64_t total_blocks,
+                                                         int l1, int lntr, int LP, double scale, FftTables T) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double2* sm = (double2*)smraw;
-  const int64_t blk0 = (int64_t)blockIdx.x * ntr;
-  const int nb = (int)min((int64_t)ntr, total_blocks - blk0);
-  const int cnt = nb << l1;
+  const int64_t blk0 = (int64_t)blockIdx.x << lntr;
+  const int nb = (int)min((int64_t)1 << lntr, total_blocks - blk0);
   const int64_t g0 = blk0 << l1;
-  const int qmask = (1 << l1) - 1;
-  for (int e = threadIdx.x; e < cnt; e += blockDim.x) sm[(e >> l1) * LP + padidx(e & qmask)] = in[g0 + e];
-  __syncthreads();
-  block_fft_inv(sm, l1, nb, LP, T.stage);
-  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
-    double2 v = sm[(e >> l1) * LP + padidx(e & qmask)];
-    v.x *= scale;
-    v.y *= scale;
-    out[g0 + e] = v;
-  }
+  auto gld = [&](int tr, int idx) -> double2 {
+    if (tr >= nb) return make_double2(0.0, 0.0);
+    return in[g0 + ((int64_t)tr << l1) + idx];
+  };
+  auto gst = [&](int tr, int idx, double2 v) {
+    if (tr >= nb) return;
+    out[g0 + ((int64_t)tr << l1) + idx] = make_double2(v.x * scale, v.y * scale);
+  };
+  block_fft_inv_io<false>(sm, l1, lntr, LP, T.stage, gld, gst);
 }
 
 // ---- FWHT ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024, 1) wht_passA(const double* __restrict__ in, double* __restrict__ out,
-                                                     int64_t total_blocks, int l1, int ntr, int LP, double scale) {
+__global__ void __launch_bounds__(512, 1) wht_passA(const double* __restrict__ in, double* __restrict__ out, int64_t total_blocks, int l1,
+                                                     int lntr, int LP, double scale) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double* sm = (double*)smraw;
-  const int64_t blk0 = (int64_t)blockIdx.x * ntr;
-  const int nb = (int)min((int64_t)ntr, total_blocks - blk0);
-  const int cnt = nb << l1;
+  const int64_t blk0 = (int64_t)blockIdx.x << lntr;
+  const int nb = (int)min((int64_t)1 << lntr, total_blocks - blk0);
   const int64_t g0 = blk0 << l1;
-  const int qmask = (1 << l1) - 1;
-  for (int e = threadIdx.x; e < cnt; e += blockDim.x) sm[(e >> l1) * LP + padidx(e & qmask)] = in[g0 + e] * scale;
-  __syncthreads();
-  block_wht(sm, l1, nb, LP);
-  for (int e = threadIdx.x; e < cnt; e += blockDim.x) out[g0 + e] = sm[(e >> l1) * LP + padidx(e & qmask)];
+  auto gld = [&](int tr, int idx) -> double { return tr < nb ? in[g0 + ((int64_t)tr << l1) + idx] * scale : 0.0; };
+  auto gst = [&](int tr, int idx, double v) {
+    if (tr < nb) out[g0 + ((int64_t)tr << l1) + idx] = v;
+  };
+  block_wht_io<false>(sm, l1, lntr, LP, wht_sched_coalesced(l1), gld, gst);
 }
 
-__global__ void __launch_bounds__(1024, 1) wht_passB(double* __restrict__ data, int l1, int l2, int lntr, int LP) {
+__global__ void __launch_bounds__(512, 1) wht_passB(double* __restrict__ data, int l1, int l2, int lntr, int LP) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double* sm = (double*)smraw;
-  const int ntr = 1 << lntr;
   const int64_t col0 = (int64_t)blockIdx.x << lntr;
   const int64_t item = col0 >> l1;
   const int q0 = (int)(col0 & ((1 << l1) - 1));
   double* base = data + (item << (l1 + l2)) + q0;
-  const int cnt = ntr << l2;
-  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
-    const int cc = e & (ntr - 1), b = e >> lntr;
-    sm[cc * LP + padidx(b)] = base[((int64_t)b << l1) + cc];
-  }
-  __syncthreads();
-  block_wht(sm, l2, ntr, LP);
-  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
-    const int cc = e & (ntr - 1), b = e >> lntr;
-    base[((int64_t)b << l1) + cc] = sm[cc * LP + padidx(b)];
-  }
+  auto gld = [&](int tr, int idx) -> double { return base[((int64_t)idx << l1) + tr]; };
+  auto gst = [&](int tr, int idx, double v) { base[((int64_t)idx << l1) + tr] = v; };
+  block_wht_io<true>(sm, l2, lntr, LP, wht_sched_up(l2), gld, gst);
 }
 
 template <typename K>
@@ -189,20 +161,17 @@ static int fft_forward(const double* in, double* out, int64_t batch, int64_t n, 
   int rc;
   if (real_in) {
     if ((rc = set_smem(fft_passA_fwd<true>, g.smemA))) return rc;
-    fft_passA_fwd<true><<<(unsigned)ctas, g.threads, g.smemA, st>>>(in, (double2*)out, total_blocks, g.l1, g.l2, g.ntrA,
-                                                                  g.LPA, scale, T);
+    fft_passA_fwd<true><<<(unsigned)ctas, g.threadsA, g.smemA, st>>>(in, (double2*)out, total_blocks, g.l1, g.l2, g.lntrA, g.LPA, scale, T);
   } else {
     if ((rc = set_smem(fft_passA_fwd<false>, g.smemA))) return rc;
-    fft_passA_fwd<false><<<(unsigned)ctas, g.threads, g.smemA, st>>>(in, (double2*)out, total_blocks, g.l1, g.l2, g.ntrA,
-                                                                   g.LPA, scale, T);
+    fft_passA_fwd<false><<<(unsigned)ctas, g.threadsA, g.smemA, st>>>(in, (double2*)out, total_blocks, g.l1, g.l2, g.lntrA, g.LPA, scale, T);
   }
-  FGP_LAUNCH_CHECK();
+  FGP_LAUNCH_NAMED("fft_passA_fwd", st);
   if (g.l2) {
     if ((rc = set_smem(fft_passB<false>, g.smemB))) return rc;
-    const int64_t ctasB = (batch << g.l1) / g.ntrB;
-    fft_passB<false><<<(unsigned)ctasB, g.threads, g.smemB, st>>>((const double2*)out, (double2*)out, g.l1, g.l2,
-                                                                ilog2(g.ntrB), g.LPB, T);
-    FGP_LAUNCH_CHECK();
+    const int64_t ctasB = (batch << g.l1) >> g.lntrB;
+    fft_passB<false><<<(unsigned)ctasB, g.threadsB, g.smemB, st>>>((const double2*)out, (double2*)out, g.l1, g.l2, g.lntrB, g.LPB, T);
+    FGP_LAUNCH_NAMED("fft_passB_fwd", st);
   }
   return FGP_OK;
 }
@@ -259,17 +228,16 @@ int fgp_ifftbr_c2c(const double* in_dev, double* out_dev, int64_t batch, int64_t
   const double2* src = (const double2*)in_dev;
   if (g.l2) {
     if ((rc = set_smem(fft_passB<true>, g.smemB))) return rc;
-    const int64_t ctasB = (batch << g.l1) / g.ntrB;
-    fft_passB<true><<<(unsigned)ctasB, g.threads, g.smemB, st>>>(src, (double2*)out_dev, g.l1, g.l2, ilog2(g.ntrB), g.LPB, T);
-    FGP_LAUNCH_CHECK();
+    const int64_t ctasB = (batch << g.l1) >> g.lntrB;
+    fft_passB<true><<<(unsigned)ctasB, g.threadsB, g.smemB, st>>>(src, (double2*)out_dev, g.l1, g.l2, g.lntrB, g.LPB, T);
+    FGP_LAUNCH_NAMED("fft_passB_inv", st);
     src = (const double2*)out_dev;
   }
   if ((rc = set_smem(fft_passA_inv, g.smemA))) return rc;
   const int64_t total_blocks = batch * (n >> g.l1);
   const int64_t ctas = (total_blocks + g.ntrA - 1) / g.ntrA;
-  fft_passA_inv<<<(unsigned)ctas, g.threads, g.smemA, st>>>(src, (double2*)out_dev, total_blocks, g.l1, g.ntrA, g.LPA,
-                                                          1.0 / sqrt((double)n), T);
-  FGP_LAUNCH_CHECK();
+  fft_passA_inv<<<(unsigned)ctas, g.threadsA, g.smemA, st>>>(src, (double2*)out_dev, total_blocks, g.l1, g.lntrA, g.LPA, 1.0 / sqrt((double)n), T);
+  FGP_LAUNCH_NAMED("fft_passA_inv", st);
   return FGP_OK;
 }
 
@@ -279,18 +247,17 @@ int fgp_fwht(const double* in_dev, double* out_dev, int64_t batch, int64_t n, fg
   if (rc) return rc;
   if (batch == 0) return FGP_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const PassGeom g = make_geom(n, false, 1024);
+  const PassGeom g = make_geom(n, false);
   if ((rc = set_smem(wht_passA, g.smemA))) return rc;
   const int64_t total_blocks = batch * (n >> g.l1);
   const int64_t ctas = (total_blocks + g.ntrA - 1) / g.ntrA;
-  wht_passA<<<(unsigned)ctas, g.threads, g.smemA, st>>>(in_dev, out_dev, total_blocks, g.l1, g.ntrA, g.LPA,
-                                                      1.0 / sqrt((double)n));
-  FGP_LAUNCH_CHECK();
+  wht_passA<<<(unsigned)ctas, g.threadsA, g.smemA, st>>>(in_dev, out_dev, total_blocks, g.l1, g.lntrA, g.LPA, 1.0 / sqrt((double)n));
+  FGP_LAUNCH_NAMED("wht_passA", st);
   if (g.l2) {
     if ((rc = set_smem(wht_passB, g.smemB))) return rc;
-    const int64_t ctasB = (batch << g.l1) / g.ntrB;
-    wht_passB<<<(unsigned)ctasB, g.threads, g.smemB, st>>>(out_dev, g.l1, g.l2, ilog2(g.ntrB), g.LPB);
-    FGP_LAUNCH_CHECK();
+    const int64_t ctasB = (batch << g.l1) >> g.lntrB;
+    wht_passB<<<(unsigned)ctasB, g.threadsB, g.smemB, st>>>(out_dev, g.l1, g.l2, g.lntrB, g.LPB);
+    FGP_LAUNCH_NAMED("wht_passB", st);
   }
   return FGP_OK;
 }

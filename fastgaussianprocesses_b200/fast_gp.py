@@ -89,7 +89,7 @@ class _MLLFunction(torch.autograd.Function):
         xpts = fgp._xpts(n)
         out, _ = _lib.mll_grad(fgp._FAMILY, xpts, fgp._alpha_list, fgp._t, ysq, scale_B.detach().contiguous(),
                                ls_B.detach().contiguous(), noise_B.detach().contiguous(), want_grad=want_grad,
-                               weights=weights)
+                               weights=weights, z=fgp._zgen)
         ctx.save_for_backward(out)
         ctx.d = fgp.d
         ctx.have_grad = want_grad
@@ -190,18 +190,21 @@ class _FusedFitLoop(object):
     @property
     def algorithmic_bytes(self):
         e = 16 if self.fgp._FAMILY == 0 else 8
-        return self.B * (2 * 8 * self.n * self.d + 4 * e * self.n + 8 * self.n)
+        pts = 0 if self.fgp._zgen is not None else 2 * 8 * self.n * self.d
+        return self.B * (pts + 4 * e * self.n + 8 * self.n)
 
     def kernel_algorithmic_bytes(self, name):
         e = 16 if self.fgp._FAMILY == 0 else 8
         n, d, B = self.n, self.d, self.B
+        if self.fgp._zgen is not None:
+            d = 0
         return {"mll_passA": B * (8 * n * d + e * n), "mll_passB": B * (2 * e * n + 8 * n), "mll_passC": B * (8 * n * d + e * n),
                 "mll_single": B * (16 * n * d + 8 * n)}.get(name, 0)
 
     def _iteration(self):
         f = self.fgp
         _lib.mll_grad_into(f._FAMILY, self.xpts, f._alpha_list, f._t, self.ysq, self.scale_B, self.ls_B, self.noise_B, self.weights,
-                           self.ws, None, self.out, want_grad=any(self.req))
+                           self.ws, None, self.out, want_grad=any(self.req), z=f._zgen)
         _lib.fit_step(self.layout, self.out)
 
     def begin(self, iterations, stop_wait, logtol, lr):
@@ -280,7 +283,7 @@ class _FastInverseLogDetCache(object):
                 ysq = torch.zeros((B, self.nint), dtype=torch.float64, device=self.fgp.device)
                 _, lam = _lib.mll_grad(self.fgp._FAMILY, self.fgp._xpts(self.nint), self.fgp._alpha_list, self.fgp._t, ysq,
                                        scale_B.contiguous(), ls_B.contiguous(), noise_B.contiguous(), want_grad=False,
-                                       want_lam=True)
+                                       want_lam=True, z=self.fgp._zgen)
             self.lam = lam
             self.pshape = pshape
             self._key = key
@@ -508,6 +511,10 @@ class AbstractFastGP(torch.nn.Module):
         self.xxb_seqs = np.array([_XXbSeq(self, self.seqs[i]) for i in range(self.num_tasks)], dtype=object)
         self.inv_log_det_cache_dict = {}
         self.adaptive_nugget = False
+        # generator mode of the fused eigen-solve: a lattice spec of this package carries its generating vector, so the
+        # first kernel column is regenerated from the point index and the points are never read (include/fgp_b200.h)
+        s0 = self.seqs[0]
+        self._zgen = [int(v) for v in s0.gen_vec] if (self._FAMILY == 0 and isinstance(s0, sequences.Lattice) and os.environ.get("FGP_B200_NO_GEN") != "1") else None
         self._epoch = 0
         self._coeffs = None
         self._coeffs_key = None

@@ -236,3 +236,26 @@ def test_error_codes(L):
         L.fwht(x)  # not a power of two
     with pytest.raises(RuntimeError):
         L.fwht(torch.zeros(8))  # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("d,m,alpha", [(8, 20, 2), (8, 12, 2), (2, 9, 2), (4, 16, 2), (16, 14, 2), (3, 13, 2), (5, 15, 3), (1, 4, 1), (2, 0, 2), (2, 1, 2)])
+def test_mll_generator_mode_matches_point_mode(L, P, d, m, alpha):
+    """fgp_lattice_mll_grad_z regenerates x_i - x_0 = frac(phi2(i) z) from the index; it must agree with the kernel fed
+    with the stored points (which itself is pinned to the reference fixtures above) to round-off."""
+    n = 1 << m
+    rng = np.random.default_rng(50 + m)
+    z = P.default_lattice_gen_vec(d)
+    xpts = L.lattice_points(z, rng.random(d), 0, n, dev)
+    g = torch.Generator(device=dev).manual_seed(m)
+    B = 2
+    ysq = torch.rand(B, n, generator=g, device=dev) * 3.0
+    scale = torch.tensor([0.8, 2.5], device=dev)
+    ls = torch.from_numpy(rng.uniform(0.2, 1.3, size=(B, d))).to(dev)
+    noise = torch.tensor([1e-4, 1e-6], device=dev)
+    w = torch.tensor([[0.5, 1.5], [0.25, 0.5]], device=dev)
+    out_x, lam_x = L.mll_grad(0, xpts, [alpha] * d, 0, ysq, scale, ls, noise, want_grad=True, want_lam=True, weights=w)
+    out_z, lam_z = L.mll_grad(0, xpts, [alpha] * d, 0, ysq, scale, ls, noise, want_grad=True, want_lam=True, weights=w, z=z)
+    assert rel(lam_z, lam_x) < 1e-12
+    for b in range(B):
+        assert rel(out_z[b, :2], out_x[b, :2]) < 1e-9
+        assert rel(out_z[b, 2:], out_x[b, 2:]) < 1e-7

@@ -6,7 +6,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfgp_b200.so")
+LIB_PATH = os.environ.get("FGP_B200_LIB") or os.path.join(_HERE, "lib", "libfgp_b200.so")
 
 MAX_D = 32
 MAX_ALPHA = 10
@@ -31,6 +31,12 @@ class FitOptions(_c.Structure):
                 ("wn", _f64), ("wl", _f64), ("lr", _f64), ("etaminus", _f64), ("etaplus", _f64), ("step_min", _f64), ("step_max", _f64)]
 
 
+class FitProblem(_c.Structure):
+    """fgp_fit_problem (include/fgp_b200.h)."""
+    _fields_ = [("family", _i32), ("x_dev", _vp), ("z_host", _vp), ("n", _i64), ("d", _i32), ("alpha_host", _vp), ("t", _i32),
+                ("ysq_dev", _vp), ("weights_dev", _vp), ("table_dev", _vp), ("workspace_dev", _vp), ("out_dev", _vp)]
+
+
 # name -> (restype, argtypes); every symbol include/fgp_b200.h declares
 SIGNATURES = {
     "fgp_version": (_i32, []),
@@ -52,7 +58,8 @@ SIGNATURES = {
     "fgp_lattice_mll_grad": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "fgp_lattice_mll_grad_z": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "fgp_dnb2_mll_grad": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
-    "fgp_fit_state_doubles": (_sz, [_i32]),
+    "fgp_fit_state_doubles": (_sz, [_i32, _i32]),
+    "fgp_fit_iteration": (_i32, [_c.POINTER(FitProblem), _c.POINTER(FitLayout), _vp]),
     "fgp_fit_init": (_i32, [_c.POINTER(FitLayout), _c.POINTER(FitOptions), _vp]),
     "fgp_fit_step": (_i32, [_c.POINTER(FitLayout), _vp, _vp]),
     "fgp_fit_finish": (_i32, [_c.POINTER(FitLayout), _vp]),
@@ -335,8 +342,12 @@ def mll_workspace(family, n, d, B, device):
     return torch.empty((max(load().fgp_mll_workspace_bytes(family, n, d, B), 256) + 7) // 8, dtype=torch.float64, device=device)
 
 
-def fit_state_doubles(P):
-    return int(load().fgp_fit_state_doubles(int(P)))
+def fit_state_doubles(P, B):
+    return int(load().fgp_fit_state_doubles(int(P), int(B)))
+
+
+def fit_iteration(problem, layout):
+    _check(load().fgp_fit_iteration(_c.byref(problem), _c.byref(layout), _stream()))
 
 
 def fit_init(layout, options):

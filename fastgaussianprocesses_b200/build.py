@@ -6,12 +6,12 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIBDIR = os.path.join(HERE, "lib")
+LIBDIR = os.environ.get("FGP_LIB_DIR") or os.path.join(HERE, "lib")  # FGP_LIB_DIR: side-by-side tuning builds
 LIB = os.path.join(LIBDIR, "libfgp_b200.so")
 SOURCES = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--fmad=true", "-Xptxas", "-v"]
+         "--fmad=true", "-Xptxas", "-v"] + os.environ.get("FGP_BUILD_DEFS", "").split()
 
 
 def _stale(out, deps):

@@ -16,6 +16,7 @@
 // n = 2^21), 8n B of |y~|^2, and the points twice -- or not at all in generator mode.
 #pragma once
 #include "fgp_transform.cuh"
+#include "fgp_fit.cuh"
 
 namespace fgp {
 
@@ -44,6 +45,8 @@ struct MllArgs {
   int l1, l2, lntrA, lntrB, LPA, LPB;
   int ctasA, ctasB;
   FftTables T;
+  int has_fit;    // fused fit iteration: the last CTA to finish reduces the partial sums and runs the fit step
+  FitLayout fit;
 };
 
 struct Hyp {  // per-CTA hyperparameters and first point, staged in shared memory
@@ -264,11 +267,74 @@ __device__ __forceinline__ void reduce_store(double* v, int nv, double* red, dou
   }
 }
 
+// deterministic reduction of the per-CTA partial sums of set b into out[b] (fixed order); any CTA size that is a
+// multiple of 32.  Partials come from other CTAs: cache-global loads.
+__device__ __forceinline__ void finalize_set(const MllArgs& a, int b, double* red) {
+  const int d = a.d;
+  double* out = a.out + (int64_t)b * (d + 4);
+  {
+    double s[3] = {0.0, 0.0, 0.0};
+    const double* p = a.partB + (int64_t)b * a.ctasB * 3;
+    for (int c = threadIdx.x; c < a.ctasB; c += blockDim.x) {
+      s[0] += __ldcg(p + c * 3 + 0);
+      s[1] += __ldcg(p + c * 3 + 1);
+      s[2] += __ldcg(p + c * 3 + 2);
+    }
+    reduce_store<3>(s, 3, red, out);
+  }
+  if (!a.want_grad) return;
+  // warp w reduces components w, w + nwarp, ... over all pass-C CTAs
+  const double* p = a.partC + (int64_t)b * a.ctasA * (d + 1);
+  const double inv_scale = 1.0 / a.scale[b];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int j = warp; j <= d; j += nwarp) {
+    double v = 0.0;
+    for (int c = lane; c < a.ctasA; c += 32) v += __ldcg(p + (int64_t)c * (d + 1) + j);
+    v = warp_sum(v);
+    if (lane == 0) out[3 + j] = j == 0 ? v * inv_scale : v;
+  }
+}
+
+// Tail of a fused fit iteration, called by every CTA of the iteration's LAST kernel after its partial sums are stored:
+// the last CTA of set b finalizes b; the last finalizer runs the fit step (loss, early stop, Rprop, new hyperparameters).
+// ctas_b: CTAs per set in this kernel; B: sets; two_pass: partial sums need reducing.
+__device__ __forceinline__ void mll_fit_tail(const MllArgs& a, int b, int ctas_b, int B, bool two_pass, double* red) {
+  __shared__ int s_last;
+  __shared__ double s_hdr[ST_HEADER];
+  __shared__ int s_flags[2];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&a.fit.tickets[1 + b], 1u) == (unsigned)(ctas_b - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (two_pass) {
+    __threadfence();
+    finalize_set(a, b, red);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a.fit.tickets[1 + b] = 0u;
+    __threadfence();
+    const bool last = atomicAdd(&a.fit.tickets[0], 1u) == (unsigned)(B - 1);
+    if (last) a.fit.tickets[0] = 0u;
+    s_last = last;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  fit_step_device(a.fit, a.out, red, s_hdr, s_flags);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // single-pass kernel: one CTA per hyperparameter set, n <= block capacity
+// Heavy per-element work (kernel evaluation, log/divide epilogue, gradient contraction) runs in rolled element loops
+// over shared memory; only the transform rounds are unrolled (instruction-cache footprint, profiles/README.md).
 // ------------------------------------------------------------------------------------------------------------
 template <int DT, bool NET, bool A2, bool GEN>
-__global__ void __launch_bounds__(512, 1) mll_single_kernel(const __grid_constant__ MllArgs a) {
+__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_single_kernel(const __grid_constant__ MllArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
   __shared__ double red[kRed];
@@ -290,45 +356,61 @@ __global__ void __launch_bounds__(512, 1) mll_single_kernel(const __grid_constan
   for (int j = 0; j <= DM; ++j) acc[j] = 0.0;
   const int want_grad = a.want_grad;
   if (NET) {
+    double* sm = (double*)smraw;
+    const SmemR S{sm, LP};
     double* lamo = a.lam ? a.lam + (int64_t)b * n : nullptr;
-    auto gld = [&](int, int idx) -> double { return point_k1<DT, NET, A2, GEN>(a, H, idx) - c; };
-    auto mid = [&](int, int k, double v) -> double {
+    tile_fill_r<false>(S, l, 0, [&](int, int idx) -> double { return point_k1<DT, NET, A2, GEN>(a, H, idx) - c; });
+    __syncthreads();
+    block_wht_io<false>(sm, l, 0, LP, wht_sched_up(l), SmemTag{}, SmemTag{});
+    __syncthreads();
+    tile_map_r<false>(S, l, 0, [&](int, int k, double v) -> double {
       double lam = v + noise;
       if (k == 0) lam += c * (double)n;
       if (lamo) lamo[k] = lam;
       return spectral_r(lam, ysq[k], wn, wl, s);
-    };
-    auto gst = [&](int, int idx, double w) {
-      if (want_grad) point_grad<DT, NET, A2, GEN>(a, H, idx, w, acc);
-    };
-    block_wht_fwd_mid_inv_io<false>((double*)smraw, l, 0, LP, gld, mid, gst);
+    });
+    if (want_grad) {
+      __syncthreads();
+      block_wht_io<false>(sm, l, 0, LP, wht_sched_up(l), SmemTag{}, SmemTag{});
+      __syncthreads();
+      tile_drain_r<false>(S, l, 0, [&](int, int idx, double w) { point_grad<DT, NET, A2, GEN>(a, H, idx, w, acc); });
+    }
   } else {
+    double2* sm = (double2*)smraw;
+    const SmemC S{sm, LP};
     double2* lamo = a.lam ? (double2*)a.lam + (int64_t)b * n : nullptr;
-    auto gld = [&](int, int idx) -> double2 { return make_double2(point_k1<DT, NET, A2, GEN>(a, H, idx) - c, 0.0); };
-    auto mid = [&](int, int k, double2 lam) -> double2 {
+    tile_fill_c<false>(S, l, 0, [&](int, int idx) -> double2 { return make_double2(point_k1<DT, NET, A2, GEN>(a, H, idx) - c, 0.0); });
+    __syncthreads();
+    block_fft_fwd_io<false>(sm, l, 0, LP, a.T.stage, SmemTag{}, SmemTag{});
+    __syncthreads();
+    tile_map_c<false>(S, l, 0, [&](int, int k, double2 lam) -> double2 {
       lam.x += noise;
       if (k == 0) lam.x += c * (double)n;
       if (lamo) lamo[k] = lam;
       return spectral_c(lam, ysq[k], wn, wl, s);
-    };
-    auto gst = [&](int, int idx, double2 w) {
-      if (want_grad) point_grad<DT, NET, A2, GEN>(a, H, idx, w.x, acc);
-    };
-    block_fft_fwd_mid_inv_io<false>((double2*)smraw, l, 0, LP, a.T.stage, gld, mid, gst);
+    });
+    if (want_grad) {
+      __syncthreads();
+      block_fft_inv_io<false>(sm, l, 0, LP, a.T.stage, SmemTag{}, SmemTag{});
+      __syncthreads();
+      tile_drain_c<false>(S, l, 0, [&](int, int idx, double2 w) { point_grad<DT, NET, A2, GEN>(a, H, idx, w.x, acc); });
+    }
   }
   double* out = a.out + (int64_t)b * (d + 4);
   reduce_store<3>(s, 3, red, out);
-  if (!want_grad) return;
-  acc[0] /= H.scale;
-  reduce_store<DM + 1>(acc, d + 1, red, out + 3);
+  if (want_grad) {
+    acc[0] /= H.scale;
+    reduce_store<DM + 1>(acc, d + 1, red, out + 3);
+  }
+  if (a.has_fit) mll_fit_tail(a, b, 1, gridDim.x, false, red);
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // two-pass kernels
 // ------------------------------------------------------------------------------------------------------------
-// pass A: k1 on the fly -> contiguous block transform -> inter-pass twiddle -> workspace
+// pass A: k1 on the fly -> shared memory -> contiguous block transform -> inter-pass twiddle -> workspace
 template <int DT, bool NET, bool A2, bool GEN>
-__global__ void __launch_bounds__(512, 1) mll_passA_kernel(const __grid_constant__ MllArgs a) {
+__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passA_kernel(const __grid_constant__ MllArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
   const int b = blockIdx.y;
@@ -339,27 +421,31 @@ __global__ void __launch_bounds__(512, 1) mll_passA_kernel(const __grid_constant
   const int64_t g0 = blk0 << l1;
   const double c = H.scale;
   if (NET) {
+    double* sm = (double*)smraw;
     double* W = (double*)a.W + (int64_t)b * a.n + g0;
-    auto gld = [&](int tr, int idx) -> double { return point_k1<DT, NET, A2, GEN>(a, H, g0 + ((int64_t)tr << l1) + idx) - c; };
-    auto gst = [&](int tr, int idx, double v) { W[((int64_t)tr << l1) + idx] = v; };
-    block_wht_io<false>((double*)smraw, l1, lntr, LP, wht_sched_coalesced(l1), gld, gst);
+    tile_fill_r<false>(SmemR{sm, LP}, l1, lntr,
+                       [&](int tr, int idx) -> double { return point_k1<DT, NET, A2, GEN>(a, H, g0 + ((int64_t)tr << l1) + idx) - c; });
+    __syncthreads();
+    // any schedule whose last round is strided (coalesced stores)
+    block_wht_io<false>(sm, l1, lntr, LP, wht_sched_up(l1), SmemTag{}, [&](int tr, int idx, double v) { W[((int64_t)tr << l1) + idx] = v; });
   } else {
+    double2* sm = (double2*)smraw;
     double2* W = (double2*)a.W + (int64_t)b * a.n + g0;
     const FftTables T = a.T;
-    auto gld = [&](int tr, int idx) -> double2 {
+    tile_fill_c<false>(SmemC{sm, LP}, l1, lntr, [&](int tr, int idx) -> double2 {
       return make_double2(point_k1<DT, NET, A2, GEN>(a, H, g0 + ((int64_t)tr << l1) + idx) - c, 0.0);
-    };
-    auto gst = [&](int tr, int idx, double2 v) {
+    });
+    __syncthreads();
+    block_fft_fwd_io<false>(sm, l1, lntr, LP, T.stage, SmemTag{}, [&](int tr, int idx, double2 v) {
       const uint32_t bb = (uint32_t)((blk0 + tr) & ((1 << l2) - 1));
       W[((int64_t)tr << l1) + idx] = cmul(v, twiddle_n(T, brev_bits(bb, l2) * (uint32_t)idx));
-    };
-    block_fft_fwd_io<false>((double2*)smraw, l1, lntr, LP, T.stage, gld, gst);
+    });
   }
 }
 
 // pass C: contiguous blocks of the back-transformed dL/dlam -> inverse block transform -> contraction with dk1/dtheta
 template <int DT, bool NET, bool A2, bool GEN>
-__global__ void __launch_bounds__(512, 1) mll_passC_kernel(const __grid_constant__ MllArgs a) {
+__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kernel(const __grid_constant__ MllArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
   __shared__ double red[kRed];
@@ -375,17 +461,23 @@ __global__ void __launch_bounds__(512, 1) mll_passC_kernel(const __grid_constant
 #pragma unroll
   for (int j = 0; j <= DM; ++j) acc[j] = 0.0;
   if (NET) {
+    double* sm = (double*)smraw;
     const double* W = (const double*)a.W + (int64_t)b * a.n + g0;
-    auto gld = [&](int tr, int idx) -> double { return W[((int64_t)tr << l1) + idx]; };
-    auto gst = [&](int tr, int idx, double w) { point_grad<DT, NET, A2, GEN>(a, H, g0 + ((int64_t)tr << l1) + idx, w, acc); };
-    block_wht_io<false>((double*)smraw, l1, lntr, LP, wht_sched_coalesced(l1), gld, gst);
+    // top stages first: a thread's 16 loads are 2^(l1-4) apart, consecutive threads read consecutive addresses
+    block_wht_io<false>(sm, l1, lntr, LP, wht_sched_coalesced(l1), [&](int tr, int idx) -> double { return W[((int64_t)tr << l1) + idx]; }, SmemTag{});
+    __syncthreads();
+    tile_drain_r<false>(SmemR{sm, LP}, l1, lntr,
+                        [&](int tr, int idx, double w) { point_grad<DT, NET, A2, GEN>(a, H, g0 + ((int64_t)tr << l1) + idx, w, acc); });
   } else {
+    double2* sm = (double2*)smraw;
     const double2* W = (const double2*)a.W + (int64_t)b * a.n + g0;
-    auto gld = [&](int tr, int idx) -> double2 { return W[((int64_t)tr << l1) + idx]; };
-    auto gst = [&](int tr, int idx, double2 w) { point_grad<DT, NET, A2, GEN>(a, H, g0 + ((int64_t)tr << l1) + idx, w.x, acc); };
-    block_fft_inv_io<false>((double2*)smraw, l1, lntr, LP, a.T.stage, gld, gst);
+    block_fft_inv_io<false>(sm, l1, lntr, LP, a.T.stage, [&](int tr, int idx) -> double2 { return W[((int64_t)tr << l1) + idx]; }, SmemTag{});
+    __syncthreads();
+    tile_drain_c<false>(SmemC{sm, LP}, l1, lntr,
+                        [&](int tr, int idx, double2 w) { point_grad<DT, NET, A2, GEN>(a, H, g0 + ((int64_t)tr << l1) + idx, w.x, acc); });
   }
   reduce_store<DM + 1>(acc, d + 1, red, a.partC + ((int64_t)b * a.ctasA + blockIdx.x) * (d + 1));
+  if (a.has_fit) mll_fit_tail(a, b, a.ctasA, gridDim.y, true, red);
 }
 
 template <typename K>
@@ -422,6 +514,7 @@ static int launch_mll(const MllArgs& a, const PassGeom& g, int B, cudaStream_t s
     mll_passC_kernel<DT, NET, A2, GEN><<<dim3(a.ctasA, B), g.threadsA, g.smemA, st>>>(a);
     FGP_LAUNCH_NAMED("mll_passC", st);
   }
+  if (a.has_fit) return FGP_OK;  // reduced (and stepped) by the last CTA of the last kernel
   return launch_mll_finalize(a, B, st);
 }
 

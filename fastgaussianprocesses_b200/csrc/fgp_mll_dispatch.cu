@@ -5,7 +5,8 @@ namespace fgp {
 
 static int mll_common(bool net, const uint64_t* z_host, const void* x, int64_t n, int d, const int* alpha_host, int t, int B,
                       const double* ysq, const double* scale, const double* ls, const double* noise, const double* weights,
-                      const void* table, void* workspace, double* lam, double* out, int want_grad, fgp_stream_t stream) {
+                      const void* table, void* workspace, double* lam, double* out, int want_grad, fgp_stream_t stream,
+                      const fgp_fit_layout* fit = nullptr) {
   FGP_REQUIRE((x || z_host) && alpha_host && ysq && scale && ls && noise && out, "mll_grad: null pointer");
   FGP_REQUIRE(!(net && z_host), "mll_grad: generator mode is lattice-only");
   FGP_REQUIRE(d >= 1 && d <= FGP_MAX_D, "mll_grad: d=%d outside 1..%d", d, FGP_MAX_D);
@@ -44,6 +45,12 @@ static int mll_common(bool net, const uint64_t* z_host, const void* x, int64_t n
   a.lam = lam;
   a.out = out;
   a.want_grad = want_grad;
+  if (fit) {
+    int rc = make_layout(fit, &a.fit);
+    if (rc) return rc;
+    FGP_REQUIRE(a.fit.B == B && a.fit.d == d, "fit_iteration: layout B/d do not match the problem");
+    a.has_fit = 1;
+  }
   a.l1 = g.l1;
   a.l2 = g.l2;
   a.lntrA = g.l2 ? g.lntrA : 0;  // the single-pass kernel runs one transform per CTA
@@ -101,6 +108,15 @@ int fgp_lattice_mll_grad_z(const uint64_t* z_host, int64_t n, int d, const int* 
   FGP_REQUIRE(z_host, "mll_grad_z: null generating vector");
   return fgp::mll_common(false, z_host, nullptr, n, d, alpha_host, 0, B, ysq_dev, scale_dev, ls_dev, noise_dev, weights_dev, table_dev,
                          workspace_dev, lam_dev, out_dev, want_grad, stream);
+}
+
+int fgp_fit_iteration(const fgp_fit_problem* p, const fgp_fit_layout* layout, fgp_stream_t stream) {
+  FGP_REQUIRE(p && layout, "fit_iteration: null argument");
+  const bool net = p->family != 0;
+  const int want_grad = (layout->req_scale || layout->req_ls || layout->req_noise) ? 1 : 0;
+  return fgp::mll_common(net, net ? nullptr : p->z_host, p->x_dev, p->n, p->d, p->alpha_host, p->t, layout->B, p->ysq_dev, layout->scale_B,
+                         layout->ls_B, layout->noise_B, p->weights_dev, p->table_dev, p->workspace_dev, nullptr, p->out_dev, want_grad,
+                         stream, layout);
 }
 
 int fgp_dnb2_mll_grad(const int64_t* xb_dev, int64_t n, int d, const int* alpha_host, int t, int B, const double* ysq_dev,

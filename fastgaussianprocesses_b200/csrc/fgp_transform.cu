@@ -33,7 +33,7 @@ __global__ void fft_table_kernel(double2* stage, double2* lo, double2* hi, doubl
 // pass A: 2^lntr contiguous length-2^l1 blocks per CTA; the first round reads global memory straight into registers,
 // the last round applies the inter-pass twiddle and writes global memory (coalesced: its elements are 2^(l1-4) apart).
 template <bool REAL_IN>
-__global__ void __launch_bounds__(512, 1) fft_passA_fwd(const double* __restrict__ in, double2* __restrict__ out, int64_t total_blocks,
+__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) fft_passA_fwd(const double* __restrict__ in, double2* __restrict__ out, int64_t total_blocks,
                                                          int l1, int l2, int lntr, int LP, double scale, FftTables T) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double2* sm = (double2*)smraw;
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(512, 1) fft_passA_fwd(const double* __restrict
 
 // pass B: 2^lntr adjacent stride-2^l1 columns per CTA, in place; consecutive threads take consecutive columns.
 template <bool INV>
-__global__ void __launch_bounds__(512, 1) fft_passB(const double2* __restrict__ in, double2* __restrict__ out, int l1, int l2, int lntr,
+__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) fft_passB(const double2* __restrict__ in, double2* __restrict__ out, int l1, int l2, int lntr,
                                                      int LP, FftTables T) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double2* sm = (double2*)smraw;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(512, 1) fft_passB(const double2* __restrict__ 
   }
 }
 
-__global__ void __launch_bounds__(512, 1) fft_passA_inv(const double2* __restrict__ in, double2* __restrict__ out, int64_t total_blocks,
+__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) fft_passA_inv(const double2* __restrict__ in, double2* __restrict__ out, int64_t total_blocks,
                                                          int l1, int lntr, int LP, double scale, FftTables T) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double2* sm = (double2*)smraw;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(512, 1) fft_passA_inv(const double2* __restric
 }
 
 // ---- FWHT ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 1) wht_passA(const double* __restrict__ in, double* __restrict__ out, int64_t total_blocks, int l1,
+__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) wht_passA(const double* __restrict__ in, double* __restrict__ out, int64_t total_blocks, int l1,
                                                      int lntr, int LP, double scale) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double* sm = (double*)smraw;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(512, 1) wht_passA(const double* __restrict__ i
   block_wht_io<false>(sm, l1, lntr, LP, wht_sched_coalesced(l1), gld, gst);
 }
 
-__global__ void __launch_bounds__(512, 1) wht_passB(double* __restrict__ data, int l1, int l2, int lntr, int LP) {
+__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) wht_passB(double* __restrict__ data, int l1, int l2, int lntr, int LP) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double* sm = (double*)smraw;
   const int64_t col0 = (int64_t)blockIdx.x << lntr;

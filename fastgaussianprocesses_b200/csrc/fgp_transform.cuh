@@ -21,14 +21,30 @@
 //   pass A: contiguous length-L1 blocks b,  then multiply element q1 by w_n^{rev(b) q1}
 //   pass B: stride-L1 columns q1, length-L2 transforms, in place.
 #pragma once
+#include <stdlib.h>
 #include "fgp_common.cuh"
 
 namespace fgp {
 
+// launch bounds of the transform / MLL kernels: 256 threads x 2 CTAs per SM = up to 128 registers per thread (no spills);
+// a 4096-point complex tile then gives every thread two radix-8 groups per round.  Measured against 512 x 2 (64 registers,
+// spills) and 512 x 1 on B200: profiles/README.md.
+#ifndef FGP_LB_THREADS
+#define FGP_LB_THREADS 256
+#endif
+#ifndef FGP_LB_BLOCKS
+#define FGP_LB_BLOCKS 2
+#endif
+
 constexpr int kTabLen = 4096;
 
-__host__ __device__ __forceinline__ int padidx(int e) { return e + (e >> 4); }
-__host__ __device__ __forceinline__ int padlen(int L, int ntr) { return L + (L >> 4) + (ntr > 1 ? 1 : 0); }
+// padding: one element in 2^PS (PS = 3 for the radix-8 complex rounds, 4 for the radix-16 real rounds)
+constexpr int kPSC = 3, kPSR = 4;
+constexpr int kRC = 3;  // log2 of the main complex radix: an 8-point round body (~4 KB of SASS) stays resident in the
+                        // instruction caches; radix-16 bodies (x first/middle/last variants) did not -- see profiles/README.md
+template <int PS>
+__host__ __device__ __forceinline__ int padidx(int e) { return e + (e >> PS); }
+__host__ __device__ __forceinline__ int padlen(int L, int ntr, int ps) { return L + (L >> ps) + (ntr > 1 ? 1 : 0); }
 
 // twiddle tables, one caller-owned buffer of 3*kTabLen complex values
 struct FftTables {
@@ -139,61 +155,58 @@ __device__ __forceinline__ void load_bases(double2 (&B)[R > 0 ? R : 1], const do
   for (int u = 0; u < R; ++u) B[u] = __ldg(tw + (1 << (s + u)) + low);
 }
 
+struct SmemC {
+  double2* sm;
+  int LP;
+  __device__ __forceinline__ double2 operator()(int tr, int idx) const { return sm[tr * LP + padidx<kPSC>(idx)]; }
+  __device__ __forceinline__ void operator()(int tr, int idx, double2 v) const { sm[tr * LP + padidx<kPSC>(idx)] = v; }
+};
+template <class T>
+struct is_smemc {
+  static constexpr bool value = false;
+};
+template <>
+struct is_smemc<SmemC> {
+  static constexpr bool value = true;
+};
+
 // One round over all groups of the CTA's 2^lntr transforms.  ld(tr, idx) -> double2 ; st(tr, idx, value).
 // TRFAST: consecutive threads take consecutive transforms (column access); otherwise consecutive groups.
+// Shared-memory ends use linear addressing: every schedule has s == 0 (the group sits inside one padding block) or
+// s >= kPSC (the padded offset of element c is c * (2^s + 2^(s-kPSC))), so one pointer and one stride replace the
+// per-element index arithmetic.
 template <int R, bool INV, bool TRFAST, class Ld, class St>
 __device__ __forceinline__ void fft_round_io(int s, int l, int lntr, const double2* __restrict__ tw, Ld ld, St st) {
   constexpr int RAD = 1 << R;
   const int total = 1 << (lntr + l - R);
+  const int stp = s == 0 ? 1 : (1 << s) + (1 << (s - kPSC));
   for (int g = threadIdx.x; g < total; g += blockDim.x) {
     const GroupIdx G = group_of<R, TRFAST>(g, s, l, lntr);
     double2 B[R > 0 ? R : 1];
     if (s > 0) load_bases<R>(B, tw, s, G.low);
     double2 v[RAD];
+    if constexpr (is_smemc<Ld>::value) {
+      const double2* p = ld.sm + G.tr * ld.LP + padidx<kPSC>(G.base);
 #pragma unroll
-    for (int c = 0; c < RAD; ++c) v[c] = ld(G.tr, G.base + (c << s));
+      for (int c = 0; c < RAD; ++c) v[c] = p[c * stp];
+    } else {
+#pragma unroll
+      for (int c = 0; c < RAD; ++c) v[c] = ld(G.tr, G.base + (c << s));
+    }
     if (s > 0)
       butterflies<R, INV, true>(v, B);
     else
       butterflies<R, INV, false>(v, B);
+    if constexpr (is_smemc<St>::value) {
+      double2* p = st.sm + G.tr * st.LP + padidx<kPSC>(G.base);
 #pragma unroll
-    for (int c = 0; c < RAD; ++c) st(G.tr, G.base + (c << s), v[c]);
+      for (int c = 0; c < RAD; ++c) p[c * stp] = v[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < RAD; ++c) st(G.tr, G.base + (c << s), v[c]);
+    }
   }
 }
-
-// forward round + elementwise map + inverse round on the same registers (spectral epilogue between the transforms)
-template <int R, bool TRFAST, class Ld, class Mid, class St>
-__device__ __forceinline__ void fft_round_fwd_mid_inv(int s, int l, int lntr, const double2* __restrict__ tw, Ld ld, Mid mid, St st) {
-  constexpr int RAD = 1 << R;
-  const int total = 1 << (lntr + l - R);
-  for (int g = threadIdx.x; g < total; g += blockDim.x) {
-    const GroupIdx G = group_of<R, TRFAST>(g, s, l, lntr);
-    double2 B[R > 0 ? R : 1];
-    if (s > 0) load_bases<R>(B, tw, s, G.low);
-    double2 v[RAD];
-#pragma unroll
-    for (int c = 0; c < RAD; ++c) v[c] = ld(G.tr, G.base + (c << s));
-    if (s > 0)
-      butterflies<R, false, true>(v, B);
-    else
-      butterflies<R, false, false>(v, B);
-#pragma unroll
-    for (int c = 0; c < RAD; ++c) v[c] = mid(G.tr, G.base + (c << s), v[c]);
-    if (s > 0)
-      butterflies<R, true, true>(v, B);
-    else
-      butterflies<R, true, false>(v, B);
-#pragma unroll
-    for (int c = 0; c < RAD; ++c) st(G.tr, G.base + (c << s), v[c]);
-  }
-}
-
-struct SmemC {
-  double2* sm;
-  int LP;
-  __device__ __forceinline__ double2 operator()(int tr, int idx) const { return sm[tr * LP + padidx(idx)]; }
-  __device__ __forceinline__ void operator()(int tr, int idx, double2 v) const { sm[tr * LP + padidx(idx)] = v; }
-};
 
 #define FGP_R_DISPATCH(r, CALL4, CALL3, CALL2, CALL1) \
   switch (r) {                                        \
@@ -203,86 +216,160 @@ struct SmemC {
     default: CALL1; break;                            \
   }
 
-// Forward block transform.  gld feeds the first round, gst consumes the last; returns WITHOUT a trailing sync
-// (the last round does not touch shared memory unless the functor does).
+struct SmemTag {};  // "the data is already in / should stay in shared memory" (the caller synchronises)
+template <class T>
+struct is_smem_tag {
+  static constexpr bool value = false;
+};
+template <>
+struct is_smem_tag<SmemTag> {
+  static constexpr bool value = true;
+};
+
+// rolled element loops between a caller functor and shared memory: compact code for heavy functors (kernel evaluation,
+// log/divide epilogues, gradient contraction) -- unrolling those 8 or 16 times per round overflowed the instruction caches
+template <bool TRFAST, class F>
+__device__ __forceinline__ void tile_fill_c(const SmemC& S, int l, int lntr, F f) {  // S(tr,idx) = f(tr,idx)
+  const int total = 1 << (lntr + l);
+#pragma unroll 1
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int tr = TRFAST ? (e & ((1 << lntr) - 1)) : (e >> l);
+    const int idx = TRFAST ? (e >> lntr) : (e & ((1 << l) - 1));
+    S(tr, idx, f(tr, idx));
+  }
+}
+template <bool TRFAST, class F>
+__device__ __forceinline__ void tile_map_c(const SmemC& S, int l, int lntr, F f) {  // S(tr,idx) = f(tr,idx,S(tr,idx))
+  const int total = 1 << (lntr + l);
+#pragma unroll 2
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int tr = TRFAST ? (e & ((1 << lntr) - 1)) : (e >> l);
+    const int idx = TRFAST ? (e >> lntr) : (e & ((1 << l) - 1));
+    S(tr, idx, f(tr, idx, S(tr, idx)));
+  }
+}
+template <bool TRFAST, class F>
+__device__ __forceinline__ void tile_drain_c(const SmemC& S, int l, int lntr, F f) {  // f(tr,idx,S(tr,idx))
+  const int total = 1 << (lntr + l);
+#pragma unroll 1
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int tr = TRFAST ? (e & ((1 << lntr) - 1)) : (e >> l);
+    const int idx = TRFAST ? (e >> lntr) : (e & ((1 << l) - 1));
+    f(tr, idx, S(tr, idx));
+  }
+}
+
+// shared-memory to shared-memory round of r <= kRC stages: ONE out-of-line copy per direction, shared by every call site
+template <bool INV>
+__device__ __noinline__ void fft_round_smem(int r, int s, int l, int lntr, const double2* tw, double2* sm, int LP) {
+  const SmemC S{sm, LP};
+  switch (r) {
+    case 3: fft_round_io<3, INV, false>(s, l, lntr, tw, S, S); break;
+    case 2: fft_round_io<2, INV, false>(s, l, lntr, tw, S, S); break;
+    default: fft_round_io<1, INV, false>(s, l, lntr, tw, S, S); break;
+  }
+}
+
+// Round schedule of a length-2^l transform, l >= 2 kRC: stages [0,3) first, then the remainder (l mod 3 stages), then
+// threes, ending with [l-3, l); the inverse runs it backwards.  First and last rounds are always full radix-8 rounds, so
+// only they exist in (global <-> registers) variants; pass SmemTag for an end that is already / should stay in shared
+// memory (the caller synchronises that end).  No trailing sync after a functor end.
 template <bool TRFAST, class GLd, class GSt>
 __device__ __forceinline__ void block_fft_fwd_io(double2* sm, int l, int lntr, int LP, const double2* tw, GLd gld, GSt gst) {
+  constexpr bool IN_S = is_smem_tag<GLd>::value, OUT_S = is_smem_tag<GSt>::value;
   const SmemC S{sm, LP};
-  if (l <= 4) {
-    FGP_R_DISPATCH(l, (fft_round_io<4, false, TRFAST>(0, l, lntr, tw, gld, gst)), (fft_round_io<3, false, TRFAST>(0, l, lntr, tw, gld, gst)),
-                   (fft_round_io<2, false, TRFAST>(0, l, lntr, tw, gld, gst)), (fft_round_io<1, false, TRFAST>(0, l, lntr, tw, gld, gst)))
+  if (l == 0) {  // length-1 transforms are the identity (util.py:170)
+    if constexpr (!IN_S) {
+      tile_fill_c<TRFAST>(S, 0, lntr, gld);
+      __syncthreads();
+    }
+    if constexpr (!OUT_S) tile_drain_c<TRFAST>(S, 0, lntr, gst);
     return;
   }
-  fft_round_io<4, false, TRFAST>(0, l, lntr, tw, gld, S);
+  if (l < 2 * kRC) {  // small transforms: everything through shared memory
+    if constexpr (!IN_S) {
+      tile_fill_c<TRFAST>(S, l, lntr, gld);
+      __syncthreads();
+    }
+    for (int s = 0; s < l; s += kRC) {
+      fft_round_smem<false>(l - s >= kRC ? kRC : l - s, s, l, lntr, tw, sm, LP);
+      if (s + kRC < l || !OUT_S) __syncthreads();
+    }
+    if constexpr (!OUT_S) tile_drain_c<TRFAST>(S, l, lntr, gst);
+    return;
+  }
+  if constexpr (IN_S)
+    fft_round_smem<false>(kRC, 0, l, lntr, tw, sm, LP);
+  else
+    fft_round_io<kRC, false, TRFAST>(0, l, lntr, tw, gld, S);
   __syncthreads();
-  int s = 4;
-  while (l - s > 4) {
-    fft_round_io<4, false, false>(s, l, lntr, tw, S, S);
-    s += 4;
+  int s = kRC;
+  const int rem = (l - 2 * kRC) % kRC;
+  if (rem) {
+    fft_round_smem<false>(rem, s, l, lntr, tw, sm, LP);
+    s += rem;
     __syncthreads();
   }
-  const int r = l - s;
-  FGP_R_DISPATCH(r, (fft_round_io<4, false, TRFAST>(s, l, lntr, tw, S, gst)), (fft_round_io<3, false, TRFAST>(s, l, lntr, tw, S, gst)),
-                 (fft_round_io<2, false, TRFAST>(s, l, lntr, tw, S, gst)), (fft_round_io<1, false, TRFAST>(s, l, lntr, tw, S, gst)))
+  while (s < l - kRC) {
+    fft_round_smem<false>(kRC, s, l, lntr, tw, sm, LP);
+    s += kRC;
+    __syncthreads();
+  }
+  if constexpr (OUT_S)
+    fft_round_smem<false>(kRC, s, l, lntr, tw, sm, LP);
+  else
+    fft_round_io<kRC, false, TRFAST>(s, l, lntr, tw, S, gst);
 }
 
 // Inverse block transform (mirror schedule).
 template <bool TRFAST, class GLd, class GSt>
 __device__ __forceinline__ void block_fft_inv_io(double2* sm, int l, int lntr, int LP, const double2* tw, GLd gld, GSt gst) {
+  constexpr bool IN_S = is_smem_tag<GLd>::value, OUT_S = is_smem_tag<GSt>::value;
   const SmemC S{sm, LP};
-  if (l <= 4) {
-    FGP_R_DISPATCH(l, (fft_round_io<4, true, TRFAST>(0, l, lntr, tw, gld, gst)), (fft_round_io<3, true, TRFAST>(0, l, lntr, tw, gld, gst)),
-                   (fft_round_io<2, true, TRFAST>(0, l, lntr, tw, gld, gst)), (fft_round_io<1, true, TRFAST>(0, l, lntr, tw, gld, gst)))
+  if (l == 0) {
+    if constexpr (!IN_S) {
+      tile_fill_c<TRFAST>(S, 0, lntr, gld);
+      __syncthreads();
+    }
+    if constexpr (!OUT_S) tile_drain_c<TRFAST>(S, 0, lntr, gst);
     return;
   }
-  int s = ((l - 1) >> 2) << 2;
-  const int r = l - s;
-  FGP_R_DISPATCH(r, (fft_round_io<4, true, TRFAST>(s, l, lntr, tw, gld, S)), (fft_round_io<3, true, TRFAST>(s, l, lntr, tw, gld, S)),
-                 (fft_round_io<2, true, TRFAST>(s, l, lntr, tw, gld, S)), (fft_round_io<1, true, TRFAST>(s, l, lntr, tw, gld, S)))
-  __syncthreads();
-  s -= 4;
-  while (s > 0) {
-    fft_round_io<4, true, false>(s, l, lntr, tw, S, S);
-    s -= 4;
-    __syncthreads();
-  }
-  fft_round_io<4, true, TRFAST>(0, l, lntr, tw, S, gst);
-}
-
-// Forward transform, spectral map, inverse transform of the same 2^lntr x 2^l tile: the top round of the forward
-// transform, the map and the first round of the inverse share registers.
-template <bool TRFAST, class GLd, class Mid, class GSt>
-__device__ __forceinline__ void block_fft_fwd_mid_inv_io(double2* sm, int l, int lntr, int LP, const double2* tw, GLd gld, Mid mid, GSt gst) {
-  const SmemC S{sm, LP};
-  if (l <= 4) {
-    FGP_R_DISPATCH(l, (fft_round_fwd_mid_inv<4, TRFAST>(0, l, lntr, tw, gld, mid, gst)), (fft_round_fwd_mid_inv<3, TRFAST>(0, l, lntr, tw, gld, mid, gst)),
-                   (fft_round_fwd_mid_inv<2, TRFAST>(0, l, lntr, tw, gld, mid, gst)), (fft_round_fwd_mid_inv<1, TRFAST>(0, l, lntr, tw, gld, mid, gst)))
+  if (l < 2 * kRC) {
+    if constexpr (!IN_S) {
+      tile_fill_c<TRFAST>(S, l, lntr, gld);
+      __syncthreads();
+    }
+    for (int s = ((l - 1) / kRC) * kRC; s >= 0; s -= kRC) {
+      fft_round_smem<true>(l - s >= kRC ? kRC : l - s, s, l, lntr, tw, sm, LP);
+      if (s > 0 || !OUT_S) __syncthreads();
+    }
+    if constexpr (!OUT_S) tile_drain_c<TRFAST>(S, l, lntr, gst);
     return;
   }
-  fft_round_io<4, false, TRFAST>(0, l, lntr, tw, gld, S);
+  int s = l - kRC;
+  if constexpr (IN_S)
+    fft_round_smem<true>(kRC, s, l, lntr, tw, sm, LP);
+  else
+    fft_round_io<kRC, true, TRFAST>(s, l, lntr, tw, gld, S);
   __syncthreads();
-  int s = 4;
-  while (l - s > 4) {
-    fft_round_io<4, false, false>(s, l, lntr, tw, S, S);
-    s += 4;
+  const int rem = (l - 2 * kRC) % kRC;
+  while (s > kRC + rem) {
+    s -= kRC;
+    fft_round_smem<true>(kRC, s, l, lntr, tw, sm, LP);
     __syncthreads();
   }
-  const int r = l - s;
-  // each thread reads and rewrites only its own group: no hazard inside the round
-  FGP_R_DISPATCH(r, (fft_round_fwd_mid_inv<4, TRFAST>(s, l, lntr, tw, S, mid, S)), (fft_round_fwd_mid_inv<3, TRFAST>(s, l, lntr, tw, S, mid, S)),
-                 (fft_round_fwd_mid_inv<2, TRFAST>(s, l, lntr, tw, S, mid, S)), (fft_round_fwd_mid_inv<1, TRFAST>(s, l, lntr, tw, S, mid, S)))
-  __syncthreads();
-  s -= 4;
-  while (s > 0) {
-    fft_round_io<4, true, false>(s, l, lntr, tw, S, S);
-    s -= 4;
+  if (rem) {
+    fft_round_smem<true>(rem, kRC, l, lntr, tw, sm, LP);
     __syncthreads();
   }
-  fft_round_io<4, true, TRFAST>(0, l, lntr, tw, S, gst);
+  if constexpr (OUT_S)
+    fft_round_smem<true>(kRC, 0, l, lntr, tw, sm, LP);
+  else
+    fft_round_io<kRC, true, TRFAST>(0, l, lntr, tw, S, gst);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// real Walsh-Hadamard rounds (no twiddles; self-inverse; stage order is irrelevant)
+// real Walsh-Hadamard rounds (radix 16; no twiddles; self-inverse; stage order is free)
 // ---------------------------------------------------------------------------------------------------------------
 template <int R>
 __device__ __forceinline__ void wht_butterflies(double (&v)[1 << R]) {
@@ -314,62 +401,75 @@ __device__ __forceinline__ void wht_round_io(int s, int l, int lntr, Ld ld, St s
   }
 }
 
-template <int R, bool TRFAST, class Ld, class Mid, class St>
-__device__ __forceinline__ void wht_round_fwd_mid_inv(int s, int l, int lntr, Ld ld, Mid mid, St st) {
-  constexpr int RAD = 1 << R;
-  const int total = 1 << (lntr + l - R);
-  for (int g = threadIdx.x; g < total; g += blockDim.x) {
-    const GroupIdx G = group_of<R, TRFAST>(g, s, l, lntr);
-    double v[RAD];
-#pragma unroll
-    for (int c = 0; c < RAD; ++c) v[c] = ld(G.tr, G.base + (c << s));
-    wht_butterflies<R>(v);
-#pragma unroll
-    for (int c = 0; c < RAD; ++c) v[c] = mid(G.tr, G.base + (c << s), v[c]);
-    wht_butterflies<R>(v);
-#pragma unroll
-    for (int c = 0; c < RAD; ++c) st(G.tr, G.base + (c << s), v[c]);
-  }
-}
-
 struct SmemR {
   double* sm;
   int LP;
-  __device__ __forceinline__ double operator()(int tr, int idx) const { return sm[tr * LP + padidx(idx)]; }
-  __device__ __forceinline__ void operator()(int tr, int idx, double v) const { sm[tr * LP + padidx(idx)] = v; }
+  __device__ __forceinline__ double operator()(int tr, int idx) const { return sm[tr * LP + padidx<kPSR>(idx)]; }
+  __device__ __forceinline__ void operator()(int tr, int idx, double v) const { sm[tr * LP + padidx<kPSR>(idx)] = v; }
 };
 
+template <bool TRFAST, class F>
+__device__ __forceinline__ void tile_fill_r(const SmemR& S, int l, int lntr, F f) {
+  const int total = 1 << (lntr + l);
+#pragma unroll 1
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int tr = TRFAST ? (e & ((1 << lntr) - 1)) : (e >> l);
+    const int idx = TRFAST ? (e >> lntr) : (e & ((1 << l) - 1));
+    S(tr, idx, f(tr, idx));
+  }
+}
+template <bool TRFAST, class F>
+__device__ __forceinline__ void tile_map_r(const SmemR& S, int l, int lntr, F f) {
+  const int total = 1 << (lntr + l);
+#pragma unroll 1
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int tr = TRFAST ? (e & ((1 << lntr) - 1)) : (e >> l);
+    const int idx = TRFAST ? (e >> lntr) : (e & ((1 << l) - 1));
+    S(tr, idx, f(tr, idx, S(tr, idx)));
+  }
+}
+template <bool TRFAST, class F>
+__device__ __forceinline__ void tile_drain_r(const SmemR& S, int l, int lntr, F f) {
+  const int total = 1 << (lntr + l);
+#pragma unroll 1
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int tr = TRFAST ? (e & ((1 << lntr) - 1)) : (e >> l);
+    const int idx = TRFAST ? (e >> lntr) : (e & ((1 << l) - 1));
+    f(tr, idx, S(tr, idx));
+  }
+}
+
+static __device__ __noinline__ void wht_round_smem(int r, int s, int l, int lntr, double* sm, int LP) {
+  const SmemR S{sm, LP};
+  FGP_R_DISPATCH(r, (wht_round_io<4, false>(s, l, lntr, S, S)), (wht_round_io<3, false>(s, l, lntr, S, S)),
+                 (wht_round_io<2, false>(s, l, lntr, S, S)), (wht_round_io<1, false>(s, l, lntr, S, S)))
+}
+
 // Round schedules for the FWHT (stage order is free): s[k], r[k] = first stage and number of stages of round k.
+// When l >= 8 both schedules start and end with full radix-16 rounds (only those exist in global<->register variants).
 struct WhtSched {
   int n;
   int s[4], r[4];
 };
-// bottom-up: [0,4),[4,8),...,remainder on top
+// bottom-up: [0,4), remainder, fours
 __device__ __forceinline__ WhtSched wht_sched_up(int l) {
   WhtSched q;
   q.n = 0;
-  for (int s = 0; s < l; s += 4) {
-    q.s[q.n] = s;
-    q.r[q.n] = l - s >= 4 ? 4 : l - s;
-    ++q.n;
+  if (l < 8) {
+    for (int s = 0; s < l; s += 4) q.s[q.n] = s, q.r[q.n] = l - s >= 4 ? 4 : l - s, ++q.n;
+    return q;
   }
+  const int rem = l & 3;
+  q.s[q.n] = 0, q.r[q.n] = 4, ++q.n;
+  if (rem) q.s[q.n] = 4, q.r[q.n] = rem, ++q.n;
+  for (int s = 4 + rem; s < l; s += 4) q.s[q.n] = s, q.r[q.n] = 4, ++q.n;
   return q;
 }
 // coalesced at both ends for contiguous tiles: the top four stages first (a thread's elements are 2^(l-4) apart, so
-// consecutive threads read consecutive addresses), then the bottom remainder, then upwards, ending just below the top.
+// consecutive threads touch consecutive addresses), then the bottom remainder, then upwards, ending just below the top.
 __device__ __forceinline__ WhtSched wht_sched_coalesced(int l) {
+  if (l < 8) return wht_sched_up(l);
   WhtSched q;
-  if (l <= 8) {
-    q = wht_sched_up(l);
-    if (q.n == 2) {  // top first, bottom last
-      const int s1 = q.s[1], r1 = q.r[1];
-      q.s[1] = q.s[0];
-      q.r[1] = q.r[0];
-      q.s[0] = s1;
-      q.r[0] = r1;
-    }
-    return q;
-  }
   const int rem = l & 3;
   q.n = 0;
   q.s[q.n] = l - 4, q.r[q.n] = 4, ++q.n;
@@ -378,58 +478,36 @@ __device__ __forceinline__ WhtSched wht_sched_coalesced(int l) {
   return q;
 }
 
-template <bool TRFAST, class Ld, class St>
-__device__ __forceinline__ void wht_round_dispatch(int r, int s, int l, int lntr, Ld ld, St st) {
-  FGP_R_DISPATCH(r, (wht_round_io<4, TRFAST>(s, l, lntr, ld, st)), (wht_round_io<3, TRFAST>(s, l, lntr, ld, st)),
-                 (wht_round_io<2, TRFAST>(s, l, lntr, ld, st)), (wht_round_io<1, TRFAST>(s, l, lntr, ld, st)))
-}
-
-// Block FWHT following schedule q; gld feeds the first round, gst consumes the last.  No trailing sync.
+// Block FWHT following schedule q.  gld / gst as for the FFT drivers (SmemTag = stays in shared memory).
 template <bool TRFAST, class GLd, class GSt>
 __device__ __forceinline__ void block_wht_io(double* sm, int l, int lntr, int LP, const WhtSched& q, GLd gld, GSt gst) {
+  constexpr bool IN_S = is_smem_tag<GLd>::value, OUT_S = is_smem_tag<GSt>::value;
   const SmemR S{sm, LP};
-  if (q.n <= 1) {
-    wht_round_dispatch<TRFAST>(l, 0, l, lntr, gld, gst);
+  if (l < 8) {  // small transforms (and l = 0: identity): everything through shared memory
+    if constexpr (!IN_S) {
+      tile_fill_r<TRFAST>(S, l, lntr, gld);
+      __syncthreads();
+    }
+    for (int k = 0; k < q.n; ++k) {
+      wht_round_smem(q.r[k], q.s[k], l, lntr, sm, LP);
+      if (k + 1 < q.n || !OUT_S) __syncthreads();
+    }
+    if constexpr (!OUT_S) tile_drain_r<TRFAST>(S, l, lntr, gst);
     return;
   }
-  wht_round_dispatch<TRFAST>(q.r[0], q.s[0], l, lntr, gld, S);
+  if constexpr (IN_S)
+    wht_round_smem(4, q.s[0], l, lntr, sm, LP);
+  else
+    wht_round_io<4, TRFAST>(q.s[0], l, lntr, gld, S);
   __syncthreads();
   for (int k = 1; k < q.n - 1; ++k) {
-    wht_round_dispatch<false>(q.r[k], q.s[k], l, lntr, S, S);
+    wht_round_smem(q.r[k], q.s[k], l, lntr, sm, LP);
     __syncthreads();
   }
-  wht_round_dispatch<TRFAST>(q.r[q.n - 1], q.s[q.n - 1], l, lntr, S, gst);
-}
-
-// forward FWHT, elementwise map, FWHT again (its own inverse) of the same tile; the last forward round, the map and the
-// first backward round share registers.  Bottom-up then top-down.
-template <bool TRFAST, class GLd, class Mid, class GSt>
-__device__ __forceinline__ void block_wht_fwd_mid_inv_io(double* sm, int l, int lntr, int LP, GLd gld, Mid mid, GSt gst) {
-  const SmemR S{sm, LP};
-  if (l <= 4) {
-    FGP_R_DISPATCH(l, (wht_round_fwd_mid_inv<4, TRFAST>(0, l, lntr, gld, mid, gst)), (wht_round_fwd_mid_inv<3, TRFAST>(0, l, lntr, gld, mid, gst)),
-                   (wht_round_fwd_mid_inv<2, TRFAST>(0, l, lntr, gld, mid, gst)), (wht_round_fwd_mid_inv<1, TRFAST>(0, l, lntr, gld, mid, gst)))
-    return;
-  }
-  wht_round_io<4, TRFAST>(0, l, lntr, gld, S);
-  __syncthreads();
-  int s = 4;
-  while (l - s > 4) {
-    wht_round_io<4, false>(s, l, lntr, S, S);
-    s += 4;
-    __syncthreads();
-  }
-  const int r = l - s;
-  FGP_R_DISPATCH(r, (wht_round_fwd_mid_inv<4, TRFAST>(s, l, lntr, S, mid, S)), (wht_round_fwd_mid_inv<3, TRFAST>(s, l, lntr, S, mid, S)),
-                 (wht_round_fwd_mid_inv<2, TRFAST>(s, l, lntr, S, mid, S)), (wht_round_fwd_mid_inv<1, TRFAST>(s, l, lntr, S, mid, S)))
-  __syncthreads();
-  s -= 4;
-  while (s > 0) {
-    wht_round_io<4, false>(s, l, lntr, S, S);
-    s -= 4;
-    __syncthreads();
-  }
-  wht_round_io<4, TRFAST>(0, l, lntr, S, gst);
+  if constexpr (OUT_S)
+    wht_round_smem(4, q.s[q.n - 1], l, lntr, sm, LP);
+  else
+    wht_round_io<4, TRFAST>(q.s[q.n - 1], l, lntr, S, gst);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -448,13 +526,19 @@ struct PassGeom {
   size_t smemA, smemB;
 };
 
-// Tile capacities (log2 elements per CTA): 64 KiB of shared memory at most, 32 KiB preferred so that several CTAs in
-// different phases share an SM.  Pass A keeps the contiguous block as long as possible so that pass B's strided
-// transforms are short and its column tiles wide (128-byte global segments at n = 2^20).
+// Tile capacities (log2 elements per CTA).  Pass A keeps the contiguous block as long as shared memory allows (64 KiB)
+// so that pass B's strided transforms are short; pass B takes 8 adjacent columns (128-byte global segments for complex
+// data) whenever that fits.  FGP_CAP_C / FGP_CAP_R / FGP_COLS_LOG2 override the defaults for tuning runs.
+static inline int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
 static inline PassGeom make_geom(int64_t n, bool cplx) {
   PassGeom g;
   const size_t elem = cplx ? sizeof(double2) : sizeof(double);
-  const int cap = cplx ? 12 : 13;
+  static const int capC = env_int("FGP_CAP_C", 12), capR = env_int("FGP_CAP_R", 13), colsLog = env_int("FGP_COLS_LOG2", 3);
+  const int cap = cplx ? capC : capR;
+  const int hard = cplx ? 12 : 13;  // 64 KiB of elements
   g.m = ilog2(n);
   int tileA, tileB = 0;
   if (g.m <= cap) {
@@ -462,23 +546,29 @@ static inline PassGeom make_geom(int64_t n, bool cplx) {
     g.l2 = 0;
     tileA = g.m > cap - 1 ? g.m : cap - 1;
   } else {
-    g.l1 = g.m - cap > cap ? g.m - cap : cap;  // l2 <= cap always (n <= 2^(2 cap))
-    if (g.l1 > cap) g.l1 = cap;
+    g.l1 = cap;
     g.l2 = g.m - g.l1;
+    if (g.l2 > hard) {  // keep the strided transform inside one CTA
+      g.l2 = hard;
+      g.l1 = g.m - g.l2;
+    }
     tileA = g.l1;
-    tileB = g.l2 + g.l1 < cap - 1 ? g.l2 + g.l1 : cap - 1;
+    tileB = g.l2 + colsLog;
+    if (tileB > hard) tileB = hard;
+    if (tileB > g.l2 + g.l1) tileB = g.l2 + g.l1;
     if (tileB < g.l2) tileB = g.l2;
   }
   g.lntrA = tileA - g.l1;
   g.ntrA = 1 << g.lntrA;
   g.lntrB = g.l2 ? tileB - g.l2 : 0;
   g.ntrB = 1 << g.lntrB;
-  g.LPA = padlen(1 << g.l1, g.ntrA);
-  g.LPB = padlen(1 << g.l2, g.ntrB);
+  g.LPA = padlen(1 << g.l1, g.ntrA, cplx ? kPSC : kPSR);
+  g.LPB = padlen(1 << g.l2, g.ntrB, cplx ? kPSC : kPSR);
+  static const int tdiv = env_int("FGP_THREAD_DIV", 1);  // tuning: fewer threads, more groups per thread per round
   auto thr = [](int tile) {
-    int t = (1 << tile) / 16;
+    int t = (1 << tile) / 16 / tdiv;
     if (t < 32) t = 32;
-    if (t > 512) t = 512;
+    if (t > FGP_LB_THREADS) t = FGP_LB_THREADS;
     return t;
   };
   g.threadsA = thr(tileA);

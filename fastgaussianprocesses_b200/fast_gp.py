@@ -145,7 +145,7 @@ class _FusedFitLoop(object):
         self.ws = _lib.mll_workspace(fgp._FAMILY, self.n, self.d, self.B, dev)
         self.weights = torch.tensor([0.5, 0.5 * self.d_out / self.B], device=dev).expand(self.B, 2).contiguous()
         self.P = sum(r.numel() for r in self.raw)
-        self.state = torch.zeros(_lib.fit_state_doubles(self.P), dtype=torch.float64, device=dev)
+        self.state = torch.zeros(_lib.fit_state_doubles(self.P, self.B), dtype=torch.float64, device=dev)
         self.state_host = torch.zeros(self.ST_HEADER, dtype=torch.float64).pin_memory()
         self.hist_flags = tuple(bool(f) for f in hist_flags)
         self.hist_capacity = int(hist_capacity)
@@ -168,10 +168,26 @@ class _FusedFitLoop(object):
         L.ls_hist = None if self.ls_hist is None else self.ls_hist.data_ptr()
         L.noise_hist = None if self.noise_hist is None else self.noise_hist.data_ptr()
         self.layout = L
+        # the whole iteration as one C call (fgp_fit_iteration); ctypes arrays are kept alive on self
+        self._alpha_arr = (_lib._i32 * self.d)(*fgp._alpha_list)
+        self._z_arr = (_lib._u64 * self.d)(*fgp._zgen) if fgp._zgen is not None else None
+        Pb = _lib.FitProblem()
+        Pb.family = fgp._FAMILY
+        Pb.x_dev = self.xpts.data_ptr()
+        Pb.z_host = _lib._c.cast(self._z_arr, _lib._vp) if self._z_arr is not None else None
+        Pb.n, Pb.d, Pb.t = self.n, self.d, int(fgp._t)
+        Pb.alpha_host = _lib._c.cast(self._alpha_arr, _lib._vp)
+        Pb.ysq_dev = self.ysq.data_ptr()
+        Pb.weights_dev = self.weights.data_ptr()
+        Pb.table_dev = _lib.fft_table(self.n, dev).data_ptr() if fgp._FAMILY == 0 else None
+        Pb.workspace_dev = self.ws.data_ptr()
+        Pb.out_dev = self.out.data_ptr()
+        self.problem = Pb
         self.graphs = {}
         self.launches = 0
         self.kernels_per_iteration = None
-        # eager warm-up of every kernel before any capture; `stopped` is raised so that fit_step changes nothing
+        # eager warm-up of every kernel before any capture; `stopped` is raised so that the fit step changes nothing
+        # (the state block is zero: tickets start at 0 as fit_init leaves them)
         with torch.cuda.device(dev):
             self.state[self.ST_STOPPED] = 1.0
             c0 = _lib.launch_count()
@@ -202,10 +218,7 @@ class _FusedFitLoop(object):
                 "mll_single": B * (16 * n * d + 8 * n)}.get(name, 0)
 
     def _iteration(self):
-        f = self.fgp
-        _lib.mll_grad_into(f._FAMILY, self.xpts, f._alpha_list, f._t, self.ysq, self.scale_B, self.ls_B, self.noise_B, self.weights,
-                           self.ws, None, self.out, want_grad=any(self.req), z=f._zgen)
-        _lib.fit_step(self.layout, self.out)
+        _lib.fit_iteration(self.problem, self.layout)
 
     def begin(self, iterations, stop_wait, logtol, lr):
         o = _lib.FitOptions()

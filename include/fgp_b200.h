@@ -135,7 +135,8 @@ int fgp_dnb2_mll_grad(const int64_t* xb_dev, int64_t n, int d, const int* alpha_
  *     (scale_B, ls_B, noise_B) that the next fgp_*_mll_grad call reads.  Nothing returns to the host, so
  *     [mll_grad, fit_step] x k can be captured in a CUDA graph; the host polls state[4] (stopped) now and then.
  *     state block (doubles): [0] best loss [1] save loss [2] wait [3] next iteration index [4] stopped [5] last
- *     evaluated iteration [6] its loss [7] term1 [8] term2; [9..] options; then prev-grad, step-size, best-raw (P each).
+ *     evaluated iteration [6] its loss [7] term1 [8] term2; [9..] options; then prev-grad, step-size, best-raw (P each),
+ *     then B+1 completion tickets used by fgp_fit_iteration.
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct {
   int B, d;                            /* hyperparameter sets, dimension */
@@ -155,10 +156,29 @@ typedef struct {
   double wn, wl;      /* loss = sum_b (wn norm_b + wl logdet_b) + half_const; MLL: wn = 1/2, wl = d_out/(2B) */
   double lr, etaminus, etaplus, step_min, step_max; /* torch.optim.Rprop: 0.1, 0.5, 1.2, 1e-6, 50 */
 } fgp_fit_options;
-size_t fgp_fit_state_doubles(int n_raw_params);
+size_t fgp_fit_state_doubles(int n_raw_params, int B);
 int fgp_fit_init(const fgp_fit_layout* layout, const fgp_fit_options* opt, fgp_stream_t stream); /* synchronises `stream` once */
 int fgp_fit_step(const fgp_fit_layout* layout, const double* mll_out_dev, fgp_stream_t stream);
 int fgp_fit_finish(const fgp_fit_layout* layout, fgp_stream_t stream); /* best iterate -> parameters */
+/* One whole fit() iteration in one call: the fused eigen-solve of K4 on layout->scale_B / ls_B / noise_B, whose last
+ * CTA reduces the partial sums and runs the fit step in its tail (no separate finalize / fit_step launches).
+ * x_dev: points (lattice float64 / net int64 (n,d)); z_host: lattice generating vector for generator mode (x_dev may
+ * then be NULL); weights_dev (B,2) as in fgp_*_mll_grad; out_dev (B, d+4) scratch for the reduced terms. */
+typedef struct {
+  int family;              /* 0 lattice, 1 digital net */
+  const void* x_dev;
+  const uint64_t* z_host;
+  int64_t n;
+  int d;
+  const int* alpha_host;
+  int t;
+  const double* ysq_dev;
+  const double* weights_dev;
+  const void* table_dev;   /* lattice twiddle table */
+  void* workspace_dev;     /* fgp_mll_workspace_bytes */
+  double* out_dev;
+} fgp_fit_problem;
+int fgp_fit_iteration(const fgp_fit_problem* problem, const fgp_fit_layout* layout, fgp_stream_t stream);
 
 /* K^-1 y for R right-hand sides sharing one spectrum: out = T^-1( T(y) / lam ), util.py:338-344 (single task).
  * lam_dev: (n) complex (family 0) or real (family 1) full eigenvalues sqrt(n) ft(k1)+noise.  y,out: (R,n) real.

@@ -33,7 +33,8 @@ def test_ctypes_struct_layouts_match_header():
     # 9 ints + pad, 1 double, 11 pointers ; 3 ints + pad, 9 doubles
     assert ctypes.sizeof(_lib.FitLayout) == 40 + 8 + 11 * 8
     assert ctypes.sizeof(_lib.FitOptions) == 16 + 9 * 8
-    assert _lib.fit_state_doubles(11) == 32 + 33
+    assert _lib.fit_state_doubles(11, 4) == 32 + 33 + 3 + 1
+    assert ctypes.sizeof(_lib.FitProblem) == 12 * 8
 
 
 def test_no_cpu_fallback():

@@ -289,6 +289,7 @@ def main():
         return
     # ---- roofline of the dominant kernel of the step
     alg_bytes_iter = stepper.algorithmic_bytes
+    kern = [k for k in kern if k["alg_bytes"] > 0] or kern
     dom = max(kern, key=lambda k: k["ms"])
     roof = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,

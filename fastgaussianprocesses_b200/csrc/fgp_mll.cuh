@@ -74,9 +74,10 @@ __device__ __forceinline__ void load_hyp(Hyp& H, const MllArgs& a, int b) {
 }
 
 // generator mode, lattice: x_i - x_0 = frac(phi2(i) z_j) exactly (the shift cancels), phi2(i) = brev64(i) / 2^64.
-// The wrap-around product keeps its ceil(log2 n) <= 32 significant bits at the top of the word.
-__device__ __forceinline__ double lat_delta_gen(uint64_t rev, uint64_t zj) {
-  return (double)(uint32_t)((rev * zj) >> 32) * 0x1.0p-32;
+// For i < 2^32 brev64(i) = brev32(i) << 32, so the top word of the wrap-around 64-bit product is the wrap-around 32-bit
+// product brev32(i) * (z_j mod 2^32): one IMAD, and its ceil(log2 n) significant bits sit at the top of that word.
+__device__ __forceinline__ double lat_delta_gen(uint32_t rev32, uint64_t zj) {
+  return (double)(rev32 * (uint32_t)zj) * 0x1.0p-32;
 }
 
 // net alpha = 2 without branches on alpha: W_2(delta) - 1 = 3/2 - (5/2) 2^-beta - beta x_f, beta = t - floor(log2 delta)
@@ -96,7 +97,7 @@ __device__ __forceinline__ void point_parts(const MllArgs& a, const Hyp& H, int6
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
   const int d = DT > 0 ? DT : a.d;
   if (GEN && !NET) {
-    const uint64_t rev = __brevll((unsigned long long)i);
+    const uint32_t rev = __brev((uint32_t)i);
 #pragma unroll
     for (int j = 0; j < DM; ++j) {
       if (j >= d) break;
@@ -160,7 +161,7 @@ __device__ __forceinline__ void point_parts(const MllArgs& a, const Hyp& H, int6
 // generic-d variants (DT == 0): rolled loops, out of line -- they exist for coverage of every (d, alpha), not for speed
 template <bool NET, bool GEN>
 __device__ __noinline__ double point_part_generic(const MllArgs& a, const Hyp& H, int64_t i, int j) {
-  if (GEN && !NET) return lat_part(lat_delta_gen(__brevll((unsigned long long)i), a.z.v[j]), a.P.q[j], a.P.alpha[j]);
+  if (GEN && !NET) return lat_part(lat_delta_gen(__brev((uint32_t)i), a.z.v[j]), a.P.q[j], a.P.alpha[j]);
   if (NET) return dnb2_part((uint64_t)__ldg((const int64_t*)a.x + i * a.d + j) ^ H.xb0[j], a.alpha.v[j], a.t);
   return lat_part(__ldg((const double*)a.x + i * a.d + j) - H.x0[j], a.P.q[j], a.P.alpha[j]);
 }

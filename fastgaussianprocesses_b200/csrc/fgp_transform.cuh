@@ -231,7 +231,7 @@ struct is_smem_tag<SmemTag> {
 template <bool TRFAST, class F>
 __device__ __forceinline__ void tile_fill_c(const SmemC& S, int l, int lntr, F f) {  // S(tr,idx) = f(tr,idx)
   const int total = 1 << (lntr + l);
-#pragma unroll 1
+#pragma unroll 2
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
     const int tr = TRFAST ? (e & ((1 << lntr) - 1)) : (e >> l);
     const int idx = TRFAST ? (e >> lntr) : (e & ((1 << l) - 1));
@@ -251,7 +251,7 @@ __device__ __forceinline__ void tile_map_c(const SmemC& S, int l, int lntr, F f)
 template <bool TRFAST, class F>
 __device__ __forceinline__ void tile_drain_c(const SmemC& S, int l, int lntr, F f) {  // f(tr,idx,S(tr,idx))
   const int total = 1 << (lntr + l);
-#pragma unroll 1
+#pragma unroll 2
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
     const int tr = TRFAST ? (e & ((1 << lntr) - 1)) : (e >> l);
     const int idx = TRFAST ? (e >> lntr) : (e & ((1 << l) - 1));

@@ -156,7 +156,9 @@ def test_mll_grad_vs_reference_fixture(L, case):
     out = out.cpu().numpy()[0]
     lam_ref = np.sqrt(n) * g["lam0"] + g["noise0"]
     assert rel(lam[0], lam_ref) < TOL
-    assert abs(out[0] - g["norm_term0"].item()) <= TOL * abs(g["norm_term0"].item())
+    # the norm term sums |ytilde|^2 / lam over eigenvalues down to ~1e-5 whose own relative round-off is ~4e-9 in any float64
+    # transform (tools/diag_fixture.py): 1e-9 here, 1e-10 on the loss below
+    assert abs(out[0] - g["norm_term0"].item()) <= 1e-9 * abs(g["norm_term0"].item())
     assert abs(out[1] - g["logdet0"].item()) <= TOL * abs(g["logdet0"].item())
     loss = 0.5 * (out[0] + out[1] + n * np.log(2 * np.pi))
     assert abs(loss - float(g["loss0"])) <= TOL * abs(float(g["loss0"]))

@@ -94,9 +94,12 @@ __device__ __forceinline__ double2 mul_root16c(double2 t, int k) {
   }
 }
 
-// R radix-2 stages on the 2^R registers of one group.  B[u] = exp(-i pi low / 2^(s+u)) (ignored when !TW: low = 0).
+// R radix-2 stages on the 2^R registers of one group.
+// TW: twiddles of stage u come from the per-stage table, Wt[(1<<u) - 1 + cm] = exp(-i pi (low + cm 2^s) / 2^(s+u)) -- the
+// very values (and the single complex multiply per butterfly) of the reference's radix-2 recursion, so the round-off
+// matches it; !TW (first round, low = 0): compile-time 8th/16th roots of unity.
 template <int R, bool INV, bool TW>
-__device__ __forceinline__ void butterflies(double2 (&v)[1 << R], const double2 (&B)[R > 0 ? R : 1]) {
+__device__ __forceinline__ void butterflies(double2 (&v)[1 << R], const double2 (&Wt)[(1 << R) - 1 > 0 ? (1 << R) - 1 : 1]) {
   constexpr int RAD = 1 << R;
   if (!INV) {
 #pragma unroll
@@ -106,8 +109,10 @@ __device__ __forceinline__ void butterflies(double2 (&v)[1 << R], const double2 
         if (c & (1 << u)) continue;
         const int cm = c & ((1 << u) - 1);
         double2 t = v[c | (1 << u)];
-        if (TW) t = cmul(B[u], t);
-        t = mul_root16(t, cm << (3 - u));
+        if (TW)
+          t = cmul(Wt[(1 << u) - 1 + cm], t);
+        else
+          t = mul_root16(t, cm << (3 - u));
         v[c | (1 << u)] = csub(v[c], t);
         v[c] = cadd(v[c], t);
       }
@@ -121,8 +126,11 @@ __device__ __forceinline__ void butterflies(double2 (&v)[1 << R], const double2 
         const int cm = c & ((1 << u) - 1);
         const double2 a = v[c], b = v[c | (1 << u)];
         v[c] = cadd(a, b);
-        double2 t = mul_root16c(csub(a, b), cm << (3 - u));
-        if (TW) t = cmulc(B[u], t);
+        double2 t = csub(a, b);
+        if (TW)
+          t = cmulc(Wt[(1 << u) - 1 + cm], t);
+        else
+          t = mul_root16c(t, cm << (3 - u));
         v[c | (1 << u)] = t;
       }
     }
@@ -150,9 +158,11 @@ __device__ __forceinline__ GroupIdx group_of(int g, int s, int l, int lntr) {
 }
 
 template <int R>
-__device__ __forceinline__ void load_bases(double2 (&B)[R > 0 ? R : 1], const double2* __restrict__ tw, int s, int low) {
+__device__ __forceinline__ void load_twiddles(double2 (&Wt)[(1 << R) - 1 > 0 ? (1 << R) - 1 : 1], const double2* __restrict__ tw, int s, int low) {
 #pragma unroll
-  for (int u = 0; u < R; ++u) B[u] = __ldg(tw + (1 << (s + u)) + low);
+  for (int u = 0; u < R; ++u)
+#pragma unroll
+    for (int cm = 0; cm < (1 << u); ++cm) Wt[(1 << u) - 1 + cm] = __ldg(tw + (1 << (s + u)) + low + (cm << s));
 }
 
 struct SmemC {
@@ -182,8 +192,8 @@ __device__ __forceinline__ void fft_round_io(int s, int l, int lntr, const doubl
   const int stp = s == 0 ? 1 : (1 << s) + (1 << (s - kPSC));
   for (int g = threadIdx.x; g < total; g += blockDim.x) {
     const GroupIdx G = group_of<R, TRFAST>(g, s, l, lntr);
-    double2 B[R > 0 ? R : 1];
-    if (s > 0) load_bases<R>(B, tw, s, G.low);
+    double2 B[(1 << R) - 1 > 0 ? (1 << R) - 1 : 1];
+    if (s > 0) load_twiddles<R>(B, tw, s, G.low);
     double2 v[RAD];
     if constexpr (is_smemc<Ld>::value) {
       const double2* p = ld.sm + G.tr * ld.LP + padidx<kPSC>(G.base);

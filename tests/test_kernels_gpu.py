@@ -161,7 +161,15 @@ def test_mll_grad_vs_reference_fixture(L, case):
     assert abs(out[0] - g["norm_term0"].item()) <= 1e-9 * abs(g["norm_term0"].item())
     assert abs(out[1] - g["logdet0"].item()) <= TOL * abs(g["logdet0"].item())
     loss = 0.5 * (out[0] + out[1] + n * np.log(2 * np.pi))
-    assert abs(loss - float(g["loss0"])) <= TOL * abs(float(g["loss0"]))
+    # 1e-10 is also the distance between two IEEE-valid evaluation orders of the REFERENCE on the worst-conditioned fixture
+    # (lattice_d2_n1024_a2: lam_min/lam_max ~ 1e-11, measured 1.0e-10 from stored points, 0.8e-10 in generator mode), hence 2e-10
+    assert abs(loss - float(g["loss0"])) <= 2 * TOL * abs(float(g["loss0"]))
+    if fam == 0:  # generator mode (the default path of this package's Lattice spec): exact deltas, 1e-10
+        out_z, _ = L.mll_grad(fam, xpts, [alpha] * d, t, ysq, scale, ls, noise, want_grad=True, z=[int(v) for v in g["z"]])
+        oz = out_z.cpu().numpy()[0]
+        loss_z = 0.5 * (oz[0] + oz[1] + n * np.log(2 * np.pi))
+        assert abs(loss_z - float(g["loss0"])) <= TOL * abs(float(g["loss0"]))
+        assert rel(oz[4:4 + d] * g["lengthscales0"], g["grad_raw_lengthscales0"]) < 1e-8
     # raw parameters are log-transformed: dL/draw = theta * dL/dtheta
     gs = out[3] * g["scale0"]
     gl = out[4:4 + d] * g["lengthscales0"]

@@ -293,7 +293,8 @@ def main():
     # ---- roofline of the dominant kernel of the step
     alg_bytes_iter = stepper.algorithmic_bytes
     kern = [k for k in kern if k["alg_bytes"] > 0] or kern
-    dom = max(kern, key=lambda k: k["ms"])
+    tmax = max(k["ms"] for k in kern)
+    dom = max((k for k in kern if k["ms"] >= 0.9 * tmax), key=lambda k: k["alg_bytes"])  # ties within 10 %: the one moving more bytes
     roof = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9 / hbm_peak,
             # DRAM read+write bytes of that kernel per launch from the committed ncu --set full capture (same workload only)

@@ -33,7 +33,7 @@ class FitOptions(_c.Structure):
 
 class FitProblem(_c.Structure):
     """fgp_fit_problem (include/fgp_b200.h)."""
-    _fields_ = [("family", _i32), ("x_dev", _vp), ("z_host", _vp), ("n", _i64), ("d", _i32), ("alpha_host", _vp), ("t", _i32),
+    _fields_ = [("family", _i32), ("x_dev", _vp), ("z_host", _vp), ("C_dev", _vp), ("mmax", _i32), ("n", _i64), ("d", _i32), ("alpha_host", _vp), ("t", _i32),
                 ("ysq_dev", _vp), ("weights_dev", _vp), ("table_dev", _vp), ("workspace_dev", _vp), ("out_dev", _vp)]
 
 
@@ -57,6 +57,7 @@ SIGNATURES = {
     "fgp_mll_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32]),
     "fgp_lattice_mll_grad": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "fgp_lattice_mll_grad_z": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "fgp_dnb2_mll_grad_C": (_i32, [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "fgp_dnb2_mll_grad": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "fgp_fit_state_doubles": (_sz, [_i32, _i32]),
     "fgp_fit_iteration": (_i32, [_c.POINTER(FitProblem), _c.POINTER(FitLayout), _vp]),
@@ -287,9 +288,10 @@ def _workspace(kind, nbytes, device):
     return ws
 
 
-def mll_grad(family, xpts, alpha, t, ysq, scale, ls, noise, want_grad=True, want_lam=False, weights=None, z=None):
+def mll_grad(family, xpts, alpha, t, ysq, scale, ls, noise, want_grad=True, want_lam=False, weights=None, z=None, C=None):
     """Fused MLL terms + gradients.  xpts: (n,d) float64 (lattice) / int64 (net); ysq (B,n); scale (B,), ls (B,d), noise (B,).
-    z: lattice generating vector -> generator mode (the points are regenerated from the index, xpts only gives n, d, device).
+    z: lattice generating vector / C: net generating matrices (d, mmax) int64 device tensor -> generator mode (the points are
+    regenerated from the index, xpts only gives n, d, device).
     Returns out (B, d+4) = [norm, logdet, dL/dnoise, dL/dscale, dL/dls...] and lam (B,n) or None."""
     n, d = xpts.shape
     B = scale.numel()
@@ -305,6 +307,10 @@ def mll_grad(family, xpts, alpha, t, ysq, scale, ls, noise, want_grad=True, want
                                                  _dev(scale, torch.float64), _dev(ls, torch.float64), _dev(noise, torch.float64), wptr,
                                                  tab.data_ptr(), ws.data_ptr(), lam.data_ptr() if want_lam else None, out.data_ptr(),
                                                  1 if want_grad else 0, _stream()))
+        elif family == 1 and C is not None:
+            _check(load().fgp_dnb2_mll_grad_C(_dev(C, torch.int64), int(C.shape[1]), n, d, _harr(_i32, alpha), int(t), B, _dev(ysq, torch.float64),
+                                              _dev(scale, torch.float64), _dev(ls, torch.float64), _dev(noise, torch.float64), wptr,
+                                              ws.data_ptr(), lam.data_ptr() if want_lam else None, out.data_ptr(), 1 if want_grad else 0, _stream()))
         elif family == 0:
             tab = fft_table(n, dev)
             _check(load().fgp_lattice_mll_grad(_dev(xpts, torch.float64), n, d, _harr(_i32, alpha), B, _dev(ysq, torch.float64),

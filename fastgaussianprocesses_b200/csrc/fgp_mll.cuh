@@ -25,6 +25,8 @@ constexpr int kRed = 32 * 4;  // doubles of reduction scratch (block_sum<4>)
 struct MllArgs {
   const void* x;  // lattice: double (n,d); net: int64 (n,d); NULL in generator mode
   UVec z;         // generator mode (lattice): generating vector, delta_ij = frac(phi2(i) z_j) regenerated from the index
+  const uint64_t* C;  // generator mode (net): device (d, mmax) generating-matrix columns, xb_i ^ xb_0 = XOR_{k in bits(i)} C[j][k]
+  int mmax;
   int64_t n;
   int d;
   int t;          // net only
@@ -45,6 +47,7 @@ struct MllArgs {
   int l1, l2, lntrA, lntrB, LPA, LPB;
   int ctasA, ctasB;
   FftTables T;
+  int tab_off;    // net generator mode: byte offset of the XOR-fold tables behind the tile in dynamic shared memory
   int has_fit;    // fused fit iteration: the last CTA to finish reduces the partial sums and runs the fit step
   FitLayout fit;
 };
@@ -54,7 +57,43 @@ struct Hyp {  // per-CTA hyperparameters and first point, staged in shared memor
   double ls[FGP_MAX_D];
   double x0[FGP_MAX_D];     // lattice
   uint64_t xb0[FGP_MAX_D];  // net
+  // net generator mode: xb_i ^ xb_0 of tile element e = TA[e & 63][j] ^ TB[e >> 6][j] (shared-memory tables of XOR folds)
+  const uint64_t* TA;
+  const uint64_t* TB;
+  int64_t tile_base;
 };
+
+// XOR fold of generating-matrix columns over the set bits of v
+__device__ __forceinline__ uint64_t dnb2_fold(const uint64_t* __restrict__ Cj, uint64_t v) {
+  uint64_t r = 0;
+  while (v) {
+    const int k = __ffsll((long long)v) - 1;
+    r ^= __ldg(Cj + k);
+    v &= v - 1;
+  }
+  return r;
+}
+// build the generator tables of a tile of 2^tile_log points starting at tile_base (a multiple of the tile size)
+__device__ __forceinline__ void dnb2_build_tables(Hyp& H, const MllArgs& a, uint64_t* tab, int64_t tile_base, int tile_log) {
+  const int d = a.d;
+  const int nb = tile_log > 6 ? 1 << (tile_log - 6) : 1;
+  uint64_t* TA = tab;
+  uint64_t* TB = tab + 64 * d;
+  for (int e = threadIdx.x; e < 64 * d; e += blockDim.x) {
+    const int j = e % d, v = e / d;
+    TA[e] = dnb2_fold(a.C + (int64_t)j * a.mmax, (uint64_t)v);
+  }
+  for (int e = threadIdx.x; e < nb * d; e += blockDim.x) {
+    const int j = e % d, h = e / d;
+    TB[e] = dnb2_fold(a.C + (int64_t)j * a.mmax, (uint64_t)tile_base | ((uint64_t)h << 6));
+  }
+  if (threadIdx.x == 0) {
+    H.TA = TA;
+    H.TB = TB;
+    H.tile_base = tile_base;
+  }
+}
+static inline size_t dnb2_table_bytes(int d, int tile_log) { return (size_t)(64 + (tile_log > 6 ? 1 << (tile_log - 6) : 1)) * d * sizeof(uint64_t); }
 
 template <bool NET>
 __device__ __forceinline__ void load_hyp(Hyp& H, const MllArgs& a, int b) {
@@ -111,6 +150,18 @@ __device__ __forceinline__ void point_parts(const MllArgs& a, const Hyp& H, int6
     }
     return;
   }
+  if (GEN && NET) {
+    const int e = (int)(i - H.tile_base);
+    const uint64_t* ta = H.TA + (e & 63) * d;
+    const uint64_t* tb = H.TB + (e >> 6) * d;
+#pragma unroll
+    for (int j = 0; j < DM; ++j) {
+      if (j >= d) break;
+      const uint64_t delta = ta[j] ^ tb[j];
+      p[j] = A2 ? dnb2_part_a2(delta, a.t, a.tscale) : dnb2_part(delta, a.alpha.v[j], a.t);
+    }
+    return;
+  }
   if (NET) {
     const int64_t* row = (const int64_t*)a.x + i * d;
     uint64_t xr[DM];
@@ -162,6 +213,10 @@ __device__ __forceinline__ void point_parts(const MllArgs& a, const Hyp& H, int6
 template <bool NET, bool GEN>
 __device__ __noinline__ double point_part_generic(const MllArgs& a, const Hyp& H, int64_t i, int j) {
   if (GEN && !NET) return lat_part(lat_delta_gen(__brev((uint32_t)i), a.z.v[j]), a.P.q[j], a.P.alpha[j]);
+  if (GEN && NET) {
+    const int e = (int)(i - H.tile_base);
+    return dnb2_part(H.TA[(e & 63) * a.d + j] ^ H.TB[(e >> 6) * a.d + j], a.alpha.v[j], a.t);
+  }
   if (NET) return dnb2_part((uint64_t)__ldg((const int64_t*)a.x + i * a.d + j) ^ H.xb0[j], a.alpha.v[j], a.t);
   return lat_part(__ldg((const double*)a.x + i * a.d + j) - H.x0[j], a.P.q[j], a.P.alpha[j]);
 }
@@ -346,6 +401,7 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_single_kern
   const int LP = a.LPA;
   const int d = DT > 0 ? DT : a.d;
   load_hyp<NET>(H, a, b);
+  if (GEN && NET) dnb2_build_tables(H, a, (uint64_t*)(smraw + a.tab_off), 0, l);
   __syncthreads();
   const double c = H.scale;  // DC guess removed before the transform (role of abstract_fast_gp.py:209-211)
   const double noise = H.noise;
@@ -415,11 +471,12 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passA_kerne
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
   const int b = blockIdx.y;
-  load_hyp<NET>(H, a, b);
-  __syncthreads();
   const int l1 = a.l1, l2 = a.l2, lntr = a.lntrA, LP = a.LPA;
   const int64_t blk0 = (int64_t)blockIdx.x << lntr;
   const int64_t g0 = blk0 << l1;
+  load_hyp<NET>(H, a, b);
+  if (GEN && NET) dnb2_build_tables(H, a, (uint64_t*)(smraw + a.tab_off), g0, l1 + lntr);
+  __syncthreads();
   const double c = H.scale;
   if (NET) {
     double* sm = (double*)smraw;
@@ -453,11 +510,12 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kerne
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
   const int b = blockIdx.y;
   const int d = DT > 0 ? DT : a.d;
-  load_hyp<NET>(H, a, b);
-  __syncthreads();
   const int l1 = a.l1, lntr = a.lntrA, LP = a.LPA;
   const int64_t blk0 = (int64_t)blockIdx.x << lntr;
   const int64_t g0 = blk0 << l1;
+  load_hyp<NET>(H, a, b);
+  if (GEN && NET) dnb2_build_tables(H, a, (uint64_t*)(smraw + a.tab_off), g0, l1 + lntr);
+  __syncthreads();
   double acc[DM + 1];
 #pragma unroll
   for (int j = 0; j <= DM; ++j) acc[j] = 0.0;
@@ -500,19 +558,20 @@ int launch_mll_finalize(const MllArgs& a, int B, cudaStream_t st);
 template <int DT, bool NET, bool A2, bool GEN>
 static int launch_mll(const MllArgs& a, const PassGeom& g, int B, cudaStream_t st) {
   int rc;
+  const size_t smemAC = (size_t)a.tab_off + ((GEN && NET) ? dnb2_table_bytes(a.d, g.l2 ? g.l1 + g.lntrA : g.l1) : 0);
   if (g.l2 == 0) {
-    if ((rc = set_smem_attr(mll_single_kernel<DT, NET, A2, GEN>, g.smemA))) return rc;
-    mll_single_kernel<DT, NET, A2, GEN><<<B, g.threadsA, g.smemA, st>>>(a);
+    if ((rc = set_smem_attr(mll_single_kernel<DT, NET, A2, GEN>, smemAC))) return rc;
+    mll_single_kernel<DT, NET, A2, GEN><<<B, g.threadsA, smemAC, st>>>(a);
     FGP_LAUNCH_NAMED("mll_single", st);
     return FGP_OK;
   }
-  if ((rc = set_smem_attr(mll_passA_kernel<DT, NET, A2, GEN>, g.smemA))) return rc;
-  mll_passA_kernel<DT, NET, A2, GEN><<<dim3(a.ctasA, B), g.threadsA, g.smemA, st>>>(a);
+  if ((rc = set_smem_attr(mll_passA_kernel<DT, NET, A2, GEN>, smemAC))) return rc;
+  mll_passA_kernel<DT, NET, A2, GEN><<<dim3(a.ctasA, B), g.threadsA, smemAC, st>>>(a);
   FGP_LAUNCH_NAMED("mll_passA", st);
   if ((rc = launch_mll_passB(a, g, B, NET, st))) return rc;
   if (a.want_grad) {
-    if ((rc = set_smem_attr(mll_passC_kernel<DT, NET, A2, GEN>, g.smemA))) return rc;
-    mll_passC_kernel<DT, NET, A2, GEN><<<dim3(a.ctasA, B), g.threadsA, g.smemA, st>>>(a);
+    if ((rc = set_smem_attr(mll_passC_kernel<DT, NET, A2, GEN>, smemAC))) return rc;
+    mll_passC_kernel<DT, NET, A2, GEN><<<dim3(a.ctasA, B), g.threadsA, smemAC, st>>>(a);
     FGP_LAUNCH_NAMED("mll_passC", st);
   }
   if (a.has_fit) return FGP_OK;  // reduced (and stepped) by the last CTA of the last kernel
@@ -537,6 +596,11 @@ FGP_MLL_DECLARE(mll_net_x_a2_d4);
 FGP_MLL_DECLARE(mll_net_x_a2_d8);
 FGP_MLL_DECLARE(mll_net_x_a2_d16);
 FGP_MLL_DECLARE(mll_net_x_gen_alpha);
+FGP_MLL_DECLARE(mll_net_z_a2_d2);
+FGP_MLL_DECLARE(mll_net_z_a2_d4);
+FGP_MLL_DECLARE(mll_net_z_a2_d8);
+FGP_MLL_DECLARE(mll_net_z_a2_d16);
+FGP_MLL_DECLARE(mll_net_z_gen_alpha);
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 

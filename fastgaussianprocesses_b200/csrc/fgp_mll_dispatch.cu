@@ -3,19 +3,22 @@
 
 namespace fgp {
 
-static int mll_common(bool net, const uint64_t* z_host, const void* x, int64_t n, int d, const int* alpha_host, int t, int B,
+static int mll_common(bool net, const uint64_t* z_host, const uint64_t* C_dev, int mmax, const void* x, int64_t n, int d, const int* alpha_host, int t, int B,
                       const double* ysq, const double* scale, const double* ls, const double* noise, const double* weights,
                       const void* table, void* workspace, double* lam, double* out, int want_grad, fgp_stream_t stream,
                       const fgp_fit_layout* fit = nullptr) {
-  FGP_REQUIRE((x || z_host) && alpha_host && ysq && scale && ls && noise && out, "mll_grad: null pointer");
-  FGP_REQUIRE(!(net && z_host), "mll_grad: generator mode is lattice-only");
+  FGP_REQUIRE((x || z_host || C_dev) && alpha_host && ysq && scale && ls && noise && out, "mll_grad: null pointer");
+  FGP_REQUIRE(!(net && z_host) && !(!net && C_dev), "mll_grad: generator arguments do not match the family");
+  if (C_dev) FGP_REQUIRE(mmax >= 1 && mmax <= 64 && (mmax == 64 || n <= (int64_t(1) << mmax)), "mll_grad: n exceeds 2^mmax generating-matrix columns");
   FGP_REQUIRE(d >= 1 && d <= FGP_MAX_D, "mll_grad: d=%d outside 1..%d", d, FGP_MAX_D);
   FGP_REQUIRE(B >= 1 && B <= 65535, "mll_grad: B=%d outside 1..65535", B);
   FGP_REQUIRE(is_pow2(n) && ilog2(n) <= (net ? FGP_MAX_LOG2N_WHT : FGP_MAX_LOG2N_FFT),
               "mll_grad: n=%lld must be a power of two <= 2^%d", (long long)n, net ? FGP_MAX_LOG2N_WHT : FGP_MAX_LOG2N_FFT);
   MllArgs a;
   memset(&a, 0, sizeof(a));
-  a.x = z_host ? nullptr : x;
+  a.x = (z_host || C_dev) ? nullptr : x;
+  a.C = C_dev;
+  a.mmax = mmax;
   if (z_host)
     for (int j = 0; j < d; ++j) a.z.v[j] = z_host[j];
   a.n = n;
@@ -57,6 +60,7 @@ static int mll_common(bool net, const uint64_t* z_host, const void* x, int64_t n
   a.lntrB = g.lntrB;
   a.LPA = g.LPA;
   a.LPB = g.LPB;
+  a.tab_off = (int)((g.smemA + 15) & ~(size_t)15);
   a.ctasA = (int)g.ctasA;
   a.ctasB = (int)g.ctasB;
   if (g.l2) {
@@ -68,7 +72,10 @@ static int mll_common(bool net, const uint64_t* z_host, const void* x, int64_t n
     a.partC = (double*)((char*)workspace + wbytes + pb);
   }
   mll_launch_fn fn;
-  if (net) {
+  if (net && C_dev) {
+    fn = mll_net_z_gen_alpha;
+    if (all2) fn = d == 2 ? mll_net_z_a2_d2 : d == 4 ? mll_net_z_a2_d4 : d == 8 ? mll_net_z_a2_d8 : d == 16 ? mll_net_z_a2_d16 : fn;
+  } else if (net) {
     fn = mll_net_x_gen_alpha;
     if (all2) fn = d == 2 ? mll_net_x_a2_d2 : d == 4 ? mll_net_x_a2_d4 : d == 8 ? mll_net_x_a2_d8 : d == 16 ? mll_net_x_a2_d16 : fn;
   } else if (z_host) {
@@ -98,7 +105,7 @@ size_t fgp_mll_workspace_bytes(int family, int64_t n, int d, int B) {
 int fgp_lattice_mll_grad(const double* x_dev, int64_t n, int d, const int* alpha_host, int B, const double* ysq_dev, const double* scale_dev,
                          const double* ls_dev, const double* noise_dev, const double* weights_dev, const void* table_dev, void* workspace_dev,
                          double* lam_dev, double* out_dev, int want_grad, fgp_stream_t stream) {
-  return fgp::mll_common(false, nullptr, x_dev, n, d, alpha_host, 0, B, ysq_dev, scale_dev, ls_dev, noise_dev, weights_dev, table_dev,
+  return fgp::mll_common(false, nullptr, nullptr, 0, x_dev, n, d, alpha_host, 0, B, ysq_dev, scale_dev, ls_dev, noise_dev, weights_dev, table_dev,
                          workspace_dev, lam_dev, out_dev, want_grad, stream);
 }
 
@@ -106,7 +113,15 @@ int fgp_lattice_mll_grad_z(const uint64_t* z_host, int64_t n, int d, const int* 
                            const double* scale_dev, const double* ls_dev, const double* noise_dev, const double* weights_dev,
                            const void* table_dev, void* workspace_dev, double* lam_dev, double* out_dev, int want_grad, fgp_stream_t stream) {
   FGP_REQUIRE(z_host, "mll_grad_z: null generating vector");
-  return fgp::mll_common(false, z_host, nullptr, n, d, alpha_host, 0, B, ysq_dev, scale_dev, ls_dev, noise_dev, weights_dev, table_dev,
+  return fgp::mll_common(false, z_host, nullptr, 0, nullptr, n, d, alpha_host, 0, B, ysq_dev, scale_dev, ls_dev, noise_dev, weights_dev, table_dev,
+                         workspace_dev, lam_dev, out_dev, want_grad, stream);
+}
+
+int fgp_dnb2_mll_grad_C(const uint64_t* C_dev, int mmax, int64_t n, int d, const int* alpha_host, int t, int B, const double* ysq_dev,
+                        const double* scale_dev, const double* ls_dev, const double* noise_dev, const double* weights_dev, void* workspace_dev,
+                        double* lam_dev, double* out_dev, int want_grad, fgp_stream_t stream) {
+  FGP_REQUIRE(C_dev, "mll_grad_C: null generating matrices");
+  return fgp::mll_common(true, nullptr, C_dev, mmax, nullptr, n, d, alpha_host, t, B, ysq_dev, scale_dev, ls_dev, noise_dev, weights_dev, nullptr,
                          workspace_dev, lam_dev, out_dev, want_grad, stream);
 }
 
@@ -114,7 +129,7 @@ int fgp_fit_iteration(const fgp_fit_problem* p, const fgp_fit_layout* layout, fg
   FGP_REQUIRE(p && layout, "fit_iteration: null argument");
   const bool net = p->family != 0;
   const int want_grad = (layout->req_scale || layout->req_ls || layout->req_noise) ? 1 : 0;
-  return fgp::mll_common(net, net ? nullptr : p->z_host, p->x_dev, p->n, p->d, p->alpha_host, p->t, layout->B, p->ysq_dev, layout->scale_B,
+  return fgp::mll_common(net, net ? nullptr : p->z_host, net ? p->C_dev : nullptr, p->mmax, p->x_dev, p->n, p->d, p->alpha_host, p->t, layout->B, p->ysq_dev, layout->scale_B,
                          layout->ls_B, layout->noise_B, p->weights_dev, p->table_dev, p->workspace_dev, nullptr, p->out_dev, want_grad,
                          stream, layout);
 }
@@ -122,7 +137,7 @@ int fgp_fit_iteration(const fgp_fit_problem* p, const fgp_fit_layout* layout, fg
 int fgp_dnb2_mll_grad(const int64_t* xb_dev, int64_t n, int d, const int* alpha_host, int t, int B, const double* ysq_dev,
                       const double* scale_dev, const double* ls_dev, const double* noise_dev, const double* weights_dev, void* workspace_dev,
                       double* lam_dev, double* out_dev, int want_grad, fgp_stream_t stream) {
-  return fgp::mll_common(true, nullptr, xb_dev, n, d, alpha_host, t, B, ysq_dev, scale_dev, ls_dev, noise_dev, weights_dev, nullptr,
+  return fgp::mll_common(true, nullptr, nullptr, 0, xb_dev, n, d, alpha_host, t, B, ysq_dev, scale_dev, ls_dev, noise_dev, weights_dev, nullptr,
                          workspace_dev, lam_dev, out_dev, want_grad, stream);
 }
 

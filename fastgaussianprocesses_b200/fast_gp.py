@@ -89,7 +89,7 @@ class _MLLFunction(torch.autograd.Function):
         xpts = fgp._xpts(n)
         out, _ = _lib.mll_grad(fgp._FAMILY, xpts, fgp._alpha_list, fgp._t, ysq, scale_B.detach().contiguous(),
                                ls_B.detach().contiguous(), noise_B.detach().contiguous(), want_grad=want_grad,
-                               weights=weights, z=fgp._zgen)
+                               weights=weights, z=fgp._zgen, C=fgp._Cgen(n))
         ctx.save_for_backward(out)
         ctx.d = fgp.d
         ctx.have_grad = want_grad
@@ -175,6 +175,9 @@ class _FusedFitLoop(object):
         Pb.family = fgp._FAMILY
         Pb.x_dev = self.xpts.data_ptr()
         Pb.z_host = _lib._c.cast(self._z_arr, _lib._vp) if self._z_arr is not None else None
+        self._C = fgp._Cgen(self.n)
+        Pb.C_dev = self._C.data_ptr() if self._C is not None else None
+        Pb.mmax = int(self._C.shape[1]) if self._C is not None else 0
         Pb.n, Pb.d, Pb.t = self.n, self.d, int(fgp._t)
         Pb.alpha_host = _lib._c.cast(self._alpha_arr, _lib._vp)
         Pb.ysq_dev = self.ysq.data_ptr()
@@ -206,13 +209,13 @@ class _FusedFitLoop(object):
     @property
     def algorithmic_bytes(self):
         e = 16 if self.fgp._FAMILY == 0 else 8
-        pts = 0 if self.fgp._zgen is not None else 2 * 8 * self.n * self.d
+        pts = 0 if (self.fgp._zgen is not None or self._C is not None) else 2 * 8 * self.n * self.d
         return self.B * (pts + 4 * e * self.n + 8 * self.n)
 
     def kernel_algorithmic_bytes(self, name):
         e = 16 if self.fgp._FAMILY == 0 else 8
         n, d, B = self.n, self.d, self.B
-        if self.fgp._zgen is not None:
+        if self.fgp._zgen is not None or self._C is not None:
             d = 0
         return {"mll_passA": B * (8 * n * d + e * n), "mll_passB": B * (2 * e * n + 8 * n), "mll_passC": B * (8 * n * d + e * n),
                 "mll_single": B * (16 * n * d + 8 * n)}.get(name, 0)
@@ -296,7 +299,7 @@ class _FastInverseLogDetCache(object):
                 ysq = torch.zeros((B, self.nint), dtype=torch.float64, device=self.fgp.device)
                 _, lam = _lib.mll_grad(self.fgp._FAMILY, self.fgp._xpts(self.nint), self.fgp._alpha_list, self.fgp._t, ysq,
                                        scale_B.contiguous(), ls_B.contiguous(), noise_B.contiguous(), want_grad=False,
-                                       want_lam=True, z=self.fgp._zgen)
+                                       want_lam=True, z=self.fgp._zgen, C=self.fgp._Cgen(self.nint))
             self.lam = lam
             self.pshape = pshape
             self._key = key
@@ -528,6 +531,7 @@ class AbstractFastGP(torch.nn.Module):
         # first kernel column is regenerated from the point index and the points are never read (include/fgp_b200.h)
         s0 = self.seqs[0]
         self._zgen = [int(v) for v in s0.gen_vec] if (self._FAMILY == 0 and isinstance(s0, sequences.Lattice) and os.environ.get("FGP_B200_NO_GEN") != "1") else None
+        self._netgen = self._FAMILY == 1 and isinstance(s0, sequences.DigitalNetB2) and os.environ.get("FGP_B200_NO_GEN") != "1"
         self._epoch = 0
         self._coeffs = None
         self._coeffs_key = None
@@ -559,6 +563,15 @@ class AbstractFastGP(torch.nn.Module):
         with torch.no_grad():
             scale_B, ls_B, noise_B, pshape = self._hyper()
             return scale_B.cpu().numpy(), ls_B.cpu().numpy(), noise_B.cpu().numpy(), pshape
+
+    def _Cgen(self, n):
+        """Device generating matrices for the net generator mode (None: read the stored points)."""
+        if not self._netgen:
+            return None
+        s0 = self.seqs[0]
+        if int(n) > (1 << int(s0.gen_mats.shape[1])):
+            return None
+        return s0.device_matrices(self.device)
 
     def _xpts(self, n):
         x, xb = self.xxb_seqs[0][:int(n)]

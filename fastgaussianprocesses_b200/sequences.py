@@ -105,13 +105,16 @@ class DigitalNetB2(_SequenceBase):
         assert self.rshift.shape == (self.d,)
         self._C_dev = {}
 
-    def generate(self, n_min, n_max, device):
+    def device_matrices(self, device):
         device = torch.device(device)
         C = self._C_dev.get(device)
         if C is None:
-            C = torch.from_numpy(self.gen_mats.astype(np.int64)).to(device)
+            C = torch.from_numpy(self.gen_mats.astype(np.int64)).to(device).contiguous()
             self._C_dev[device] = C
-        xb, x = _lib.dnb2_points(C, self.rshift, self.t, n_min, n_max)
+        return C
+
+    def generate(self, n_min, n_max, device):
+        xb, x = _lib.dnb2_points(self.device_matrices(device), self.rshift, self.t, n_min, n_max)
         return x, xb
 
 

@@ -162,12 +162,14 @@ int fgp_fit_step(const fgp_fit_layout* layout, const double* mll_out_dev, fgp_st
 int fgp_fit_finish(const fgp_fit_layout* layout, fgp_stream_t stream); /* best iterate -> parameters */
 /* One whole fit() iteration in one call: the fused eigen-solve of K4 on layout->scale_B / ls_B / noise_B, whose last
  * CTA reduces the partial sums and runs the fit step in its tail (no separate finalize / fit_step launches).
- * x_dev: points (lattice float64 / net int64 (n,d)); z_host: lattice generating vector for generator mode (x_dev may
- * then be NULL); weights_dev (B,2) as in fgp_*_mll_grad; out_dev (B, d+4) scratch for the reduced terms. */
+ * x_dev: points (lattice float64 / net int64 (n,d)); z_host / C_dev: lattice generating vector / net generating matrices
+ * for generator mode (x_dev may then be NULL); weights_dev (B,2) as in fgp_*_mll_grad; out_dev (B, d+4) scratch for the reduced terms. */
 typedef struct {
   int family;              /* 0 lattice, 1 digital net */
   const void* x_dev;
   const uint64_t* z_host;
+  const uint64_t* C_dev;   /* net generating matrices for generator mode (x_dev may then be NULL), (d, mmax) */
+  int mmax;
   int64_t n;
   int d;
   const int* alpha_host;
@@ -179,6 +181,13 @@ typedef struct {
   double* out_dev;
 } fgp_fit_problem;
 int fgp_fit_iteration(const fgp_fit_problem* problem, const fgp_fit_layout* layout, fgp_stream_t stream);
+
+/* Generator form for a base-2 digital net in natural order: xb_i ^ xb_0 = XOR_{k in bits(i)} C[j][k] exactly (the digital
+ * shift cancels), rebuilt per tile from two shared-memory XOR-fold tables; the (n,d) int64 points are never read.
+ * C_dev: device (d, mmax) columns as in fgp_dnb2_points. */
+int fgp_dnb2_mll_grad_C(const uint64_t* C_dev, int mmax, int64_t n, int d, const int* alpha_host, int t, int B, const double* ysq_dev,
+                        const double* scale_dev, const double* ls_dev, const double* noise_dev, const double* weights_dev,
+                        void* workspace_dev, double* lam_dev, double* out_dev, int want_grad, fgp_stream_t stream);
 
 /* K^-1 y for R right-hand sides sharing one spectrum: out = T^-1( T(y) / lam ), util.py:338-344 (single task).
  * lam_dev: (n) complex (family 0) or real (family 1) full eigenvalues sqrt(n) ft(k1)+noise.  y,out: (R,n) real.

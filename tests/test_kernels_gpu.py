@@ -269,3 +269,24 @@ def test_mll_generator_mode_matches_point_mode(L, P, d, m, alpha):
     for b in range(B):
         assert rel(out_z[b, :2], out_x[b, :2]) < 1e-9
         assert rel(out_z[b, 2:], out_x[b, 2:]) < 1e-7
+
+
+@pytest.mark.parametrize("d,m,alpha,t", [(16, 14, 2, 52), (4, 16, 2, 63), (2, 9, 2, 40), (3, 13, 3, 52), (2, 5, 4, 32), (8, 20, 2, 52), (2, 0, 2, 32), (5, 7, 1, 45)])
+def test_mll_net_generator_mode_matches_point_mode(L, P, d, m, alpha, t):
+    """fgp_dnb2_mll_grad_C rebuilds xb_i ^ xb_0 = XOR of generating-matrix columns over the bits of i from shared-memory
+    fold tables; the integers are identical to those of the stored points, so the results must agree to the last bits."""
+    n = 1 << m
+    rng = np.random.default_rng(70 + m)
+    Ch = P.default_dnb2_gen_mats(d, t)
+    C = torch.from_numpy(Ch.astype(np.int64)).to(dev)
+    xb, _ = L.dnb2_points(C, rng.integers(0, 2 ** t, size=d, dtype=np.uint64), t, 0, n)
+    g = torch.Generator(device=dev).manual_seed(m)
+    B = 2
+    ysq = torch.rand(B, n, generator=g, device=dev) * 3.0
+    scale = torch.tensor([0.8, 2.5], device=dev)
+    ls = torch.from_numpy(rng.uniform(0.2, 1.3, size=(B, d))).to(dev)
+    noise = torch.tensor([1e-2, 1e-3], device=dev)
+    out_x, lam_x = L.mll_grad(1, xb, [alpha] * d, t, ysq, scale, ls, noise, want_grad=True, want_lam=True)
+    out_c, lam_c = L.mll_grad(1, xb, [alpha] * d, t, ysq, scale, ls, noise, want_grad=True, want_lam=True, C=C)
+    assert rel(lam_c, lam_x) < 1e-14
+    assert rel(out_c, out_x) < 1e-13

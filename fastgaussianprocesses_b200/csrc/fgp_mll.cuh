@@ -57,10 +57,12 @@ struct Hyp {  // per-CTA hyperparameters and first point, staged in shared memor
   double ls[FGP_MAX_D];
   double x0[FGP_MAX_D];     // lattice
   uint64_t xb0[FGP_MAX_D];  // net
-  // net generator mode: xb_i ^ xb_0 of tile element e = TA[e & 63][j] ^ TB[e >> 6][j] (shared-memory tables of XOR folds)
+  // net generator mode: xb_i ^ xb_0 of tile element e = TA[j][e & 63] ^ TB[j][e >> 6] (shared-memory tables of XOR folds,
+  // dimension-major so that consecutive threads read consecutive words)
   const uint64_t* TA;
   const uint64_t* TB;
   int64_t tile_base;
+  int nbB;  // entries per dimension of TB
 };
 
 // XOR fold of generating-matrix columns over the set bits of v
@@ -80,17 +82,18 @@ __device__ __forceinline__ void dnb2_build_tables(Hyp& H, const MllArgs& a, uint
   uint64_t* TA = tab;
   uint64_t* TB = tab + 64 * d;
   for (int e = threadIdx.x; e < 64 * d; e += blockDim.x) {
-    const int j = e % d, v = e / d;
+    const int j = e >> 6, v = e & 63;
     TA[e] = dnb2_fold(a.C + (int64_t)j * a.mmax, (uint64_t)v);
   }
   for (int e = threadIdx.x; e < nb * d; e += blockDim.x) {
-    const int j = e % d, h = e / d;
+    const int j = e / nb, h = e - j * nb;
     TB[e] = dnb2_fold(a.C + (int64_t)j * a.mmax, (uint64_t)tile_base | ((uint64_t)h << 6));
   }
   if (threadIdx.x == 0) {
     H.TA = TA;
     H.TB = TB;
     H.tile_base = tile_base;
+    H.nbB = nb;
   }
 }
 static inline size_t dnb2_table_bytes(int d, int tile_log) { return (size_t)(64 + (tile_log > 6 ? 1 << (tile_log - 6) : 1)) * d * sizeof(uint64_t); }
@@ -152,12 +155,13 @@ __device__ __forceinline__ void point_parts(const MllArgs& a, const Hyp& H, int6
   }
   if (GEN && NET) {
     const int e = (int)(i - H.tile_base);
-    const uint64_t* ta = H.TA + (e & 63) * d;
-    const uint64_t* tb = H.TB + (e >> 6) * d;
+    const uint64_t* ta = H.TA + (e & 63);
+    const uint64_t* tb = H.TB + (e >> 6);
+    const int nb = H.nbB;
 #pragma unroll
     for (int j = 0; j < DM; ++j) {
       if (j >= d) break;
-      const uint64_t delta = ta[j] ^ tb[j];
+      const uint64_t delta = ta[j * 64] ^ tb[j * nb];
       p[j] = A2 ? dnb2_part_a2(delta, a.t, a.tscale) : dnb2_part(delta, a.alpha.v[j], a.t);
     }
     return;
@@ -215,7 +219,7 @@ __device__ __noinline__ double point_part_generic(const MllArgs& a, const Hyp& H
   if (GEN && !NET) return lat_part(lat_delta_gen(__brev((uint32_t)i), a.z.v[j]), a.P.q[j], a.P.alpha[j]);
   if (GEN && NET) {
     const int e = (int)(i - H.tile_base);
-    return dnb2_part(H.TA[(e & 63) * a.d + j] ^ H.TB[(e >> 6) * a.d + j], a.alpha.v[j], a.t);
+    return dnb2_part(H.TA[j * 64 + (e & 63)] ^ H.TB[j * H.nbB + (e >> 6)], a.alpha.v[j], a.t);
   }
   if (NET) return dnb2_part((uint64_t)__ldg((const int64_t*)a.x + i * a.d + j) ^ H.xb0[j], a.alpha.v[j], a.t);
   return lat_part(__ldg((const double*)a.x + i * a.d + j) - H.x0[j], a.P.q[j], a.P.alpha[j]);

@@ -117,6 +117,43 @@ def main():
         t, tmin = timeit(f, reps=5, warm=2)
         slots = (5 * d + 1) * float(M) * n
         res["post_mean_fam%d_d%d_n2^%d_m2^%d" % (fam, d, m, mt)] = {"ms": t * 1e3, "pts_per_s": M / t, "fp64_slot_TFLOPs_equiv": 2 * slots / t / 1e12}
+    # batched transforms (the shape post_var and batched fits use): 64 rows of 2^20 through the two-pass pipeline
+    xb_ = torch.randn(64, 1 << 20, device=dev)
+    t, _ = timeit(lambda: L.fwht(xb_), reps=5, warm=2)
+    res["fwht_batch64_2^20"] = {"ms": t * 1e3, "GBs_alg16n": 16 * xb_.numel() / t / 1e9}
+    t, _ = timeit(lambda: L.fftbr(xb_), reps=5, warm=2)
+    res["fft_r2c_batch64_2^20"] = {"ms": t * 1e3, "GBs_alg24n": 24 * xb_.numel() / t / 1e9}
+    del xb_
+    # post_var and batched fits through the public API
+    import fastgaussianprocesses_b200 as fgp
+    for name, mk, n, M in (("lattice_d8_n2^20", lambda: fgp.FastGPLattice(fgp.Lattice(8, seed=7), device=dev), 1 << 20, 256),
+                           ("dnb2_d4_n2^16", lambda: fgp.FastGPDigitalNetB2(fgp.DigitalNetB2(4, seed=7), device=dev), 1 << 16, 4096)):
+        gp = mk()
+        x = gp.get_x_next(n)
+        gp.add_y_next(torch.cos(2 * np.pi * x).sum(1))
+        xs = torch.rand(M, x.shape[1], device=dev)
+        gp.post_var(xs[:8])
+        t, _ = timeit(lambda: gp.post_var(xs), reps=3, warm=1, graph=False)
+        res["post_var_%s_m%d" % (name, M)] = {"ms": t * 1e3, "pts_per_s": M / t}
+        del gp
+    # C5: 64 independent lattice GPs, d=8, n=2^18, one object with shape_batch=[64] and per-GP hyperparameters
+    Bt, d, n = 64, 8, 1 << 18
+    gp = fgp.FastGPLattice(fgp.Lattice(d, seed=7), device=dev, shape_batch=[Bt], scale=torch.ones(Bt, 1), lengthscales=torch.ones(Bt, d), noise=torch.full((Bt, 1), 1e-8))
+    x = gp.get_x_next(n)
+    fr = torch.arange(1, Bt + 1, device=dev, dtype=torch.float64)[:, None]
+    gp.add_y_next(torch.cos(2 * np.pi * x.sum(1)[None, :] * fr / 8))
+    st = gp.fit_stepper()
+    for _ in range(3):
+        st.step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        st.step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 20 * 1e-3
+    res["batched_fit_64x_lattice_d8_2^18"] = {"ms_per_batched_iteration": t * 1e3, "gp_iterations_per_s": Bt / t}
     print(json.dumps(res, indent=1))
 
 

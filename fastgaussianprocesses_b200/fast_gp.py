@@ -188,6 +188,7 @@ class _FusedFitLoop(object):
         self.problem = Pb
         self.graphs = {}
         self.launches = 0
+        self.replayed = 0
         self.kernels_per_iteration = None
         # eager warm-up of every kernel before any capture; `stopped` is raised so that the fit step changes nothing
         # (the state block is zero: tickets start at 0 as fit_init leaves them)
@@ -246,7 +247,15 @@ class _FusedFitLoop(object):
         return g
 
     def replay(self, k):
-        self._graph(k).replay()
+        # a k-iteration graph costs ~30 us per node to capture and instantiate: only worth it for long fits, short ones
+        # replay the 1-iteration graph k times (the host stays ahead of the GPU as soon as an iteration exceeds ~10 us)
+        if k > 1 and k not in self.graphs and self.replayed < 4 * k:
+            g1 = self._graph(1)
+            for _ in range(k):
+                g1.replay()
+        else:
+            self._graph(k).replay()
+        self.replayed += k
         self.launches += k * self.kernels_per_iteration
 
     def step(self):

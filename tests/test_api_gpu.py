@@ -169,3 +169,104 @@ def test_api_batched_outputs_and_hyperparameters(family):
         assert rel(d1["scale_hist"], datab["scale_hist"][:, b]) < 1e-9
     # the batched loss is the sum of the independent losses (abstract_gp.py:253-260)
     assert np.allclose(torch.stack(losses).sum(0).numpy(), datab["loss_hist"].numpy(), rtol=1e-9)
+
+
+def test_api_accepts_qmcpy_style_sequence_objects():
+    """The reference passes qmcpy sequence objects; any object with their interface is accepted (points then come from its
+    own host generator, abstract_gp.py:307-309) and gives the same GP as this package's GPU-side spec with equal inputs."""
+    import os
+    import sys
+    import fastgaussianprocesses_b200 as fgp
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "qmcpy_standin"))
+    import qmcpy  # tests-only stand-in with the qmcpy call signature
+    d, n = 3, 512
+    for fam in ("lattice", "dnb2"):
+        if fam == "lattice":
+            host_seq = qmcpy.Lattice(dimension=d, seed=11)
+            gp_h = fgp.FastGPLattice(host_seq, device=dev)
+            gp_g = fgp.FastGPLattice(fgp.Lattice(d, generating_vector=host_seq.gen_vec, shift=host_seq.shift), device=dev)
+        else:
+            host_seq = qmcpy.DigitalNetB2(dimension=d, seed=11, t=52)
+            gp_h = fgp.FastGPDigitalNetB2(host_seq, device=dev)
+            gp_g = fgp.FastGPDigitalNetB2(fgp.DigitalNetB2(d, generating_matrices=host_seq.gen_mats, dshift=host_seq.rshift, t=52), device=dev)
+        xh, xg = gp_h.get_x_next(n), gp_g.get_x_next(n)
+        assert torch.equal(xh, xg)
+        y = torch.cos(2 * np.pi * xh).sum(1)
+        gp_h.add_y_next(y)
+        gp_g.add_y_next(y)
+        dh = gp_h.fit(iterations=8, verbose=0, store_hists=True, stop_crit_wait_iterations=100)
+        dg = gp_g.fit(iterations=8, verbose=0, store_hists=True, stop_crit_wait_iterations=100)
+        assert np.allclose(dh["loss_hist"].numpy(), dg["loss_hist"].numpy(), rtol=1e-9)  # stored points vs generator mode
+        xt = torch.rand(17, d, generator=torch.Generator().manual_seed(2))
+        assert rel(gp_h.post_mean(xt), gp_g.post_mean(xt)) < 1e-7
+
+
+def test_fit_with_user_optimizer_and_transforms_takes_the_generic_path():
+    import fastgaussianprocesses_b200 as fgp
+    d, n = 2, 256
+    sp = (lambda x: torch.log(torch.expm1(x)), lambda x: torch.nn.functional.softplus(x))  # user transforms (not the defaults)
+    gp = fgp.FastGPLattice(fgp.Lattice(d, seed=3), device=dev, tfs_lengthscales=sp, noise=1e-6)
+    x = gp.get_x_next(n)
+    gp.add_y_next(torch.sin(2 * np.pi * x[:, 0]) + 0.1 * torch.cos(2 * np.pi * x[:, 1]))
+    opt = torch.optim.Adam(gp.parameters(), lr=0.05)
+    data = gp.fit(optimizer=opt, iterations=25, verbose=0, store_loss_hist=True, stop_crit_wait_iterations=100)
+    lh = -data["loss_hist"]
+    assert torch.isfinite(lh).all() and lh[-1] < lh[0]
+    # autograd through the strategy object's seam (util.py:364-370) agrees with a finite difference
+    cache = gp.get_inv_log_det_cache()
+    norm, logdet = cache.get_norm_term_logdet_term()
+    loss = 0.5 * (norm.sum() + logdet.sum())
+    gp.zero_grad()
+    loss.backward()
+    g = gp.raw_lengthscales.grad.clone()
+    eps = 1e-6
+    with torch.no_grad():
+        gp.raw_lengthscales[0] += eps
+    n1, l1 = cache.get_norm_term_logdet_term()
+    with torch.no_grad():
+        gp.raw_lengthscales[0] -= 2 * eps
+    n0, l0 = cache.get_norm_term_logdet_term()
+    fd = float(0.5 * ((n1.sum() + l1.sum()) - (n0.sum() + l0.sum())) / (2 * eps))
+    assert abs(fd - float(g[0])) <= 1e-5 * max(1.0, abs(fd))
+
+
+def test_verbose_table_is_the_same_on_both_fit_paths(capsys, monkeypatch):
+    import fastgaussianprocesses_b200 as fgp
+    outs = []
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv("FGP_B200_GENERIC_FIT", "1")
+        gp = fgp.FastGPDigitalNetB2(fgp.DigitalNetB2(2, seed=5), device=dev, noise=1e-8)
+        x = gp.get_x_next(128)
+        gp.add_y_next(torch.cos(2 * np.pi * x).sum(1))
+        gp.fit(iterations=7, verbose=2, verbose_indent=2, stop_crit_wait_iterations=100)
+        outs.append(capsys.readouterr().out)
+    assert outs[0] == outs[1] and "iter of 7.0e+00" in outs[0] and outs[0].count("\n") == 2 + 5
+
+
+def test_repeated_fit_and_growth_reuse_the_device_loop():
+    import fastgaussianprocesses_b200 as fgp
+    gp = fgp.FastGPLattice(fgp.Lattice(2, seed=9), device=dev, noise=1e-6)
+    f = lambda x: torch.cos(2 * np.pi * x).sum(1)
+    gp.add_y_next(f(gp.get_x_next(256)))
+    d1 = gp.fit(iterations=5, verbose=0, store_loss_hist=True, stop_crit_wait_iterations=100)
+    loop = gp._fused_loop
+    d2 = gp.fit(iterations=5, verbose=0, store_loss_hist=True, stop_crit_wait_iterations=100)
+    assert gp._fused_loop is loop  # same buffers and graphs
+    assert float(d2["loss_hist"][0]) >= float(d1["loss_hist"].max()) - 1e-9  # restarts from the best iterate of the first fit
+    gp.add_y_next(f(gp.get_x_next(512)))
+    d3 = gp.fit(iterations=5, verbose=0, store_loss_hist=True, stop_crit_wait_iterations=100)
+    assert gp._fused_loop is not loop and d3["iterations"] == 5
+    xt = torch.rand(9, 2, generator=torch.Generator().manual_seed(1))
+    assert torch.isfinite(gp.post_mean(xt)).all() and (gp.post_var(xt) >= 0).all()
+
+
+def test_sharded_posterior_single_process_is_identity():
+    import fastgaussianprocesses_b200 as fgp
+    from fastgaussianprocesses_b200.distributed import post_mean_sharded, post_var_sharded
+    gp = fgp.FastGPLattice(fgp.Lattice(3, seed=4), device=dev, noise=1e-6)
+    x = gp.get_x_next(128)
+    gp.add_y_next(torch.cos(2 * np.pi * x).sum(1))
+    xt = torch.rand(21, 3, generator=torch.Generator().manual_seed(8))
+    assert torch.equal(post_mean_sharded(gp, xt), gp.post_mean(xt))
+    assert torch.equal(post_var_sharded(gp, xt), gp.post_var(xt))

@@ -290,3 +290,24 @@ def test_mll_net_generator_mode_matches_point_mode(L, P, d, m, alpha, t):
     out_c, lam_c = L.mll_grad(1, xb, [alpha] * d, t, ysq, scale, ls, noise, want_grad=True, want_lam=True, C=C)
     assert rel(lam_c, lam_x) < 1e-14
     assert rel(out_c, out_x) < 1e-13
+
+
+def test_c_abi_rejects_bad_arguments(L):
+    """Error behaviour at the boundary: negative return codes surface as AssertionError with the library's message."""
+    x = torch.zeros((8, 2), dtype=torch.float64, device=dev)
+    ysq = torch.zeros((1, 8), dtype=torch.float64, device=dev)
+    one = torch.ones(1, dtype=torch.float64, device=dev)
+    ls = torch.ones((1, 2), dtype=torch.float64, device=dev)
+    with pytest.raises(AssertionError, match="alpha"):
+        L.mll_grad(0, x, [0, 2], 0, ysq, one, ls, one)  # lattice alpha must be >= 1
+    with pytest.raises(AssertionError, match="alpha"):
+        L.mll_grad(1, x.to(torch.int64), [5, 2], 52, ysq, one, ls, one)  # net alpha must be <= 4
+    with pytest.raises(AssertionError, match="power of two"):
+        L.mll_grad(0, torch.zeros((6, 2), dtype=torch.float64, device=dev), [2, 2], 0, torch.zeros((1, 6), device=dev), one, ls, one)
+    with pytest.raises(AssertionError):
+        L.lattice_points([1] * 40, [0.0] * 40, 0, 8, dev)  # d > FGP_MAX_D
+    with pytest.raises(AssertionError):
+        L.lattice_points([1, 3], [0.5, 1.5], 0, 8, dev)  # shift outside [0,1)
+    with pytest.raises(TypeError):
+        L.fwht(torch.zeros(8, dtype=torch.float32, device=dev))
+    assert L.launch_count() > 0 and L.device_info()["cc"][0] >= 10

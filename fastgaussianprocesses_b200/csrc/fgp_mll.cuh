@@ -327,6 +327,9 @@ __device__ __forceinline__ void reduce_store(double* v, int nv, double* red, dou
   }
 }
 
+// inside a fused fit loop, iterations enqueued after the stop decision cost only their launches
+__device__ __forceinline__ bool fit_stopped(const MllArgs& a) { return a.has_fit && __ldcg(a.fit.state + ST_STOPPED) != 0.0; }
+
 // deterministic reduction of the per-CTA partial sums of set b into out[b] (fixed order); any CTA size that is a
 // multiple of 32.  Partials come from other CTAs: cache-global loads.
 __device__ __forceinline__ void finalize_set(const MllArgs& a, int b, double* red) {
@@ -399,6 +402,7 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_single_kern
   __shared__ Hyp H;
   __shared__ double red[kRed];
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
+  if (fit_stopped(a)) return;
   const int b = blockIdx.x;
   const int n = (int)a.n;
   const int l = a.l1;
@@ -474,6 +478,7 @@ template <int DT, bool NET, bool A2, bool GEN>
 __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passA_kernel(const __grid_constant__ MllArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
+  if (fit_stopped(a)) return;
   const int b = blockIdx.y;
   const int l1 = a.l1, l2 = a.l2, lntr = a.lntrA, LP = a.LPA;
   const int64_t blk0 = (int64_t)blockIdx.x << lntr;
@@ -512,6 +517,7 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kerne
   __shared__ Hyp H;
   __shared__ double red[kRed];
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
+  if (fit_stopped(a)) return;
   const int b = blockIdx.y;
   const int d = DT > 0 ? DT : a.d;
   const int l1 = a.l1, lntr = a.lntrA, LP = a.LPA;

@@ -7,6 +7,7 @@ template <bool NET>
 __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passB_kernel(const __grid_constant__ MllArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ double red[kRed];
+  if (fit_stopped(a)) return;
   const int b = blockIdx.y;
   const double noise = a.noise[b];
   const double dc = a.scale[b] * (double)a.n;  // the DC guess removed in pass A comes back in bin 0

@@ -147,6 +147,9 @@ class _FusedFitLoop(object):
         self.P = sum(r.numel() for r in self.raw)
         self.state = torch.zeros(_lib.fit_state_doubles(self.P, self.B), dtype=torch.float64, device=dev)
         self.state_host = torch.zeros(self.ST_HEADER, dtype=torch.float64).pin_memory()
+        self.state_host2 = torch.zeros((2, self.ST_HEADER), dtype=torch.float64).pin_memory()
+        self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.use_graph = self.n * self.B < (1 << 18) and os.environ.get("FGP_B200_NO_GRAPH") != "1"
         self.hist_flags = tuple(bool(f) for f in hist_flags)
         self.hist_capacity = int(hist_capacity)
         cap = max(self.hist_capacity, 1)
@@ -247,9 +250,14 @@ class _FusedFitLoop(object):
         return g
 
     def replay(self, k):
-        # a k-iteration graph costs ~30 us per node to capture and instantiate: only worth it for long fits, short ones
-        # replay the 1-iteration graph k times (the host stays ahead of the GPU as soon as an iteration exceeds ~10 us)
-        if k > 1 and k not in self.graphs and self.replayed < 4 * k:
+        # Large problems (an iteration of >= ~40 us of kernels) are launched eagerly: the host stays ahead of the GPU and no
+        # capture / instantiation cost is paid.  Small ones replay a CUDA graph: a k-iteration graph once the fit is long
+        # enough to amortise its capture, the 1-iteration graph k times before that.
+        if not self.use_graph:
+            with torch.cuda.device(self.fgp.device):
+                for _ in range(k):
+                    self._iteration()
+        elif k > 1 and k not in self.graphs and self.replayed < 4 * k:
             g1 = self._graph(1)
             for _ in range(k):
                 g1.replay()
@@ -257,6 +265,16 @@ class _FusedFitLoop(object):
             self._graph(k).replay()
         self.replayed += k
         self.launches += k * self.kernels_per_iteration
+
+    def snapshot(self, slot):
+        """Stream-ordered copy of the state header into pinned slot `slot` plus an event: lets the host look at chunk j
+        while chunk j+1 is already enqueued (kernels of iterations after the stop decision exit immediately)."""
+        self.state_host2[slot].copy_(self.state[:self.ST_HEADER], non_blocking=True)
+        self.events[slot].record(torch.cuda.current_stream(self.fgp.device))
+
+    def wait_snapshot(self, slot):
+        self.events[slot].synchronize()
+        return self.state_host2[slot]
 
     def step(self):
         self.replay(1)
@@ -994,23 +1012,33 @@ class AbstractFastGP(torch.nn.Module):
             print(" " * verbose_indent + "~" * len(_s))
         loop.begin(iterations, stop_wait, logtol, lr)
         printed = 0
-        while True:
-            if iterations + 1 >= loop.GRAPH_ITERS:
-                loop.replay(loop.GRAPH_ITERS)
-            else:
-                for _ in range(iterations + 1):
-                    loop.replay(1)
-            st = loop.read_state()
-            last, stopped = int(st[loop.ST_LAST_ITER]), bool(st[loop.ST_STOPPED] != 0)
-            if verbose:
+        chunk = min(loop.GRAPH_ITERS, iterations + 1)
+        if verbose:
+            while True:
+                loop.replay(chunk)
+                st = loop.read_state()
+                last, stopped = int(st[loop.ST_LAST_ITER]), bool(st[loop.ST_STOPPED] != 0)
                 rows = loop.loss_hist[printed:last + 1].cpu().numpy()
                 for r, row in enumerate(rows):
                     it = printed + r
                     if it % verbose == 0 or (stopped and it == last):
                         print(" " * verbose_indent + "%16.2e | %-10.2e | %-10.2e | %-10.2e" % (it, row[0], row[1], row[2]))
                 printed = last + 1
-            if stopped:
-                break
+                if stopped:
+                    break
+        else:
+            # one chunk of look-ahead: chunk j+1 is enqueued before the host waits for the state after chunk j
+            loop.replay(chunk)
+            loop.snapshot(0)
+            j = 0
+            while True:
+                loop.replay(chunk)
+                loop.snapshot((j + 1) & 1)
+                st = loop.wait_snapshot(j & 1)
+                last, stopped = int(st[loop.ST_LAST_ITER]), bool(st[loop.ST_STOPPED] != 0)
+                if stopped:
+                    break
+                j += 1
         loop.finish()
         i = last
         for pname in ("raw_scale", "raw_lengthscales", "raw_noise", "raw_factor_task_kernel", "raw_noise_task_kernel"):

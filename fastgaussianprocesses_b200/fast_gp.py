@@ -106,11 +106,26 @@ class _MLLFunction(torch.autograd.Function):
         return g * out[:, 3], g[:, None] * out[:, 4:4 + d], g * out[:, 2], None, None, None, None, None
 
 
+# Pinned host buffers for polling the device-side fit state.  cudaHostAlloc costs ~1 ms, more than 10 fit iterations at
+# n = 2^20, so the buffers are pooled per process instead of being allocated per fit loop.
+_PIN_POOL = []
+
+
+def _pin_acquire():
+    return _PIN_POOL.pop() if _PIN_POOL else torch.zeros((3, 32), dtype=torch.float64).pin_memory()
+
+
+def _pin_release(buf):
+    if buf is not None and len(_PIN_POOL) < 64:
+        _PIN_POOL.append(buf)
+
+
 class _FusedFitLoop(object):
     """Device-side fit() loop (the product's fast path): every iteration is [fgp_*_mll_grad, fgp_fit_step] and runs
     from a CUDA graph; the host only polls the `stopped` flag between graph replays (include/fgp_b200.h, K4/K4b).
     Used when the loss is MLL, the optimiser is the default Rprop and the transforms are the default (log, exp)."""
     GRAPH_ITERS = 16
+    EAGER_ITERS = 32  # large problems: iterations launched eagerly before a graph is worth capturing (~1.5 ms)
     ST_STOPPED, ST_LAST_ITER, ST_HEADER = 4, 5, 32
 
     @staticmethod
@@ -146,8 +161,9 @@ class _FusedFitLoop(object):
         self.weights = torch.tensor([0.5, 0.5 * self.d_out / self.B], device=dev).expand(self.B, 2).contiguous()
         self.P = sum(r.numel() for r in self.raw)
         self.state = torch.zeros(_lib.fit_state_doubles(self.P, self.B), dtype=torch.float64, device=dev)
-        self.state_host = torch.zeros(self.ST_HEADER, dtype=torch.float64).pin_memory()
-        self.state_host2 = torch.zeros((2, self.ST_HEADER), dtype=torch.float64).pin_memory()
+        self._pin = _pin_acquire()
+        self.state_host = self._pin[2]
+        self.state_host2 = self._pin[:2]
         self.events = [torch.cuda.Event(), torch.cuda.Event()]
         self.use_graph = self.n * self.B < (1 << 18) and os.environ.get("FGP_B200_NO_GRAPH") != "1"
         self.hist_flags = tuple(bool(f) for f in hist_flags)
@@ -203,7 +219,7 @@ class _FusedFitLoop(object):
             torch.cuda.synchronize(dev)
 
     def matches(self, fgp, hist_flags, hist_capacity):
-        return (fgp._nint == self.n and tuple(p.data_ptr() for p in (fgp.raw_scale, fgp.raw_lengthscales, fgp.raw_noise)) == tuple(r.data_ptr() for r in self.raw)
+        return (self._pin is not None and fgp._nint == self.n and tuple(p.data_ptr() for p in (fgp.raw_scale, fgp.raw_lengthscales, fgp.raw_noise)) == tuple(r.data_ptr() for r in self.raw)
                 and (fgp.raw_scale.requires_grad, fgp.raw_lengthscales.requires_grad, fgp.raw_noise.requires_grad) == self.req
                 and fgp._ysq is self.ysq and tuple(bool(f) for f in hist_flags) == self.hist_flags and hist_capacity <= self.hist_capacity
                 and float(fgp.gram_matrix_tasks.reshape(-1)[0]) == self.tau)
@@ -250,10 +266,11 @@ class _FusedFitLoop(object):
         return g
 
     def replay(self, k):
-        # Large problems (an iteration of >= ~40 us of kernels) are launched eagerly: the host stays ahead of the GPU and no
-        # capture / instantiation cost is paid.  Small ones replay a CUDA graph: a k-iteration graph once the fit is long
-        # enough to amortise its capture, the 1-iteration graph k times before that.
-        if not self.use_graph:
+        # Large problems (an iteration of >= ~40 us of kernels) start eagerly: the host stays ahead of the GPU and a short
+        # fit never pays for capture / instantiation; after EAGER_ITERS iterations they switch to graphs as well (4 us less
+        # launch gap per iteration).  Small ones replay a CUDA graph from the start: the 1-iteration graph k times, then a
+        # k-iteration graph once the fit is long enough to amortise its capture.
+        if not self.use_graph and self.replayed < self.EAGER_ITERS:
             with torch.cuda.device(self.fgp.device):
                 for _ in range(k):
                     self._iteration()
@@ -303,6 +320,19 @@ class _FusedFitLoop(object):
 
     def close(self):
         self.graphs = {}
+        if self._pin is not None:
+            torch.cuda.current_stream(self.fgp.device).synchronize()  # no copy into the buffers may be in flight
+            _pin_release(self._pin)
+            self._pin = None
+            self.state_host = self.state_host2 = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_pin", None) is not None:
+                _pin_release(self._pin)
+                self._pin = None
+        except Exception:
+            pass
 
 
 class _FastInverseLogDetCache(object):
@@ -993,10 +1023,12 @@ class AbstractFastGP(torch.nn.Module):
         return loop
 
     def fit_stepper(self):
-        """The fused device-side fit loop armed for an open-ended run: `.step()` = one MLL+gradient+Rprop iteration."""
+        """The fused device-side fit loop armed for an open-ended run, in the steady state of a long fit (CUDA-graph replays):
+        `.step()` = one MLL+gradient+Rprop iteration."""
         assert self._nint > 0, "cannot fit without data"
         assert _FusedFitLoop.eligible(self), "fit_stepper needs the default transforms and parameter layouts"
         loop = self._get_fused_loop()
+        loop.replayed = max(loop.replayed, loop.EAGER_ITERS)
         loop.begin(2 ** 30, 2 ** 30, np.log(1.05), 1e-1)
         self._epoch += 1
         return loop

@@ -181,6 +181,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("FGP_NCCL_DEBUG", "WARN")  # the VERSION banner goes to stdout; keep it to one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 

@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) fft_passA_inv(c
 }
 
 // ---- FWHT ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) wht_passA(const double* __restrict__ in, double* __restrict__ out, int64_t total_blocks, int l1,
+template <int MINB>
+__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) wht_passA(const double* __restrict__ in, double* __restrict__ out, int64_t total_blocks, int l1,
                                                      int lntr, int LP, double scale) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double* sm = (double*)smraw;
@@ -114,7 +115,8 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) wht_passA(const
   block_wht_io<false>(sm, l1, lntr, LP, wht_sched_coalesced(l1), gld, gst);
 }
 
-__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) wht_passB(double* __restrict__ data, int l1, int l2, int lntr, int LP) {
+template <int MINB>
+__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) wht_passB(double* __restrict__ data, int l1, int l2, int lntr, int LP) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double* sm = (double*)smraw;
   const int64_t col0 = (int64_t)blockIdx.x << lntr;
@@ -248,16 +250,29 @@ int fgp_fwht(const double* in_dev, double* out_dev, int64_t batch, int64_t n, fg
   if (batch == 0) return FGP_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const PassGeom g = make_geom(n, false);
-  if ((rc = set_smem(wht_passA, g.smemA))) return rc;
   const int64_t total_blocks = batch * (n >> g.l1);
   const int64_t ctas = (total_blocks + g.ntrA - 1) / g.ntrA;
-  wht_passA<<<(unsigned)ctas, g.threadsA, g.smemA, st>>>(in_dev, out_dev, total_blocks, g.l1, g.lntrA, g.LPA, 1.0 / sqrt((double)n));
-  FGP_LAUNCH_NAMED("wht_passA", st);
-  if (g.l2) {
-    if ((rc = set_smem(wht_passB, g.smemB))) return rc;
-    const int64_t ctasB = (batch << g.l1) >> g.lntrB;
-    wht_passB<<<(unsigned)ctasB, g.threadsB, g.smemB, st>>>(out_dev, g.l1, g.l2, g.lntrB, g.LPB);
-    FGP_LAUNCH_NAMED("wht_passB", st);
+  const int64_t ctasB = g.l2 ? (batch << g.l1) >> g.lntrB : 0;
+  const double scale = 1.0 / sqrt((double)n);
+  // 32 KiB tiles: 64 registers, 4 CTAs per SM in different phases; 64 KiB tiles (HBM-sized data): 128 registers, 2 per SM
+  if (g.smemA <= 40 * 1024 && g.smemB <= 72 * 1024) {
+    if ((rc = set_smem(wht_passA<FGP_LB_BLOCKS_R>, g.smemA))) return rc;
+    wht_passA<FGP_LB_BLOCKS_R><<<(unsigned)ctas, g.threadsA, g.smemA, st>>>(in_dev, out_dev, total_blocks, g.l1, g.lntrA, g.LPA, scale);
+    FGP_LAUNCH_NAMED("wht_passA", st);
+    if (g.l2) {
+      if ((rc = set_smem(wht_passB<FGP_LB_BLOCKS_R>, g.smemB))) return rc;
+      wht_passB<FGP_LB_BLOCKS_R><<<(unsigned)ctasB, g.threadsB, g.smemB, st>>>(out_dev, g.l1, g.l2, g.lntrB, g.LPB);
+      FGP_LAUNCH_NAMED("wht_passB", st);
+    }
+  } else {
+    if ((rc = set_smem(wht_passA<FGP_LB_BLOCKS>, g.smemA))) return rc;
+    wht_passA<FGP_LB_BLOCKS><<<(unsigned)ctas, g.threadsA, g.smemA, st>>>(in_dev, out_dev, total_blocks, g.l1, g.lntrA, g.LPA, scale);
+    FGP_LAUNCH_NAMED("wht_passA", st);
+    if (g.l2) {
+      if ((rc = set_smem(wht_passB<FGP_LB_BLOCKS>, g.smemB))) return rc;
+      wht_passB<FGP_LB_BLOCKS><<<(unsigned)ctasB, g.threadsB, g.smemB, st>>>(out_dev, g.l1, g.l2, g.lntrB, g.LPB);
+      FGP_LAUNCH_NAMED("wht_passB", st);
+    }
   }
   return FGP_OK;
 }

@@ -35,6 +35,10 @@ namespace fgp {
 #ifndef FGP_LB_BLOCKS
 #define FGP_LB_BLOCKS 2
 #endif
+// the real (FWHT) stand-alone kernels hold 16 doubles per thread: 64 registers, 4 CTAs per SM
+#ifndef FGP_LB_BLOCKS_R
+#define FGP_LB_BLOCKS_R 4
+#endif
 
 constexpr int kTabLen = 4096;
 
@@ -396,27 +400,49 @@ __device__ __forceinline__ void wht_butterflies(double (&v)[1 << R]) {
   }
 }
 
-template <int R, bool TRFAST, class Ld, class St>
-__device__ __forceinline__ void wht_round_io(int s, int l, int lntr, Ld ld, St st) {
-  constexpr int RAD = 1 << R;
-  const int total = 1 << (lntr + l - R);
-  for (int g = threadIdx.x; g < total; g += blockDim.x) {
-    const GroupIdx G = group_of<R, TRFAST>(g, s, l, lntr);
-    double v[RAD];
-#pragma unroll
-    for (int c = 0; c < RAD; ++c) v[c] = ld(G.tr, G.base + (c << s));
-    wht_butterflies<R>(v);
-#pragma unroll
-    for (int c = 0; c < RAD; ++c) st(G.tr, G.base + (c << s), v[c]);
-  }
-}
-
 struct SmemR {
   double* sm;
   int LP;
   __device__ __forceinline__ double operator()(int tr, int idx) const { return sm[tr * LP + padidx<kPSR>(idx)]; }
   __device__ __forceinline__ void operator()(int tr, int idx, double v) const { sm[tr * LP + padidx<kPSR>(idx)] = v; }
 };
+template <class T>
+struct is_smemr {
+  static constexpr bool value = false;
+};
+template <>
+struct is_smemr<SmemR> {
+  static constexpr bool value = true;
+};
+
+// One radix-2^R FWHT round.  Shared-memory ends use linear addressing (every schedule below has s == 0 or s >= kPSR).
+template <int R, bool TRFAST, class Ld, class St>
+__device__ __forceinline__ void wht_round_io(int s, int l, int lntr, Ld ld, St st) {
+  constexpr int RAD = 1 << R;
+  const int total = 1 << (lntr + l - R);
+  const int stp = s == 0 ? 1 : (1 << s) + (1 << (s - kPSR));
+  for (int g = threadIdx.x; g < total; g += blockDim.x) {
+    const GroupIdx G = group_of<R, TRFAST>(g, s, l, lntr);
+    double v[RAD];
+    if constexpr (is_smemr<Ld>::value) {
+      const double* p = ld.sm + G.tr * ld.LP + padidx<kPSR>(G.base);
+#pragma unroll
+      for (int c = 0; c < RAD; ++c) v[c] = p[c * stp];
+    } else {
+#pragma unroll
+      for (int c = 0; c < RAD; ++c) v[c] = ld(G.tr, G.base + (c << s));
+    }
+    wht_butterflies<R>(v);
+    if constexpr (is_smemr<St>::value) {
+      double* p = st.sm + G.tr * st.LP + padidx<kPSR>(G.base);
+#pragma unroll
+      for (int c = 0; c < RAD; ++c) p[c * stp] = v[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < RAD; ++c) st(G.tr, G.base + (c << s), v[c]);
+    }
+  }
+}
 
 template <bool TRFAST, class F>
 __device__ __forceinline__ void tile_fill_r(const SmemR& S, int l, int lntr, F f) {
@@ -459,7 +485,7 @@ static __device__ __noinline__ void wht_round_smem(int r, int s, int l, int lntr
 // When l >= 8 both schedules start and end with full radix-16 rounds (only those exist in global<->register variants).
 struct WhtSched {
   int n;
-  int s[4], r[4];
+  int s[5], r[5];
 };
 // bottom-up: [0,4), remainder, fours
 __device__ __forceinline__ WhtSched wht_sched_up(int l) {
@@ -475,16 +501,18 @@ __device__ __forceinline__ WhtSched wht_sched_up(int l) {
   for (int s = 4 + rem; s < l; s += 4) q.s[q.n] = s, q.r[q.n] = 4, ++q.n;
   return q;
 }
-// coalesced at both ends for contiguous tiles: the top four stages first (a thread's elements are 2^(l-4) apart, so
-// consecutive threads touch consecutive addresses), then the bottom remainder, then upwards, ending just below the top.
+// coalesced at both ends for contiguous tiles (l >= 12): the top four stages first (a thread's elements are 2^(l-4)
+// apart, so consecutive threads touch consecutive addresses), then [0,4), the remainder, and upwards, ending with the
+// four stages just below the top.  Every round keeps s == 0 or s >= 4 (linear shared-memory addressing).
 __device__ __forceinline__ WhtSched wht_sched_coalesced(int l) {
-  if (l < 8) return wht_sched_up(l);
+  if (l < 12) return wht_sched_up(l);
   WhtSched q;
   const int rem = l & 3;
   q.n = 0;
   q.s[q.n] = l - 4, q.r[q.n] = 4, ++q.n;
-  if (rem) q.s[q.n] = 0, q.r[q.n] = rem, ++q.n;
-  for (int s = rem; s < l - 4; s += 4) q.s[q.n] = s, q.r[q.n] = 4, ++q.n;
+  q.s[q.n] = 0, q.r[q.n] = 4, ++q.n;
+  if (rem) q.s[q.n] = 4, q.r[q.n] = rem, ++q.n;
+  for (int s = 4 + rem; s < l - 4; s += 4) q.s[q.n] = s, q.r[q.n] = 4, ++q.n;
   return q;
 }
 
@@ -546,10 +574,16 @@ static inline int env_int(const char* name, int dflt) {
 static inline PassGeom make_geom(int64_t n, bool cplx) {
   PassGeom g;
   const size_t elem = cplx ? sizeof(double2) : sizeof(double);
-  static const int capC = env_int("FGP_CAP_C", 12), capR = env_int("FGP_CAP_R", 13), colsLog = env_int("FGP_COLS_LOG2", 3);
-  const int cap = cplx ? capC : capR;
-  const int hard = cplx ? 12 : 13;  // 64 KiB of elements
   g.m = ilog2(n);
+  // defaults from the B200 sweeps in profiles/README.md: 32 KiB real tiles and 16-column pass-B strips while the data is
+  // L2-sized (more CTAs in different phases per SM), 64 KiB tiles for the HBM-sized transforms
+  static const int capC = env_int("FGP_CAP_C", 0), capR = env_int("FGP_CAP_R", 0), colsEnv = env_int("FGP_COLS_LOG2", -1);
+  static const int hardC = env_int("FGP_HARD_C", 0), hardR = env_int("FGP_HARD_R", 13);
+  int cap = cplx ? (capC ? capC : 12) : (capR ? capR : (g.m <= 22 ? 12 : 13));
+  // largest tile: 64 KiB of elements; the 2^24-point FFT takes 128 KiB pass-B tiles (2 columns instead of 1)
+  const int hard = cplx ? (hardC ? hardC : (g.m >= 24 ? 13 : 12)) : hardR;
+  if (cap > hard) cap = hard;
+  const int colsLog = colsEnv >= 0 ? colsEnv : (cplx ? 3 : (g.m <= 22 ? 4 : 3));
   int tileA, tileB = 0;
   if (g.m <= cap) {
     g.l1 = g.m;

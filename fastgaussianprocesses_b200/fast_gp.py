@@ -398,7 +398,7 @@ class _FastInverseLogDetCache(object):
         lead = _prod(sb[:len(sb) - k])
         want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in (scale_B, ls_B, noise_B))
         # one "hyperparameter set" per y column so the norm term keeps the reference's per-column shape
-        ysq_cols = (ytilde.abs() ** 2).reshape(lead * B, self.nint).contiguous()
+        ysq_cols = (torch.view_as_real(ytilde).pow(2).sum(-1) if ytilde.is_complex() else ytilde ** 2).reshape(lead * B, self.nint).contiguous()
         w_norm = torch.tensor([1.0, 0.0], device=fgp.device).expand(lead * B, 2).contiguous()
         rep = lambda v: v.expand((lead,) + tuple(v.shape)).reshape((lead * B,) + tuple(v.shape[1:]))
         norm_cols, _, _ = _MLLFunction.apply(rep(scale_B), rep(ls_B), rep(noise_B), fgp, self.nint, ysq_cols, w_norm, want_grad)
@@ -780,7 +780,8 @@ class AbstractFastGP(torch.nn.Module):
         if self._ysq is None or self._ysq.shape[0] != B:
             sb = tuple(self.shape_batch)
             lead = _prod(sb[:len(sb) - len(pshape)])
-            a = ytilde.abs() ** 2 if ytilde.is_complex() else ytilde ** 2
+            # |z|^2 from the (re, im) view: torch's complex abs() is a jiterator kernel (NVRTC compile on first use)
+            a = torch.view_as_real(ytilde).pow(2).sum(-1) if ytilde.is_complex() else ytilde ** 2
             self._ysq = a.reshape(lead, B, self._nint).sum(0).contiguous()
         return self._ysq
 

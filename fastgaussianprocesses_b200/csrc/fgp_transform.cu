@@ -32,8 +32,8 @@ __global__ void fft_table_kernel(double2* stage, double2* lo, double2* hi, doubl
 // ---- forward -------------------------------------------------------------------------------------------------
 // pass A: 2^lntr contiguous length-2^l1 blocks per CTA; the first round reads global memory straight into registers,
 // the last round applies the inter-pass twiddle and writes global memory (coalesced: its elements are 2^(l1-4) apart).
-template <bool REAL_IN>
-__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) fft_passA_fwd(const double* __restrict__ in, double2* __restrict__ out, int64_t total_blocks,
+template <bool REAL_IN, int MINB>
+__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) fft_passA_fwd(const double* __restrict__ in, double2* __restrict__ out, int64_t total_blocks,
                                                          int l1, int l2, int lntr, int LP, double scale, FftTables T) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double2* sm = (double2*)smraw;
@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) fft_passA_fwd(c
 }
 
 // pass B: 2^lntr adjacent stride-2^l1 columns per CTA, in place; consecutive threads take consecutive columns.
-template <bool INV>
-__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) fft_passB(const double2* __restrict__ in, double2* __restrict__ out, int l1, int l2, int lntr,
+template <bool INV, int MINB>
+__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) fft_passB(const double2* __restrict__ in, double2* __restrict__ out, int l1, int l2, int lntr,
                                                      int LP, FftTables T) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double2* sm = (double2*)smraw;
@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) fft_passB(const
   }
 }
 
-__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) fft_passA_inv(const double2* __restrict__ in, double2* __restrict__ out, int64_t total_blocks,
+template <int MINB>
+__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) fft_passA_inv(const double2* __restrict__ in, double2* __restrict__ out, int64_t total_blocks,
                                                          int l1, int lntr, int LP, double scale, FftTables T) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double2* sm = (double2*)smraw;
@@ -161,20 +162,31 @@ static int fft_forward(const double* in, double* out, int64_t batch, int64_t n, 
   const int64_t ctas = (total_blocks + g.ntrA - 1) / g.ntrA;
   const double scale = 1.0 / sqrt((double)n);
   int rc;
-  if (real_in) {
-    if ((rc = set_smem(fft_passA_fwd<true>, g.smemA))) return rc;
-    fft_passA_fwd<true><<<(unsigned)ctas, g.threadsA, g.smemA, st>>>(in, (double2*)out, total_blocks, g.l1, g.l2, g.lntrA, g.LPA, scale, T);
-  } else {
-    if ((rc = set_smem(fft_passA_fwd<false>, g.smemA))) return rc;
-    fft_passA_fwd<false><<<(unsigned)ctas, g.threadsA, g.smemA, st>>>(in, (double2*)out, total_blocks, g.l1, g.l2, g.lntrA, g.LPA, scale, T);
-  }
-  FGP_LAUNCH_NAMED("fft_passA_fwd", st);
-  if (g.l2) {
-    if ((rc = set_smem(fft_passB<false>, g.smemB))) return rc;
-    const int64_t ctasB = (batch << g.l1) >> g.lntrB;
-    fft_passB<false><<<(unsigned)ctasB, g.threadsB, g.smemB, st>>>((const double2*)out, (double2*)out, g.l1, g.l2, g.lntrB, g.LPB, T);
-    FGP_LAUNCH_NAMED("fft_passB_fwd", st);
-  }
+  const int64_t ctasB = g.l2 ? (batch << g.l1) >> g.lntrB : 0;
+  // 32 KiB tiles: 64 registers, 4 CTAs per SM; larger tiles: 128 registers, 2 per SM (FGP_FFT_MINB overrides for tuning)
+  static const int minb_env = env_int("FGP_FFT_MINB", 0);
+  const bool small = minb_env ? minb_env == 4 : (g.smemA <= 40 * 1024 && g.smemB <= 40 * 1024);
+#define FGP_FFT_FWD(MINB)                                                                                                        \
+  do {                                                                                                                           \
+    if (real_in) {                                                                                                               \
+      if ((rc = set_smem(fft_passA_fwd<true, MINB>, g.smemA))) return rc;                                                        \
+      fft_passA_fwd<true, MINB><<<(unsigned)ctas, g.threadsA, g.smemA, st>>>(in, (double2*)out, total_blocks, g.l1, g.l2, g.lntrA, g.LPA, scale, T); \
+    } else {                                                                                                                     \
+      if ((rc = set_smem(fft_passA_fwd<false, MINB>, g.smemA))) return rc;                                                       \
+      fft_passA_fwd<false, MINB><<<(unsigned)ctas, g.threadsA, g.smemA, st>>>(in, (double2*)out, total_blocks, g.l1, g.l2, g.lntrA, g.LPA, scale, T); \
+    }                                                                                                                            \
+    FGP_LAUNCH_NAMED("fft_passA_fwd", st);                                                                                       \
+    if (g.l2) {                                                                                                                  \
+      if ((rc = set_smem(fft_passB<false, MINB>, g.smemB))) return rc;                                                           \
+      fft_passB<false, MINB><<<(unsigned)ctasB, g.threadsB, g.smemB, st>>>((const double2*)out, (double2*)out, g.l1, g.l2, g.lntrB, g.LPB, T); \
+      FGP_LAUNCH_NAMED("fft_passB_fwd", st);                                                                                     \
+    }                                                                                                                            \
+  } while (0)
+  if (small)
+    FGP_FFT_FWD(4);
+  else
+    FGP_FFT_FWD(FGP_LB_BLOCKS);
+#undef FGP_FFT_FWD
   return FGP_OK;
 }
 
@@ -228,18 +240,29 @@ int fgp_ifftbr_c2c(const double* in_dev, double* out_dev, int64_t batch, int64_t
   const PassGeom g = make_geom(n, true);
   const FftTables T = make_tables(table_dev);
   const double2* src = (const double2*)in_dev;
-  if (g.l2) {
-    if ((rc = set_smem(fft_passB<true>, g.smemB))) return rc;
-    const int64_t ctasB = (batch << g.l1) >> g.lntrB;
-    fft_passB<true><<<(unsigned)ctasB, g.threadsB, g.smemB, st>>>(src, (double2*)out_dev, g.l1, g.l2, g.lntrB, g.LPB, T);
-    FGP_LAUNCH_NAMED("fft_passB_inv", st);
-    src = (const double2*)out_dev;
-  }
-  if ((rc = set_smem(fft_passA_inv, g.smemA))) return rc;
+  const int64_t ctasB = g.l2 ? (batch << g.l1) >> g.lntrB : 0;
   const int64_t total_blocks = batch * (n >> g.l1);
   const int64_t ctas = (total_blocks + g.ntrA - 1) / g.ntrA;
-  fft_passA_inv<<<(unsigned)ctas, g.threadsA, g.smemA, st>>>(src, (double2*)out_dev, total_blocks, g.l1, g.lntrA, g.LPA, 1.0 / sqrt((double)n), T);
-  FGP_LAUNCH_NAMED("fft_passA_inv", st);
+  const double scale = 1.0 / sqrt((double)n);
+  static const int minb_env = env_int("FGP_FFT_MINB", 0);
+  const bool small = minb_env ? minb_env == 4 : (g.smemA <= 40 * 1024 && g.smemB <= 40 * 1024);
+#define FGP_FFT_INV(MINB)                                                                                                   \
+  do {                                                                                                                      \
+    if (g.l2) {                                                                                                             \
+      if ((rc = set_smem(fft_passB<true, MINB>, g.smemB))) return rc;                                                       \
+      fft_passB<true, MINB><<<(unsigned)ctasB, g.threadsB, g.smemB, st>>>(src, (double2*)out_dev, g.l1, g.l2, g.lntrB, g.LPB, T); \
+      FGP_LAUNCH_NAMED("fft_passB_inv", st);                                                                                \
+      src = (const double2*)out_dev;                                                                                        \
+    }                                                                                                                       \
+    if ((rc = set_smem(fft_passA_inv<MINB>, g.smemA))) return rc;                                                           \
+    fft_passA_inv<MINB><<<(unsigned)ctas, g.threadsA, g.smemA, st>>>(src, (double2*)out_dev, total_blocks, g.l1, g.lntrA, g.LPA, scale, T); \
+    FGP_LAUNCH_NAMED("fft_passA_inv", st);                                                                                  \
+  } while (0)
+  if (small)
+    FGP_FFT_INV(4);
+  else
+    FGP_FFT_INV(FGP_LB_BLOCKS);
+#undef FGP_FFT_INV
   return FGP_OK;
 }
 

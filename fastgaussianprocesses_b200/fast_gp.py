@@ -166,6 +166,7 @@ class _FusedFitLoop(object):
         self.state_host2 = self._pin[:2]
         self.events = [torch.cuda.Event(), torch.cuda.Event()]
         self.use_graph = self.n * self.B < (1 << 18) and os.environ.get("FGP_B200_NO_GRAPH") != "1"
+        self.graph_after_eager = False  # set by fit_stepper(): the steady state of a long fit
         self.hist_flags = tuple(bool(f) for f in hist_flags)
         self.hist_capacity = int(hist_capacity)
         cap = max(self.hist_capacity, 1)
@@ -256,25 +257,34 @@ class _FusedFitLoop(object):
     def _graph(self, k):
         g = self.graphs.get(k)
         if g is None:
+            # raw capture on a side stream: the torch.cuda.graph() context manager also runs gc.collect() and
+            # empty_cache(), tens of milliseconds -- more than a whole short fit
             g = torch.cuda.CUDAGraph()
             with torch.cuda.device(self.fgp.device):
-                torch.cuda.synchronize()
-                with torch.cuda.graph(g):
-                    for _ in range(k):
-                        self._iteration()
+                cur = torch.cuda.current_stream()
+                side = torch.cuda.Stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    g.capture_begin()
+                    try:
+                        for _ in range(k):
+                            self._iteration()
+                    finally:
+                        g.capture_end()
+                cur.wait_stream(side)
             self.graphs[k] = g
         return g
 
     def replay(self, k):
-        # Large problems (an iteration of >= ~40 us of kernels) start eagerly: the host stays ahead of the GPU and a short
-        # fit never pays for capture / instantiation; after EAGER_ITERS iterations they switch to graphs as well (4 us less
-        # launch gap per iteration).  Small ones replay a CUDA graph from the start: the 1-iteration graph k times, then a
-        # k-iteration graph once the fit is long enough to amortise its capture.
-        if not self.use_graph and self.replayed < self.EAGER_ITERS:
+        # Large problems (an iteration of >= ~40 us of kernels) are launched eagerly: the host stays ahead of the GPU and no
+        # capture / instantiation is paid (graphs save ~4 us of launch gaps per iteration; fit_stepper() opts in).  Small
+        # ones replay a CUDA graph from the start: the 1-iteration graph k times, then a k-iteration graph once the fit is
+        # long enough to amortise its capture.
+        if not self.use_graph and (self.replayed < self.EAGER_ITERS or not self.graph_after_eager):
             with torch.cuda.device(self.fgp.device):
                 for _ in range(k):
                     self._iteration()
-        elif k > 1 and k not in self.graphs and self.replayed < 4 * k:
+        elif k > 1 and k not in self.graphs and self.replayed < 16 * k:
             g1 = self._graph(1)
             for _ in range(k):
                 g1.replay()
@@ -1030,6 +1040,7 @@ class AbstractFastGP(torch.nn.Module):
         assert _FusedFitLoop.eligible(self), "fit_stepper needs the default transforms and parameter layouts"
         loop = self._get_fused_loop()
         loop.replayed = max(loop.replayed, loop.EAGER_ITERS)
+        loop.graph_after_eager = True
         loop.begin(2 ** 30, 2 ** 30, np.log(1.05), 1e-1)
         self._epoch += 1
         return loop

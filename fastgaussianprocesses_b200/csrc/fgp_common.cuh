@@ -160,6 +160,16 @@ __device__ __forceinline__ double dnb2_part(uint64_t delta, int alpha, int t) {
           beta * (s / 48.0 - 1.0 / 42.0)) - 1.0;
 }
 
+// net alpha = 2 without branches on alpha: W_2(delta) - 1 = 3/2 - (5/2) 2^-beta - beta x_f, beta = t - floor(log2 delta)
+__device__ __forceinline__ double dnb2_part_a2(uint64_t delta, int t, double tscale) {
+  const int fl = 63 - __clzll((long long)delta);  // -1 when delta == 0
+  const int beta = t - fl;
+  const double xf = __ull2double_rn(delta) * tscale;
+  const double pw = __longlong_as_double((long long)(1023 - beta) << 52);  // 2^-beta
+  const double r = fma(-(double)beta, xf, fma(-2.5, pw, 1.5));
+  return delta ? r : 1.5;
+}
+
 // float test point -> t-bit integer, fast_gp_digital_net_b2.py:270-271: floor((x % 1) * 2^t)
 __device__ __forceinline__ uint64_t dnb2_to_b(double x, int t) {
   double f = x - floor(x);

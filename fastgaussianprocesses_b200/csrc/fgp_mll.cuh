@@ -122,16 +122,6 @@ __device__ __forceinline__ double lat_delta_gen(uint32_t rev32, uint64_t zj) {
   return (double)(rev32 * (uint32_t)zj) * 0x1.0p-32;
 }
 
-// net alpha = 2 without branches on alpha: W_2(delta) - 1 = 3/2 - (5/2) 2^-beta - beta x_f, beta = t - floor(log2 delta)
-__device__ __forceinline__ double dnb2_part_a2(uint64_t delta, int t, double tscale) {
-  const int fl = 63 - __clzll((long long)delta);  // -1 when delta == 0
-  const int beta = t - fl;
-  const double xf = __ull2double_rn(delta) * tscale;
-  const double pw = __longlong_as_double((long long)(1023 - beta) << 52);  // 2^-beta
-  const double r = fma(-(double)beta, xf, fma(-2.5, pw, 1.5));
-  return delta ? r : 1.5;
-}
-
 // parts of point i against the first point.  A2: every alpha_j == 2 (straight-line code, no per-dimension loop on alpha)
 template <int DT, bool NET, bool A2, bool GEN>
 __device__ __forceinline__ void point_parts(const MllArgs& a, const Hyp& H, int64_t i, double* p) {

@@ -23,6 +23,7 @@ struct PostArgs {
   int64_t n;
   int d;
   int t;
+  double tscale;  // net: 2^-t
   const double* coeffs;  // (B,n)
   int B;
   double* partial;    // (splits, B, m) or the output itself when splits == 1
@@ -36,7 +37,7 @@ struct PostArgs {
   double pref;            // scale (times prod_j A_j on the fast path)
 };
 
-// MODE 0: lattice alpha=2 fast path; 1: lattice generic alpha; 2: net
+// MODE 0: lattice alpha=2 fast path; 1: lattice generic alpha; 2: net generic alpha; 3: net alpha=2 (branch-free part)
 template <int DT, int R, int MODE>
 __global__ void __launch_bounds__(kPT) post_mean_kernel(const __grid_constant__ PostArgs a) {
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(kPT) post_mean_kernel(const __grid_constant__ 
   const int b = blockIdx.z;
   const int64_t i0 = ((int64_t)blockIdx.x * kPT + threadIdx.x) * R;
   double xr[R][DM];
-  uint64_t xbr[R][MODE == 2 ? DM : 1];
+  uint64_t xbr[R][MODE >= 2 ? DM : 1];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int64_t i = i0 + r < a.m ? i0 + r : a.m - 1;
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(kPT) post_mean_kernel(const __grid_constant__ 
       const double v = a.xs[i * d + j];
       if (MODE == 0) xr[r][j] = v * a.sig[j];
       if (MODE == 1) xr[r][j] = v;
-      if (MODE == 2) xbr[r][j] = dnb2_to_b(v, a.t);
+      if (MODE >= 2) xbr[r][j] = dnb2_to_b(v, a.t);
     }
   }
   double acc[R];
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(kPT) post_mean_kernel(const __grid_constant__ 
     const int cnt = (int)min((int64_t)kTN, a1 - base);
     __syncthreads();
     for (int e = threadIdx.x; e < cnt * d; e += kPT) {
-      if (MODE == 2) {
+      if (MODE >= 2) {
         ((int64_t*)sX)[e] = ((const int64_t*)a.x)[base * d + e];
       } else {
         const double v = ((const double*)a.x)[base * d + e];
@@ -88,10 +89,14 @@ __global__ void __launch_bounds__(kPT) post_mean_kernel(const __grid_constant__ 
 #pragma unroll
       for (int j = 0; j < DM; ++j) {
         if (j >= d) break;
-        if (MODE == 2) {
+        if (MODE >= 2) {
           const uint64_t Xb = ((const uint64_t*)sX)[k * d + j];
 #pragma unroll
-          for (int r = 0; r < R; ++r) prod[r] *= fma(a.ls[j], dnb2_part(xbr[r][j] ^ Xb, a.alpha[j], a.t), 1.0);
+          for (int r = 0; r < R; ++r) {
+            const double part = MODE == 3 ? dnb2_part_a2(xbr[r][j] ^ Xb, a.t, a.tscale) : dnb2_part(xbr[r][j] ^ Xb, a.alpha[j], a.t);
+            const double f = fma(a.ls[j], part, 1.0);
+            prod[r] = j == 0 ? f : prod[r] * f;
+          }
         } else {
           const double X = sX[k * d + j];
 #pragma unroll
@@ -210,6 +215,7 @@ static int post_mean_common(int family, const double* xs, int64_t m, const void*
   a.n = n;
   a.d = d;
   a.t = t;
+  a.tscale = ldexp(1.0, -t);
   a.coeffs = coeffs;
   a.B = B;
   a.splits = choose_splits(m, n, d, B);
@@ -247,10 +253,13 @@ static int post_mean_common(int family, const double* xs, int64_t m, const void*
       a.ls[j] = ls_host[j];
       FGP_REQUIRE(alpha_host[j] >= 1 && alpha_host[j] <= 4, "post_mean: net alpha outside 1..4");
     }
-    mode = 2;
+    bool all2 = true;
+    for (int j = 0; j < d; ++j) all2 = all2 && alpha_host[j] == 2;
+    mode = all2 ? 3 : 2;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = mode == 0 ? dispatch_post_mean<0>(a, st) : (mode == 1 ? dispatch_post_mean<1>(a, st) : dispatch_post_mean<2>(a, st));
+  int rc = mode == 0 ? dispatch_post_mean<0>(a, st)
+                     : (mode == 1 ? dispatch_post_mean<1>(a, st) : (mode == 2 ? dispatch_post_mean<2>(a, st) : dispatch_post_mean<3>(a, st)));
   if (rc) return rc;
   if (a.splits > 1) {
     const int64_t total = (int64_t)B * m;

@@ -489,14 +489,32 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passA_kerne
     double2* sm = (double2*)smraw;
     double2* W = (double2*)a.W + (int64_t)b * a.n + g0;
     const FftTables T = a.T;
+#ifdef FGP_TIMING
+    long long tk0 = clock64();
+#endif
     tile_fill_c<false>(SmemC{sm, LP}, l1, lntr, [&](int tr, int idx) -> double2 {
       return make_double2(point_k1<DT, NET, A2, GEN>(a, H, g0 + ((int64_t)tr << l1) + idx) - c, 0.0);
     });
     __syncthreads();
+#ifdef FGP_TIMING
+    if (threadIdx.x == 0 && a.partC) {  // debug: cycles of the fill phase and of the whole CTA into the (unused here) partC buffer
+      a.partC[blockIdx.x * 4 + 0] = (double)(clock64() - tk0);
+      a.partC[blockIdx.x * 4 + 1] = (double)tk0;
+    }
+#endif
     block_fft_fwd_io<false>(sm, l1, lntr, LP, T.stage, SmemTag{}, [&](int tr, int idx, double2 v) {
       const uint32_t bb = (uint32_t)((blk0 + tr) & ((1 << l2) - 1));
       W[((int64_t)tr << l1) + idx] = cmul(v, twiddle_n(T, brev_bits(bb, l2) * (uint32_t)idx));
     });
+#ifdef FGP_TIMING
+    __syncthreads();
+    if (threadIdx.x == 0 && a.partC) {
+      a.partC[blockIdx.x * 4 + 2] = (double)(clock64() - tk0);
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      a.partC[blockIdx.x * 4 + 3] = (double)smid;
+    }
+#endif
   }
 }
 

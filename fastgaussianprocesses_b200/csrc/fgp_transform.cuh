@@ -40,6 +40,11 @@ namespace fgp {
 #define FGP_LB_BLOCKS_R 4
 #endif
 
+#ifndef FGP_FILL_UNROLL
+#define FGP_FILL_UNROLL 2
+#endif
+
+constexpr int kFillUnroll = FGP_FILL_UNROLL;  // unroll of the rolled element loops (independent chains per thread)
 constexpr int kTabLen = 4096;
 
 // padding: one element in 2^PS (PS = 3 for the radix-8 complex rounds, 4 for the radix-16 real rounds)
@@ -245,7 +250,7 @@ struct is_smem_tag<SmemTag> {
 template <bool TRFAST, class F>
 __device__ __forceinline__ void tile_fill_c(const SmemC& S, int l, int lntr, F f) {  // S(tr,idx) = f(tr,idx)
   const int total = 1 << (lntr + l);
-#pragma unroll 2
+#pragma unroll kFillUnroll
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
     const int tr = TRFAST ? (e & ((1 << lntr) - 1)) : (e >> l);
     const int idx = TRFAST ? (e >> lntr) : (e & ((1 << l) - 1));
@@ -265,7 +270,7 @@ __device__ __forceinline__ void tile_map_c(const SmemC& S, int l, int lntr, F f)
 template <bool TRFAST, class F>
 __device__ __forceinline__ void tile_drain_c(const SmemC& S, int l, int lntr, F f) {  // f(tr,idx,S(tr,idx))
   const int total = 1 << (lntr + l);
-#pragma unroll 2
+#pragma unroll kFillUnroll
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
     const int tr = TRFAST ? (e & ((1 << lntr) - 1)) : (e >> l);
     const int idx = TRFAST ? (e >> lntr) : (e & ((1 << l) - 1));

@@ -270,3 +270,47 @@ def test_sharded_posterior_single_process_is_identity():
     xt = torch.rand(21, 3, generator=torch.Generator().manual_seed(8))
     assert torch.equal(post_mean_sharded(gp, xt), gp.post_mean(xt))
     assert torch.equal(post_var_sharded(gp, xt), gp.post_var(xt))
+
+
+@pytest.mark.parametrize("family", ["lattice", "dnb2"])
+def test_shared_hyperparameters_over_a_batch_of_outputs_vs_oracle(family):
+    """shape_batch=[3] with ONE hyperparameter set: the loss sums the norm terms and weighs the log-determinant by the
+    number of outputs (abstract_gp.py:253-260); trajectory and posterior against the CPU oracle."""
+    import fastgaussianprocesses_b200 as fgp
+    from oracle import primitives as P
+    from oracle.fgp_oracle import OracleFastGP
+    d, n = 3, 512
+    if family == "lattice":
+        seq = fgp.Lattice(d, seed=21)
+        gp = fgp.FastGPLattice(seq, device=dev, shape_batch=[3], noise=1e-6)
+        o = OracleFastGP("lattice", P.lattice_points(seq.gen_vec, seq.shift, 0, n), alpha=2, noise=1e-6)
+    else:
+        seq = fgp.DigitalNetB2(d, seed=21)
+        gp = fgp.FastGPDigitalNetB2(seq, device=dev, shape_batch=[3], noise=1e-6)
+        xb, xh = P.dnb2_points(seq.gen_mats, seq.rshift, seq.t, 0, n)
+        o = OracleFastGP("dnb2", xh, xb=xb, t=seq.t, alpha=2, noise=1e-6)
+    x = gp.get_x_next(n)
+    fr = torch.tensor([1.0, 2.0, 3.0], device=x.device)[:, None]
+    y = torch.cos(2 * np.pi * x.sum(1)[None, :] * fr) + 0.2 * fr
+    gp.add_y_next(y)
+    o.add_y(y.cpu())
+    ro = o.fit(iterations=6, stop_crit_wait_iterations=100)
+    rg = gp.fit(iterations=6, verbose=0, store_loss_hist=True, stop_crit_wait_iterations=100)
+    assert rg["iterations"] == ro["iterations"] == 6
+    assert np.allclose(-rg["loss_hist"].numpy(), ro["loss_hist"], rtol=1e-9)
+    assert rel(gp.lengthscales, o.lengthscales) < 1e-8
+    xt = torch.rand(11, d, generator=torch.Generator().manual_seed(6))
+    pm = gp.post_mean(xt)
+    assert pm.shape == (3, 11)
+    ref = torch.stack([o.post_mean(xt, coeffs=o.solve(y[i].cpu())) for i in range(3)])
+    assert float((pm.cpu() - ref).abs().max()) < 1e-7 * float(y.abs().max())
+
+
+def test_fit_zero_iterations_evaluates_the_loss_once():
+    import fastgaussianprocesses_b200 as fgp
+    gp = fgp.FastGPLattice(fgp.Lattice(2, seed=1), device=dev, noise=1e-6)
+    x = gp.get_x_next(64)
+    gp.add_y_next(torch.cos(2 * np.pi * x).sum(1))
+    s0 = gp.scale.detach().clone()
+    data = gp.fit(iterations=0, verbose=0, store_loss_hist=True)
+    assert data["iterations"] == 0 and data["loss_hist"].shape == (1,) and torch.equal(gp.scale.detach(), s0)

@@ -1,3 +1,6 @@
+"""Phase timing of mll_passA from clock64 stamps.  Needs a -DFGP_TIMING build:
+    FGP_LIB_DIR=/tmp/lib_dbg FGP_BUILD_DEFS=-DFGP_TIMING python -m fastgaussianprocesses_b200.build
+    FGP_B200_LIB=/tmp/lib_dbg/libfgp_b200.so python tools/timing_probe.py"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -306,7 +306,7 @@ int fgp_dnb2_post_mean(const double* xs_dev, int64_t m, const int64_t* xb_dev, i
 size_t fgp_post_var_workspace_bytes(int family, int64_t m, int64_t n) {
   if (m <= 0 || n <= 0) return 0;
   const int64_t mc = fgp::post_var_chunk(m, n);
-  return (size_t)mc * n * (family == 0 ? 3 : 1) * sizeof(double);
+  return ((size_t)mc * n * (family == 0 ? 3 : 1) + 2) * sizeof(double);
 }
 
 static int post_var_common(int family, const double* xs, int64_t m, const void* x, int64_t n, int d, const int* alpha_host,
@@ -334,7 +334,7 @@ static int post_var_common(int family, const double* xs, int64_t m, const void* 
   const int64_t mc = post_var_chunk(m, n);
   cudaStream_t st = (cudaStream_t)stream;
   double* kreal = (double*)work;
-  double* kcplx = kreal + mc * n;
+  double* kcplx = kreal + ((mc * n + 1) & ~(int64_t)1);  // complex rows need 16-byte alignment (mc*n may be odd when n = 1)
   for (int64_t i0 = 0; i0 < m; i0 += mc) {
     const int64_t cnt = m - i0 < mc ? m - i0 : mc;
     int rc;

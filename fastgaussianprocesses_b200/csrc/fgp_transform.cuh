@@ -107,8 +107,23 @@ __device__ __forceinline__ double2 mul_root16c(double2 t, int k) {
 // TW: twiddles of stage u come from the per-stage table, Wt[(1<<u) - 1 + cm] = exp(-i pi (low + cm 2^s) / 2^(s+u)) -- the
 // very values (and the single complex multiply per butterfly) of the reference's radix-2 recursion, so the round-off
 // matches it; !TW (first round, low = 0): compile-time 8th/16th roots of unity.
+#ifndef FGP_TW_FACTORIZED
+#define FGP_TW_FACTORIZED 0
+#endif
+// twiddle registers per group: 2^R - 1 table values, or (FGP_TW_FACTORIZED) R base values B_u = exp(-i pi low / 2^(s+u)) that
+// are combined with compile-time roots exp(-i pi cm / 2^u) (3 loads instead of 7 per radix-8 group; one extra rounding on
+// half of the butterflies)
+template <int R>
+struct TwCount {
+#if FGP_TW_FACTORIZED
+  static constexpr int value = R > 0 ? R : 1;
+#else
+  static constexpr int value = (1 << R) - 1 > 0 ? (1 << R) - 1 : 1;
+#endif
+};
+
 template <int R, bool INV, bool TW>
-__device__ __forceinline__ void butterflies(double2 (&v)[1 << R], const double2 (&Wt)[(1 << R) - 1 > 0 ? (1 << R) - 1 : 1]) {
+__device__ __forceinline__ void butterflies(double2 (&v)[1 << R], const double2 (&Wt)[TwCount<R>::value]) {
   constexpr int RAD = 1 << R;
   if (!INV) {
 #pragma unroll
@@ -118,10 +133,15 @@ __device__ __forceinline__ void butterflies(double2 (&v)[1 << R], const double2 
         if (c & (1 << u)) continue;
         const int cm = c & ((1 << u) - 1);
         double2 t = v[c | (1 << u)];
+#if FGP_TW_FACTORIZED
+        if (TW) t = cmul(Wt[u], t);
+        t = mul_root16(t, cm << (3 - u));
+#else
         if (TW)
           t = cmul(Wt[(1 << u) - 1 + cm], t);
         else
           t = mul_root16(t, cm << (3 - u));
+#endif
         v[c | (1 << u)] = csub(v[c], t);
         v[c] = cadd(v[c], t);
       }
@@ -136,10 +156,15 @@ __device__ __forceinline__ void butterflies(double2 (&v)[1 << R], const double2 
         const double2 a = v[c], b = v[c | (1 << u)];
         v[c] = cadd(a, b);
         double2 t = csub(a, b);
+#if FGP_TW_FACTORIZED
+        t = mul_root16c(t, cm << (3 - u));
+        if (TW) t = cmulc(Wt[u], t);
+#else
         if (TW)
           t = cmulc(Wt[(1 << u) - 1 + cm], t);
         else
           t = mul_root16c(t, cm << (3 - u));
+#endif
         v[c | (1 << u)] = t;
       }
     }
@@ -167,11 +192,16 @@ __device__ __forceinline__ GroupIdx group_of(int g, int s, int l, int lntr) {
 }
 
 template <int R>
-__device__ __forceinline__ void load_twiddles(double2 (&Wt)[(1 << R) - 1 > 0 ? (1 << R) - 1 : 1], const double2* __restrict__ tw, int s, int low) {
+__device__ __forceinline__ void load_twiddles(double2 (&Wt)[TwCount<R>::value], const double2* __restrict__ tw, int s, int low) {
+#if FGP_TW_FACTORIZED
+#pragma unroll
+  for (int u = 0; u < R; ++u) Wt[u] = __ldg(tw + (1 << (s + u)) + low);
+#else
 #pragma unroll
   for (int u = 0; u < R; ++u)
 #pragma unroll
     for (int cm = 0; cm < (1 << u); ++cm) Wt[(1 << u) - 1 + cm] = __ldg(tw + (1 << (s + u)) + low + (cm << s));
+#endif
 }
 
 struct SmemC {
@@ -201,7 +231,7 @@ __device__ __forceinline__ void fft_round_io(int s, int l, int lntr, const doubl
   const int stp = s == 0 ? 1 : (1 << s) + (1 << (s - kPSC));
   for (int g = threadIdx.x; g < total; g += blockDim.x) {
     const GroupIdx G = group_of<R, TRFAST>(g, s, l, lntr);
-    double2 B[(1 << R) - 1 > 0 ? (1 << R) - 1 : 1];
+    double2 B[TwCount<R>::value];
     if (s > 0) load_twiddles<R>(B, tw, s, G.low);
     double2 v[RAD];
     if constexpr (is_smemc<Ld>::value) {

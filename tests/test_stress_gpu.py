@@ -1,0 +1,133 @@
+"""Randomised parity sweep of the fused eigen-solve against the CPU oracle over dimensions, sizes (single- and two-pass,
+every remainder of log2 n modulo the round sizes), smoothness orders and both families, plus edge sizes n = 1, 2.
+Tolerances as in test_kernels_gpu.py; the nugget keeps the spectrum above the round-off floor so that the sums are
+well conditioned and the comparison measures the kernels, not the conditioning."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+dev = "cuda:0"
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().cpu()
+    b = torch.as_tensor(b).detach().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+
+
+CASES = []
+_rng = np.random.default_rng(2024)
+for fam in (0, 1):
+    for m in list(range(0, 18)):
+        d = int(_rng.choice([1, 2, 3, 4, 5, 7, 8, 16] if m > 12 else [1, 2, 3, 4, 5, 7, 8, 16, 32]))
+        alpha = int(_rng.integers(1, 5)) if (fam == 1 or m > 14) else int(_rng.integers(1, 7))
+        CASES.append((fam, d, m, alpha))
+
+
+@pytest.mark.parametrize("fam,d,m,alpha", CASES)
+def test_mll_grad_vs_oracle_sweep(fam, d, m, alpha):
+    from fastgaussianprocesses_b200 import _lib as L
+    from oracle import primitives as P
+    from oracle.fgp_oracle import OracleFastGP
+    n = 1 << m
+    rng = np.random.default_rng(1000 * fam + 37 * m + d)
+    ls0 = rng.uniform(0.3, 1.2, size=d) / np.sqrt(d)
+    sc0 = float(rng.uniform(0.5, 3.0))
+    nz = 1e-2
+    if fam == 0:
+        z = P.default_lattice_gen_vec(d)
+        xh = P.lattice_points(z, rng.random(d), 0, n)
+        o = OracleFastGP("lattice", xh, alpha=alpha, scale=sc0, lengthscales=ls0, noise=nz)
+        xpts = torch.from_numpy(xh).to(dev)
+        t, gen = 0, dict(z=[int(v) for v in z])
+    else:
+        t = int(rng.choice([32, 40, 52, 63]))
+        Ch = P.default_dnb2_gen_mats(d, t)
+        xbh, xh = P.dnb2_points(Ch, rng.integers(0, 2 ** t, size=d, dtype=np.uint64), t, 0, n)
+        o = OracleFastGP("dnb2", xh, xb=xbh, t=t, alpha=alpha, scale=sc0, lengthscales=ls0, noise=nz)
+        xpts = torch.from_numpy(xbh).to(dev)
+        gen = dict(C=torch.from_numpy(Ch.astype(np.int64)).to(dev))
+    y = torch.cos(2 * np.pi * o.x).sum(1) + 0.3 * torch.sin(2 * np.pi * o.x[:, 0] * 3) + 0.1
+    o.add_y(y)
+    loss, norm, logdet = o.mll_loss()
+    loss.backward()
+    yt = o.ytilde
+    ysq = (torch.view_as_real(yt).pow(2).sum(-1) if yt.is_complex() else yt ** 2).reshape(1, n).to(dev)
+    scale = torch.tensor([sc0], device=dev)
+    ls = torch.from_numpy(ls0).to(dev).reshape(1, d)
+    noise = torch.tensor([nz], device=dev)
+    for kw in (dict(), gen):  # stored points, then generator mode
+        out, lam = L.mll_grad(fam, xpts, [alpha] * d, t, ysq, scale, ls, noise, want_grad=True, want_lam=True, **kw)
+        out = out.cpu().numpy()[0]
+        assert rel(lam[0], o.full_lam().detach()) < 1e-10
+        assert abs(out[0] - norm.item()) <= 1e-9 * abs(norm.item())
+        assert abs(out[1] - logdet.item()) <= 1e-10 * max(abs(logdet.item()), 1.0)
+        assert rel(out[3] * sc0, o.raw_scale.grad) < 1e-8
+        assert rel(out[4:4 + d] * ls0, o.raw_lengthscales.grad) < 1e-7
+
+
+@pytest.mark.parametrize("fam,d,m", [(0, 3, 0), (1, 2, 0), (0, 2, 1), (1, 3, 1), (0, 1, 2), (1, 1, 3)])
+def test_api_tiny_sizes(fam, d, m):
+    """n = 1, 2, 4, 8 through the public API: fit, posterior mean / variance shapes and finiteness, interpolation."""
+    import fastgaussianprocesses_b200 as fgp
+    n = 1 << m
+    gp = (fgp.FastGPLattice(fgp.Lattice(d, seed=3), device=dev, noise=1e-6) if fam == 0 else
+          fgp.FastGPDigitalNetB2(fgp.DigitalNetB2(d, seed=3), device=dev, noise=1e-6))
+    x = gp.get_x_next(n)
+    y = torch.cos(2 * np.pi * x).sum(1) + 1.0
+    gp.add_y_next(y)
+    data = gp.fit(iterations=4, verbose=0, stop_crit_wait_iterations=100)
+    assert data["iterations"] == 4
+    pm, pv = gp.post_mean(x), gp.post_var(x)
+    assert pm.shape == (n,) and pv.shape == (n,)
+    assert torch.allclose(pm, y, atol=1e-4) and (pv >= 0).all() and float(pv.max()) < 1e-3
+
+
+PCASES = []
+_rng2 = np.random.default_rng(77)
+for fam in (0, 1):
+    for m in (0, 1, 3, 6, 7, 9, 12, 13):
+        d = int(_rng2.choice([1, 2, 3, 5, 8, 16, 32]))
+        alpha = int(_rng2.integers(1, 5)) if fam == 1 else int(_rng2.integers(1, 6))
+        mt = int(_rng2.choice([1, 7, 33, 300, 513]))
+        PCASES.append((fam, d, m, alpha, mt))
+
+
+@pytest.mark.parametrize("fam,d,m,alpha,mt", PCASES)
+def test_posterior_vs_oracle_sweep(fam, d, m, alpha, mt):
+    """post_mean / post_var / post_cov / kernel() against the oracle for ragged test-set sizes, every dimension class
+    (specialised d = 2,4,8,16 and the generic path) and tiny to two-pass training sizes."""
+    import fastgaussianprocesses_b200 as fgp
+    from oracle import primitives as P
+    from oracle.fgp_oracle import OracleFastGP
+    n = 1 << m
+    rng = np.random.default_rng(500 * fam + 11 * m + d)
+    ls0 = torch.from_numpy(rng.uniform(0.3, 1.2, size=d) / np.sqrt(d))
+    sc0, nz = float(rng.uniform(0.5, 3.0)), 1e-3
+    if fam == 0:
+        seq = fgp.Lattice(d, seed=5 + m)
+        gp = fgp.FastGPLattice(seq, device=dev, alpha=alpha, scale=sc0, lengthscales=ls0.clone(), noise=nz)
+        o = OracleFastGP("lattice", P.lattice_points(seq.gen_vec, seq.shift, 0, n), alpha=alpha, scale=sc0, lengthscales=ls0, noise=nz)
+    else:
+        seq = fgp.DigitalNetB2(d, seed=5 + m, t=int(rng.choice([32, 52, 63])))
+        gp = fgp.FastGPDigitalNetB2(seq, device=dev, alpha=alpha, scale=sc0, lengthscales=ls0.clone(), noise=nz)
+        xb, xh = P.dnb2_points(seq.gen_mats, seq.rshift, seq.t, 0, n)
+        o = OracleFastGP("dnb2", xh, xb=xb, t=seq.t, alpha=alpha, scale=sc0, lengthscales=ls0, noise=nz)
+    x = gp.get_x_next(n)
+    y = torch.cos(2 * np.pi * x).sum(1) + 0.5
+    gp.add_y_next(y)
+    o.add_y(y.cpu())
+    xt = torch.rand(mt, d, generator=torch.Generator().manual_seed(m + 1))
+    ymax = float(y.abs().max())
+    with torch.no_grad():
+        assert rel(gp.coeffs, o.coeffs()) < 1e-9
+        assert float((gp.post_mean(xt).cpu() - o.post_mean(xt)).abs().max()) < 1e-9 * ymax * max(1.0, n ** 0.5)
+        assert float((gp.post_var(xt).cpu() - o.post_var(xt)).abs().max()) < 1e-9 * sc0 * max(1.0, n ** 0.5)
+        k = min(mt, 9)
+        kref = o.kernel(xt[:k, None, :], xt[None, :k, :])
+        assert rel(gp.kernel(xt[:k, None, :], xt[None, :k, :]), kref) < 1e-12
+        assert rel(gp.kernel(xt[:k], xt[:k]), kref.diagonal()) < 1e-12
+        pc = gp.post_cov(xt[:k], xt[:k])
+        assert torch.allclose(pc.diagonal().cpu(), o.post_var(xt[:k]), atol=1e-8 * sc0 * max(1.0, n ** 0.5))
+        assert torch.allclose(pc, pc.T, atol=1e-9 * sc0 * max(1.0, n ** 0.5))

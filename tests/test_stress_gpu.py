@@ -121,7 +121,8 @@ def test_posterior_vs_oracle_sweep(fam, d, m, alpha, mt):
     xt = torch.rand(mt, d, generator=torch.Generator().manual_seed(m + 1))
     ymax = float(y.abs().max())
     with torch.no_grad():
-        assert rel(gp.coeffs, o.coeffs()) < 1e-9
+        # K^-1 y is conditioned like lam_max / lam_min ~ n * scale / noise ~ 1e7 here: 1e-16 * 1e7 with some margin
+        assert rel(gp.coeffs, o.coeffs()) < 1e-8
         assert float((gp.post_mean(xt).cpu() - o.post_mean(xt)).abs().max()) < 1e-9 * ymax * max(1.0, n ** 0.5)
         assert float((gp.post_var(xt).cpu() - o.post_var(xt)).abs().max()) < 1e-9 * sc0 * max(1.0, n ** 0.5)
         k = min(mt, 9)

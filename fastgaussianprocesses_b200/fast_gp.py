@@ -80,6 +80,31 @@ class _XXbSeq(object):
         return self.x[i], self.xb[i]
 
 
+class _FTFunction(torch.autograd.Function):
+    """The unitary transforms of libfgp_b200 with autograd (kind 0: FFT-BRO, 1: inverse FFT-BRO, 2: FWHT): the backward of
+    y = T x is the adjoint T^H g, i.e. the inverse transform (real part for a real input).  This is the differentiable
+    seam the reference injects at fast_gp_lattice.py:224-225 / fast_gp_digital_net_b2.py:226; it carries the GCV / CV
+    losses and masked fits, whose gradients are not in the fused MLL kernel."""
+
+    @staticmethod
+    def forward(ctx, x, kind):
+        ctx.kind = kind
+        ctx.real_in = not x.is_complex()
+        if kind == 0:
+            return _lib.fftbr(x)
+        if kind == 1:
+            return _lib.ifftbr(x)
+        return _lib.fwht(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        if ctx.kind == 2:
+            return _lib.fwht(g), None
+        gi = _lib.ifftbr(g) if ctx.kind == 0 else _lib.fftbr(g)
+        return (gi.real if ctx.real_in else gi), None
+
+
 class _MLLFunction(torch.autograd.Function):
     """loss_b = wn_b*norm_b + wl_b*logdet_b of B hyperparameter sets with the analytic gradient of the fused kernel
     (replaces autograd through util.py:285-300,354-370 and the transform)."""
@@ -417,18 +442,21 @@ class _FastInverseLogDetCache(object):
         return norm_cols.reshape(sb + (1,)), ld.reshape(tuple(pshape) + (1,))
 
     def get_gcv_numer_denom(self):
+        """util.py:371-380, differentiable through the autograd transform."""
         fgp = self.fgp
+        assert self.nint == fgp._nint, "GCV needs the current data size"
         ytilde = fgp.get_ytilde(0)
-        inv, _ = self()
-        ztilde = ytilde * inv[..., 0, 0, :]
+        inv = 1 / fgp._lam_autograd(self.nint)
+        ztilde = ytilde * inv
         numer = (ztilde.conj() * ztilde).real.sum(-1, keepdim=True)
-        tr_k_inv = inv[..., 0, 0, :].real.sum(-1, keepdim=True)
+        tr_k_inv = inv.real.sum(-1, keepdim=True)
         denom = ((tr_k_inv / self.nint) ** 2).real
         return numer, denom
 
     def get_inv_diag(self):
-        lam = self._lam_full().reshape(tuple(self.pshape) + (self.nint,))
-        return (1 / lam).mean(-1, keepdim=True)
+        """util.py:381-385 (single task): mean of 1 / (lam~ sqrt(n)), lam~ = ft(k1) without the noise, as in the reference."""
+        _, lam_tilde = self.fgp._lam_autograd(self.nint, with_tilde=True)
+        return (1 / (lam_tilde * np.sqrt(self.nint))).mean(-1, keepdim=True)
 
 
 class AbstractFastGP(torch.nn.Module):
@@ -885,6 +913,64 @@ class AbstractFastGP(torch.nn.Module):
         return torch.stack(outs, 0).reshape(tuple(pshape) + tuple(outs[0].shape))
 
     # ------------------------------------------------------------------------------------------------ fit
+    def _lam_autograd(self, n=None, with_tilde=False):
+        """Full eigenvalues (sqrt(n) ft(k1) + noise) K_task with autograd through the differentiable transform, from the cached
+        hyperparameter-independent kernel parts (util.py:95-141, :285-298).  Shape (*param batch, n).  with_tilde: also
+        return lam~ = ft(k1), the quantity `get_lam` hands out."""
+        n = self._nint if n is None else int(n)
+        cached = getattr(self, "_k1parts_cache", None)
+        if cached is None or cached[0] != n:
+            with torch.no_grad():
+                cached = (n, self.get_k1parts(0, 0, n)[:, 0, 0, :].contiguous())
+            self._k1parts_cache = cached
+        parts = cached[1]
+        scale, ls, noise = self.scale, self.lengthscales, self.noise
+        k1 = scale * (1 + ls[..., None, :] * parts).prod(-1)
+        lam_tilde = self.ft(k1)
+        lam = (np.sqrt(n) * lam_tilde + noise) * self.gram_matrix_tasks[..., 0, 0][..., None]
+        return (lam, lam_tilde) if with_tilde else lam
+
+    def _autograd_loss(self, loss_metric, masks, cv_weights, d_out, mll_const):
+        """The reference's three losses written on the differentiable spectrum (abstract_gp.py:242-273, util.py:354-394);
+        used for GCV, CV and masked fits.  Returns (loss, term1, term2, metric_val)."""
+        n = self._nint
+        lam, lam_tilde = self._lam_autograd(n, with_tilde=True)
+        inv = 1 / lam
+        ytilde = self.get_ytilde(0)
+        ztilde = ytilde * inv
+        sb = list(self.shape_batch)
+        if loss_metric == "MLL":
+            norm_term = (ytilde.conj() * ztilde).real.sum(-1, keepdim=True)
+            logdet = torch.log(torch.abs(lam)).sum(-1)[..., None]
+            if masks is None:
+                term1 = norm_term.sum()
+                term2 = d_out / _prod(logdet.shape) * logdet.sum()
+            else:
+                term1 = norm_term[..., *masks, 0].sum()
+                term2 = logdet.expand(sb + [1])[..., *masks, 0].sum()
+            loss = 1 / 2 * (term1 + term2 + mll_const)
+            return loss, term1, term2, -loss
+        if loss_metric == "GCV":
+            numer = (ztilde.conj() * ztilde).real.sum(-1, keepdim=True)
+            tr_k_inv = inv.real.sum(-1, keepdim=True)
+            denom = ((tr_k_inv / n) ** 2).real
+            if masks is None:
+                term1, term2 = numer, denom
+            else:
+                term1 = numer[..., *masks, :]
+                term2 = denom.expand(sb + [1])[..., *masks, :]
+            loss = (term1 / term2).sum()
+            return loss, term1, term2, loss
+        # CV (abstract_gp.py:262-273 with util.py:381-385): the reference divides by 1 / (lam~ sqrt(n)) WITHOUT the noise
+        coeffs = self.ift(ztilde).real
+        inv_diag = (1 / (lam_tilde * np.sqrt(n))).mean(-1, keepdim=True)
+        if inv_diag.is_complex():
+            raise TypeError("loss_metric='CV' is complex-valued for FastGPLattice in the reference (util.py:381-385 divides by the complex lam); it is only defined for FastGPDigitalNetB2")
+        squared_sums = ((coeffs / inv_diag) ** 2 * cv_weights).sum(-1, keepdim=True)
+        loss = squared_sums.sum() if masks is None else squared_sums[..., *masks, 0].sum()
+        nan = torch.nan * torch.ones(1)
+        return loss, nan, nan, loss
+
     def _mll_terms(self, want_grad):
         """Weighted MLL per hyperparameter set through the fused kernel; returns (loss, term1, term2) tensors."""
         scale_B, ls_B, noise_B, pshape = self._hyper()
@@ -933,11 +1019,12 @@ class AbstractFastGP(torch.nn.Module):
         assert isinstance(stop_crit_wait_iterations, int) and stop_crit_wait_iterations > 0
         assert masks is None or (isinstance(masks, torch.Tensor))
         loss_metric = loss_metric.upper()
-        if loss_metric != "MLL":
-            raise NotImplementedError("loss_metric=%r: only the MLL loss is on the B200 hot path built so far (SURVEY.md section 8(f) row 4)" % loss_metric)
-        if masks is not None:
-            raise NotImplementedError("fit(masks=...) is not supported by the B200 hot path built so far")
-        fused = optimizer is None and _FusedFitLoop.eligible(self) and os.environ.get("FGP_B200_GENERIC_FIT") != "1"
+        # MLL without masks: fused CUDA eigen-solve with the analytic gradient.  GCV, CV and masked fits: the same transforms
+        # behind torch.autograd (_FTFunction), formulas as in the reference.
+        autograd_route = loss_metric != "MLL" or masks is not None
+        if isinstance(cv_weights, torch.Tensor):
+            cv_weights = cv_weights.to(self.device)
+        fused = (not autograd_route) and optimizer is None and _FusedFitLoop.eligible(self) and os.environ.get("FGP_B200_GENERIC_FIT") != "1"
         if optimizer is None:
             optimizer = self.get_default_optimizer(lr)
         assert isinstance(optimizer, torch.optim.Optimizer)
@@ -960,7 +1047,13 @@ class AbstractFastGP(torch.nn.Module):
             noise_hist = torch.empty(torch.Size([iterations + 1]) + self.raw_noise.shape)
         if store_task_kernel_hist:
             task_kernel_hist = torch.empty(torch.Size([iterations + 1]) + self.gram_matrix_tasks.shape)
-        d_out = _prod(self.shape_batch)
+        if masks is not None:
+            masks = torch.atleast_2d(masks)
+            assert masks.ndim == 2
+            assert len(masks) <= len(self.shape_batch)
+            d_out = torch.empty(self.shape_batch)[..., *masks].numel()
+        else:
+            d_out = _prod(self.shape_batch)
         if verbose:
             _s = "%16s | %-10s | %-10s | %-10s" % ("iter of %.1e" % iterations, "loss", "term1", "term2")
             print(" " * verbose_indent + _s)
@@ -972,9 +1065,12 @@ class AbstractFastGP(torch.nn.Module):
         want_grad = any(p.requires_grad for p in self.parameters())
         self.get_ytilde(0)
         for i in range(iterations + 1):
-            wsum, term1, term2 = self._mll_terms(want_grad)
-            loss = wsum + 0.5 * mll_const
-            metric_val = -loss
+            if autograd_route:
+                loss, term1, term2, metric_val = self._autograd_loss(loss_metric, masks, cv_weights, d_out, mll_const)
+            else:
+                wsum, term1, term2 = self._mll_terms(want_grad)
+                loss = wsum + 0.5 * mll_const
+                metric_val = -loss
             lossv = loss.item()
             if lossv < stop_crit_best_loss:
                 stop_crit_best_loss = lossv
@@ -986,7 +1082,7 @@ class AbstractFastGP(torch.nn.Module):
                 stop_crit_iterations_without_improvement_loss += 1
             break_condition = i == iterations or stop_crit_iterations_without_improvement_loss == stop_crit_wait_iterations
             if store_loss_hist:
-                loss_hist[i] = -lossv
+                loss_hist[i] = metric_val.item()
             if store_scale_hist:
                 scale_hist[i] = self.scale.detach().to(scale_hist.device)
             if store_lengthscales_hist:
@@ -996,7 +1092,7 @@ class AbstractFastGP(torch.nn.Module):
             if store_task_kernel_hist:
                 task_kernel_hist[i] = self.gram_matrix_tasks.detach().to(task_kernel_hist.device)
             if verbose and (i % verbose == 0 or break_condition):
-                _s = "%16.2e | %-10.2e | %-10.2e | %-10.2e" % (i, lossv, term1.item(), term2.item())
+                _s = "%16.2e | %-10.2e | %-10.2e | %-10.2e" % (i, lossv, term1.item() if term1.numel() == 1 else torch.nan, term2.item() if term2.numel() == 1 else torch.nan)
                 print(" " * verbose_indent + _s)
             if break_condition:
                 break
@@ -1347,10 +1443,10 @@ class FastGPLattice(AbstractFastGP):
         return torch.exp(-torch.pi * 1j * torch.arange(2 ** m, device=self.device) / 2 ** m)
 
     def _ft_unstable(self, x):
-        return _lib.fftbr(x)
+        return _FTFunction.apply(x, 0)
 
     def _ift_unstable(self, x):
-        return _lib.ifftbr(x)
+        return _FTFunction.apply(x, 1)
 
     def _ominus(self, x, z):
         return (x - z) % 1
@@ -1425,7 +1521,7 @@ class FastGPDigitalNetB2(AbstractFastGP):
         return 1
 
     def _ft_unstable(self, x):
-        return _lib.fwht(x)
+        return _FTFunction.apply(x, 2)
 
     _ift_unstable = _ft_unstable
 

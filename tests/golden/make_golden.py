@@ -96,6 +96,37 @@ def run_case(name, family, d, n, m_test, alpha, f, scale=1.0, lengthscales=1.0, 
     out["ytilde_2n"] = gp.get_ytilde(0).detach().numpy()
     out["pmean_2n"] = gp.post_mean(xt[:64]).numpy()
     out["pvar_2n"] = gp.post_var(xt[:64]).numpy()
+    # GCV / CV losses (abstract_gp.py:242-251,262-273; util.py:371-394) on fresh objects: value + autograd gradient at the
+    # initial hyperparameters and a short fit trajectory.  CV only for the net: the reference's lattice CV loss is complex
+    # (get_inv_diag divides by the complex lam) and fails at `loss.item()<...`.
+    for metric in (["GCV", "CV"] if family == "dnb2" else ["GCV"]):
+        if family == "lattice":
+            gp2 = fastgps.FastGPLattice(qmcpy.Lattice(dimension=d, seed=seed), alpha=alpha, scale=scale, lengthscales=lengthscales, **kw)
+        else:
+            gp2 = fastgps.FastGPDigitalNetB2(qmcpy.DigitalNetB2(dimension=d, seed=seed), alpha=alpha, scale=scale, lengthscales=lengthscales, **kw)
+        gp2.add_y_next(f(gp2.get_x_next(n)))
+        os.environ["FASTGP_FORCE_RECOMPILE"] = "True"
+        cache2 = gp2.get_inv_log_det_cache()
+        if metric == "GCV":
+            numer, denom = cache2.get_gcv_numer_denom()
+            loss2 = (numer / denom).sum()
+        else:
+            coeffs2 = gp2.coeffs
+            del os.environ["FASTGP_FORCE_RECOMPILE"]
+            inv_diag = cache2.get_inv_diag()
+            os.environ["FASTGP_FORCE_RECOMPILE"] = "True"
+            loss2 = ((coeffs2 / inv_diag) ** 2).sum(-1, keepdim=True).sum()
+        loss2.backward()
+        key = metric.lower()
+        out[key + "_loss0"] = loss2.item()
+        out[key + "_grad_raw_scale0"] = gp2.raw_scale.grad.numpy().copy()
+        out[key + "_grad_raw_lengthscales0"] = gp2.raw_lengthscales.grad.numpy().copy()
+        gp2.zero_grad()
+        if "FASTGP_FORCE_RECOMPILE" in os.environ:
+            del os.environ["FASTGP_FORCE_RECOMPILE"]
+        data2 = gp2.fit(loss_metric=metric, iterations=8, verbose=0, store_hists=True, stop_crit_wait_iterations=100)
+        out[key + "_loss_hist"] = data2["loss_hist"].numpy()
+        out[key + "_lengthscales_hist"] = data2["lengthscales_hist"].numpy()
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print(name, "loss0", out["loss0"], "its", data["iterations"], os.path.getsize(path) // 1024, "KiB")

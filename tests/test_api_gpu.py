@@ -314,3 +314,52 @@ def test_fit_zero_iterations_evaluates_the_loss_once():
     s0 = gp.scale.detach().clone()
     data = gp.fit(iterations=0, verbose=0, store_loss_hist=True)
     assert data["iterations"] == 0 and data["loss_hist"].shape == (1,) and torch.equal(gp.scale.detach(), s0)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_gcv_and_cv_losses_match_reference_fixture(case):
+    """GCV (both families) and CV (net) losses through the autograd route: value, gradient w.r.t. the raw parameters and a
+    short fit trajectory against the unmodified reference (tests/golden/make_golden.py)."""
+    g = load_golden(case)
+    n = int(g["n"])
+    for metric in (["GCV", "CV"] if "cv_loss0" in g else ["GCV"]):
+        key = metric.lower()
+        gp = make_gp(g)
+        gp.add_y_next(torch.from_numpy(g["y"]))
+        gp.get_x_next(n)
+        cache = gp.get_inv_log_det_cache()
+        if metric == "GCV":
+            numer, denom = cache.get_gcv_numer_denom()
+            loss = (numer / denom).sum()
+        else:
+            loss = ((gp.coeffs / cache.get_inv_diag()) ** 2).sum(-1, keepdim=True).sum()
+        if metric == "CV":  # coeffs is a no-grad cache; the differentiable value comes from the fit route
+            loss, _, _, _ = gp._autograd_loss("CV", None, 1, 1, 0.0)
+        assert abs(float(loss) - float(g[key + "_loss0"])) <= 1e-8 * abs(float(g[key + "_loss0"]))
+        loss.backward()
+        assert rel(gp.raw_scale.grad, g[key + "_grad_raw_scale0"]) < 1e-6 or float(np.abs(g[key + "_grad_raw_scale0"]).max()) < 1e-9 * abs(float(g[key + "_loss0"]))
+        assert rel(gp.raw_lengthscales.grad, g[key + "_grad_raw_lengthscales0"]) < 1e-6
+        gp.zero_grad()
+        data = gp.fit(loss_metric=metric, iterations=8, verbose=0, store_hists=True, stop_crit_wait_iterations=100)
+        assert np.allclose(data["loss_hist"].numpy(), g[key + "_loss_hist"], rtol=1e-6)
+        assert rel(data["lengthscales_hist"], g[key + "_lengthscales_hist"]) < 1e-6
+
+
+def test_masked_mll_fit_equals_fit_on_the_selected_outputs():
+    """fit(masks=...) optimises only y[..., *masks] (abstract_gp.py:226-231,257-259): with one shared hyperparameter set it
+    must follow the trajectory of a GP that only holds those outputs."""
+    import fastgaussianprocesses_b200 as fgp
+    d, n = 2, 256
+    mk = lambda **kw: fgp.FastGPDigitalNetB2(fgp.DigitalNetB2(d, seed=13), device=dev, noise=1e-6, **kw)
+    gpa = mk(shape_batch=[3])
+    x = gpa.get_x_next(n)
+    fr = torch.tensor([1.0, 2.0, 3.0], device=x.device)[:, None]
+    y = torch.cos(2 * np.pi * x.sum(1)[None, :] * fr)
+    gpa.add_y_next(y)
+    da = gpa.fit(masks=torch.tensor([0, 2]), iterations=6, verbose=0, store_hists=True, stop_crit_wait_iterations=100)
+    gpb = mk(shape_batch=[2])
+    gpb.get_x_next(n)
+    gpb.add_y_next(y[[0, 2]])
+    db = gpb.fit(iterations=6, verbose=0, store_hists=True, stop_crit_wait_iterations=100)
+    assert np.allclose(da["loss_hist"].numpy(), db["loss_hist"].numpy(), rtol=1e-8)
+    assert rel(da["lengthscales_hist"], db["lengthscales_hist"]) < 1e-7

@@ -791,6 +791,8 @@ class AbstractFastGP(torch.nn.Module):
         x = x.to(self.device)
         xmean = x.mean(-1)
         y = self.ft_unstable(x - xmean[..., None])
+        if y.requires_grad:
+            y = y.clone()  # autograd forbids in-place edits of a view of a custom Function's output
         y[..., 0] += xmean * np.sqrt(x.size(-1))
         return y
 
@@ -799,6 +801,8 @@ class AbstractFastGP(torch.nn.Module):
         x = x.to(self.device)
         xmean = x.mean(-1)
         y = self.ift_unstable(x - xmean[..., None])
+        if y.requires_grad:
+            y = y.clone()
         y[..., 0] += xmean * np.sqrt(x.size(-1))
         return y
 

@@ -337,7 +337,9 @@ def test_gcv_and_cv_losses_match_reference_fixture(case):
             loss, _, _, _ = gp._autograd_loss("CV", None, 1, 1, 0.0)
         assert abs(float(loss) - float(g[key + "_loss0"])) <= 1e-8 * abs(float(g[key + "_loss0"]))
         loss.backward()
-        assert rel(gp.raw_scale.grad, g[key + "_grad_raw_scale0"]) < 1e-6 or float(np.abs(g[key + "_grad_raw_scale0"]).max()) < 1e-9 * abs(float(g[key + "_loss0"]))
+        # GCV is invariant to the scale up to the nugget: that derivative is a cancellation residue ~1e-9 of the loss
+        gs_ref = float(g[key + "_grad_raw_scale0"][0])
+        assert abs(float(gp.raw_scale.grad[0]) - gs_ref) <= 1e-6 * abs(gs_ref) + 1e-10 * abs(float(g[key + "_loss0"]))
         assert rel(gp.raw_lengthscales.grad, g[key + "_grad_raw_lengthscales0"]) < 1e-6
         gp.zero_grad()
         data = gp.fit(loss_metric=metric, iterations=8, verbose=0, store_hists=True, stop_crit_wait_iterations=100)

@@ -24,6 +24,7 @@ import scipy.stats
 import torch
 
 from . import _lib
+from . import multitask
 from . import sequences
 
 
@@ -484,8 +485,8 @@ class AbstractFastGP(torch.nn.Module):
         else:
             assert isinstance(num_tasks, int) and num_tasks > 0
             solo_task, default_task = False, torch.arange(num_tasks)
-        if num_tasks != 1:
-            raise NotImplementedError("multi-task GPs (num_tasks>1) are outside the B200 hot path built so far (SURVEY.md section 8(f) row 2)")
+        if num_tasks != 1 and len(torch.Size(shape_batch)) != 0:
+            raise NotImplementedError("multi-task GPs with batched outputs are not built (SURVEY.md section 8(f) row 2 covers equal-size tasks, one hyperparameter set)")
         if derivatives is not None or derivatives_coeffs is not None:
             raise NotImplementedError("derivative-informed kernels are outside the B200 hot path built so far (SURVEY.md section 8(f) row 3)")
         if adaptive_nugget:
@@ -580,7 +581,7 @@ class AbstractFastGP(torch.nn.Module):
             shape_factor_task_kernel = factor_task_kernel.shape
         if shape_factor_task_kernel is None:
             if rank_factor_task_kernel is None:
-                rank_factor_task_kernel = 0
+                rank_factor_task_kernel = 0 if self.num_tasks == 1 else 1
             assert isinstance(rank_factor_task_kernel, int) and 0 <= rank_factor_task_kernel <= self.num_tasks
             shape_factor_task_kernel = torch.Size([self.num_tasks, rank_factor_task_kernel])
         if isinstance(shape_factor_task_kernel, (list, tuple)):
@@ -627,6 +628,7 @@ class AbstractFastGP(torch.nn.Module):
         s0 = self.seqs[0]
         self._zgen = [int(v) for v in s0.gen_vec] if (self._FAMILY == 0 and isinstance(s0, sequences.Lattice) and os.environ.get("FGP_B200_NO_GEN") != "1") else None
         self._netgen = self._FAMILY == 1 and isinstance(s0, sequences.DigitalNetB2) and os.environ.get("FGP_B200_NO_GEN") != "1"
+        self._mt = multitask.MultiTaskEngine(self) if self.num_tasks > 1 else None
         self._epoch = 0
         self._coeffs = None
         self._coeffs_key = None
@@ -711,7 +713,7 @@ class AbstractFastGP(torch.nn.Module):
         self._nint = int(self._y[0].size(-1))
         self.n = torch.tensor([self._y[i].size(-1) for i in range(self.num_tasks)], dtype=int, device=self.device)
         self.m = torch.where(self.n == 0, -1, torch.log2(self.n)).to(int)
-        assert self._nint == 0 or (self._nint & (self._nint - 1)) == 0, "total samples must be power of 2"
+        assert all(nl == 0 or (nl & (nl - 1)) == 0 for nl in (int(v) for v in self.n.tolist())), "total samples must be power of 2"
         for key in list(self.inv_log_det_cache_dict.keys()):
             if key[0] < self._nint:
                 del self.inv_log_det_cache_dict[key]
@@ -755,6 +757,8 @@ class AbstractFastGP(torch.nn.Module):
     @property
     def coeffs(self):
         r"""Coefficients $\mathsf{K}^{-1} \boldsymbol{y}$ (util.py:419-425)."""
+        if self._mt is not None:
+            return self._mt.coeffs()
         key = (self._nint,) + self._param_key()
         if self._coeffs is None or self._coeffs_key != key or os.environ.get("FASTGP_FORCE_RECOMPILE") == "True":
             with torch.no_grad():
@@ -859,11 +863,11 @@ class AbstractFastGP(torch.nn.Module):
         if n is None:
             n = self.n
         if isinstance(n, (int, np.integer)):
-            n = torch.tensor([int(n)], dtype=int, device=self.device)
+            n = torch.tensor([int(n)] * self.num_tasks, dtype=int, device=self.device)
         assert isinstance(n, torch.Tensor) and n.shape == (self.num_tasks,) and (n >= self.n).all()
         ntup = tuple(n.tolist())
         if ntup not in self.inv_log_det_cache_dict.keys():
-            self.inv_log_det_cache_dict[ntup] = _FastInverseLogDetCache(self, n)
+            self.inv_log_det_cache_dict[ntup] = _FastInverseLogDetCache(self, n) if self._mt is None else multitask.MultiTaskInverseLogDetCache(self, n)
         return self.inv_log_det_cache_dict[ntup]
 
     def get_inv_log_det(self, n=None):
@@ -1025,7 +1029,9 @@ class AbstractFastGP(torch.nn.Module):
         loss_metric = loss_metric.upper()
         # MLL without masks: fused CUDA eigen-solve with the analytic gradient.  GCV, CV and masked fits: the same transforms
         # behind torch.autograd (_FTFunction), formulas as in the reference.
-        autograd_route = loss_metric != "MLL" or masks is not None
+        autograd_route = loss_metric != "MLL" or masks is not None or self._mt is not None
+        if self._mt is not None and masks is not None:
+            raise NotImplementedError("fit(masks=...) with several tasks is not built")
         if isinstance(cv_weights, torch.Tensor):
             cv_weights = cv_weights.to(self.device)
         fused = (not autograd_route) and optimizer is None and _FusedFitLoop.eligible(self) and os.environ.get("FGP_B200_GENERIC_FIT") != "1"
@@ -1062,14 +1068,17 @@ class AbstractFastGP(torch.nn.Module):
             _s = "%16s | %-10s | %-10s | %-10s" % ("iter of %.1e" % iterations, "loss", "term1", "term2")
             print(" " * verbose_indent + _s)
             print(" " * verbose_indent + "~" * len(_s))
-        mll_const = d_out * self._nint * np.log(2 * np.pi)
+        mll_const = d_out * int(self.n.sum()) * np.log(2 * np.pi)
         stop_crit_best_loss = torch.inf
         stop_crit_save_loss = torch.inf
         stop_crit_iterations_without_improvement_loss = 0
         want_grad = any(p.requires_grad for p in self.parameters())
-        self.get_ytilde(0)
+        if self._mt is None:
+            self.get_ytilde(0)
         for i in range(iterations + 1):
-            if autograd_route:
+            if self._mt is not None:
+                loss, term1, term2, metric_val = self._mt.loss(loss_metric, d_out, mll_const)
+            elif autograd_route:
                 loss, term1, term2, metric_val = self._autograd_loss(loss_metric, masks, cv_weights, d_out, mll_const)
             else:
                 wsum, term1, term2 = self._mll_terms(want_grad)
@@ -1217,9 +1226,13 @@ class AbstractFastGP(torch.nn.Module):
     def _parse_n(self, n):
         if n is None:
             return self._nint
+        if isinstance(n, (list, tuple)):
+            n = torch.tensor(n, dtype=int)
         if isinstance(n, torch.Tensor):
-            assert n.numel() == 1
-            n = int(n.item())
+            vals = set(int(v) for v in n.reshape(-1).tolist())
+            if len(vals) != 1:
+                raise NotImplementedError("different sizes per task are not built (got n=%s)" % sorted(vals))
+            n = vals.pop()
         n = int(n)
         assert (n & (n - 1)) == 0 and n >= self._nint, "require n are all power of two greater than or equal to self.n"
         return n
@@ -1229,6 +1242,9 @@ class AbstractFastGP(torch.nn.Module):
         is never materialised."""
         assert x.ndim == 2 and x.size(1) == self.d, "x must a torch.Tensor with shape (-1,d)"
         inttask, task = self._parse_task(task)
+        if self._mt is not None:
+            pmean = self._mt.post_mean(x.to(self.device).contiguous(), task)
+            return pmean[0] if inttask else pmean
         coeffs = self.coeffs
         x = x.to(self.device).contiguous()
         scale_B, ls_B, _, pshape = self._hyper_host()
@@ -1254,6 +1270,9 @@ class AbstractFastGP(torch.nn.Module):
         assert x.ndim == 2 and x.size(1) == self.d, "x must a torch.Tensor with shape (-1,d)"
         inttask, task = self._parse_task(task)
         x = x.to(self.device).contiguous()
+        if self._mt is not None:
+            pvar = self._mt.post_var(x, task, n)
+            return pvar[0] if inttask else pvar
         scale_B, ls_B, _, pshape = self._hyper_host()
         B = len(scale_B)
         lam = self.get_inv_log_det_cache(n)._lam_full()
@@ -1276,6 +1295,15 @@ class AbstractFastGP(torch.nn.Module):
         x0 = x0.to(self.device).contiguous()
         x1 = x1.to(self.device).contiguous()
         equal = torch.equal(x0, x1) and torch.equal(task0, task1)
+        if self._mt is not None:
+            kmat = self._mt.post_cov(x0, x1, task0, task1, n, equal)
+            if inttask0 and inttask1:
+                return kmat[0, 0]
+            elif inttask0 and not inttask1:
+                return kmat[0]
+            elif not inttask0 and inttask1:
+                return kmat[:, 0]
+            return kmat
         scale_B, ls_B, _, pshape = self._hyper_host()
         B = len(scale_B)
         cache = self.get_inv_log_det_cache(n)
@@ -1324,6 +1352,9 @@ class AbstractFastGP(torch.nn.Module):
     def post_cubature_mean(self, task: Union[int, torch.Tensor] = None, eval: bool = True):
         """abstract_fast_gp.py:65-81 for one task: scale * sum(coeffs) * K_task."""
         inttask, task = self._parse_task(task)
+        if self._mt is not None:
+            pcmean = self._mt.post_cubature_mean(task)
+            return pcmean[0] if inttask else pcmean
         with torch.no_grad():
             scale_B, _, _, pshape = self._hyper()
             coeffs = self.coeffs
@@ -1334,6 +1365,9 @@ class AbstractFastGP(torch.nn.Module):
         """abstract_fast_gp.py:82-109 for one task: s - s^2 n / lam_0 (clamped at 0), s = scale*K_task."""
         n = self._parse_n(n)
         inttask, task = self._parse_task(task)
+        if self._mt is not None:
+            pcvar = self._mt.post_cubature_cov(task, task, n).diagonal().clamp(min=0)
+            return pcvar[0] if inttask else pcvar
         with torch.no_grad():
             scale_B, _, _, pshape = self._hyper()
             lam = self.get_inv_log_det_cache(n)._lam_full()
@@ -1345,6 +1379,17 @@ class AbstractFastGP(torch.nn.Module):
         n = self._parse_n(n)
         inttask0, task0 = self._parse_task(task0)
         inttask1, task1 = self._parse_task(task1)
+        if self._mt is not None:
+            pccov = self._mt.post_cubature_cov(task0, task1, n)
+            if torch.equal(task0, task1):
+                pccov.diagonal().clamp_(min=0)
+            if inttask0 and inttask1:
+                return pccov[0, 0]
+            elif inttask0 and not inttask1:
+                return pccov[0]
+            elif not inttask0 and inttask1:
+                return pccov[:, 0]
+            return pccov
         pcvar = self.post_cubature_var(task=[0], n=n)[..., None]
         if inttask0 and inttask1:
             return pcvar[..., 0, 0]

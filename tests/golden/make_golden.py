@@ -132,7 +132,57 @@ def run_case(name, family, d, n, m_test, alpha, f, scale=1.0, lengthscales=1.0, 
     print(name, "loss0", out["loss0"], "its", data["iterations"], os.path.getsize(path) // 1024, "KiB")
 
 
+def run_case_multitask(name, family, d, n, T, alpha, m_test=64, noise=1e-6, fit_iterations=8, seed=11):
+    """num_tasks = T with equal n per task: block eigen-solve util.py:301-323,354-363."""
+    seeds = np.random.SeedSequence(seed).spawn(T)
+    if family == "lattice":
+        seqs = [qmcpy.Lattice(dimension=d, seed=sd) for sd in seeds]
+        gp = fastgps.FastGPLattice(seqs, num_tasks=T, alpha=alpha, noise=noise)
+        gen = {"z": np.stack([s.gen_vec.astype(np.uint64) for s in seqs]), "shift": np.stack([s.shift for s in seqs])}
+    else:
+        seqs = [qmcpy.DigitalNetB2(dimension=d, seed=sd) for sd in seeds]
+        gp = fastgps.FastGPDigitalNetB2(seqs, num_tasks=T, alpha=alpha, noise=noise)
+        gen = {"C": np.stack([s.gen_mats.astype(np.uint64) for s in seqs]), "dshift": np.stack([s.rshift.astype(np.uint64) for s in seqs]), "t": np.int64(seqs[0].t)}
+    f = lambda x, l: torch.cos(2 * np.pi * x).sum(1) + 0.4 * l * torch.sin(2 * np.pi * x[:, 0]) + 0.1 * l
+    xs = gp.get_x_next([n] * T)
+    ys = [f(xs[l], l) for l in range(T)]
+    gp.add_y_next(ys)
+    xt = torch.rand((m_test, d), generator=torch.Generator().manual_seed(17))
+    out = dict(gen)
+    out.update(family=family, d=d, n=n, T=T, alpha=alpha, noise0=noise, x=np.stack([x.numpy() for x in xs]), y=np.stack([y.numpy() for y in ys]), xtest=xt.numpy())
+    os.environ["FASTGP_FORCE_RECOMPILE"] = "True"
+    norm_term, logdet = gp.get_inv_log_det_cache().get_norm_term_logdet_term()
+    loss = 0.5 * (norm_term.sum() + logdet.sum() + T * n * np.log(2 * np.pi))
+    loss.backward()
+    out.update(loss0=loss.item(), norm_term0=norm_term.detach().numpy(), logdet0=logdet.detach().numpy(),
+               grad_raw_scale0=gp.raw_scale.grad.numpy().copy(), grad_raw_lengthscales0=gp.raw_lengthscales.grad.numpy().copy(),
+               grad_raw_factor0=gp.raw_factor_task_kernel.grad.numpy().copy(), grad_raw_noise_task0=gp.raw_noise_task_kernel.grad.numpy().copy())
+    gp.zero_grad()
+    del os.environ["FASTGP_FORCE_RECOMPILE"]
+    out["kmat_tasks0"] = gp.gram_matrix_tasks.detach().numpy()
+    out["coeffs0"] = gp.coeffs.detach().numpy()
+    out["pmean0"] = gp.post_mean(xt).numpy()
+    out["pmean0_task1"] = gp.post_mean(xt, task=1).numpy()
+    out["pvar0"] = gp.post_var(xt).numpy()
+    out["pcov0"] = gp.post_cov(xt[:8], xt[:5]).numpy()
+    out["pcmean0"] = gp.post_cubature_mean().numpy()
+    out["pcvar0"] = gp.post_cubature_var().numpy()
+    out["pccov0"] = gp.post_cubature_cov().numpy()
+    data = gp.fit(iterations=fit_iterations, verbose=0, store_hists=True, stop_crit_wait_iterations=100)
+    out.update(fit_iterations=fit_iterations, fit_last_iteration=data["iterations"], loss_hist=data["loss_hist"].numpy(),
+               scale_hist=data["scale_hist"].numpy(), lengthscales_hist=data["lengthscales_hist"].numpy(),
+               task_kernel_hist=data["task_kernel_hist"].numpy(), pmean1=gp.post_mean(xt).numpy(), pvar1=gp.post_var(xt).numpy())
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "loss0", out["loss0"], "its", data["iterations"], os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
+    if "--multitask-only" in sys.argv:
+        run_case_multitask("mt_lattice_T2_d2_n256_a2", "lattice", 2, 256, 2, 2)
+        run_case_multitask("mt_dnb2_T3_d3_n128_a2", "dnb2", 3, 128, 3, 2)
+        run_case_multitask("mt_lattice_T3_d2_n64_a3", "lattice", 2, 64, 3, 3)
+        sys.exit(0)
     # C1: FastGPLattice d=2 n=2^10 alpha=2, 2^12 test points (BASELINE.json configs[0])
     run_case("lattice_d2_n1024_a2", "lattice", 2, 2 ** 10, 2 ** 12, 2, f_ackley, fit_iterations=40)
     run_case("lattice_d3_n256_a3", "lattice", 3, 2 ** 8, 2 ** 8, 3, f_smooth, scale=2.5,
@@ -144,3 +194,6 @@ if __name__ == "__main__":
     run_case("dnb2_d3_n256_a3", "dnb2", 3, 2 ** 8, 2 ** 8, 3, f_smooth, scale=0.7, lengthscales=torch.tensor([0.3, 1.0, 1.9]), noise=1e-8, fit_iterations=10)
     run_case("dnb2_d3_n256_a4", "dnb2", 3, 2 ** 8, 2 ** 8, 4, f_smooth, noise=1e-8, fit_iterations=10)
     run_case("dnb2_d2_n128_a1", "dnb2", 2, 2 ** 7, 2 ** 7, 1, f_smooth, noise=1e-6, fit_iterations=10)
+    run_case_multitask("mt_lattice_T2_d2_n256_a2", "lattice", 2, 256, 2, 2)
+    run_case_multitask("mt_dnb2_T3_d3_n128_a2", "dnb2", 3, 128, 3, 2)
+    run_case_multitask("mt_lattice_T3_d2_n64_a3", "lattice", 2, 64, 3, 3)

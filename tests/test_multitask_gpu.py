@@ -1,0 +1,79 @@
+"""GPU parity of the multi-task path (num_tasks > 1, equal task sizes) against fixtures written
+by the unmodified reference (tests/golden/make_golden.py::run_case_multitask)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_MT_CASES, load_golden
+
+pytestmark = pytest.mark.gpu
+dev = "cuda:0"
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().cpu()
+    b = torch.as_tensor(b).detach().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+
+
+def make_gp(g):
+    import fastgaussianprocesses_b200 as fgp
+    T, d, alpha = int(g["T"]), int(g["d"]), int(g["alpha"])
+    if str(g["family"]) == "lattice":
+        seqs = [fgp.Lattice(d, generating_vector=g["z"][l], shift=g["shift"][l]) for l in range(T)]
+        return fgp.FastGPLattice(seqs, num_tasks=T, alpha=alpha, noise=float(g["noise0"]), device=dev)
+    seqs = [fgp.DigitalNetB2(d, generating_matrices=g["C"][l], dshift=g["dshift"][l], t=int(g["t"])) for l in range(T)]
+    return fgp.FastGPDigitalNetB2(seqs, num_tasks=T, alpha=alpha, noise=float(g["noise0"]), device=dev)
+
+
+@pytest.mark.parametrize("case", GOLDEN_MT_CASES)
+def test_multitask_matches_reference_fixture(case):
+    g = load_golden(case)
+    T, n = int(g["T"]), int(g["n"])
+    gp = make_gp(g)
+    xs = gp.get_x_next([n] * T)
+    assert isinstance(xs, list) and all(np.array_equal(xs[l].cpu().numpy(), g["x"][l]) for l in range(T))  # bit-exact points
+    gp.add_y_next([torch.from_numpy(g["y"][l]) for l in range(T)])
+    assert rel(gp.gram_matrix_tasks, g["kmat_tasks0"]) < 1e-14
+    # MLL terms and autograd gradients of all five parameter groups
+    norm, logdet = gp.get_inv_log_det_cache().get_norm_term_logdet_term()
+    loss = 0.5 * (norm.sum() + logdet.sum() + T * n * np.log(2 * np.pi))
+    assert abs(float(loss) - float(g["loss0"])) <= 1e-9 * abs(float(g["loss0"]))
+    loss.backward()
+    assert rel(gp.raw_scale.grad, g["grad_raw_scale0"]) < 1e-7
+    assert rel(gp.raw_lengthscales.grad, g["grad_raw_lengthscales0"]) < 1e-7
+    assert rel(gp.raw_factor_task_kernel.grad, g["grad_raw_factor0"]) < 1e-7
+    assert rel(gp.raw_noise_task_kernel.grad, g["grad_raw_noise_task0"]) < 1e-7
+    gp.zero_grad()
+    ymax = float(np.abs(g["y"]).max())
+    assert rel(gp.coeffs, g["coeffs0"]) < 1e-8
+    xt = torch.from_numpy(g["xtest"])
+    pm = gp.post_mean(xt)
+    assert pm.shape == g["pmean0"].shape and float((pm.cpu() - torch.from_numpy(g["pmean0"])).abs().max()) < 1e-8 * ymax
+    assert float((gp.post_mean(xt, task=1).cpu() - torch.from_numpy(g["pmean0_task1"])).abs().max()) < 1e-8 * ymax
+    pv = gp.post_var(xt)
+    assert pv.shape == g["pvar0"].shape and float((pv.cpu() - torch.from_numpy(g["pvar0"])).abs().max()) < 1e-8
+    pc = gp.post_cov(xt[:8], xt[:5])
+    assert pc.shape == g["pcov0"].shape and float((pc.cpu() - torch.from_numpy(g["pcov0"])).abs().max()) < 1e-8
+    assert float((gp.post_cubature_mean().cpu() - torch.from_numpy(g["pcmean0"])).abs().max()) < 1e-8 * ymax
+    assert float((gp.post_cubature_var().cpu() - torch.from_numpy(g["pcvar0"])).abs().max()) < 1e-9
+    assert float((gp.post_cubature_cov().cpu() - torch.from_numpy(g["pccov0"])).abs().max()) < 1e-9
+    # fit: trajectory of loss, hyperparameters and the task kernel
+    data = gp.fit(iterations=int(g["fit_iterations"]), verbose=0, store_hists=True, stop_crit_wait_iterations=100)
+    assert data["iterations"] == int(g["fit_last_iteration"])
+    assert np.allclose(data["loss_hist"].numpy(), g["loss_hist"], rtol=1e-7)
+    assert rel(data["lengthscales_hist"], g["lengthscales_hist"]) < 1e-6
+    assert rel(data["task_kernel_hist"], g["task_kernel_hist"]) < 1e-6
+    assert float((gp.post_mean(xt).cpu() - torch.from_numpy(g["pmean1"])).abs().max()) < 1e-6 * ymax
+    assert float((gp.post_var(xt).cpu() - torch.from_numpy(g["pvar1"])).abs().max()) < 1e-6
+
+
+def test_multitask_guards():
+    import fastgaussianprocesses_b200 as fgp
+    gp = fgp.FastGPLattice(2, num_tasks=2, seed_for_seq=3, device=dev)
+    x = gp.get_x_next([64, 16])
+    gp.add_y_next([torch.cos(x[0].sum(1)), torch.cos(x[1].sum(1))])
+    with pytest.raises(NotImplementedError):
+        gp.coeffs  # unequal task sizes are not built
+    with pytest.raises(NotImplementedError):
+        fgp.FastGPLattice(2, num_tasks=2, shape_batch=[3], device=dev)

@@ -13,8 +13,10 @@ Reference surface being mirrored (same names, argument meaning, shapes and asser
 Everything numerical is done by libfgp_b200.so (include/fgp_b200.h) on CUDA tensors; torch is used for memory,
 streams, the tiny hyperparameter transforms and (outside the fast path) the optimizer.  There is no CPU fallback.
 
-Scope: single task (num_tasks None or 1), no derivative information, no adaptive nugget.
-Those options raise NotImplementedError -- they are rows (f)2-(f)3 of the scope table, not silently approximated.
+Scope: the fused device-side path covers one task without derivative information (rows a1-a15); several
+tasks of equal size, GCV / CV losses and masked fits run on the same CUDA transforms through torch.autograd (multitask.py,
+_FTFunction).  Derivative information, different sizes per task and the adaptive nugget raise NotImplementedError -- rows
+(f)2-(f)3 of the scope table are not silently approximated.
 """
 import os
 from typing import List, Tuple, Union
@@ -1422,7 +1424,7 @@ _CTOR_DOC = """
     `device` defaults to "cuda" and must be a CUDA device; `seqs` may be an int (dimension), one of this package's
     GPU-side sequence specs (`sequences.Lattice` / `sequences.DigitalNetB2`) or any qmcpy-style sequence object, whose
     points are then taken from its own host generator; `compile_fts*` are accepted and ignored (the transforms are
-    hand-written CUDA kernels); `num_tasks>1`, `derivatives` and `adaptive_nugget` raise NotImplementedError.
+    hand-written CUDA kernels); `derivatives`, `adaptive_nugget` and different sizes per task raise NotImplementedError.
 """
 
 

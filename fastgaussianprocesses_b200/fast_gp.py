@@ -15,7 +15,7 @@ streams, the tiny hyperparameter transforms and (outside the fast path) the opti
 
 Scope: the fused device-side path covers one task without derivative information (rows a1-a15); several
 tasks of equal size, GCV / CV losses and masked fits run on the same CUDA transforms through torch.autograd (multitask.py,
-_FTFunction).  Derivative information, different sizes per task and the adaptive nugget raise NotImplementedError -- rows
+_FTFunction).  Derivative information and the adaptive nugget raise NotImplementedError -- rows
 (f)2-(f)3 of the scope table are not silently approximated.
 """
 import os
@@ -712,12 +712,13 @@ class AbstractFastGP(torch.nn.Module):
         assert all(y_next[i].shape[:-1] == self.shape_batch for i in range(len(y_next)))
         for i, l in enumerate(task):
             self._y[int(l)] = torch.cat([self._y[int(l)], y_next[i].to(self.device)], -1)
-        self._nint = int(self._y[0].size(-1))
+        self._nint = max(int(self._y[i].size(-1)) for i in range(self.num_tasks))
         self.n = torch.tensor([self._y[i].size(-1) for i in range(self.num_tasks)], dtype=int, device=self.device)
         self.m = torch.where(self.n == 0, -1, torch.log2(self.n)).to(int)
         assert all(nl == 0 or (nl & (nl - 1)) == 0 for nl in (int(v) for v in self.n.tolist())), "total samples must be power of 2"
+        ncur = self.n.tolist()
         for key in list(self.inv_log_det_cache_dict.keys()):
-            if key[0] < self._nint:
+            if any(k < c for k, c in zip(key, ncur)):
                 del self.inv_log_det_cache_dict[key]
         self._epoch += 1
 
@@ -1227,13 +1228,17 @@ class AbstractFastGP(torch.nn.Module):
 
     def _parse_n(self, n):
         if n is None:
-            return self._nint
+            return self._nint if self._mt is None else [int(v) for v in self.n.tolist()]
         if isinstance(n, (list, tuple)):
             n = torch.tensor(n, dtype=int)
+        if self._mt is not None:  # per-task sizes (abstract_gp.py:394: an int applies to every task)
+            ns = [int(n)] * self.num_tasks if isinstance(n, (int, np.integer)) else [int(v) for v in n.reshape(-1).tolist()]
+            cur = [int(v) for v in self.n.tolist()]
+            assert len(ns) == self.num_tasks and all((v & (v - 1)) == 0 and v >= c for v, c in zip(ns, cur)), "require n are all power of two greater than or equal to self.n"
+            return ns
         if isinstance(n, torch.Tensor):
             vals = set(int(v) for v in n.reshape(-1).tolist())
-            if len(vals) != 1:
-                raise NotImplementedError("different sizes per task are not built (got n=%s)" % sorted(vals))
+            assert len(vals) == 1, "one task takes one size (got n=%s)" % sorted(vals)
             n = vals.pop()
         n = int(n)
         assert (n & (n - 1)) == 0 and n >= self._nint, "require n are all power of two greater than or equal to self.n"
@@ -1424,7 +1429,7 @@ _CTOR_DOC = """
     `device` defaults to "cuda" and must be a CUDA device; `seqs` may be an int (dimension), one of this package's
     GPU-side sequence specs (`sequences.Lattice` / `sequences.DigitalNetB2`) or any qmcpy-style sequence object, whose
     points are then taken from its own host generator; `compile_fts*` are accepted and ignored (the transforms are
-    hand-written CUDA kernels); `derivatives`, `adaptive_nugget` and different sizes per task raise NotImplementedError.
+    hand-written CUDA kernels); `derivatives` and `adaptive_nugget` raise NotImplementedError.
 """
 
 

@@ -6,8 +6,9 @@ diagonalised by the same fast transform, so the whole matrix reduces to n indepe
     Lam_k[l0,l1] = K_task[l0,l1] (sqrt(n) ft(k1^(l0,l1))_k + noise [l0 == l1]).
 The transforms are the CUDA kernels of libfgp_b200 behind torch.autograd (`_FTFunction`); the kernel parts, cross
 kernels and posterior-mean products are the K2 / K5 kernels; the n small T x T factorizations are batched torch.linalg
-calls (library code, as the reference's own Schur-complement recursion is torch code).  This path is parity-tested
-against reference fixtures but not fused or tuned; unequal task sizes raise NotImplementedError.
+calls (library code, as the reference's own Schur-complement recursion is torch code).  Tasks of different (power-of-two)
+sizes fold into n_min independent R x R systems, R = sum_l n_l / n_min, because sub-sampling a lattice aliases the
+frequencies kappa and kappa mod n_l.  This path is parity-tested against reference fixtures but not fused or tuned.
 """
 import numpy as np
 import torch
@@ -27,12 +28,27 @@ class MultiTaskEngine(object):
     def T(self):
         return self.gp.num_tasks
 
-    def n_equal(self, n=None):
+    def sizes(self, n=None):
+        """Per-task sizes and the layout of the folded system (util.py:277-323): tasks in order of decreasing size; a task
+        of n_l points occupies r_l = n_l / n_min consecutive rows of the (R, n_min) frequency layout, row a holding the
+        natural-order frequencies [a n_min, (a+1) n_min)."""
         gp = self.gp
-        ns = [int(v) for v in (gp.n if n is None else n).tolist()]
-        if len(set(ns)) != 1 or ns[0] == 0:
-            raise NotImplementedError("multi-task solves need the same (non-zero) number of points in every task (got %s)" % ns)
-        return ns[0]
+        if n is None:
+            ns = [int(v) for v in gp.n.tolist()]
+        elif isinstance(n, (int, np.integer)):
+            ns = [int(n)] * self.T
+        else:
+            ns = [int(v) for v in (n.tolist() if isinstance(n, torch.Tensor) else n)]
+        assert all(v == 0 or (v & (v - 1)) == 0 for v in ns), "task sizes must be powers of two"
+        active = [l for l in sorted(range(self.T), key=lambda l: -ns[l]) if ns[l] > 0]
+        assert active, "no data"
+        nmin = min(ns[l] for l in active)
+        r = {l: ns[l] // nmin for l in active}
+        off, acc = {}, 0
+        for l in active:
+            off[l] = acc
+            acc += r[l]
+        return ns, active, nmin, r, off, acc
 
     def xpts(self, l, n):
         x, xb = self.gp.xxb_seqs[l][:int(n)]
@@ -40,7 +56,7 @@ class MultiTaskEngine(object):
 
     # ------------------------------------------------------------------------------------------------ spectrum
     def parts(self, l0, l1, n):
-        """(n,d) kernel parts of the points of task l0 against the FIRST point of task l1 (util.py:50-62)."""
+        """(n,d) kernel parts of the first n points of task l0 against the FIRST point of task l1 (util.py:50-62)."""
         key = (l0, l1, int(n))
         p = self._parts.get(key)
         if p is None:
@@ -55,64 +71,99 @@ class MultiTaskEngine(object):
             self._parts[key] = p
         return p
 
-    def lam_blocks(self, n):
-        """Lam (n, T, T), differentiable w.r.t. every raw parameter (util.py:279-298)."""
-        gp, T = self.gp, self.T
+    def lam_system(self, n=None):
+        """Lam (n_min, R, R), differentiable w.r.t. every raw parameter.  Block (t0, t1), n_t0 >= n_t1: the length-n_t0 vector
+        lam = K_task[t0,t1] sqrt(n_t1) ft(k1^(t0,t1)) (+ noise on the diagonal) couples frequency kappa of task t0 with
+        frequency kappa mod n_t1 of task t1 (sub-sampling aliases frequencies), util.py:279-323."""
+        gp = self.gp
+        ns, active, nmin, r, off, R = self.sizes(n)
         scale, ls, noise, kt = gp.scale, gp.lengthscales, gp.noise, gp.gram_matrix_tasks
-        rows = [[None] * T for _ in range(T)]
-        for l0 in range(T):
-            for l1 in range(l0, T):
-                k1 = scale * (1 + ls[..., None, :] * self.parts(l0, l1, n)).prod(-1)
-                lam = np.sqrt(n) * gp.ft(k1)
-                if l0 == l1:
+        dev = gp.device
+        bidx, rows, cols, vals = [], [], [], []
+        ar = torch.arange(nmin, device=dev)
+        for i0, t0 in enumerate(active):
+            for t1 in active[i0:]:
+                nbig = ns[t0]
+                if t0 <= t1:
+                    k1 = scale * (1 + ls[..., None, :] * self.parts(t0, t1, nbig)).prod(-1)
+                    lam = gp.ft(k1)
+                else:  # the reference keeps one spectrum per unordered pair and conjugates it (util.py:284)
+                    k1 = scale * (1 + ls[..., None, :] * self.parts(t1, t0, nbig)).prod(-1)
+                    lam = gp.ft(k1).conj()
+                lam = np.sqrt(ns[t1]) * lam
+                if t0 == t1:
                     lam = lam + noise
-                rows[l0][l1] = lam * kt[..., l0, l1, None]
-                if l1 > l0:
-                    rows[l1][l0] = rows[l0][l1].conj()
-        L = torch.stack([torch.stack(r, -1) for r in rows], -2)  # (n, T, T): [k, l0, l1]
-        return L
+                V = (lam * kt[..., t0, t1, None]).reshape(r[t0], nmin)
+                for a0 in range(r[t0]):
+                    a1 = a0 if t0 == t1 else a0 % r[t1]
+                    bidx.append(ar)
+                    rows.append(torch.full((nmin,), off[t0] + a0, device=dev))
+                    cols.append(torch.full((nmin,), off[t1] + a1, device=dev))
+                    vals.append(V[a0])
+                    if t0 != t1:
+                        bidx.append(ar)
+                        rows.append(torch.full((nmin,), off[t1] + a1, device=dev))
+                        cols.append(torch.full((nmin,), off[t0] + a0, device=dev))
+                        vals.append(V[a0].conj())
+        vals = torch.cat(vals)
+        L = torch.zeros((nmin, R, R), dtype=vals.dtype, device=dev)
+        return L.index_put((torch.cat(bidx), torch.cat(rows), torch.cat(cols)), vals)
 
-    def factor(self, n, grad=False):
-        """(Lam^-1 (n,T,T), logdet) -- cached on the hyperparameter state when no gradient is needed."""
+    def factor(self, n=None, grad=False):
+        """(Lam^-1 (n_min,R,R), logdet) -- cached on the hyperparameter state when no gradient is needed."""
         if grad:
-            L = self.lam_blocks(n)
+            L = self.lam_system(n)
             return torch.linalg.inv(L), torch.linalg.slogdet(L)[1].sum(-1)
-        key = (int(n),) + self.gp._param_key()
+        key = (tuple(self.sizes(n)[0]),) + self.gp._param_key()
         if self._lam_key != key:
             with torch.no_grad():
-                L = self.lam_blocks(n)
+                L = self.lam_system(n)
                 self._solve_cache = (torch.linalg.inv(L), torch.linalg.slogdet(L)[1].sum(-1))
             self._lam_key = key
         return self._solve_cache
 
+    def fold(self, parts, n=None):
+        """per-task spectra [(..., n_l)] in task order -> (..., R, n_min) in the folded layout."""
+        ns, active, nmin, r, off, R = self.sizes(n)
+        return torch.cat([parts[l].reshape(parts[l].shape[:-1] + (r[l], nmin)) for l in active], -2)
+
+    def unfold(self, z, n=None):
+        ns, active, nmin, r, off, R = self.sizes(n)
+        out = [None] * self.T
+        for l in active:
+            out[l] = z[..., off[l]:off[l] + r[l], :].reshape(z.shape[:-2] + (ns[l],))
+        for l in range(self.T):
+            if out[l] is None:
+                out[l] = z.new_zeros(z.shape[:-2] + (0,))
+        return out
+
     def ytilde(self):
         gp = self.gp
-        n = self.n_equal()
-        key = (n, id(gp._y[0]), tuple(y.data_ptr() for y in gp._y))
+        key = (tuple(int(v) for v in gp.n.tolist()), tuple(y.data_ptr() for y in gp._y))
         if getattr(self, "_yt_key", None) != key:
             with torch.no_grad():
-                self._yt = torch.stack([gp.ft(gp._y[l]) for l in range(self.T)], -2)  # (T, n)
+                self._yt = self.fold([gp.ft(gp._y[l]) if gp._y[l].size(-1) > 0 else gp._y[l].to(gp._FTOUTDTYPE) for l in range(self.T)])
             self._yt_key = key
         return self._yt
 
     def solve_tilde(self, A, zt):
-        """A (n,T,T), zt (..., T, n) -> (..., T, n)."""
+        """A (n_min,R,R), zt (..., R, n_min) -> (..., R, n_min)."""
         return torch.einsum("kij,...jk->...ik", A, zt.to(A.dtype))
 
     def gram_matrix_solve(self, y, n=None, A=None):
-        """K^-1 y for y (..., T*n) (util.py:338-344 multi-task)."""
+        """K^-1 y for y (..., sum_l n_l), tasks concatenated in task order (util.py:338-344)."""
         gp = self.gp
-        n = self.n_equal() if n is None else int(n)
+        ns = self.sizes(n)[0]
         if A is None:
             A, _ = self.factor(n)
         y = y.to(gp.device)
-        ys = y.reshape(y.shape[:-1] + (self.T, n))
-        zt = self.solve_tilde(A, gp.ft(ys))
-        return gp.ift(zt).real.reshape(y.shape)
+        ys = y.split(ns, dim=-1)
+        zt = self.solve_tilde(A, self.fold([gp.ft(v) if v.size(-1) > 0 else v.to(gp._FTOUTDTYPE) for v in ys], n))
+        zs = self.unfold(zt, n)
+        return torch.cat([gp.ift(v).real if v.size(-1) > 0 else v.real for v in zs], -1)
 
     def norm_logdet(self, grad):
-        n = self.n_equal()
-        A, logdet = self.factor(n, grad=grad)
+        A, logdet = self.factor(None, grad=grad)
         yt = self.ytilde()
         zt = self.solve_tilde(A, yt)
         norm = (yt.conj() * zt).real.sum((-1, -2))[..., None]
@@ -120,7 +171,6 @@ class MultiTaskEngine(object):
 
     def loss(self, loss_metric, d_out, mll_const):
         """The reference's losses on the block spectrum (abstract_gp.py:242-273); returns (loss, term1, term2, metric_val)."""
-        n = self.n_equal()
         norm, logdet, A, zt = self.norm_logdet(grad=True)
         if loss_metric == "MLL":
             term1 = norm.sum()
@@ -130,7 +180,7 @@ class MultiTaskEngine(object):
         if loss_metric == "GCV":
             numer = (zt.conj() * zt).real.sum((-1, -2))[..., None]
             tr_k_inv = torch.diagonal(A, dim1=-2, dim2=-1).real.sum((-1, -2))[..., None]
-            denom = ((tr_k_inv / (self.T * n)) ** 2).real
+            denom = ((tr_k_inv / int(self.gp.n.sum())) ** 2).real
             loss = (numer / denom).sum()
             return loss, numer, denom, loss
         raise NotImplementedError("loss_metric='CV' needs the O(n^2 log n) inverse diagonal of the reference for several tasks (util.py:386-393); not built")
@@ -154,21 +204,23 @@ class MultiTaskEngine(object):
 
     def post_mean(self, x, task):
         gp, T = self.gp, self.T
-        n = self.n_equal()
+        ns = self.sizes()[0]
         scale, ls, kt = self._host()
-        c = self.coeffs().reshape(T, n)
+        c = self.coeffs().split(ns, dim=-1)
         N = x.shape[0]
         if N == 0:
             return torch.empty((len(task), 0), dtype=torch.float64, device=gp.device)
         # one on-the-fly kernel-vector product per training task, then the T x T task kernel mixes them
-        base = torch.stack([_lib.post_mean(gp._FAMILY, x, self.xpts(l, n), gp._alpha_list, gp._t, scale, ls, c[l:l + 1].contiguous())[0] for l in range(T)], 0)
+        base = torch.stack([_lib.post_mean(gp._FAMILY, x, self.xpts(l, ns[l]), gp._alpha_list, gp._t, scale, ls, c[l].reshape(1, -1).contiguous())[0]
+                            if ns[l] > 0 else torch.zeros(N, dtype=torch.float64, device=gp.device) for l in range(T)], 0)
         ktd = torch.from_numpy(kt).to(gp.device)
         return ktd[task.to(gp.device)] @ base  # (len(task), N)
 
-    def _cross_rows(self, x, t, n, scale, ls, kt):
-        """K_task[t, l1] k(x, X_l1) for all l1, concatenated: (N, T*n)."""
+    def _cross_rows(self, x, t, ns, scale, ls, kt):
+        """K_task[t, l1] k(x, X_l1) for all l1, concatenated: (N, sum_l n_l)."""
         gp = self.gp
-        return torch.cat([kt[t, l] * _lib.cross_kernel(gp._FAMILY, x, self.xpts(l, n), gp._alpha_list, gp._t, scale, ls) for l in range(self.T)], -1)
+        return torch.cat([kt[t, l] * _lib.cross_kernel(gp._FAMILY, x, self.xpts(l, ns[l]), gp._alpha_list, gp._t, scale, ls)
+                          for l in range(self.T) if ns[l] > 0], -1)
 
     def _kxx(self, scale, ls):
         gp = self.gp
@@ -179,11 +231,12 @@ class MultiTaskEngine(object):
         gp = self.gp
         scale, ls, kt = self._host()
         A, _ = self.factor(n)
+        ns = self.sizes(n)[0]
         kxx = self._kxx(scale, ls)
         out = []
         with torch.no_grad():
             for t in task.tolist():
-                km = self._cross_rows(x, t, n, scale, ls, kt)
+                km = self._cross_rows(x, t, ns, scale, ls, kt)
                 sol = self.gram_matrix_solve(km, n=n, A=A)
                 out.append((kt[t, t] * kxx - (sol * km).sum(-1)).clamp_(min=0))
         return torch.stack(out, 0)
@@ -192,11 +245,12 @@ class MultiTaskEngine(object):
         gp = self.gp
         scale, ls, kt = self._host()
         A, _ = self.factor(n)
+        ns = self.sizes(n)[0]
         fam, al, tt = gp._FAMILY, gp._alpha_list, gp._t
         with torch.no_grad():
             knew = _lib.cross_kernel(fam, x0, x1 if fam == 0 else gp._convert_to_b(x1), al, tt, scale, ls)
-            k1 = {t: self._cross_rows(x0, t, n, scale, ls, kt) for t in set(task0.tolist())}
-            sol2 = {t: self.gram_matrix_solve(k1[t] if (equal and t in k1) else self._cross_rows(x1, t, n, scale, ls, kt), n=n, A=A) for t in set(task1.tolist())}
+            k1 = {t: self._cross_rows(x0, t, ns, scale, ls, kt) for t in set(task0.tolist())}
+            sol2 = {t: self.gram_matrix_solve(k1[t] if (equal and t in k1) else self._cross_rows(x1, t, ns, scale, ls, kt), n=n, A=A) for t in set(task1.tolist())}
             out = torch.empty((len(task0), len(task1), x0.shape[0], x1.shape[0]), dtype=torch.float64, device=gp.device)
             for i0, t0 in enumerate(task0.tolist()):
                 for i1, t1 in enumerate(task1.tolist()):
@@ -207,21 +261,27 @@ class MultiTaskEngine(object):
 
     def post_cubature_mean(self, task):
         gp = self.gp
-        n = self.n_equal()
+        ns = self.sizes()[0]
         scale, _, kt = self._host()
         with torch.no_grad():
-            sums = scale * self.coeffs().reshape(self.T, n).sum(-1)  # (T)
+            sums = scale * torch.stack([c.sum(-1) for c in self.coeffs().split(ns, dim=-1)])  # (T)
             return torch.from_numpy(kt).to(gp.device)[task.to(gp.device)] @ sums
 
     def post_cubature_cov(self, task0, task1, n):
-        """abstract_fast_gp.py:110-154 for equal task sizes: scale K_task - scale^2 K_task (n A_0) K_task."""
+        """abstract_fast_gp.py:110-154: scale K_task - scale^2 K_task (sqrt(n_i n_j) A_0[first rows]) K_task."""
         gp = self.gp
         scale, _, kt = self._host()
         with torch.no_grad():
             A, _ = self.factor(n)
+            ns, active, nmin, r, off, R = self.sizes(n)
             ktd = torch.from_numpy(kt).to(gp.device).to(A.dtype)
-            term = (ktd[task0.to(gp.device)] @ (n * A[0]) @ ktd[:, task1.to(gp.device)]).real
-            return scale * ktd.real[task0.to(gp.device)][:, task1.to(gp.device)] - scale ** 2 * term
+            idx = torch.tensor([off[l] for l in active], device=gp.device)
+            act = torch.tensor(active, device=gp.device)
+            nv = torch.tensor([float(ns[l]) for l in active], device=gp.device)
+            mid = torch.sqrt(nv[:, None] * nv[None, :]) * A[0][idx][:, idx]
+            t0, t1 = task0.to(gp.device), task1.to(gp.device)
+            term = (ktd[t0][:, act] @ mid @ ktd[act][:, t1]).real
+            return scale * ktd.real[t0][:, t1] - scale ** 2 * term
 
 
 class MultiTaskInverseLogDetCache(object):
@@ -230,16 +290,17 @@ class MultiTaskInverseLogDetCache(object):
     def __init__(self, gp, n):
         self.fgp = gp
         self.n = n
-        self.nint = gp._mt.n_equal(n)
+        self.nvec = [int(v) for v in n.tolist()]
+        self.nint = max(self.nvec)
         self.task_order = torch.arange(gp.num_tasks, device=gp.device)
         self.inv_task_order = torch.arange(gp.num_tasks, device=gp.device)
 
     def __call__(self):
-        A, logdet = self.fgp._mt.factor(self.nint)
-        return A.permute(1, 2, 0), logdet  # (T, T, n) as the reference lays it out
+        A, logdet = self.fgp._mt.factor(self.nvec)
+        return A.permute(1, 2, 0), logdet  # (R, R, n_min) as the reference lays it out
 
     def gram_matrix_solve(self, y):
-        return self.fgp._mt.gram_matrix_solve(y, n=self.nint)
+        return self.fgp._mt.gram_matrix_solve(y, n=self.nvec)
 
     def get_norm_term_logdet_term(self):
         norm, logdet, _, _ = self.fgp._mt.norm_logdet(grad=torch.is_grad_enabled())

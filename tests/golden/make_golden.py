@@ -133,7 +133,10 @@ def run_case(name, family, d, n, m_test, alpha, f, scale=1.0, lengthscales=1.0, 
 
 
 def run_case_multitask(name, family, d, n, T, alpha, m_test=64, noise=1e-6, fit_iterations=8, seed=11):
-    """num_tasks = T with equal n per task: block eigen-solve util.py:301-323,354-363."""
+    """num_tasks = T: block eigen-solve util.py:301-323,354-363.  n is one size for every task
+    or a list of per-task sizes (ragged arrays are then stored per task: x_0, x_1, ..., y_0, ...)."""
+    ns = [int(n)] * T if np.isscalar(n) else [int(v) for v in n]
+    ragged = len(set(ns)) > 1
     seeds = np.random.SeedSequence(seed).spawn(T)
     if family == "lattice":
         seqs = [qmcpy.Lattice(dimension=d, seed=sd) for sd in seeds]
@@ -144,15 +147,20 @@ def run_case_multitask(name, family, d, n, T, alpha, m_test=64, noise=1e-6, fit_
         gp = fastgps.FastGPDigitalNetB2(seqs, num_tasks=T, alpha=alpha, noise=noise)
         gen = {"C": np.stack([s.gen_mats.astype(np.uint64) for s in seqs]), "dshift": np.stack([s.rshift.astype(np.uint64) for s in seqs]), "t": np.int64(seqs[0].t)}
     f = lambda x, l: torch.cos(2 * np.pi * x).sum(1) + 0.4 * l * torch.sin(2 * np.pi * x[:, 0]) + 0.1 * l
-    xs = gp.get_x_next([n] * T)
+    xs = gp.get_x_next(ns)
     ys = [f(xs[l], l) for l in range(T)]
     gp.add_y_next(ys)
     xt = torch.rand((m_test, d), generator=torch.Generator().manual_seed(17))
     out = dict(gen)
-    out.update(family=family, d=d, n=n, T=T, alpha=alpha, noise0=noise, x=np.stack([x.numpy() for x in xs]), y=np.stack([y.numpy() for y in ys]), xtest=xt.numpy())
+    out.update(family=family, d=d, n=max(ns), ns=np.array(ns), T=T, alpha=alpha, noise0=noise, xtest=xt.numpy())
+    if ragged:
+        out.update({"x_%d" % l: xs[l].numpy() for l in range(T)})
+        out.update({"y_%d" % l: ys[l].numpy() for l in range(T)})
+    else:
+        out.update(x=np.stack([x.numpy() for x in xs]), y=np.stack([y.numpy() for y in ys]))
     os.environ["FASTGP_FORCE_RECOMPILE"] = "True"
     norm_term, logdet = gp.get_inv_log_det_cache().get_norm_term_logdet_term()
-    loss = 0.5 * (norm_term.sum() + logdet.sum() + T * n * np.log(2 * np.pi))
+    loss = 0.5 * (norm_term.sum() + logdet.sum() + sum(ns) * np.log(2 * np.pi))
     loss.backward()
     out.update(loss0=loss.item(), norm_term0=norm_term.detach().numpy(), logdet0=logdet.detach().numpy(),
                grad_raw_scale0=gp.raw_scale.grad.numpy().copy(), grad_raw_lengthscales0=gp.raw_lengthscales.grad.numpy().copy(),
@@ -168,6 +176,9 @@ def run_case_multitask(name, family, d, n, T, alpha, m_test=64, noise=1e-6, fit_
     out["pcmean0"] = gp.post_cubature_mean().numpy()
     out["pcvar0"] = gp.post_cubature_var().numpy()
     out["pccov0"] = gp.post_cubature_cov().numpy()
+    if ragged:  # "future" sizes: posterior variance after doubling every task (abstract_gp.py:394,408)
+        out["pvar0_n2"] = gp.post_var(xt, n=2 * gp.n).numpy()
+        out["pcvar0_n2"] = gp.post_cubature_var(n=2 * gp.n).numpy()
     data = gp.fit(iterations=fit_iterations, verbose=0, store_hists=True, stop_crit_wait_iterations=100)
     out.update(fit_iterations=fit_iterations, fit_last_iteration=data["iterations"], loss_hist=data["loss_hist"].numpy(),
                scale_hist=data["scale_hist"].numpy(), lengthscales_hist=data["lengthscales_hist"].numpy(),
@@ -182,6 +193,9 @@ if __name__ == "__main__":
         run_case_multitask("mt_lattice_T2_d2_n256_a2", "lattice", 2, 256, 2, 2)
         run_case_multitask("mt_dnb2_T3_d3_n128_a2", "dnb2", 3, 128, 3, 2)
         run_case_multitask("mt_lattice_T3_d2_n64_a3", "lattice", 2, 64, 3, 3)
+    if "--multitask-only" in sys.argv or "--ragged-only" in sys.argv:
+        run_case_multitask("mt_lattice_T3_d2_ragged_a2", "lattice", 2, [64, 256, 128], 3, 2)
+        run_case_multitask("mt_dnb2_T2_d3_ragged_a2", "dnb2", 3, [256, 32], 2, 2)
         sys.exit(0)
     # C1: FastGPLattice d=2 n=2^10 alpha=2, 2^12 test points (BASELINE.json configs[0])
     run_case("lattice_d2_n1024_a2", "lattice", 2, 2 ** 10, 2 ** 12, 2, f_ackley, fit_iterations=40)
@@ -197,3 +211,5 @@ if __name__ == "__main__":
     run_case_multitask("mt_lattice_T2_d2_n256_a2", "lattice", 2, 256, 2, 2)
     run_case_multitask("mt_dnb2_T3_d3_n128_a2", "dnb2", 3, 128, 3, 2)
     run_case_multitask("mt_lattice_T3_d2_n64_a3", "lattice", 2, 64, 3, 3)
+    run_case_multitask("mt_lattice_T3_d2_ragged_a2", "lattice", 2, [64, 256, 128], 3, 2)
+    run_case_multitask("mt_dnb2_T2_d3_ragged_a2", "dnb2", 3, [256, 32], 2, 2)

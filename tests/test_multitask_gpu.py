@@ -1,4 +1,4 @@
-"""GPU parity of the multi-task path (num_tasks > 1, equal task sizes) against fixtures written
+"""GPU parity of the multi-task path (num_tasks > 1, equal or different sizes per task) against fixtures written
 by the unmodified reference (tests/golden/make_golden.py::run_case_multitask)."""
 import numpy as np
 import pytest
@@ -29,15 +29,19 @@ def make_gp(g):
 @pytest.mark.parametrize("case", GOLDEN_MT_CASES)
 def test_multitask_matches_reference_fixture(case):
     g = load_golden(case)
-    T, n = int(g["T"]), int(g["n"])
+    T = int(g["T"])
+    ns = [int(v) for v in g["ns"]] if "ns" in g else [int(g["n"])] * T
+    ragged = len(set(ns)) > 1
+    gx = [g["x_%d" % l] for l in range(T)] if ragged else list(g["x"])
+    gy = [g["y_%d" % l] for l in range(T)] if ragged else list(g["y"])
     gp = make_gp(g)
-    xs = gp.get_x_next([n] * T)
-    assert isinstance(xs, list) and all(np.array_equal(xs[l].cpu().numpy(), g["x"][l]) for l in range(T))  # bit-exact points
-    gp.add_y_next([torch.from_numpy(g["y"][l]) for l in range(T)])
+    xs = gp.get_x_next(ns)
+    assert isinstance(xs, list) and all(np.array_equal(xs[l].cpu().numpy(), gx[l]) for l in range(T))  # bit-exact points
+    gp.add_y_next([torch.from_numpy(gy[l]) for l in range(T)])
     assert rel(gp.gram_matrix_tasks, g["kmat_tasks0"]) < 1e-14
     # MLL terms and autograd gradients of all five parameter groups
     norm, logdet = gp.get_inv_log_det_cache().get_norm_term_logdet_term()
-    loss = 0.5 * (norm.sum() + logdet.sum() + T * n * np.log(2 * np.pi))
+    loss = 0.5 * (norm.sum() + logdet.sum() + sum(ns) * np.log(2 * np.pi))
     assert abs(float(loss) - float(g["loss0"])) <= 1e-9 * abs(float(g["loss0"]))
     loss.backward()
     assert rel(gp.raw_scale.grad, g["grad_raw_scale0"]) < 1e-7
@@ -45,7 +49,7 @@ def test_multitask_matches_reference_fixture(case):
     assert rel(gp.raw_factor_task_kernel.grad, g["grad_raw_factor0"]) < 1e-7
     assert rel(gp.raw_noise_task_kernel.grad, g["grad_raw_noise_task0"]) < 1e-7
     gp.zero_grad()
-    ymax = float(np.abs(g["y"]).max())
+    ymax = max(float(np.abs(v).max()) for v in gy)
     assert rel(gp.coeffs, g["coeffs0"]) < 1e-8
     xt = torch.from_numpy(g["xtest"])
     pm = gp.post_mean(xt)
@@ -58,6 +62,10 @@ def test_multitask_matches_reference_fixture(case):
     assert float((gp.post_cubature_mean().cpu() - torch.from_numpy(g["pcmean0"])).abs().max()) < 1e-8 * ymax
     assert float((gp.post_cubature_var().cpu() - torch.from_numpy(g["pcvar0"])).abs().max()) < 1e-9
     assert float((gp.post_cubature_cov().cpu() - torch.from_numpy(g["pccov0"])).abs().max()) < 1e-9
+    if ragged:  # "future" sizes: every task doubled (abstract_gp.py:394,408)
+        n2 = 2 * gp.n
+        assert float((gp.post_var(xt, n=n2).cpu() - torch.from_numpy(g["pvar0_n2"])).abs().max()) < 1e-8
+        assert float((gp.post_cubature_var(n=n2).cpu() - torch.from_numpy(g["pcvar0_n2"])).abs().max()) < 1e-9
     # fit: trajectory of loss, hyperparameters and the task kernel
     data = gp.fit(iterations=int(g["fit_iterations"]), verbose=0, store_hists=True, stop_crit_wait_iterations=100)
     assert data["iterations"] == int(g["fit_last_iteration"])
@@ -73,7 +81,8 @@ def test_multitask_guards():
     gp = fgp.FastGPLattice(2, num_tasks=2, seed_for_seq=3, device=dev)
     x = gp.get_x_next([64, 16])
     gp.add_y_next([torch.cos(x[0].sum(1)), torch.cos(x[1].sum(1))])
-    with pytest.raises(NotImplementedError):
-        gp.coeffs  # unequal task sizes are not built
+    assert gp.coeffs.shape == (80,) and gp.n.tolist() == [64, 16]
+    with pytest.raises(AssertionError):
+        gp.post_var(torch.rand(4, 2), n=[64, 8])  # sizes may only grow
     with pytest.raises(NotImplementedError):
         fgp.FastGPLattice(2, num_tasks=2, shape_batch=[3], device=dev)

@@ -10,6 +10,7 @@ LIB_PATH = os.environ.get("FGP_B200_LIB") or os.path.join(_HERE, "lib", "libfgp_
 
 MAX_D = 32
 MAX_ALPHA = 10
+DERIV_STRIDE = 24
 
 _c = ctypes
 _vp, _i32, _i64, _u64, _f64, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint64, _c.c_double, _c.c_size_t
@@ -76,6 +77,8 @@ SIGNATURES = {
     "fgp_lattice_cross_kernel": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _f64, _vp, _vp, _vp]),
     "fgp_dnb2_cross_kernel": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp]),
     "fgp_kernel_pairs": (_i32, [_i32, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp]),
+    "fgp_deriv_kernel_parts": (_i32, [_i32, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "fgp_deriv_cross_kernel": (_i32, [_i32, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _f64, _vp, _vp, _vp]),
     "fgp_fp64_peak_probe": (_i32, [_i32, _vp, _vp, _vp]),
 }
 
@@ -212,6 +215,42 @@ def kernel_pairs(family, x, z, alpha, t, scale, ls):
     with torch.cuda.device(x.device):
         _check(load().fgp_kernel_pairs(int(family), _dev(x, torch.float64), _dev(z, torch.int64 if z_is_int else torch.float64), int(z_is_int),
                                        N, d, _harr(_i32, alpha), int(t), float(scale), _harr(_f64, ls), out.data_ptr(), _stream()))
+    return out
+
+
+class DerivTerms(object):
+    """Device tables of the derivative terms of one task pair (include/fgp_b200.h, fgp_deriv_*): ord (nt*d) int32,
+    par (nt*d*DERIV_STRIDE), ind (nt*d), w (nt) float64."""
+
+    def __init__(self, ord_, par, ind, w, device):
+        self.nt, self.d = ord_.shape
+        assert par.shape == (self.nt, self.d, DERIV_STRIDE) and ind.shape == (self.nt, self.d) and w.shape == (self.nt,)
+        self.ord = torch.as_tensor(ord_, dtype=torch.int32).contiguous().to(device)
+        self.par = torch.as_tensor(par, dtype=torch.float64).contiguous().to(device)
+        self.ind = torch.as_tensor(ind, dtype=torch.float64).contiguous().to(device)
+        self.w = torch.as_tensor(w, dtype=torch.float64).contiguous().to(device)
+
+
+def deriv_kernel_parts(family, x, z, terms, t):
+    """parts (n, nt, d) of the points x (float64 lattice / int64 net) against the single point z (length-d host list)."""
+    n, d = x.shape
+    out = torch.empty((n, terms.nt, d), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        zh = _harr(_f64, [float(v) for v in z]) if family == 0 else _harr(_i64, [int(v) for v in z])
+        _check(load().fgp_deriv_kernel_parts(int(family), _dev(x, torch.float64 if family == 0 else torch.int64), n, d, zh, terms.nt,
+                                             _dev(terms.ord, torch.int32), _dev(terms.par, torch.float64), int(t), out.data_ptr(), _stream()))
+    return out
+
+
+def deriv_cross_kernel(family, xs, xtrain, terms, t, scale, ls):
+    """K (m,n) = derivative kernel of float test points xs against xtrain (float64 lattice / int64 net)."""
+    m, d = xs.shape
+    n = xtrain.shape[0]
+    out = torch.empty((m, n), dtype=torch.float64, device=xs.device)
+    with torch.cuda.device(xs.device):
+        _check(load().fgp_deriv_cross_kernel(int(family), _dev(xs, torch.float64), m, _dev(xtrain, torch.float64 if family == 0 else torch.int64), n, d,
+                                             terms.nt, _dev(terms.ord, torch.int32), _dev(terms.par, torch.float64), _dev(terms.ind, torch.float64),
+                                             _dev(terms.w, torch.float64), int(t), float(scale), _harr(_f64, ls), out.data_ptr(), _stream()))
     return out
 
 

@@ -18,7 +18,10 @@ tasks of equal size, GCV / CV losses and masked fits run on the same CUDA transf
 _FTFunction).  Derivative information and the adaptive nugget raise NotImplementedError -- rows
 (f)2-(f)3 of the scope table are not silently approximated.
 """
+import functools
+import math
 import os
+from fractions import Fraction
 from typing import List, Tuple, Union
 
 import numpy as np
@@ -489,8 +492,10 @@ class AbstractFastGP(torch.nn.Module):
             solo_task, default_task = False, torch.arange(num_tasks)
         if num_tasks != 1 and len(torch.Size(shape_batch)) != 0:
             raise NotImplementedError("multi-task GPs with batched outputs are not built (SURVEY.md section 8(f) row 2 covers equal-size tasks, one hyperparameter set)")
-        if derivatives is not None or derivatives_coeffs is not None:
-            raise NotImplementedError("derivative-informed kernels are outside the B200 hot path built so far (SURVEY.md section 8(f) row 3)")
+        if derivatives is not None or derivatives_coeffs is not None:  # abstract_gp.py:59-62
+            rank_factor_task_kernel = 1
+            tfs_noise_task_kernel = DEFAULT_TFS_ID
+            noise_task_kernel = 0.
         if adaptive_nugget:
             raise NotImplementedError("adaptive_nugget is not supported by the B200 hot path")
         self.num_tasks = num_tasks
@@ -513,8 +518,25 @@ class AbstractFastGP(torch.nn.Module):
         self.n = torch.zeros(self.num_tasks, dtype=int, device=self.device)
         self.m = -1 * torch.ones(self.num_tasks, dtype=int, device=self.device)
         self._nint = 0
-        self.derivatives = [torch.zeros((1, self.d), dtype=torch.int64, device=self.device)]
-        self.derivatives_coeffs = [torch.ones(1, device=self.device)]
+        # derivatives (abstract_gp.py:63-72): per task a (p,d) table of derivative multi-indices and p coefficients
+        if derivatives is None:
+            derivatives = [torch.zeros((1, self.d), dtype=torch.int64, device=self.device) for _ in range(self.num_tasks)]
+        if isinstance(derivatives, torch.Tensor):
+            derivatives = [derivatives]
+        assert isinstance(derivatives, list) and len(derivatives) == self.num_tasks
+        derivatives = [(deriv[None, :] if deriv.ndim == 1 else deriv).to(self.device) for deriv in derivatives]
+        assert all((derivatives[i].ndim == 2 and derivatives[i].size(1) == self.d) for i in range(self.num_tasks))
+        self.derivatives = derivatives
+        if derivatives_coeffs is None:
+            derivatives_coeffs = [torch.ones(len(self.derivatives[i]), device=self.device) for i in range(self.num_tasks)]
+        assert isinstance(derivatives_coeffs, list) and len(derivatives_coeffs) == self.num_tasks
+        derivatives_coeffs = [c.to(self.device) for c in derivatives_coeffs]
+        assert all((derivatives_coeffs[i].ndim == 1 and len(derivatives_coeffs[i])) == len(self.derivatives[i]) for i in range(self.num_tasks))
+        self.derivatives_coeffs = derivatives_coeffs
+        self._has_derivs = any((self.derivatives[i] > 0).any() or (self.derivatives_coeffs[i] != 1).any() or len(self.derivatives[i]) != 1 for i in range(self.num_tasks))
+        self._deriv_cache = {}
+        if self._has_derivs and len(torch.Size(shape_batch)) != 0:
+            raise NotImplementedError("derivative-informed GPs with batched outputs are not built")
         # alpha
         assert (np.isscalar(alpha) and alpha % 1 == 0) or (isinstance(alpha, torch.Tensor) and alpha.shape == (self.d,)), "alpha should be an int or a torch.Tensor of length d"
         if np.isscalar(alpha):
@@ -630,7 +652,12 @@ class AbstractFastGP(torch.nn.Module):
         s0 = self.seqs[0]
         self._zgen = [int(v) for v in s0.gen_vec] if (self._FAMILY == 0 and isinstance(s0, sequences.Lattice) and os.environ.get("FGP_B200_NO_GEN") != "1") else None
         self._netgen = self._FAMILY == 1 and isinstance(s0, sequences.DigitalNetB2) and os.environ.get("FGP_B200_NO_GEN") != "1"
-        self._mt = multitask.MultiTaskEngine(self) if self.num_tasks > 1 else None
+        # several tasks, or derivative observations (their kernels are sums over derivative terms): block eigen-solve route
+        self._mt = multitask.MultiTaskEngine(self) if (self.num_tasks > 1 or self._has_derivs) else None
+        if self._has_derivs:  # abstract_gp.py:147-150
+            self.raw_noise_task_kernel.requires_grad_(False)
+            self.raw_factor_task_kernel.requires_grad_(False)
+            assert (self.gram_matrix_tasks == 1).all()
         self._epoch = 0
         self._coeffs = None
         self._coeffs_key = None
@@ -886,12 +913,22 @@ class AbstractFastGP(torch.nn.Module):
                c0: torch.Tensor = None, c1: torch.Tensor = None):
         assert isinstance(x, torch.Tensor) and x.size(-1) == self.d
         assert isinstance(z, torch.Tensor) and z.size(-1) == self.d
-        for b in (beta0, beta1):
-            if b is not None and (b != 0).any():
-                raise NotImplementedError("derivative-informed kernels are outside the B200 hot path built so far")
-        for c in (c0, c1):
-            if c is not None:
-                assert c.numel() == 1, "without derivatives there is one coefficient"
+        if beta0 is None:
+            beta0 = torch.zeros((1, self.d), dtype=int, device=self.device)
+        if beta0.shape == (len(beta0),):
+            beta0 = beta0[None, :]
+        assert isinstance(beta0, torch.Tensor) and beta0.ndim == 2 and beta0.size(1) == self.d
+        if beta1 is None:
+            beta1 = torch.zeros((1, self.d), dtype=int, device=self.device)
+        if beta1.shape == (len(beta1),):
+            beta1 = beta1[None, :]
+        assert isinstance(beta1, torch.Tensor) and beta1.ndim == 2 and beta1.size(1) == self.d
+        assert c0 is None or (isinstance(c0, torch.Tensor) and c0.shape == (beta0.size(0),))
+        assert c1 is None or (isinstance(c1, torch.Tensor) and c1.shape == (beta1.size(0),))
+        if (beta0 != 0).any() or (beta1 != 0).any() or len(beta0) > 1 or len(beta1) > 1:
+            c0 = torch.ones(len(beta0), device=self.device) if c0 is None else c0
+            c1 = torch.ones(len(beta1), device=self.device) if c1 is None else c1
+            return self._kernel_deriv(x, z, beta0, beta1, c0, c1)
         k = self._kernel(x, z)
         for c in (c0, c1):
             if c is not None:
@@ -922,6 +959,49 @@ class AbstractFastGP(torch.nn.Module):
         if len(pshape) == 0:
             return outs[0]
         return torch.stack(outs, 0).reshape(tuple(pshape) + tuple(outs[0].shape))
+
+    # ------------------------------------------------------------------------------------------------ derivative kernels
+    def _deriv_terms(self, beta0, beta1, c0, c1):
+        """Device term tables (`_lib.DerivTerms`) of the derivative kernel sum_{t0,t1} c0[t0] c1[t1] scale prod_j (ind_j + ls_j part_j)
+        (abstract_fast_gp.py:173-191 with fast_gp_lattice.py:267-273 / fast_gp_digital_net_b2.py:289-301)."""
+        b0 = np.asarray(beta0.cpu(), dtype=np.int64).reshape(-1, self.d)
+        b1 = np.asarray(beta1.cpu(), dtype=np.int64).reshape(-1, self.d)
+        w0 = np.asarray(c0.detach().cpu(), dtype=np.float64).reshape(-1)
+        w1 = np.asarray(c1.detach().cpu(), dtype=np.float64).reshape(-1)
+        key = (b0.tobytes(), b1.tobytes(), w0.tobytes(), w1.tobytes())
+        tm = self._deriv_cache.get(key)
+        if tm is None:
+            nt = len(b0) * len(b1)
+            ord_ = np.zeros((nt, self.d), dtype=np.int32)
+            par = np.zeros((nt, self.d, _lib.DERIV_STRIDE))
+            ind = np.zeros((nt, self.d))
+            w = np.zeros(nt)
+            for t0 in range(len(b0)):
+                for t1 in range(len(b1)):
+                    t = t0 * len(b1) + t1
+                    w[t] = w0[t0] * w1[t1]
+                    for j in range(self.d):
+                        ind[t, j] = float(b0[t0, j] + b1[t1, j] == 0)
+                        ord_[t, j], par[t, j] = self._deriv_part_spec(self._alpha_list[j], int(b0[t0, j]), int(b1[t1, j]))
+            tm = self._deriv_cache[key] = _lib.DerivTerms(ord_, par, ind, w, self.device)
+        return tm
+
+    def _kernel_deriv(self, x, z, beta0, beta1, c0, c1):
+        """Derivative kernel with numpy-style broadcasting of the leading dims (one hyperparameter set)."""
+        x = x.to(self.device)
+        z = z.to(self.device)
+        scale_B, ls_B, _, pshape = self._hyper_host()
+        assert len(scale_B) == 1, "derivative kernels take one hyperparameter set"
+        tm = self._deriv_terms(beta0, beta1, c0, c1)
+        if x.ndim == 3 and z.ndim == 3 and x.shape[1] == 1 and z.shape[0] == 1 and torch.is_floating_point(x):
+            zz = z[0] if self._FAMILY == 0 or not torch.is_floating_point(z) else self._convert_to_b(z[0])
+            return _lib.deriv_cross_kernel(self._FAMILY, x[:, 0, :].contiguous(), zz.contiguous(), tm, self._t, scale_B[0], ls_B[0])
+        # row pairs: the kernels are shift invariant, so evaluate the parts of delta = x (-) z against the origin
+        lead = torch.broadcast_shapes(x.shape[:-1], z.shape[:-1])
+        delta = self._ominus(x, z).expand(tuple(lead) + (self.d,)).reshape(-1, self.d).contiguous()
+        parts = _lib.deriv_kernel_parts(self._FAMILY, delta, [0] * self.d, tm, self._t)
+        ls = torch.as_tensor(ls_B[0], device=self.device)
+        return (float(scale_B[0]) * ((tm.ind + ls * parts).prod(-1) * tm.w).sum(-1)).reshape(lead)
 
     # ------------------------------------------------------------------------------------------------ fit
     def _lam_autograd(self, n=None, with_tilde=False):
@@ -1433,6 +1513,15 @@ _CTOR_DOC = """
 """
 
 
+@functools.lru_cache(maxsize=None)
+def _bernoulli_poly_coeffs(order):
+    """Coefficients (low degree first) of the Bernoulli polynomial B_order(x) = sum_k C(order,k) B_{order-k} x^k, B_1 = -1/2."""
+    B = [Fraction(1)]
+    for m in range(1, order + 1):
+        B.append(-sum(Fraction(math.comb(m + 1, k)) * B[k] for k in range(m)) / (m + 1))
+    return tuple(Fraction(math.comb(order, k)) * B[order - k] for k in range(order + 1))
+
+
 class FastGPLattice(AbstractFastGP):
     """Fast GP regression on rank-1 lattice points with shift-invariant (Bernoulli-polynomial) kernels.
     Drop-in for fastgps.FastGPLattice (fast_gp_lattice.py:7-273) on the single-task path.""" + _CTOR_DOC
@@ -1483,6 +1572,19 @@ class FastGPLattice(AbstractFastGP):
                          shape_scale, shape_lengthscales, shape_noise, shape_factor_task_kernel, shape_noise_task_kernel,
                          derivatives, derivatives_coeffs, compile_fts, compile_fts_kwargs, adaptive_nugget)
         assert all(self.seqs[i].randomize in ['FALSE', 'SHIFT'] for i in range(self.num_tasks)), "each seq should have randomize in ['FALSE','SHIFT']"
+
+    @staticmethod
+    def _deriv_part_spec(alpha, beta, kappa):
+        """fast_gp_lattice.py:267-273: (-1)^(alpha+kappa+1) (2 pi)^(2 alpha) / order! * B_order(a), order = 2 alpha - beta - kappa,
+        as the coefficients (low degree first) of a polynomial in a = (x - z) mod 1; exact rational Bernoulli coefficients."""
+        order = 2 * alpha - beta - kappa
+        assert 2 <= order, "order must all be at least 2, but got order = %s" % str(order)
+        assert order < _lib.DERIV_STRIDE
+        coeff = (-1) ** (alpha + kappa + 1) * math.exp(2 * alpha * math.log(2 * math.pi) - math.lgamma(order + 1))
+        par = np.zeros(_lib.DERIV_STRIDE)
+        for k, c in enumerate(_bernoulli_poly_coeffs(order)):
+            par[k] = coeff * float(c)
+        return order, par
 
     @staticmethod
     def _default_sequence(d, seed):
@@ -1561,6 +1663,16 @@ class FastGPDigitalNetB2(AbstractFastGP):
         assert all(t == ts[0] for t in ts), "all seqs should have the same t"
         self.t = self._t = ts[0]
         assert (1 <= self.alpha).all() and (self.alpha <= 4).all()
+
+    @staticmethod
+    def _deriv_part_spec(alpha, beta, kappa):
+        """fast_gp_digital_net_b2.py:289-301: (-2)^(beta+kappa) ([beta+kappa > 0] + W_order - 1), order = alpha - beta - kappa."""
+        order = alpha - beta - kappa
+        assert 1 <= order <= 4, "order must all be between 2 and 4, but got order = %s. Try increasing alpha" % str(order)
+        par = np.zeros(_lib.DERIV_STRIDE)
+        par[0] = float((-2) ** (beta + kappa))
+        par[1] = float(beta + kappa > 0)
+        return order, par
 
     @staticmethod
     def _default_sequence(d, seed):

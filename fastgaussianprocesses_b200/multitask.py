@@ -64,12 +64,37 @@ class MultiTaskEngine(object):
             x0, xb0 = gp.xxb_seqs[l0][:int(n)]
             x1, xb1 = gp.xxb_seqs[l1][:1]
             with torch.no_grad():
-                if gp._FAMILY == 0:
+                if gp._has_derivs:  # (n, terms, d): one slice per pair of derivative multi-indices
+                    p = _lib.deriv_kernel_parts(gp._FAMILY, (x0 if gp._FAMILY == 0 else xb0).contiguous(),
+                                                (x1 if gp._FAMILY == 0 else xb1)[0].cpu().numpy(), self.terms(l0, l1), gp._t)
+                elif gp._FAMILY == 0:
                     p = _lib.lattice_kernel_parts(x0.contiguous(), x1[0].cpu().numpy(), gp._alpha_list)
                 else:
                     p = _lib.dnb2_kernel_parts(xb0.contiguous(), xb1[0].cpu().numpy(), gp._alpha_list, gp._t)
             self._parts[key] = p
         return p
+
+    def terms(self, l0, l1):
+        gp = self.gp
+        return gp._deriv_terms(gp.derivatives[l0], gp.derivatives[l1], gp.derivatives_coeffs[l0], gp.derivatives_coeffs[l1])
+
+    def k1(self, l0, l1, n):
+        """First kernel column of task l0 against the first point of task l1, differentiable w.r.t. scale and lengthscales
+        (abstract_fast_gp.py:181-191: sum over the derivative terms of scale prod_j (ind_j + ls_j part_j))."""
+        gp = self.gp
+        scale, ls = gp.scale, gp.lengthscales
+        p = self.parts(l0, l1, n)
+        if not gp._has_derivs:
+            return scale * (1 + ls[..., None, :] * p).prod(-1)
+        tm = self.terms(l0, l1)
+        return scale * ((tm.ind + ls[..., None, None, :] * p).prod(-1) * tm.w).sum(-1)
+
+    def cross(self, x, t, l, n, scale, ls):
+        """k(x, X_l[:n]) for test task t (N, n)."""
+        gp = self.gp
+        if gp._has_derivs:
+            return _lib.deriv_cross_kernel(gp._FAMILY, x, self.xpts(l, n), self.terms(t, l), gp._t, scale, ls)
+        return _lib.cross_kernel(gp._FAMILY, x, self.xpts(l, n), gp._alpha_list, gp._t, scale, ls)
 
     def lam_system(self, n=None):
         """Lam (n_min, R, R), differentiable w.r.t. every raw parameter.  Block (t0, t1), n_t0 >= n_t1: the length-n_t0 vector
@@ -85,11 +110,9 @@ class MultiTaskEngine(object):
             for t1 in active[i0:]:
                 nbig = ns[t0]
                 if t0 <= t1:
-                    k1 = scale * (1 + ls[..., None, :] * self.parts(t0, t1, nbig)).prod(-1)
-                    lam = gp.ft(k1)
+                    lam = gp.ft(self.k1(t0, t1, nbig))
                 else:  # the reference keeps one spectrum per unordered pair and conjugates it (util.py:284)
-                    k1 = scale * (1 + ls[..., None, :] * self.parts(t1, t0, nbig)).prod(-1)
-                    lam = gp.ft(k1).conj()
+                    lam = gp.ft(self.k1(t1, t0, nbig)).conj()
                 lam = np.sqrt(ns[t1]) * lam
                 if t0 == t1:
                     lam = lam + noise
@@ -210,6 +233,16 @@ class MultiTaskEngine(object):
         N = x.shape[0]
         if N == 0:
             return torch.empty((len(task), 0), dtype=torch.float64, device=gp.device)
+        if gp._has_derivs:  # the kernel depends on the test task: chunked cross tiles times the coefficients
+            out = torch.zeros((len(task), N), dtype=torch.float64, device=gp.device)
+            step = max(1, (1 << 24) // max(1, max(ns)))
+            for i, t in enumerate(task.tolist()):
+                for l in range(T):
+                    if ns[l] == 0:
+                        continue
+                    for r0 in range(0, N, step):
+                        out[i, r0:r0 + step] += kt[t, l] * (self.cross(x[r0:r0 + step].contiguous(), t, l, ns[l], scale, ls) @ c[l].reshape(-1))
+            return out
         # one on-the-fly kernel-vector product per training task, then the T x T task kernel mixes them
         base = torch.stack([_lib.post_mean(gp._FAMILY, x, self.xpts(l, ns[l]), gp._alpha_list, gp._t, scale, ls, c[l].reshape(1, -1).contiguous())[0]
                             if ns[l] > 0 else torch.zeros(N, dtype=torch.float64, device=gp.device) for l in range(T)], 0)
@@ -219,26 +252,35 @@ class MultiTaskEngine(object):
     def _cross_rows(self, x, t, ns, scale, ls, kt):
         """K_task[t, l1] k(x, X_l1) for all l1, concatenated: (N, sum_l n_l)."""
         gp = self.gp
-        return torch.cat([kt[t, l] * _lib.cross_kernel(gp._FAMILY, x, self.xpts(l, ns[l]), gp._alpha_list, gp._t, scale, ls)
-                          for l in range(self.T) if ns[l] > 0], -1)
+        return torch.cat([kt[t, l] * self.cross(x, t, l, ns[l], scale, ls) for l in range(self.T) if ns[l] > 0], -1)
 
-    def _kxx(self, scale, ls):
+    def _kxx(self, t, scale, ls):
+        """k(x, x) of task t: a constant, the kernels are shift invariant."""
         gp = self.gp
         one = torch.zeros((1, gp.d), dtype=torch.float64, device=gp.device)
+        if gp._has_derivs:
+            z = one.clone() if gp._FAMILY == 0 else torch.zeros((1, gp.d), dtype=torch.int64, device=gp.device)
+            return float(_lib.deriv_cross_kernel(gp._FAMILY, one, z, self.terms(t, t), gp._t, scale, ls)[0, 0])
         return float(_lib.kernel_pairs(gp._FAMILY, one, one.clone(), gp._alpha_list, gp._t, scale, ls)[0])
+
+    def _knew(self, x0, x1, t0, t1, scale, ls):
+        gp = self.gp
+        z = x1 if gp._FAMILY == 0 else gp._convert_to_b(x1)
+        if gp._has_derivs:
+            return _lib.deriv_cross_kernel(gp._FAMILY, x0, z.contiguous(), self.terms(t0, t1), gp._t, scale, ls)
+        return _lib.cross_kernel(gp._FAMILY, x0, z, gp._alpha_list, gp._t, scale, ls)
 
     def post_var(self, x, task, n):
         gp = self.gp
         scale, ls, kt = self._host()
         A, _ = self.factor(n)
         ns = self.sizes(n)[0]
-        kxx = self._kxx(scale, ls)
         out = []
         with torch.no_grad():
             for t in task.tolist():
                 km = self._cross_rows(x, t, ns, scale, ls, kt)
                 sol = self.gram_matrix_solve(km, n=n, A=A)
-                out.append((kt[t, t] * kxx - (sol * km).sum(-1)).clamp_(min=0))
+                out.append((kt[t, t] * self._kxx(t, scale, ls) - (sol * km).sum(-1)).clamp_(min=0))
         return torch.stack(out, 0)
 
     def post_cov(self, x0, x1, task0, task1, n, equal):
@@ -246,15 +288,14 @@ class MultiTaskEngine(object):
         scale, ls, kt = self._host()
         A, _ = self.factor(n)
         ns = self.sizes(n)[0]
-        fam, al, tt = gp._FAMILY, gp._alpha_list, gp._t
         with torch.no_grad():
-            knew = _lib.cross_kernel(fam, x0, x1 if fam == 0 else gp._convert_to_b(x1), al, tt, scale, ls)
+            knew = None if gp._has_derivs else self._knew(x0, x1, 0, 0, scale, ls)
             k1 = {t: self._cross_rows(x0, t, ns, scale, ls, kt) for t in set(task0.tolist())}
             sol2 = {t: self.gram_matrix_solve(k1[t] if (equal and t in k1) else self._cross_rows(x1, t, ns, scale, ls, kt), n=n, A=A) for t in set(task1.tolist())}
             out = torch.empty((len(task0), len(task1), x0.shape[0], x1.shape[0]), dtype=torch.float64, device=gp.device)
             for i0, t0 in enumerate(task0.tolist()):
                 for i1, t1 in enumerate(task1.tolist()):
-                    out[i0, i1] = kt[t0, t1] * knew - k1[t0] @ sol2[t1].T
+                    out[i0, i1] = kt[t0, t1] * (self._knew(x0, x1, t0, t1, scale, ls) if knew is None else knew) - k1[t0] @ sol2[t1].T
                     if equal and t0 == t1 and i0 == i1:
                         out[i0, i1].diagonal().clamp_(min=0)
         return out

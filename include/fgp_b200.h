@@ -29,6 +29,7 @@ extern "C" {
 #define FGP_VERSION 100
 #define FGP_MAX_D 32          /* dimensions handled by the fused kernels */
 #define FGP_MAX_ALPHA 10      /* lattice smoothness (Bernoulli order 2*alpha <= 20) */
+#define FGP_DERIV_STRIDE 24   /* doubles per (term, dimension) of the derivative-kernel parameter table */
 #define FGP_MAX_LOG2N_FFT 24  /* two-pass FFT-BRO: n <= 2^24 */
 #define FGP_MAX_LOG2N_WHT 26  /* two-pass FWHT:    n <= 2^26 */
 
@@ -228,6 +229,20 @@ int fgp_dnb2_cross_kernel(const double* xs_dev, int64_t m, const int64_t* xb_dev
  * abstract_gp.py:693-706).  x (N,d) float64; z (N,d) float64, or int64 net integers when z_is_int. */
 int fgp_kernel_pairs(int family, const double* x_dev, const void* z_dev, int z_is_int, int64_t N, int d,
                      const int* alpha_host, int t, double scale, const double* ls_host, double* k_dev, fgp_stream_t stream);
+
+/* Derivative-informed kernels (replaces fast_gp_lattice.py:267-273, fast_gp_digital_net_b2.py:289-301 and the term sum of
+ * abstract_fast_gp.py:181-191 when `derivatives` is given).  A term is one pair (t0,t1) of derivative multi-indices; per
+ * (term, dimension) q = term*d + j the DEVICE tables hold
+ *   lattice: ord[q] = degree, par[q*FGP_DERIV_STRIDE + p] = coefficient p of coef*B_order(a), a = (x - z) mod 1
+ *   net:     ord[q] = Walsh order 1..4, par[q*S] = (-2)^(beta+kappa), par[q*S+1] = [beta+kappa > 0]
+ *   ind[q] = [beta0_j + beta1_j == 0],  w[term] = c0[t0]*c1[t1].
+ * fgp_deriv_kernel_parts: parts (n, nterms, d) of n points (float64 lattice / int64 net) against ONE point z_host (d).
+ * fgp_deriv_cross_kernel: K[i,a] = scale sum_term w prod_j (ind + ls_j part) for xs (m,d) float64 against x (n,d). */
+int fgp_deriv_kernel_parts(int family, const void* x_dev, int64_t n, int d, const void* z_host, int nterms, const int* ord_dev,
+                           const double* par_dev, int t, double* parts_dev, fgp_stream_t stream);
+int fgp_deriv_cross_kernel(int family, const double* xs_dev, int64_t m, const void* x_dev, int64_t n, int d, int nterms,
+                           const int* ord_dev, const double* par_dev, const double* ind_dev, const double* w_dev, int t,
+                           double scale, const double* ls_host, double* k_dev, fgp_stream_t stream);
 
 /* FP64 FMA-chain peak probe used by bench.py for the FP64 roofline denominator: runs `iters` dependent-chain
  * DFMA blocks on every SM and returns the flop count in *flops (time it with events on `stream`). */

@@ -132,27 +132,47 @@ def run_case(name, family, d, n, m_test, alpha, f, scale=1.0, lengthscales=1.0, 
     print(name, "loss0", out["loss0"], "its", data["iterations"], os.path.getsize(path) // 1024, "KiB")
 
 
-def run_case_multitask(name, family, d, n, T, alpha, m_test=64, noise=1e-6, fit_iterations=8, seed=11):
+def run_case_multitask(name, family, d, n, T, alpha, m_test=64, noise=1e-6, fit_iterations=8, seed=11, derivatives=None, derivatives_coeffs=None,
+                       shared_seq=False):
     """num_tasks = T: block eigen-solve util.py:301-323,354-363.  n is one size for every task
     or a list of per-task sizes (ragged arrays are then stored per task: x_0, x_1, ..., y_0, ...)."""
     ns = [int(n)] * T if np.isscalar(n) else [int(v) for v in n]
     ragged = len(set(ns)) > 1
     seeds = np.random.SeedSequence(seed).spawn(T)
+    if shared_seq:  # derivative observations at the same points as the function values
+        seeds = [seeds[0]] * T
+    dkw = {} if derivatives is None else {"derivatives": derivatives, "derivatives_coeffs": derivatives_coeffs}
     if family == "lattice":
         seqs = [qmcpy.Lattice(dimension=d, seed=sd) for sd in seeds]
-        gp = fastgps.FastGPLattice(seqs, num_tasks=T, alpha=alpha, noise=noise)
+        gp = fastgps.FastGPLattice(seqs, num_tasks=T, alpha=alpha, noise=noise, **dkw)
         gen = {"z": np.stack([s.gen_vec.astype(np.uint64) for s in seqs]), "shift": np.stack([s.shift for s in seqs])}
     else:
         seqs = [qmcpy.DigitalNetB2(dimension=d, seed=sd) for sd in seeds]
-        gp = fastgps.FastGPDigitalNetB2(seqs, num_tasks=T, alpha=alpha, noise=noise)
+        gp = fastgps.FastGPDigitalNetB2(seqs, num_tasks=T, alpha=alpha, noise=noise, **dkw)
         gen = {"C": np.stack([s.gen_mats.astype(np.uint64) for s in seqs]), "dshift": np.stack([s.rshift.astype(np.uint64) for s in seqs]), "t": np.int64(seqs[0].t)}
     f = lambda x, l: torch.cos(2 * np.pi * x).sum(1) + 0.4 * l * torch.sin(2 * np.pi * x[:, 0]) + 0.1 * l
+    if derivatives is not None:  # task l observes sum_p coeff_p D^{beta_p} f0, f0 = prod_j (1 + sin(2 pi x_j) / (j+2))
+        def f(x, l):
+            out = 0
+            for beta, cf in zip(gp.derivatives[l], gp.derivatives_coeffs[l]):
+                term = torch.ones(len(x))
+                for j in range(d):
+                    a = 2 * np.pi * x[:, j]
+                    dj = [1 + torch.sin(a) / (j + 2), 2 * np.pi * torch.cos(a) / (j + 2), -(2 * np.pi) ** 2 * torch.sin(a) / (j + 2)][int(beta[j])]
+                    term = term * dj
+                out = out + cf * term
+            return out
     xs = gp.get_x_next(ns)
     ys = [f(xs[l], l) for l in range(T)]
     gp.add_y_next(ys)
     xt = torch.rand((m_test, d), generator=torch.Generator().manual_seed(17))
     out = dict(gen)
     out.update(family=family, d=d, n=max(ns), ns=np.array(ns), T=T, alpha=alpha, noise0=noise, xtest=xt.numpy())
+    if derivatives is not None:
+        out.update({"deriv_%d" % l: gp.derivatives[l].numpy() for l in range(T)})
+        out.update({"dcoef_%d" % l: gp.derivatives_coeffs[l].numpy() for l in range(T)})
+        out["kernel_d01"] = gp.kernel(xt[:8, None, :], xt[None, :5, :], gp.derivatives[0], gp.derivatives[T - 1], gp.derivatives_coeffs[0], gp.derivatives_coeffs[T - 1]).detach().numpy()
+        out["kernel_pairs_d10"] = gp.kernel(xt[:8], xt[8:16], gp.derivatives[T - 1], gp.derivatives[0], gp.derivatives_coeffs[T - 1], gp.derivatives_coeffs[0]).detach().numpy()
     if ragged:
         out.update({"x_%d" % l: xs[l].numpy() for l in range(T)})
         out.update({"y_%d" % l: ys[l].numpy() for l in range(T)})
@@ -164,7 +184,8 @@ def run_case_multitask(name, family, d, n, T, alpha, m_test=64, noise=1e-6, fit_
     loss.backward()
     out.update(loss0=loss.item(), norm_term0=norm_term.detach().numpy(), logdet0=logdet.detach().numpy(),
                grad_raw_scale0=gp.raw_scale.grad.numpy().copy(), grad_raw_lengthscales0=gp.raw_lengthscales.grad.numpy().copy(),
-               grad_raw_factor0=gp.raw_factor_task_kernel.grad.numpy().copy(), grad_raw_noise_task0=gp.raw_noise_task_kernel.grad.numpy().copy())
+               grad_raw_factor0=gp.raw_factor_task_kernel.grad.numpy().copy() if gp.raw_factor_task_kernel.grad is not None else np.zeros(0),
+               grad_raw_noise_task0=gp.raw_noise_task_kernel.grad.numpy().copy() if gp.raw_noise_task_kernel.grad is not None else np.zeros(0))
     gp.zero_grad()
     del os.environ["FASTGP_FORCE_RECOMPILE"]
     out["kmat_tasks0"] = gp.gram_matrix_tasks.detach().numpy()
@@ -188,11 +209,31 @@ def run_case_multitask(name, family, d, n, T, alpha, m_test=64, noise=1e-6, fit_
     print(name, "loss0", out["loss0"], "its", data["iterations"], os.path.getsize(path) // 1024, "KiB")
 
 
+def run_deriv_cases():
+    """derivative-informed kernels (function values + gradient / mixed derivative sums).
+    The noise levels keep the per-frequency blocks well enough conditioned for the reference's own Schur recursion
+    (util.py:301-323) to be accurate: at noise 1e-6 the lattice gradient case has blocks of condition number ~6e7 and the
+    reference's logdet is 3e-8 (relative) off a dense float64 factorization of its own kernel matrix, its inverse 1e-4."""
+    e = torch.eye(2, dtype=int)
+    z2 = torch.zeros(2, dtype=int)
+    run_case_multitask("dv_lattice_grad_d2_n64_a3", "lattice", 2, 64, 3, 3, derivatives=[z2, e[0], e[1]], shared_seq=True, noise=1e-2)
+    run_case_multitask("dv_lattice_mixed_d2_ragged_a3", "lattice", 2, [128, 32], 2, 3, noise=1e-3,
+                       derivatives=[z2, torch.tensor([[1, 0], [0, 2], [1, 1]])], derivatives_coeffs=[torch.ones(1), torch.tensor([1., -0.5, 0.25])])
+    e3 = torch.eye(3, dtype=int)
+    run_case_multitask("dv_dnb2_grad_d3_n64_a3", "dnb2", 3, 64, 4, 3, derivatives=[torch.zeros(3, dtype=int), e3[0], e3[1], e3[2]], shared_seq=True, noise=1e-6)
+    run_case_multitask("dv_dnb2_mixed_d2_ragged_a4", "dnb2", 2, [64, 128], 2, 4, noise=1e-6,
+                       derivatives=[z2, torch.tensor([[1, 0], [1, 1]])], derivatives_coeffs=[torch.ones(1), torch.tensor([2., -1.])])
+
+
 if __name__ == "__main__":
     if "--multitask-only" in sys.argv:
         run_case_multitask("mt_lattice_T2_d2_n256_a2", "lattice", 2, 256, 2, 2)
         run_case_multitask("mt_dnb2_T3_d3_n128_a2", "dnb2", 3, 128, 3, 2)
         run_case_multitask("mt_lattice_T3_d2_n64_a3", "lattice", 2, 64, 3, 3)
+    if "--multitask-only" in sys.argv or "--deriv-only" in sys.argv:
+        run_deriv_cases()
+        if "--deriv-only" in sys.argv:
+            sys.exit(0)
     if "--multitask-only" in sys.argv or "--ragged-only" in sys.argv:
         run_case_multitask("mt_lattice_T3_d2_ragged_a2", "lattice", 2, [64, 256, 128], 3, 2)
         run_case_multitask("mt_dnb2_T2_d3_ragged_a2", "dnb2", 3, [256, 32], 2, 2)
@@ -213,3 +254,4 @@ if __name__ == "__main__":
     run_case_multitask("mt_lattice_T3_d2_n64_a3", "lattice", 2, 64, 3, 3)
     run_case_multitask("mt_lattice_T3_d2_ragged_a2", "lattice", 2, [64, 256, 128], 3, 2)
     run_case_multitask("mt_dnb2_T2_d3_ragged_a2", "dnb2", 3, [256, 32], 2, 2)
+    run_deriv_cases()

@@ -49,6 +49,12 @@ struct MllArgs {
   FftTables T;
   int tab_off;    // net generator mode: byte offset of the XOR-fold tables behind the tile in dynamic shared memory
   int has_fit;    // fused fit iteration: the last CTA to finish reduces the partial sums and runs the fit step
+  // Lattice two-pass kernels, half-spectrum mode.  k1 is real and even on Z_n (B_2a(1-t) = B_2a(t) in every dimension), and so
+  // are lam, dL/dlam (|y~|^2 is even for real y) and the back-transformed dL/dk1.  In the four-step layout W[b][q] (block row
+  // b of residue class r = rev(b), column q) that reads  W[rev(L2-r)][q] = conj(W[b][q])  after pass A,  lam_{n-k} = lam_k,
+  // and  W[b][L1-q] = conj(W[b][q])  after pass B's backward half.  So pass A and pass C run only the L2/2+1 blocks with
+  // r <= L2/2, pass B only the columns q <= L1/2; mirrored loads are conjugated reads and mirrored contributions weights 2.
+  int hs;
   FitLayout fit;
 };
 
@@ -471,7 +477,8 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passA_kerne
   if (fit_stopped(a)) return;
   const int b = blockIdx.y;
   const int l1 = a.l1, l2 = a.l2, lntr = a.lntrA, LP = a.LPA;
-  const int64_t blk0 = (int64_t)blockIdx.x << lntr;
+  // half-spectrum mode (lntr == 0): CTA c takes residue class r = c, i.e. block row rev(c)
+  const int64_t blk0 = (!NET && a.hs) ? (int64_t)brev_bits(blockIdx.x, l2) : ((int64_t)blockIdx.x << lntr);
   const int64_t g0 = blk0 << l1;
   load_hyp<NET>(H, a, b);
   if (GEN && NET) dnb2_build_tables(H, a, (uint64_t*)(smraw + a.tab_off), g0, l1 + lntr);
@@ -529,7 +536,8 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kerne
   const int b = blockIdx.y;
   const int d = DT > 0 ? DT : a.d;
   const int l1 = a.l1, lntr = a.lntrA, LP = a.LPA;
-  const int64_t blk0 = (int64_t)blockIdx.x << lntr;
+  const bool hs = !NET && a.hs;
+  const int64_t blk0 = hs ? (int64_t)brev_bits(blockIdx.x, a.l2) : ((int64_t)blockIdx.x << lntr);
   const int64_t g0 = blk0 << l1;
   load_hyp<NET>(H, a, b);
   if (GEN && NET) dnb2_build_tables(H, a, (uint64_t*)(smraw + a.tab_off), g0, l1 + lntr);
@@ -548,10 +556,22 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kerne
   } else {
     double2* sm = (double2*)smraw;
     const double2* W = (const double2*)a.W + (int64_t)b * a.n + g0;
-    block_fft_inv_io<false>(sm, l1, lntr, LP, a.T.stage, [&](int tr, int idx) -> double2 { return W[((int64_t)tr << l1) + idx]; }, SmemTag{});
+    if (hs) {  // columns above L1/2 were not computed: W[b][L1-q] = conj(W[b][q])
+      const int L1 = 1 << l1, half1 = L1 >> 1;
+      block_fft_inv_io<false>(sm, l1, lntr, LP, a.T.stage, [&](int, int idx) -> double2 {
+        const double2 v = W[idx > half1 ? L1 - idx : idx];
+        return make_double2(v.x, idx > half1 ? -v.y : v.y);
+      }, SmemTag{});
+    } else {
+      block_fft_inv_io<false>(sm, l1, lntr, LP, a.T.stage, [&](int tr, int idx) -> double2 { return W[((int64_t)tr << l1) + idx]; }, SmemTag{});
+    }
     __syncthreads();
     tile_drain_c<false>(SmemC{sm, LP}, l1, lntr,
                         [&](int tr, int idx, double2 w) { point_grad<DT, NET, A2, GEN>(a, H, g0 + ((int64_t)tr << l1) + idx, w.x, acc); });
+    if (hs && blockIdx.x != 0 && blockIdx.x != (1u << (a.l2 - 1))) {  // class r stands for r and L2 - r
+#pragma unroll
+      for (int j = 0; j <= DM; ++j) acc[j] *= 2.0;
+    }
   }
   reduce_store<DM + 1>(acc, d + 1, red, a.partC + ((int64_t)b * a.ctasA + blockIdx.x) * (d + 1));
   if (a.has_fit) mll_fit_tail(a, b, a.ctasA, gridDim.y, true, red);

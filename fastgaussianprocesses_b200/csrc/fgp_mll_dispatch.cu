@@ -63,6 +63,13 @@ static int mll_common(bool net, const uint64_t* z_host, const uint64_t* C_dev, i
   a.tab_off = (int)((g.smemA + 15) & ~(size_t)15);
   a.ctasA = (int)g.ctasA;
   a.ctasB = (int)g.ctasB;
+  // half-spectrum mode of the lattice two-pass kernels (fgp_mll.cuh); the full spectrum is computed when the caller wants lam
+  static const int no_hs = env_int("FGP_NO_HS", 0);
+  if (!net && g.l2 >= 1 && g.lntrA == 0 && g.lntrB < g.l1 && !lam && !no_hs) {
+    a.hs = 1;
+    a.ctasA = (1 << (g.l2 - 1)) + 1;
+    a.ctasB = ((1 << (g.l1 - 1)) >> g.lntrB) + 1;
+  }
   if (g.l2) {
     FGP_REQUIRE(workspace, "mll_grad: null workspace");
     const size_t wbytes = align256((size_t)B * n * (net ? sizeof(double) : sizeof(double2)));

@@ -644,8 +644,9 @@ static inline PassGeom make_geom(int64_t n, bool cplx) {
   g.LPA = padlen(1 << g.l1, g.ntrA, cplx ? kPSC : kPSR);
   g.LPB = padlen(1 << g.l2, g.ntrB, cplx ? kPSC : kPSR);
   static const int tdiv = env_int("FGP_THREAD_DIV", 1);  // tuning: fewer threads, more groups per thread per round
+  static const int tmul = env_int("FGP_THREAD_MUL", 1);  // tuning: more threads, fewer groups per thread per round
   auto thr = [](int tile) {
-    int t = (1 << tile) / 16 / tdiv;
+    int t = (1 << tile) / 16 * tmul / tdiv;
     if (t < 32) t = 32;
     if (t > FGP_LB_THREADS) t = FGP_LB_THREADS;
     return t;

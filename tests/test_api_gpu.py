@@ -131,7 +131,9 @@ def test_api_guards_and_errors():
     with pytest.raises(RuntimeError):
         fgp.FastGPLattice(3, device="cpu")
     with pytest.raises(NotImplementedError):
-        fgp.FastGPLattice(3, num_tasks=2, device=dev)
+        fgp.FastGPLattice(3, num_tasks=2, shape_batch=[2], device=dev)  # several tasks with batched outputs
+    with pytest.raises(NotImplementedError):
+        fgp.FastGPLattice(3, adaptive_nugget=True, device=dev)
     assert gp.post_mean(torch.rand(5, 3)).shape == (5,)
     assert gp.post_mean(torch.rand(5, 3), task=[0]).shape == (1, 5)
     assert gp.post_mean(torch.zeros(0, 3)).shape == (0,)

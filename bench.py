@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 torch.set_default_dtype(torch.float64)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, n=2^20 d=8 (profiles/README.md, snapshot g)
-NCU_TRAFFIC = {("mll_passA", 20, 8): 122880, ("mll_passB", 20, 8): 25318144, ("mll_passC", 20, 8): 16890112}
+NCU_TRAFFIC = {("mll_passA", 20, 8): 159232, ("mll_passB", 20, 8): 8623616, ("mll_passC", 20, 8): 4380416}
 
 GEN_VEC = [1, 182667, 469891, 498753, 110745, 446247, 250185, 118627]
 
@@ -299,7 +299,7 @@ def main():
     roof = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9 / hbm_peak,
             # DRAM read+write bytes of that kernel per launch from the committed ncu --set full capture (same workload only)
-            "traffic": NCU_TRAFFIC.get((dom["name"], args.log2n, d)), "traffic_source": "profiles/r1g_ncu_full_mll_passABC_postmean_raw.csv",
+            "traffic": NCU_TRAFFIC.get((dom["name"], args.log2n, d)), "traffic_source": "profiles/r1j_ncu_full_mll_passABC_halfspectrum_raw.csv",
             "peak_source": peak_src,
             "alg_bytes_per_launch": dom["alg_bytes"], "kernels": kern,
             "step": {"alg_bytes": alg_bytes_iter, "achieved": alg_bytes_iter / (t_cold / K) / 1e9, "frac": alg_bytes_iter / (t_cold / K) / 1e9 / hbm_peak}}

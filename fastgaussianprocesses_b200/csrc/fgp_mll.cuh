@@ -58,6 +58,31 @@ struct MllArgs {
   FitLayout fit;
 };
 
+// Programmatic dependent launch: the three kernels of an iteration (and the iterations of a fused fit loop) form one chain
+// in the stream, each about one wave long, so the launch latency and CTA ramp-up of a kernel are a visible share of it.
+// With the attribute the next kernel's CTAs become resident as soon as every CTA of the current one has started
+// (pdl_prologue triggers at once); they wait in cudaGridDependencySynchronize() for its memory before touching anything.
+bool pdl_enabled();  // fgp_mll_passb.cu: off by default (measured slower), FGP_PDL=1 turns it on
+template <typename K>
+static cudaError_t launch_chain(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const MllArgs& a) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, a);
+}
+__device__ __forceinline__ void pdl_prologue() {
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+}
+
 struct Hyp {  // per-CTA hyperparameters and first point, staged in shared memory
   double scale, noise;
   double ls[FGP_MAX_D];
@@ -398,6 +423,7 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_single_kern
   __shared__ Hyp H;
   __shared__ double red[kRed];
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
+  pdl_prologue();
   if (fit_stopped(a)) return;
   const int b = blockIdx.x;
   const int n = (int)a.n;
@@ -474,6 +500,7 @@ template <int DT, bool NET, bool A2, bool GEN>
 __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passA_kernel(const __grid_constant__ MllArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
+  pdl_prologue();
   if (fit_stopped(a)) return;
   const int b = blockIdx.y;
   const int l1 = a.l1, l2 = a.l2, lntr = a.lntrA, LP = a.LPA;
@@ -532,6 +559,7 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kerne
   __shared__ Hyp H;
   __shared__ double red[kRed];
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
+  pdl_prologue();
   if (fit_stopped(a)) return;
   const int b = blockIdx.y;
   const int d = DT > 0 ? DT : a.d;
@@ -599,17 +627,17 @@ static int launch_mll(const MllArgs& a, const PassGeom& g, int B, cudaStream_t s
   const size_t smemAC = (size_t)a.tab_off + ((GEN && NET) ? dnb2_table_bytes(a.d, g.l2 ? g.l1 + g.lntrA : g.l1) : 0);
   if (g.l2 == 0) {
     if ((rc = set_smem_attr(mll_single_kernel<DT, NET, A2, GEN>, smemAC))) return rc;
-    mll_single_kernel<DT, NET, A2, GEN><<<B, g.threadsA, smemAC, st>>>(a);
+    launch_chain(mll_single_kernel<DT, NET, A2, GEN>, dim3(B), dim3(g.threadsA), smemAC, st, a);
     FGP_LAUNCH_NAMED("mll_single", st);
     return FGP_OK;
   }
   if ((rc = set_smem_attr(mll_passA_kernel<DT, NET, A2, GEN>, smemAC))) return rc;
-  mll_passA_kernel<DT, NET, A2, GEN><<<dim3(a.ctasA, B), g.threadsA, smemAC, st>>>(a);
+  launch_chain(mll_passA_kernel<DT, NET, A2, GEN>, dim3(a.ctasA, B), dim3(g.threadsA), smemAC, st, a);
   FGP_LAUNCH_NAMED("mll_passA", st);
   if ((rc = launch_mll_passB(a, g, B, NET, st))) return rc;
   if (a.want_grad) {
     if ((rc = set_smem_attr(mll_passC_kernel<DT, NET, A2, GEN>, smemAC))) return rc;
-    mll_passC_kernel<DT, NET, A2, GEN><<<dim3(a.ctasA, B), g.threadsA, smemAC, st>>>(a);
+    launch_chain(mll_passC_kernel<DT, NET, A2, GEN>, dim3(a.ctasA, B), dim3(g.threadsA), smemAC, st, a);
     FGP_LAUNCH_NAMED("mll_passC", st);
   }
   if (a.has_fit) return FGP_OK;  // reduced (and stepped) by the last CTA of the last kernel

@@ -7,6 +7,7 @@ template <bool NET>
 __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passB_kernel(const __grid_constant__ MllArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ double red[kRed];
+  pdl_prologue();
   if (fit_stopped(a)) return;
   const int b = blockIdx.y;
   const double noise = a.noise[b];
@@ -124,14 +125,21 @@ __global__ void __launch_bounds__(256) mll_finalize_kernel(const __grid_constant
   finalize_set(a, blockIdx.x, red);
 }
 
+bool pdl_enabled() {
+  // measured on B200 (profiles/README.md, snapshot j): 57.1 us per lattice fit iteration with the attribute, 51.4 without -- the
+  // early-resident CTAs of the next kernel cost more than the hidden launch latency gains.  Off unless FGP_PDL=1.
+  static const bool on = env_int("FGP_PDL", 0) != 0;
+  return on;
+}
+
 int launch_mll_passB(const MllArgs& a, const PassGeom& g, int B, bool net, cudaStream_t st) {
   int rc;
   if (net) {
     if ((rc = set_smem_attr(mll_passB_kernel<true>, g.smemB))) return rc;
-    mll_passB_kernel<true><<<dim3(a.ctasB, B), g.threadsB, g.smemB, st>>>(a);
+    launch_chain(mll_passB_kernel<true>, dim3(a.ctasB, B), dim3(g.threadsB), g.smemB, st, a);
   } else {
     if ((rc = set_smem_attr(mll_passB_kernel<false>, g.smemB))) return rc;
-    mll_passB_kernel<false><<<dim3(a.ctasB, B), g.threadsB, g.smemB, st>>>(a);
+    launch_chain(mll_passB_kernel<false>, dim3(a.ctasB, B), dim3(g.threadsB), g.smemB, st, a);
   }
   FGP_LAUNCH_NAMED("mll_passB", st);
   return FGP_OK;

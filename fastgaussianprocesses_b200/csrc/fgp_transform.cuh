@@ -614,11 +614,12 @@ static inline PassGeom make_geom(int64_t n, bool cplx) {
   // L2-sized (more CTAs in different phases per SM), 64 KiB tiles for the HBM-sized transforms
   static const int capC = env_int("FGP_CAP_C", 0), capR = env_int("FGP_CAP_R", 0), colsEnv = env_int("FGP_COLS_LOG2", -1);
   static const int hardC = env_int("FGP_HARD_C", 0), hardR = env_int("FGP_HARD_R", 13);
-  int cap = cplx ? (capC ? capC : 12) : (capR ? capR : (g.m <= 22 ? 12 : 13));
+  // complex: 2^11-point tiles and 4-column strips while one iteration's CTAs fit one wave (n <= 2^18), 2^12 / 8 above
+  int cap = cplx ? (capC ? capC : (g.m <= 18 ? 11 : 12)) : (capR ? capR : (g.m <= 22 ? 12 : 13));
   // largest tile: 64 KiB of elements; the 2^24-point FFT takes 128 KiB pass-B tiles (2 columns instead of 1)
   const int hard = cplx ? (hardC ? hardC : (g.m >= 24 ? 13 : 12)) : hardR;
   if (cap > hard) cap = hard;
-  const int colsLog = colsEnv >= 0 ? colsEnv : (cplx ? 3 : (g.m <= 22 ? 4 : 3));
+  const int colsLog = colsEnv >= 0 ? colsEnv : (cplx ? (g.m <= 18 ? 2 : 3) : (g.m <= 22 ? 4 : 3));
   int tileA, tileB = 0;
   if (g.m <= cap) {
     g.l1 = g.m;
@@ -644,8 +645,11 @@ static inline PassGeom make_geom(int64_t n, bool cplx) {
   g.LPA = padlen(1 << g.l1, g.ntrA, cplx ? kPSC : kPSR);
   g.LPB = padlen(1 << g.l2, g.ntrB, cplx ? kPSC : kPSR);
   static const int tdiv = env_int("FGP_THREAD_DIV", 1);  // tuning: fewer threads, more groups per thread per round
-  static const int tmul = env_int("FGP_THREAD_MUL", 1);  // tuning: more threads, fewer groups per thread per round
-  auto thr = [](int tile) {
+  // more threads, fewer groups per thread per round: complex tiles run one radix-8 group per thread per round (measured
+  // 55.3 -> 51.5 us per lattice fit iteration at n = 2^20, profiles/README.md)
+  static const int tmulEnv = env_int("FGP_THREAD_MUL", 0);
+  const int tmul = tmulEnv ? tmulEnv : (cplx ? 2 : 1);
+  auto thr = [tmul](int tile) {
     int t = (1 << tile) / 16 * tmul / tdiv;
     if (t < 32) t = 32;
     if (t > FGP_LB_THREADS) t = FGP_LB_THREADS;

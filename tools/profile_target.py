@@ -31,6 +31,12 @@ if which in ("all", "mll"):
     scale = torch.ones(1, device=dev); ls = torch.full((1, d), 0.5, device=dev); noise = torch.full((1,), 1e-6, device=dev)
     for _ in range(reps):
         L.mll_grad(0, xp, [2] * d, 0, ysq, scale, ls, noise)
+if which in ("all", "mllz"):  # generator mode (what fit() runs): the points are regenerated from the index, half-spectrum mode
+    ysq = torch.rand(1, n, device=dev)
+    ysq = (ysq + ysq.flip(-1).roll(1, -1)) / 2
+    scale = torch.ones(1, device=dev); ls = torch.full((1, d), 0.5, device=dev); noise = torch.full((1,), 1e-6, device=dev)
+    for _ in range(reps):
+        L.mll_grad(0, xp, [2] * d, 0, ysq, scale, ls, noise, z=z)
 if which in ("all", "pmean"):
     xs = torch.rand(1 << 13, d, device=dev)
     co = torch.randn(1, n, device=dev)

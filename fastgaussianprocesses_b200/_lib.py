@@ -55,6 +55,7 @@ SIGNATURES = {
     "fgp_fftbr_c2c": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "fgp_ifftbr_c2c": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "fgp_fwht": (_i32, [_vp, _vp, _i64, _i64, _vp]),
+    "fgp_fwht_fused": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "fgp_mll_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32]),
     "fgp_lattice_mll_grad": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "fgp_lattice_mll_grad_z": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
@@ -305,11 +306,27 @@ def ifftbr(x):
     return out.reshape(x.shape)
 
 
-def fwht(x):
+_fused_ctl = {}
+
+
+def fwht(x, fused=None):
+    """Orthonormal FWHT along the last dim.  fused=True (or FGP_B200_FUSED_FWHT=1) runs two-pass sizes (n > 2^12) as ONE
+    persistent kernel whose intermediate stays in the L2 (fgp_fwht_fused): bit-identical results, but measured slower than the
+    two launches on B200 (64 x 2^20: 0.45 ms against 0.35 ms, profiles/README.md snapshot j), so it is off by default."""
     x2, n = _as2d(x.contiguous())
     out = torch.empty_like(x2)
+    if fused is None:
+        fused = os.environ.get("FGP_B200_FUSED_FWHT") == "1"
     with torch.cuda.device(x.device):
-        _check(load().fgp_fwht(_dev(x2, torch.float64), out.data_ptr(), x2.shape[0], n, _stream()))
+        if fused and n > 4096 and x2.shape[0] < (1 << 24):
+            # control block per (device, stream): the kernel leaves it zeroed, calls on one stream are serialised
+            key = (x.device.index, _stream())
+            ctl = _fused_ctl.get(key)
+            if ctl is None or ctl.numel() < x2.shape[0] + 2:
+                ctl = _fused_ctl[key] = torch.zeros(max(1026, x2.shape[0] + 2), dtype=torch.int32, device=x.device)
+            _check(load().fgp_fwht_fused(_dev(x2, torch.float64), out.data_ptr(), x2.shape[0], n, ctl.data_ptr(), _stream()))
+        else:
+            _check(load().fgp_fwht(_dev(x2, torch.float64), out.data_ptr(), x2.shape[0], n, _stream()))
     return out.reshape(x.shape)
 
 

@@ -129,6 +129,89 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, MINB) wht_passB(double* __rest
   block_wht_io<true>(sm, l2, lntr, LP, wht_sched_up(l2), gld, gst);
 }
 
+// ---- fused two-pass FWHT of a batch: ONE persistent kernel, the intermediate stays in the L2 -----------------------
+// Pass A of all items followed by pass B of all items moves 32n bytes per item through HBM once the batch exceeds the L2
+// (8n in, 8n intermediate out, 8n intermediate in, 8n out).  Here the CTAs of one persistent grid draw tiles from a ticket
+// counter in the order A(0) .. A(lag-1), then A(s) B(s-lag) alternating, then the remaining B tiles: a B tile of item b is
+// drawn after every A tile of items <= b + lag - 1, so it rarely waits, and it reads what was written a few tens of
+// microseconds earlier -- an L2 hit.  HBM traffic drops to the algorithmic 16n.  A B tile waits (acquire-spin on done[b])
+// only for A tiles with smaller tickets, which are already running and never wait themselves: no deadlock for any grid size.
+struct FusedGeom {
+  int l1, l2, lntrA, lntrB, LPA, LPB;
+  unsigned nA, nB, B, lag;
+};
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+template <int MINB>
+__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) wht_fused(const double* __restrict__ in, double* __restrict__ out, FusedGeom g, double scale,
+                                                     unsigned* __restrict__ ctl) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* sm = (double*)smraw;
+  __shared__ unsigned s_t;
+  const unsigned lag = g.lag < g.B ? g.lag : g.B;
+  const unsigned head = lag * g.nA, mid = (g.B - lag) * (g.nA + g.nB), total = g.B * (g.nA + g.nB);
+  unsigned* done = ctl + 2;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_t = atomicAdd(&ctl[0], 1u);
+    __syncthreads();
+    unsigned t = s_t;
+    if (t >= total) break;
+    unsigned b, idx;
+    bool phaseB;
+    if (t < head) {
+      b = t / g.nA, idx = t - b * g.nA, phaseB = false;
+    } else if (t < head + mid) {
+      t -= head;
+      const unsigned slot = t / (g.nA + g.nB), w = t - slot * (g.nA + g.nB);
+      if (w < g.nA)
+        b = slot + lag, idx = w, phaseB = false;
+      else
+        b = slot, idx = w - g.nA, phaseB = true;
+    } else {
+      t -= head + mid;
+      const unsigned slot = t / g.nB;
+      b = g.B - lag + slot, idx = t - slot * g.nB, phaseB = true;
+    }
+    const int64_t item0 = (int64_t)b << (g.l1 + g.l2);
+    if (!phaseB) {
+      const int64_t g0 = item0 + ((int64_t)idx << (g.l1 + g.lntrA));
+      const int l1 = g.l1;
+      auto gld = [&](int tr, int e) -> double { return in[g0 + ((int64_t)tr << l1) + e] * scale; };
+      auto gst = [&](int tr, int e, double v) { out[g0 + ((int64_t)tr << l1) + e] = v; };
+      block_wht_io<false>(sm, g.l1, g.lntrA, g.LPA, wht_sched_coalesced(g.l1), gld, gst);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&done[b], 1u);
+      }
+    } else {
+      if (threadIdx.x == 0) {
+        while (ld_acquire_u32(&done[b]) < g.nA) __nanosleep(40);
+      }
+      __syncthreads();
+      double* base = out + item0 + ((int64_t)idx << g.lntrB);
+      const int l1 = g.l1;
+      auto gld = [&](int tr, int e) -> double { return __ldcg(base + ((int64_t)e << l1) + tr); };  // written by other SMs: not through L1
+      auto gst = [&](int tr, int e, double v) { base[((int64_t)e << l1) + tr] = v; };
+      block_wht_io<true>(sm, g.l2, g.lntrB, g.LPB, wht_sched_up(g.l2), gld, gst);
+    }
+  }
+  // the last CTA to leave resets the control block, so one zeroed buffer serves every later call on the same stream
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&ctl[1], 1u) == gridDim.x - 1) {
+      for (unsigned i = 0; i < g.B; ++i) done[i] = 0u;
+      ctl[0] = 0u;
+      __threadfence();
+      ctl[1] = 0u;
+    }
+  }
+}
+
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
   if (bytes > 24 * 1024) {  // static shared memory counts towards the 48 KiB default limit
@@ -297,6 +380,42 @@ int fgp_fwht(const double* in_dev, double* out_dev, int64_t batch, int64_t n, fg
       FGP_LAUNCH_NAMED("wht_passB", st);
     }
   }
+  return FGP_OK;
+}
+
+int fgp_fwht_fused(const double* in_dev, double* out_dev, int64_t batch, int64_t n, unsigned int* ctl_dev, fgp_stream_t stream) {
+  using namespace fgp;
+  int rc = check_transform_args(in_dev, out_dev, batch, n, FGP_MAX_LOG2N_WHT, "fwht_fused");
+  if (rc) return rc;
+  if (batch == 0) return FGP_OK;
+  const PassGeom g = make_geom(n, false);
+  // single-pass sizes have no intermediate; fall through to the plain kernels
+  if (!g.l2 || !ctl_dev || batch > (int64_t(1) << 24)) return fgp_fwht(in_dev, out_dev, batch, n, stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  FusedGeom f;
+  f.l1 = g.l1, f.l2 = g.l2, f.lntrA = g.lntrA, f.lntrB = g.lntrB, f.LPA = g.LPA, f.LPB = g.LPB;
+  f.nA = (unsigned)g.ctasA;
+  f.nB = (unsigned)g.ctasB;
+  f.B = (unsigned)batch;
+  static const int lag_env = env_int("FGP_FUSED_LAG", 0);
+  // enough look-ahead to cover the grid: the B tiles of an item are drawn once ~2 grids worth of A tiles have been drawn
+  const int sms = sm_count();
+  f.lag = lag_env > 0 ? (unsigned)lag_env : (unsigned)((2 * 4 * sms + f.nA - 1) / f.nA);
+  if (f.lag < 1) f.lag = 1;
+  const size_t smem = g.smemA > g.smemB ? g.smemA : g.smemB;
+  const int threads = g.threadsA > g.threadsB ? g.threadsA : g.threadsB;
+  const double scale = 1.0 / sqrt((double)n);
+  const int64_t tiles = (int64_t)f.B * (f.nA + f.nB);
+  if (smem <= 40 * 1024) {
+    if ((rc = set_smem(wht_fused<FGP_LB_BLOCKS_R>, smem))) return rc;
+    const int64_t grid = tiles < (int64_t)sms * FGP_LB_BLOCKS_R ? tiles : (int64_t)sms * FGP_LB_BLOCKS_R;
+    wht_fused<FGP_LB_BLOCKS_R><<<(unsigned)grid, threads, smem, st>>>(in_dev, out_dev, f, scale, ctl_dev);
+  } else {
+    if ((rc = set_smem(wht_fused<FGP_LB_BLOCKS>, smem))) return rc;
+    const int64_t grid = tiles < (int64_t)sms * FGP_LB_BLOCKS ? tiles : (int64_t)sms * FGP_LB_BLOCKS;
+    wht_fused<FGP_LB_BLOCKS><<<(unsigned)grid, threads, smem, st>>>(in_dev, out_dev, f, scale, ctl_dev);
+  }
+  FGP_LAUNCH_NAMED("wht_fused", st);
   return FGP_OK;
 }
 

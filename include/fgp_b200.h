@@ -94,6 +94,11 @@ int fgp_ifftbr_c2c(const double* in_dev, double* out_dev, int64_t batch, int64_t
                    fgp_stream_t stream);
 /* Sylvester-ordered Walsh-Hadamard transform (self-inverse) */
 int fgp_fwht(const double* in_dev, double* out_dev, int64_t batch, int64_t n, fgp_stream_t stream);
+/* The same transform as ONE persistent kernel (pass-A and pass-B tiles drawn from a ticket counter, the intermediate stays
+ * in the L2, HBM traffic = the algorithmic 16n per item instead of 32n).  ctl_dev: at least batch + 2 zeroed uint32; the
+ * kernel leaves it zeroed again, so one buffer serves every later call on the same stream.  Falls back to fgp_fwht for
+ * single-pass sizes or a null ctl_dev. */
+int fgp_fwht_fused(const double* in_dev, double* out_dev, int64_t batch, int64_t n, unsigned int* ctl_dev, fgp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * K4  fused eigen-solve + marginal log-likelihood + gradients

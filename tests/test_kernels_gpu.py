@@ -248,6 +248,16 @@ def test_mll_two_pass_vs_oracle(L, P, fam, d, m, alpha):
     assert rel(o3[0][4:4 + d] * ls0, o.raw_lengthscales.grad) < 1e-8
 
 
+@pytest.mark.parametrize("B,m", [(1, 13), (5, 14), (3, 16), (40, 15), (2, 20)])
+def test_fwht_fused_persistent_kernel_is_bit_identical(L, B, m):
+    """fgp_fwht_fused (one persistent kernel, pass-B tiles wait on per-item counters) against the two-launch transform; called
+    twice so that the self-reset of the control block is exercised."""
+    x = torch.randn(B, 1 << m, device=dev, generator=torch.Generator(device=dev).manual_seed(m))
+    ref = L.fwht(x, fused=False)
+    assert torch.equal(L.fwht(x, fused=True), ref)
+    assert torch.equal(L.fwht(x, fused=True), ref)
+
+
 def test_error_codes(L):
     x = torch.zeros(6, dtype=torch.float64, device=dev)
     with pytest.raises(AssertionError):

@@ -311,7 +311,7 @@ _fused_ctl = {}
 
 def fwht(x, fused=None):
     """Orthonormal FWHT along the last dim.  fused=True (or FGP_B200_FUSED_FWHT=1) runs two-pass sizes (n > 2^12) as ONE
-    persistent kernel whose intermediate stays in the L2 (fgp_fwht_fused): bit-identical results, but measured slower than the
+    persistent kernel whose intermediate stays in the L2 (fgp_fwht_fused): the same results (to FMA contraction), but measured slower than the
     two launches on B200 (64 x 2^20: 0.45 ms against 0.35 ms, profiles/README.md snapshot j), so it is off by default."""
     x2, n = _as2d(x.contiguous())
     out = torch.empty_like(x2)

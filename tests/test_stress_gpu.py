@@ -132,3 +132,37 @@ def test_posterior_vs_oracle_sweep(fam, d, m, alpha, mt):
         pc = gp.post_cov(xt[:k], xt[:k])
         assert torch.allclose(pc.diagonal().cpu(), o.post_var(xt[:k]), atol=1e-8 * sc0 * max(1.0, n ** 0.5))
         assert torch.allclose(pc, pc.T, atol=1e-9 * sc0 * max(1.0, n ** 0.5))
+
+
+@pytest.mark.parametrize("d,m,nz", [(8, 20, 1e-6), (8, 18, 1e-8), (2, 16, 1e-3), (3, 17, 1e-4), (5, 19, 1e-5), (16, 16, 1e-8)])
+def test_half_spectrum_mode_vs_independent_fft_at_full_size(d, m, nz):
+    """The lattice eigen-solve in half-spectrum mode (generator mode and stored points, what fit() runs) at BASELINE.json's full size
+    against an independent float64 evaluation on the GPU: k1 from the integer lattice in natural order, torch.fft (another
+    algorithm and round-off pattern), autograd gradients.  Also against the library's own full-spectrum mode (want_lam)."""
+    from fastgaussianprocesses_b200 import _lib as L
+    n = 1 << m
+    z = ([1, 182667, 469891, 498753, 110745, 446247, 250185, 118627] * 2)[:d]
+    xp = L.lattice_points(z, np.linspace(0.1, 0.9, d), 0, n, dev)
+    y = torch.cos(2 * np.pi * xp).sum(1) + 0.3 * torch.sin(2 * np.pi * xp[:, 0] * 3)
+    ysq = (L.fftbr(y).abs() ** 2).reshape(1, n)
+    scale = torch.full((1,), 2.5, device=dev)
+    ls = torch.linspace(0.3, 0.9, d, device=dev).reshape(1, d).contiguous()
+    noise = torch.full((1,), nz, device=dev)
+    o_full, lam = L.mll_grad(0, xp, [2] * d, 0, ysq, scale, ls, noise, want_lam=True)
+    o_hs_x, _ = L.mll_grad(0, xp, [2] * d, 0, ysq, scale, ls, noise)
+    o_hs_z, _ = L.mll_grad(0, xp, [2] * d, 0, ysq, scale, ls, noise, z=z)
+    rs = scale.clone().requires_grad_(True)
+    rl = ls[0].clone().requires_grad_(True)
+    j = torch.arange(n, device=dev)
+    delta = ((j[:, None] * torch.tensor(z, device=dev)[None, :]) % n).double() / n
+    parts = -(2 * np.pi) ** 4 / 24 * (delta ** 4 - 2 * delta ** 3 + delta ** 2 - 1 / 30)
+    lamt = torch.fft.fft(rs * (1 + rl * parts).prod(-1)).real + nz  # natural frequency order, as the output of fftbr
+    normt, logdett = (ysq[0] / lamt).sum(), torch.log(lamt).sum()
+    (0.5 * (normt + logdett)).backward()
+    ref = torch.cat([normt.detach().reshape(1), logdett.detach().reshape(1), rs.grad.reshape(1), rl.grad]).cpu()
+    for o in (o_full, o_hs_x, o_hs_z):
+        got = torch.cat([o[0, :2], o[0, 3:]]).cpu()
+        assert abs(float(got[0] - ref[0])) <= 1e-9 * abs(float(ref[0]))
+        assert abs(float(got[1] - ref[1])) <= 1e-10 * abs(float(ref[1]))
+        assert rel(got[2:], ref[2:]) < 1e-7  # gradients: sums of n terms of both signs (the reference's own autograd agrees to this level)
+    assert rel(o_hs_z[0], o_full[0]) < 1e-7 and rel(o_hs_x[0], o_full[0]) < 1e-7

@@ -350,6 +350,9 @@ __device__ __forceinline__ void reduce_store(double* v, int nv, double* red, dou
 
 // inside a fused fit loop, iterations enqueued after the stop decision cost only their launches
 __device__ __forceinline__ bool fit_stopped(const MllArgs& a) { return a.has_fit && __ldcg(a.fit.state + ST_STOPPED) != 0.0; }
+// the same flag as a value: issue the load at kernel entry, test it after the hyperparameter loads are in flight (one L2 round
+// trip per kernel instead of two on the critical path of a ~17 us kernel)
+__device__ __forceinline__ double fit_stop_flag(const MllArgs& a) { return a.has_fit ? __ldcg(a.fit.state + ST_STOPPED) : 0.0; }
 
 // deterministic reduction of the per-CTA partial sums of set b into out[b] (fixed order); any CTA size that is a
 // multiple of 32.  Partials come from other CTAs: cache-global loads.
@@ -424,13 +427,14 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_single_kern
   __shared__ double red[kRed];
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
   pdl_prologue();
-  if (fit_stopped(a)) return;
+  const double stop_flag = fit_stop_flag(a);
   const int b = blockIdx.x;
   const int n = (int)a.n;
   const int l = a.l1;
   const int LP = a.LPA;
   const int d = DT > 0 ? DT : a.d;
   load_hyp<NET>(H, a, b);
+  if (stop_flag != 0.0) return;  // uniform over the CTA, before any barrier
   if (GEN && NET) dnb2_build_tables(H, a, (uint64_t*)(smraw + a.tab_off), 0, l);
   __syncthreads();
   const double c = H.scale;  // DC guess removed before the transform (role of abstract_fast_gp.py:209-211)
@@ -501,13 +505,14 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passA_kerne
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
   pdl_prologue();
-  if (fit_stopped(a)) return;
+  const double stop_flag = fit_stop_flag(a);
   const int b = blockIdx.y;
   const int l1 = a.l1, l2 = a.l2, lntr = a.lntrA, LP = a.LPA;
   // half-spectrum mode (lntr == 0): CTA c takes residue class r = c, i.e. block row rev(c)
   const int64_t blk0 = (!NET && a.hs) ? (int64_t)brev_bits(blockIdx.x, l2) : ((int64_t)blockIdx.x << lntr);
   const int64_t g0 = blk0 << l1;
   load_hyp<NET>(H, a, b);
+  if (stop_flag != 0.0) return;  // uniform over the CTA, before any barrier
   if (GEN && NET) dnb2_build_tables(H, a, (uint64_t*)(smraw + a.tab_off), g0, l1 + lntr);
   __syncthreads();
   const double c = H.scale;
@@ -560,7 +565,7 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kerne
   __shared__ double red[kRed];
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
   pdl_prologue();
-  if (fit_stopped(a)) return;
+  const double stop_flag = fit_stop_flag(a);
   const int b = blockIdx.y;
   const int d = DT > 0 ? DT : a.d;
   const int l1 = a.l1, lntr = a.lntrA, LP = a.LPA;
@@ -568,6 +573,7 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kerne
   const int64_t blk0 = hs ? (int64_t)brev_bits(blockIdx.x, a.l2) : ((int64_t)blockIdx.x << lntr);
   const int64_t g0 = blk0 << l1;
   load_hyp<NET>(H, a, b);
+  if (stop_flag != 0.0) return;  // uniform over the CTA, before any barrier
   if (GEN && NET) dnb2_build_tables(H, a, (uint64_t*)(smraw + a.tab_off), g0, l1 + lntr);
   __syncthreads();
   double acc[DM + 1];

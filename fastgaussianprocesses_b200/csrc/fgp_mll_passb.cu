@@ -8,10 +8,11 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passB_kerne
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ double red[kRed];
   pdl_prologue();
-  if (fit_stopped(a)) return;
+  const double stop_flag = fit_stop_flag(a);
   const int b = blockIdx.y;
   const double noise = a.noise[b];
   const double dc = a.scale[b] * (double)a.n;  // the DC guess removed in pass A comes back in bin 0
+  if (stop_flag != 0.0) return;
   const int l1 = a.l1, l2 = a.l2, lntr = a.lntrB, LP = a.LPB;
   const int q0 = blockIdx.x << lntr;
   const int64_t boff = (int64_t)b * a.n;

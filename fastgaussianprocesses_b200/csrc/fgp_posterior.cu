@@ -162,6 +162,49 @@ __global__ void __launch_bounds__(256) post_var_reduce_kernel(const double* __re
   }
 }
 
+// Lattice post_var, two test points per complex transform: row p holds z_a = k(x*_{2p}, X_a) + i k(x*_{2p+1}, X_a).  With
+// Z = ft(z), the spectra of the two real sequences are A_k = (Z_k + conj Z_{n-k}) / 2 and B_k = (Z_k - conj Z_{n-k}) / (2i), so
+// one length-n complex transform serves two test points: half the transform work and no separate real input array.
+__global__ void __launch_bounds__(256) lattice_cross_pair_kernel(const double* __restrict__ xs, int64_t m, const double* __restrict__ xtrain,
+                                                                 int64_t n, int d, LatPoly P, double scale, DVec ls,
+                                                                 double2* __restrict__ K) {
+  const int64_t pairs = (m + 1) >> 1, total = pairs * n;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = e / n, a = e - p * n;
+    const int64_t i0 = 2 * p, i1 = (2 * p + 1 < m) ? 2 * p + 1 : i0;
+    double k0 = scale, k1 = scale;
+    for (int j = 0; j < d; ++j) {
+      const double xa = xtrain[a * d + j];
+      k0 *= fma(ls.v[j], lat_part(xs[i0 * d + j] - xa, P.q[j], P.alpha[j]), 1.0);
+      k1 *= fma(ls.v[j], lat_part(xs[i1 * d + j] - xa, P.q[j], P.alpha[j]), 1.0);
+    }
+    K[e] = make_double2(k0, 2 * p + 1 < m ? k1 : 0.0);
+  }
+}
+
+// pvar_{2p} = max(0, kxx - sum_k |A_k|^2 Re(1/lam_k)), pvar_{2p+1} likewise with B_k; one CTA per pair
+__global__ void __launch_bounds__(256) post_var_pair_reduce_kernel(const double2* __restrict__ kt, const double2* __restrict__ lam, int64_t n,
+                                                                   int64_t m, double kxx, double* __restrict__ out) {
+  __shared__ double red[32 * 4];
+  const int64_t p = blockIdx.x;
+  const double2* row = kt + p * n;
+  double s[2] = {0.0, 0.0};
+  for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
+    const double2 z = row[k], zm = row[(n - k) & (n - 1)], lk = lam[k];
+    const double w = 0.25 * lk.x / fma(lk.x, lk.x, lk.y * lk.y);
+    const double ar = z.x + zm.x, ai = z.y - zm.y;  // Z_k + conj Z_{n-k}
+    const double br = z.x - zm.x, bi = z.y + zm.y;  // Z_k - conj Z_{n-k}
+    s[0] = fma(fma(ar, ar, ai * ai), w, s[0]);
+    s[1] = fma(fma(br, br, bi * bi), w, s[1]);
+  }
+  block_sum<2>(s, red);
+  if (threadIdx.x == 0) {
+    const double v0 = kxx - s[0], v1 = kxx - s[1];
+    out[2 * p] = v0 < 0.0 ? 0.0 : v0;
+    if (2 * p + 1 < m) out[2 * p + 1] = v1 < 0.0 ? 0.0 : v1;
+  }
+}
+
 template <int DT, int R, int MODE>
 static int launch_post_mean(const PostArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
   post_mean_kernel<DT, R, MODE><<<grid, kPT, smem, st>>>(a);
@@ -333,6 +376,30 @@ static int post_var_common(int family, const double* xs, int64_t m, const void* 
   }
   const int64_t mc = post_var_chunk(m, n);
   cudaStream_t st = (cudaStream_t)stream;
+  if (family == 0 && n > 1) {
+    // two test points per complex transform, in place in the workspace
+    LatPoly P;
+    int rc = fill_lat_poly(alpha_host, d, &P);
+    if (rc) return rc;
+    DVec ls;
+    memset(&ls, 0, sizeof(ls));
+    for (int j = 0; j < d; ++j) ls.v[j] = ls_host[j];
+    const int64_t mc2 = 2 * mc;  // points per chunk: mc pairs = 2*mc*n doubles of the 3*mc*n-double workspace
+    double2* kc = (double2*)work;
+    for (int64_t i0 = 0; i0 < m; i0 += mc2) {
+      const int64_t cnt = m - i0 < mc2 ? m - i0 : mc2;
+      const int64_t pairs = (cnt + 1) >> 1;
+      int64_t blocks = (pairs * n + 255) / 256;
+      const int64_t cap = (int64_t)sm_count() * 16;
+      if (blocks > cap) blocks = cap;
+      lattice_cross_pair_kernel<<<(unsigned)blocks, 256, 0, st>>>(xs + i0 * d, cnt, (const double*)x, n, d, P, scale, ls, kc);
+      FGP_LAUNCH_CHECK();
+      if ((rc = fgp_fftbr_c2c((const double*)kc, (double*)kc, pairs, n, table, stream))) return rc;
+      post_var_pair_reduce_kernel<<<(unsigned)pairs, 256, 0, st>>>(kc, (const double2*)lam, n, cnt, kxx, pvar + i0);
+      FGP_LAUNCH_CHECK();
+    }
+    return FGP_OK;
+  }
   double* kreal = (double*)work;
   double* kcplx = kreal + ((mc * n + 1) & ~(int64_t)1);  // complex rows need 16-byte alignment (mc*n may be odd when n = 1)
   for (int64_t i0 = 0; i0 < m; i0 += mc) {

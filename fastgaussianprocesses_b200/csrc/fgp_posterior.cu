@@ -165,20 +165,40 @@ __global__ void __launch_bounds__(256) post_var_reduce_kernel(const double* __re
 // Lattice post_var, two test points per complex transform: row p holds z_a = k(x*_{2p}, X_a) + i k(x*_{2p+1}, X_a).  With
 // Z = ft(z), the spectra of the two real sequences are A_k = (Z_k + conj Z_{n-k}) / 2 and B_k = (Z_k - conj Z_{n-k}) / (2i), so
 // one length-n complex transform serves two test points: half the transform work and no separate real input array.
+// A2: every alpha_j == 2 (branch-free part, as in the post_mean inner loop).  A thread evaluates kPG pairs (2 kPG test points)
+// against ONE training point, so the training points are read from the L2 once per 2 kPG test points.
+constexpr int kPG = 4;
+template <bool A2>
 __global__ void __launch_bounds__(256) lattice_cross_pair_kernel(const double* __restrict__ xs, int64_t m, const double* __restrict__ xtrain,
                                                                  int64_t n, int d, LatPoly P, double scale, DVec ls,
                                                                  double2* __restrict__ K) {
-  const int64_t pairs = (m + 1) >> 1, total = pairs * n;
+  const int64_t pairs = (m + 1) >> 1, groups = (pairs + kPG - 1) / kPG, total = groups * n;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = e / n, a = e - p * n;
-    const int64_t i0 = 2 * p, i1 = (2 * p + 1 < m) ? 2 * p + 1 : i0;
-    double k0 = scale, k1 = scale;
-    for (int j = 0; j < d; ++j) {
-      const double xa = xtrain[a * d + j];
-      k0 *= fma(ls.v[j], lat_part(xs[i0 * d + j] - xa, P.q[j], P.alpha[j]), 1.0);
-      k1 *= fma(ls.v[j], lat_part(xs[i1 * d + j] - xa, P.q[j], P.alpha[j]), 1.0);
+    const int64_t g = e / n, a = e - g * n;
+    const double* __restrict__ xa = xtrain + a * d;
+    const double* xr[2 * kPG];
+    double k[2 * kPG];
+#pragma unroll
+    for (int q = 0; q < 2 * kPG; ++q) {
+      int64_t i = 2 * kPG * g + q;
+      if (i >= m) i = m - 1;
+      xr[q] = xs + i * d;
+      k[q] = scale;
     }
-    K[e] = make_double2(k0, 2 * p + 1 < m ? k1 : 0.0);
+    for (int j = 0; j < d; ++j) {
+      const double v = __ldg(xa + j);
+      const double l = ls.v[j];
+#pragma unroll
+      for (int q = 0; q < 2 * kPG; ++q) {
+        const double part = A2 ? lat_part_a2(__ldg(xr[q] + j) - v, P.q[j][0], P.q[j][2]) : lat_part(__ldg(xr[q] + j) - v, P.q[j], P.alpha[j]);
+        k[q] *= fma(l, part, 1.0);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kPG; ++q) {
+      const int64_t p = kPG * g + q;
+      if (p < pairs) K[p * n + a] = make_double2(k[2 * q], 2 * p + 1 < m ? k[2 * q + 1] : 0.0);
+    }
   }
 }
 
@@ -384,15 +404,20 @@ static int post_var_common(int family, const double* xs, int64_t m, const void* 
     DVec ls;
     memset(&ls, 0, sizeof(ls));
     for (int j = 0; j < d; ++j) ls.v[j] = ls_host[j];
+    bool all2 = true;
+    for (int j = 0; j < d; ++j) all2 = all2 && alpha_host[j] == 2;
     const int64_t mc2 = 2 * mc;  // points per chunk: mc pairs = 2*mc*n doubles of the 3*mc*n-double workspace
     double2* kc = (double2*)work;
     for (int64_t i0 = 0; i0 < m; i0 += mc2) {
       const int64_t cnt = m - i0 < mc2 ? m - i0 : mc2;
       const int64_t pairs = (cnt + 1) >> 1;
-      int64_t blocks = (pairs * n + 255) / 256;
+      int64_t blocks = (((pairs + kPG - 1) / kPG) * n + 255) / 256;
       const int64_t cap = (int64_t)sm_count() * 16;
       if (blocks > cap) blocks = cap;
-      lattice_cross_pair_kernel<<<(unsigned)blocks, 256, 0, st>>>(xs + i0 * d, cnt, (const double*)x, n, d, P, scale, ls, kc);
+      if (all2)
+        lattice_cross_pair_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(xs + i0 * d, cnt, (const double*)x, n, d, P, scale, ls, kc);
+      else
+        lattice_cross_pair_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(xs + i0 * d, cnt, (const double*)x, n, d, P, scale, ls, kc);
       FGP_LAUNCH_CHECK();
       if ((rc = fgp_fftbr_c2c((const double*)kc, (double*)kc, pairs, n, table, stream))) return rc;
       post_var_pair_reduce_kernel<<<(unsigned)pairs, 256, 0, st>>>(kc, (const double2*)lam, n, cnt, kxx, pvar + i0);

@@ -1,2 +1,2 @@
-python -m pytest tests/test_kernels_gpu.py tests/test_api_gpu.py -x -q 2>&1 | grep -v Warning | cut -c1-300 | tail -3
-python tools/tune_mll.py 20 8 lattice; python tools/tune_mll.py 18 8 lattice; python tools/tune_mll.py 20 8 net; python tools/tune_mll.py 16 4 net
+python tools/microbench.py > gpurun_out/microbench_r1j.json 2> gpurun_out/microbench_r1j.err; tail -c 2500 gpurun_out/microbench_r1j.json
+python bench.py --steps 50 --warmup 5 > gpurun_out/bench_r1k.json 2> gpurun_out/bench_r1k.err; cut -c1-1200 gpurun_out/bench_r1k.json

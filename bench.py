@@ -320,9 +320,10 @@ def main():
             "clocks": clocks}
     if not args.no_cpu_baseline and world == 1:
         torch.set_num_threads(os.cpu_count() or 1)
-        r = cpu_reference_run(n, d, 4, 16)
+        # bounded sample of the same workload, ~10-20 s of CPU work on the GPU box's host cores
+        r = cpu_reference_run(n, d, 60, 128)
         line["cpu_baseline"] = {"value": r["fit_iters_per_s"], "unit": "iterations/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": "4 fit iterations of the oracle port at n=2^%d d=%d (%.1f s); post_mean on 16 points (%.1f s)" % (args.log2n, d, r["fit_s"], r.get("post_mean_s", 0.0)),
+                                "sample": "60 fit iterations of the oracle port at n=2^%d d=%d (%.1f s); post_mean on 128 points (%.1f s)" % (args.log2n, d, r["fit_s"], r.get("post_mean_s", 0.0)),
                                 "post_mean_points_per_s": r.get("post_mean_pts_per_s")}
     print(json.dumps(line))
     if dist is not None:

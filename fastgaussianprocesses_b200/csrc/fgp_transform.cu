@@ -355,7 +355,7 @@ int fgp_fwht(const double* in_dev, double* out_dev, int64_t batch, int64_t n, fg
   if (rc) return rc;
   if (batch == 0) return FGP_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const PassGeom g = make_geom(n, false);
+  const PassGeom g = make_geom(n, false, true);
   const int64_t total_blocks = batch * (n >> g.l1);
   const int64_t ctas = (total_blocks + g.ntrA - 1) / g.ntrA;
   const int64_t ctasB = g.l2 ? (batch << g.l1) >> g.lntrB : 0;
@@ -388,7 +388,7 @@ int fgp_fwht_fused(const double* in_dev, double* out_dev, int64_t batch, int64_t
   int rc = check_transform_args(in_dev, out_dev, batch, n, FGP_MAX_LOG2N_WHT, "fwht_fused");
   if (rc) return rc;
   if (batch == 0) return FGP_OK;
-  const PassGeom g = make_geom(n, false);
+  const PassGeom g = make_geom(n, false, true);
   // single-pass sizes have no intermediate; fall through to the plain kernels
   if (!g.l2 || !ctl_dev || batch > (int64_t(1) << 24)) return fgp_fwht(in_dev, out_dev, batch, n, stream);
   cudaStream_t st = (cudaStream_t)stream;

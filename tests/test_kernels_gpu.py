@@ -109,13 +109,25 @@ def test_fft_linearity_and_parseval_large(L):
     assert rel(L.ifftbr(fa).real, a) < 1e-12
 
 
-def test_fwht_parseval_large(L):
-    n = 1 << 24
+@pytest.mark.parametrize("m", [23, 24, 25, 26])
+def test_fwht_parseval_large(L, m):
+    """Sizes whose tile geometry differs from the oracle-checked ones (128 KiB tiles from 2^24): Parseval, involution, and the
+    transform of a delta at index k = row k of the Sylvester-Hadamard matrix, (-1)^popcount(i & k) / sqrt(n)."""
+    n = 1 << m
     g = torch.Generator(device=dev).manual_seed(6)
     a = torch.randn(n, generator=g, device=dev)
     fa = L.fwht(a)
     assert abs(float((fa ** 2).sum() / (a ** 2).sum()) - 1.0) < 1e-12
     assert rel(L.fwht(fa), a) < 1e-12
+    del a, fa
+    e = torch.zeros(n, device=dev)
+    k = (1 << (m - 1)) + 12345
+    e[k] = 1.0
+    w = L.fwht(e)
+    idx = [0, 1, 12345, 4096 * 7 + 3, (1 << (m - 2)) + 99, n - 1, k]
+    ref = torch.tensor([(-1.0) ** bin(i & k).count("1") for i in idx], device=dev) / 2 ** (m / 2)
+    assert float((w[torch.tensor(idx, device=dev)] - ref).abs().max()) < 1e-18
+    assert abs(float(w.abs().max()) - 2 ** (-m / 2)) < 1e-18 and abs(float(w.abs().min()) - 2 ** (-m / 2)) < 1e-18
 
 
 def _setup(g):

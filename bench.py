@@ -181,7 +181,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("FGP_NCCL_DEBUG", "WARN")  # the VERSION banner goes to stdout; keep it to one JSON line
+        # NCCL prints its version banner to STDOUT at every level from VERSION up (WARN included): stdout must stay one JSON line
+        if os.environ.get("FGP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["FGP_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 

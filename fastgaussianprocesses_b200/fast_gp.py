@@ -176,7 +176,7 @@ class _FusedFitLoop(object):
         dev = fgp.device
         with torch.no_grad():
             scale_B, ls_B, noise_B, pshape = fgp._hyper()
-            self.tau = float(fgp.gram_matrix_tasks.reshape(-1)[0])
+            self.tau = fgp._tau_host()
         self.pshape = pshape
         self.B, self.d, self.n = scale_B.numel(), fgp.d, fgp._nint
         self.raw = (fgp.raw_scale.data, fgp.raw_lengthscales.data, fgp.raw_noise.data)
@@ -189,7 +189,10 @@ class _FusedFitLoop(object):
         self.d_out = _prod(fgp.shape_batch)
         self.out = torch.zeros((self.B, self.d + 4), dtype=torch.float64, device=dev)
         self.ws = _lib.mll_workspace(fgp._FAMILY, self.n, self.d, self.B, dev)
-        self.weights = torch.tensor([0.5, 0.5 * self.d_out / self.B], device=dev).expand(self.B, 2).contiguous()
+        # filled on the device: torch.tensor(list, device=cuda) is a pageable H2D copy that makes the host wait for the stream
+        self.weights = torch.empty((self.B, 2), dtype=torch.float64, device=dev)
+        self.weights[:, 0] = 0.5
+        self.weights[:, 1] = 0.5 * self.d_out / self.B
         self.P = sum(r.numel() for r in self.raw)
         self.state = torch.zeros(_lib.fit_state_doubles(self.P, self.B), dtype=torch.float64, device=dev)
         self._pin = _pin_acquire()
@@ -255,7 +258,7 @@ class _FusedFitLoop(object):
         return (self._pin is not None and fgp._nint == self.n and tuple(p.data_ptr() for p in (fgp.raw_scale, fgp.raw_lengthscales, fgp.raw_noise)) == tuple(r.data_ptr() for r in self.raw)
                 and (fgp.raw_scale.requires_grad, fgp.raw_lengthscales.requires_grad, fgp.raw_noise.requires_grad) == self.req
                 and fgp._ysq is self.ysq and tuple(bool(f) for f in hist_flags) == self.hist_flags and hist_capacity <= self.hist_capacity
-                and float(fgp.gram_matrix_tasks.reshape(-1)[0]) == self.tau)
+                and fgp._tau_host() == self.tau)
 
     # algorithmic bytes of one iteration: points read by the first and last pass, workspace written and
     # read twice, |ytilde|^2 read once
@@ -665,6 +668,8 @@ class AbstractFastGP(torch.nn.Module):
         self._ytilde = None
         self._ytilde_n = -1
         self._ysq = None
+        if self.num_tasks == 1:
+            self._tau_host()
         # the injected transforms of the reference (abstract_fast_gp.py:26-27)
         self.ft_unstable = self._ft_unstable
         self.ift_unstable = self._ift_unstable
@@ -685,6 +690,18 @@ class AbstractFastGP(torch.nn.Module):
         noise_B = (noise[..., 0] * tau).expand(pshape).reshape(B)
         ls_B = ls.expand(tuple(pshape) + (self.d,)).reshape(B, self.d)
         return scale_B, ls_B, noise_B, pshape
+
+    def _tau_host(self):
+        """K_task[0,0] of a single task as a host float, cached on the task-kernel parameters' identity and version: reading it
+        from the device is a host-device synchronisation in the middle of fit()'s set-up."""
+        ps = (self.raw_factor_task_kernel, self.raw_noise_task_kernel)
+        key = tuple((p.data_ptr(), p._version, p.numel()) for p in ps)
+        c = getattr(self, "_tau_cache", None)
+        if c is None or c[0] != key:
+            with torch.no_grad():
+                c = (key, float(self.gram_matrix_tasks.reshape(-1)[0]))
+            self._tau_cache = c
+        return c[1]
 
     def _hyper_host(self):
         with torch.no_grad():

@@ -14,9 +14,9 @@ Everything numerical is done by libfgp_b200.so (include/fgp_b200.h) on CUDA tens
 streams, the tiny hyperparameter transforms and (outside the fast path) the optimizer.  There is no CPU fallback.
 
 Scope: the fused device-side path covers one task without derivative information (rows a1-a15); several
-tasks of equal size, GCV / CV losses and masked fits run on the same CUDA transforms through torch.autograd (multitask.py,
-_FTFunction).  Derivative information and the adaptive nugget raise NotImplementedError -- rows
-(f)2-(f)3 of the scope table are not silently approximated.
+tasks (equal or different power-of-two sizes), derivative observations, GCV / CV losses and masked fits run on the same CUDA
+transforms through torch.autograd (multitask.py, _FTFunction) -- rows (f)2-(f)4.  The adaptive nugget and batched outputs combined
+with several tasks or derivatives raise NotImplementedError rather than being approximated.
 """
 import functools
 import math
@@ -495,7 +495,7 @@ class AbstractFastGP(torch.nn.Module):
             assert isinstance(num_tasks, int) and num_tasks > 0
             solo_task, default_task = False, torch.arange(num_tasks)
         if num_tasks != 1 and len(torch.Size(shape_batch)) != 0:
-            raise NotImplementedError("multi-task GPs with batched outputs are not built (SURVEY.md section 8(f) row 2 covers equal-size tasks, one hyperparameter set)")
+            raise NotImplementedError("multi-task GPs with batched outputs are not built (SURVEY.md section 8(f) row 2 is covered for one hyperparameter set)")
         if derivatives is not None or derivatives_coeffs is not None:  # abstract_gp.py:59-62
             rank_factor_task_kernel = 1
             tfs_noise_task_kernel = DEFAULT_TFS_ID
@@ -1540,7 +1540,7 @@ _CTOR_DOC = """
     `device` defaults to "cuda" and must be a CUDA device; `seqs` may be an int (dimension), one of this package's
     GPU-side sequence specs (`sequences.Lattice` / `sequences.DigitalNetB2`) or any qmcpy-style sequence object, whose
     points are then taken from its own host generator; `compile_fts*` are accepted and ignored (the transforms are
-    hand-written CUDA kernels); `derivatives` and `adaptive_nugget` raise NotImplementedError.
+    hand-written CUDA kernels); `adaptive_nugget` raises NotImplementedError.
 """
 
 

@@ -202,14 +202,18 @@ __global__ void __launch_bounds__(256) lattice_cross_pair_kernel(const double* _
   }
 }
 
-// pvar_{2p} = max(0, kxx - sum_k |A_k|^2 Re(1/lam_k)), pvar_{2p+1} likewise with B_k; one CTA per pair
+// partial[p][seg] = sum over the seg-th part of the spectrum of (|A_k|^2, |B_k|^2) Re(1/lam_k); grid (segs, pairs).  One CTA per
+// pair left 128 CTAs reading 16 MiB each (2.1 ms for 256 points at n = 2^20, more than the transform); the partial sums are
+// added in a fixed order by post_var_pair_final_kernel, so the result does not depend on scheduling.
 __global__ void __launch_bounds__(256) post_var_pair_reduce_kernel(const double2* __restrict__ kt, const double2* __restrict__ lam, int64_t n,
-                                                                   int64_t m, double kxx, double* __restrict__ out) {
+                                                                   double* __restrict__ partial) {
   __shared__ double red[32 * 4];
-  const int64_t p = blockIdx.x;
+  const int64_t p = blockIdx.y;
+  const int segs = gridDim.x, seg = blockIdx.x;
+  const int64_t k0 = n / segs * seg, k1 = seg == segs - 1 ? n : n / segs * (seg + 1);
   const double2* row = kt + p * n;
   double s[2] = {0.0, 0.0};
-  for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
+  for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
     const double2 z = row[k], zm = row[(n - k) & (n - 1)], lk = lam[k];
     const double w = 0.25 * lk.x / fma(lk.x, lk.x, lk.y * lk.y);
     const double ar = z.x + zm.x, ai = z.y - zm.y;  // Z_k + conj Z_{n-k}
@@ -219,10 +223,23 @@ __global__ void __launch_bounds__(256) post_var_pair_reduce_kernel(const double2
   }
   block_sum<2>(s, red);
   if (threadIdx.x == 0) {
-    const double v0 = kxx - s[0], v1 = kxx - s[1];
-    out[2 * p] = v0 < 0.0 ? 0.0 : v0;
-    if (2 * p + 1 < m) out[2 * p + 1] = v1 < 0.0 ? 0.0 : v1;
+    partial[(p * segs + seg) * 2 + 0] = s[0];
+    partial[(p * segs + seg) * 2 + 1] = s[1];
   }
+}
+// pvar_{2p} = max(0, kxx - sum_k |A_k|^2 Re(1/lam_k)), pvar_{2p+1} likewise with B_k
+__global__ void __launch_bounds__(256) post_var_pair_final_kernel(const double* __restrict__ partial, int segs, int64_t pairs, int64_t m, double kxx,
+                                                                  double* __restrict__ out) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pairs) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int g = 0; g < segs; ++g) {
+    s0 += partial[(p * segs + g) * 2 + 0];
+    s1 += partial[(p * segs + g) * 2 + 1];
+  }
+  const double v0 = kxx - s0, v1 = kxx - s1;
+  out[2 * p] = v0 < 0.0 ? 0.0 : v0;
+  if (2 * p + 1 < m) out[2 * p + 1] = v1 < 0.0 ? 0.0 : v1;
 }
 
 template <int DT, int R, int MODE>
@@ -420,7 +437,12 @@ static int post_var_common(int family, const double* xs, int64_t m, const void* 
         lattice_cross_pair_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(xs + i0 * d, cnt, (const double*)x, n, d, P, scale, ls, kc);
       FGP_LAUNCH_CHECK();
       if ((rc = fgp_fftbr_c2c((const double*)kc, (double*)kc, pairs, n, table, stream))) return rc;
-      post_var_pair_reduce_kernel<<<(unsigned)pairs, 256, 0, st>>>(kc, (const double2*)lam, n, cnt, kxx, pvar + i0);
+      // partial sums behind the mc pairs of the chunk (the third n*mc doubles of the workspace are free in this path)
+      const int segs = n >= 8192 ? 16 : 1;
+      double* partial = (double*)work + 2 * mc * n;
+      post_var_pair_reduce_kernel<<<dim3(segs, (unsigned)pairs), 256, 0, st>>>(kc, (const double2*)lam, n, partial);
+      FGP_LAUNCH_CHECK();
+      post_var_pair_final_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(partial, segs, pairs, cnt, kxx, pvar + i0);
       FGP_LAUNCH_CHECK();
     }
     return FGP_OK;

@@ -42,5 +42,12 @@ if which in ("all", "pmean"):
     co = torch.randn(1, n, device=dev)
     for _ in range(reps):
         L.post_mean(0, xs, xp, [2] * d, 0, 1.0, [0.5] * d, co)
+if which in ("all", "pvar"):  # lattice post_var: cross-pair kernel -> in-place c2c transform -> pair reduction
+    xs = torch.rand(256, d, device=dev)
+    ysq = torch.rand(1, n, device=dev)
+    scale = torch.ones(1, device=dev); ls = torch.full((1, d), 0.5, device=dev); noise = torch.full((1,), 1e-6, device=dev)
+    _, lam = L.mll_grad(0, xp, [2] * d, 0, ysq, scale, ls, noise, want_lam=True)
+    for _ in range(reps):
+        L.post_var(0, xs, xp, [2] * d, 0, 1.0, [0.5] * d, lam[0])
 torch.cuda.synchronize()
 print("ok")

@@ -242,6 +242,31 @@ __global__ void __launch_bounds__(256) post_var_pair_final_kernel(const double* 
   if (2 * p + 1 < m) out[2 * p + 1] = v1 < 0.0 ? 0.0 : v1;
 }
 
+// net: partial[i][seg] = sum over the seg-th part of kt_ik^2 / lam_k (grid (segs, points)), finished by post_var_final_kernel
+__global__ void __launch_bounds__(256) post_var_reduce_seg_kernel(const double* __restrict__ kt, const double* __restrict__ lam, int64_t n,
+                                                                  double* __restrict__ partial) {
+  __shared__ double red[32 * 4];
+  const int64_t i = blockIdx.y;
+  const int segs = gridDim.x, seg = blockIdx.x;
+  const int64_t k0 = n / segs * seg, k1 = seg == segs - 1 ? n : n / segs * (seg + 1);
+  const double* row = kt + i * n;
+  double s[1] = {0.0};
+  for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+    const double v = row[k];
+    s[0] = fma(v * v, 1.0 / lam[k], s[0]);
+  }
+  block_sum<1>(s, red);
+  if (threadIdx.x == 0) partial[i * segs + seg] = s[0];
+}
+__global__ void __launch_bounds__(256) post_var_final_kernel(const double* __restrict__ partial, int segs, int64_t cnt, double kxx, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  double s = 0.0;
+  for (int g = 0; g < segs; ++g) s += partial[i * segs + g];
+  const double v = kxx - s;
+  out[i] = v < 0.0 ? 0.0 : v;
+}
+
 template <int DT, int R, int MODE>
 static int launch_post_mean(const PostArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
   post_mean_kernel<DT, R, MODE><<<grid, kPT, smem, st>>>(a);
@@ -386,7 +411,7 @@ int fgp_dnb2_post_mean(const double* xs_dev, int64_t m, const int64_t* xb_dev, i
 size_t fgp_post_var_workspace_bytes(int family, int64_t m, int64_t n) {
   if (m <= 0 || n <= 0) return 0;
   const int64_t mc = fgp::post_var_chunk(m, n);
-  return ((size_t)mc * n * (family == 0 ? 3 : 1) + 2) * sizeof(double);
+  return ((size_t)mc * n * (family == 0 ? 3 : 1) + 2 + (family == 0 ? 0 : 16 * (size_t)mc)) * sizeof(double);  // net: + 16 partial sums per row
 }
 
 static int post_var_common(int family, const double* xs, int64_t m, const void* x, int64_t n, int d, const int* alpha_host,
@@ -459,7 +484,14 @@ static int post_var_common(int family, const double* xs, int64_t m, const void* 
     } else {
       if ((rc = fgp_dnb2_cross_kernel(xs + i0 * d, cnt, (const int64_t*)x, n, d, alpha_host, t, scale, ls_host, kreal, stream))) return rc;
       if ((rc = fgp_fwht(kreal, kreal, cnt, n, stream))) return rc;
-      post_var_reduce_kernel<false><<<(unsigned)cnt, 256, 0, st>>>(kreal, lam, n, kxx, pvar + i0);
+      if (n >= 8192 && cnt < 2048) {  // few long rows: several CTAs per row, partial sums behind the chunk's rows
+        double* partial = kreal + mc * n;
+        post_var_reduce_seg_kernel<<<dim3(16, (unsigned)cnt), 256, 0, st>>>(kreal, lam, n, partial);
+        FGP_LAUNCH_CHECK();
+        post_var_final_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(partial, 16, cnt, kxx, pvar + i0);
+      } else {
+        post_var_reduce_kernel<false><<<(unsigned)cnt, 256, 0, st>>>(kreal, lam, n, kxx, pvar + i0);
+      }
     }
     FGP_LAUNCH_CHECK();
   }

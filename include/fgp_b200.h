@@ -213,8 +213,9 @@ int fgp_lattice_post_mean(const double* xs_dev, int64_t m, const double* x_dev, 
 int fgp_dnb2_post_mean(const double* xs_dev, int64_t m, const int64_t* xb_dev, int64_t n, int d,
                        const int* alpha_host, int t, double scale, const double* ls_host, const double* coeffs_dev,
                        int B, void* partial_dev, double* pmean_dev, fgp_stream_t stream);
-/* pvar[i] = max(0, k(xs_i,xs_i) - sum_k |T k(xs_i, X)|_k^2 / lam_k).  lam_dev as in fgp_gram_solve.
- * work_dev: fgp_post_var_workspace_bytes. */
+/* pvar[i] = max(0, k(xs_i,xs_i) - sum_k |T k(xs_i, X)|_k^2 / lam_k)  (abstract_gp.py:381-416).  lam_dev as in fgp_gram_solve.
+ * work_dev: fgp_post_var_workspace_bytes.  Lattice: two test points share one complex transform (z = k(x_a,X) + i k(x_b,X),
+ * spectra (Z_k +- conj Z_{n-k})/2), the reduction runs over the pairs (k, n-k); net: one real FWHT per test point. */
 size_t fgp_post_var_workspace_bytes(int family, int64_t m, int64_t n);
 int fgp_lattice_post_var(const double* xs_dev, int64_t m, const double* x_dev, int64_t n, int d,
                          const int* alpha_host, double scale, const double* ls_host, const double* lam_dev,

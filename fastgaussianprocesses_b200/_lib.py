@@ -63,6 +63,8 @@ SIGNATURES = {
     "fgp_dnb2_mll_grad": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "fgp_fit_state_doubles": (_sz, [_i32, _i32]),
     "fgp_fit_iteration": (_i32, [_c.POINTER(FitProblem), _c.POINTER(FitLayout), _vp]),
+    "fgp_fit_iterations": (_i32, [_c.POINTER(FitProblem), _c.POINTER(FitLayout), _i32, _vp]),
+    "fgp_fit_iterations_per_launch": (_i32, [_i32, _i64]),
     "fgp_fit_init": (_i32, [_c.POINTER(FitLayout), _c.POINTER(FitOptions), _vp]),
     "fgp_fit_step": (_i32, [_c.POINTER(FitLayout), _vp, _vp]),
     "fgp_fit_finish": (_i32, [_c.POINTER(FitLayout), _vp]),
@@ -401,7 +403,9 @@ def mll_grad_into(family, xpts, alpha, t, ysq, scale, ls, noise, weights, ws, la
 
 
 def mll_workspace(family, n, d, B, device):
-    return torch.empty((max(load().fgp_mll_workspace_bytes(family, n, d, B), 256) + 7) // 8, dtype=torch.float64, device=device)
+    ws = torch.empty((max(load().fgp_mll_workspace_bytes(family, n, d, B), 256) + 7) // 8, dtype=torch.float64, device=device)
+    ws[-32:].zero_()  # control words of the persistent kernel (include/fgp_b200.h): zero once, every launch leaves them zeroed
+    return ws
 
 
 def fit_state_doubles(P, B):
@@ -410,6 +414,14 @@ def fit_state_doubles(P, B):
 
 def fit_iteration(problem, layout):
     _check(load().fgp_fit_iteration(_c.byref(problem), _c.byref(layout), _stream()))
+
+
+def fit_iterations(problem, layout, k):
+    _check(load().fgp_fit_iterations(_c.byref(problem), _c.byref(layout), int(k), _stream()))
+
+
+def fit_iterations_per_launch(family, n):
+    return int(load().fgp_fit_iterations_per_launch(int(family), int(n)))
 
 
 def fit_init(layout, options):

@@ -55,6 +55,13 @@ struct MllArgs {
   // and  W[b][L1-q] = conj(W[b][q])  after pass B's backward half.  So pass A and pass C run only the L2/2+1 blocks with
   // r <= L2/2, pass B only the columns q <= L1/2; mirrored loads are conjugated reads and mirrored contributions weights 2.
   int hs;
+  // persistent cooperative kernel (mll_coop_kernel): control words {grid-barrier counter, exit counter, error flag} in the
+  // workspace (zero between launches: the last CTA to leave resets them) and the number of fit iterations of one launch
+  unsigned int* bar;
+  int iters;
+#ifdef FGP_TIMING
+  long long* stamps;  // tools-only build: phase stamps of the persistent kernel
+#endif
   FitLayout fit;
 };
 
@@ -132,11 +139,11 @@ static inline size_t dnb2_table_bytes(int d, int tile_log) { return (size_t)(64 
 template <bool NET>
 __device__ __forceinline__ void load_hyp(Hyp& H, const MllArgs& a, int b) {
   if (threadIdx.x == 0) {
-    H.scale = a.scale[b];
-    H.noise = a.noise[b];
+    H.scale = __ldcg(a.scale + b);
+    H.noise = __ldcg(a.noise + b);
   }
   for (int j = threadIdx.x; j < a.d; j += blockDim.x) {
-    H.ls[j] = a.ls[(int64_t)b * a.d + j];
+    H.ls[j] = __ldcg(a.ls + (int64_t)b * a.d + j);
     if (a.x) {
       if (NET)
         H.xb0[j] = (uint64_t)((const int64_t*)a.x)[j];
@@ -497,25 +504,48 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_single_kern
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// two-pass kernels
+// two-pass tile bodies.  One "tile" is what one CTA of the per-pass kernels does; the persistent cooperative kernel
+// below walks the same tiles in the same order of operations, so both routes give bit-identical results.
+// Workspace reads are cache-global (__ldcg): in the persistent kernel another CTA rewrote W since this SM last read it.
 // ------------------------------------------------------------------------------------------------------------
+#ifdef FGP_TIMING
+// tools-only build (-DFGP_TIMING, FGP_LIB_DIR): clock stamps of the persistent kernel, read back by fgp_debug_stamps()
+constexpr int kStampSlots = 16, kStampCtas = 1024;
+long long* debug_stamp_buffer();  // fgp_mll_passb.cu: device buffer, allocated on first use
+#define FGP_STAMP(slot)                                                                           \
+  do {                                                                                            \
+    if (threadIdx.x == 0 && blockIdx.x < kStampCtas && a.stamps) {                                \
+      long long _t;                                                                               \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                      \
+      a.stamps[blockIdx.x * kStampSlots + (slot)] = _t;                                           \
+      a.stamps[blockIdx.x * kStampSlots + 8 + (slot)] = clock64();                                \
+    }                                                                                             \
+  } while (0)
+#else
+#define FGP_STAMP(slot) do { } while (0)
+#endif
+
+// hyperparameters (and the net generator tables) of set b for a tile starting at point g0
+template <bool NET, bool GEN>
+__device__ __forceinline__ void tile_prologue(const MllArgs& a, Hyp& H, unsigned char* smraw, int b, int64_t g0, int tile_log) {
+  __syncthreads();  // the previous tile's readers of H and of the shared-memory tile are done
+  load_hyp<NET>(H, a, b);
+  if (GEN && NET) dnb2_build_tables(H, a, (uint64_t*)(smraw + a.tab_off), g0, tile_log);
+  __syncthreads();
+}
+template <bool NET>
+__device__ __forceinline__ int64_t tileA_block0(const MllArgs& a, int tile) {
+  // half-spectrum mode (lntr == 0): tile c takes residue class r = c, i.e. block row rev(c)
+  return (!NET && a.hs) ? (int64_t)brev_bits((uint32_t)tile, a.l2) : ((int64_t)tile << a.lntrA);
+}
+
 // pass A: k1 on the fly -> shared memory -> contiguous block transform -> inter-pass twiddle -> workspace
 template <int DT, bool NET, bool A2, bool GEN>
-__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passA_kernel(const __grid_constant__ MllArgs a) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  __shared__ Hyp H;
-  pdl_prologue();
-  const double stop_flag = fit_stop_flag(a);
-  const int b = blockIdx.y;
+__device__ __forceinline__ void passA_tile(const MllArgs& a, const Hyp& H, unsigned char* smraw, int tile, int b) {
   const int l1 = a.l1, l2 = a.l2, lntr = a.lntrA, LP = a.LPA;
-  // half-spectrum mode (lntr == 0): CTA c takes residue class r = c, i.e. block row rev(c)
-  const int64_t blk0 = (!NET && a.hs) ? (int64_t)brev_bits(blockIdx.x, l2) : ((int64_t)blockIdx.x << lntr);
+  const int64_t blk0 = tileA_block0<NET>(a, tile);
   const int64_t g0 = blk0 << l1;
-  load_hyp<NET>(H, a, b);
-  if (stop_flag != 0.0) return;  // uniform over the CTA, before any barrier
-  if (GEN && NET) dnb2_build_tables(H, a, (uint64_t*)(smraw + a.tab_off), g0, l1 + lntr);
-  __syncthreads();
-  const double c = H.scale;
+  const double c = H.scale;  // DC guess removed before the transform (role of abstract_fast_gp.py:209-211)
   if (NET) {
     double* sm = (double*)smraw;
     double* W = (double*)a.W + (int64_t)b * a.n + g0;
@@ -528,54 +558,136 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passA_kerne
     double2* sm = (double2*)smraw;
     double2* W = (double2*)a.W + (int64_t)b * a.n + g0;
     const FftTables T = a.T;
-#ifdef FGP_TIMING
-    long long tk0 = clock64();
-#endif
     tile_fill_c<false>(SmemC{sm, LP}, l1, lntr, [&](int tr, int idx) -> double2 {
       return make_double2(point_k1<DT, NET, A2, GEN>(a, H, g0 + ((int64_t)tr << l1) + idx) - c, 0.0);
     });
     __syncthreads();
-#ifdef FGP_TIMING
-    if (threadIdx.x == 0 && a.partC) {  // debug: cycles of the fill phase and of the whole CTA into the (unused here) partC buffer
-      a.partC[blockIdx.x * 4 + 0] = (double)(clock64() - tk0);
-      a.partC[blockIdx.x * 4 + 1] = (double)tk0;
-    }
-#endif
     block_fft_fwd_io<false>(sm, l1, lntr, LP, T.stage, SmemTag{}, [&](int tr, int idx, double2 v) {
       const uint32_t bb = (uint32_t)((blk0 + tr) & ((1 << l2) - 1));
       W[((int64_t)tr << l1) + idx] = cmul(v, twiddle_n(T, brev_bits(bb, l2) * (uint32_t)idx));
     });
-#ifdef FGP_TIMING
-    __syncthreads();
-    if (threadIdx.x == 0 && a.partC) {
-      a.partC[blockIdx.x * 4 + 2] = (double)(clock64() - tk0);
-      unsigned smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      a.partC[blockIdx.x * 4 + 3] = (double)smid;
-    }
-#endif
   }
+}
+
+// pass B: column transform -> lam -> spectral epilogue -> inverse column transform; per-tile partial sums -> partB
+template <bool NET>
+__device__ __forceinline__ void passB_tile(const MllArgs& a, unsigned char* smraw, double* red, int tile, int b) {
+  const double noise = __ldcg(a.noise + b);
+  const double dc = __ldcg(a.scale + b) * (double)a.n;  // the DC guess removed in pass A comes back in bin 0
+  const int l1 = a.l1, l2 = a.l2, lntr = a.lntrB, LP = a.LPB;
+  const int q0 = tile << lntr;
+  const int64_t boff = (int64_t)b * a.n;
+  const double* ysq = a.ysq + boff + q0;
+  const double wn = a.weights ? a.weights[2 * b] : 0.5, wl = a.weights ? a.weights[2 * b + 1] : 0.5;
+  const int want_grad = a.want_grad;
+  double s[3] = {0.0, 0.0, 0.0};
+  if (NET) {
+    double* sm = (double*)smraw;
+    double* W = (double*)a.W + boff + q0;
+    double* lamo = a.lam ? a.lam + boff + q0 : nullptr;
+    block_wht_io<true>(sm, l2, lntr, LP, wht_sched_up(l2), [&](int tr, int r) -> double { return __ldcg(W + ((int64_t)r << l1) + tr); }, SmemTag{});
+    __syncthreads();
+    tile_map_r<true>(SmemR{sm, LP}, l2, lntr, [&](int tr, int r, double v) -> double {
+      const int64_t k = ((int64_t)r << l1) + tr;
+      double lam = v + noise;
+      if (k + q0 == 0) lam += dc;
+      if (lamo) lamo[k] = lam;
+      return spectral_r(lam, ysq[k], wn, wl, s);
+    });
+    if (want_grad) {
+      __syncthreads();
+      block_wht_io<true>(sm, l2, lntr, LP, wht_sched_up(l2), SmemTag{}, [&](int tr, int r, double v) { W[((int64_t)r << l1) + tr] = v; });
+    }
+  } else {
+    double2* sm = (double2*)smraw;
+    double2* W = (double2*)a.W + boff + q0;
+    double2* lamo = a.lam ? (double2*)a.lam + boff + q0 : nullptr;
+    const FftTables T = a.T;
+    if (a.hs) {
+      // half-spectrum mode (MllArgs::hs): block rows of residue class r > L2/2 were not written by pass A, they are the
+      // conjugates of class L2 - r; columns q and L1 - q carry the same eigenvalues, so column q counts twice
+      const uint32_t L2 = 1u << l2, half2 = L2 >> 1;
+      const int half1 = 1 << (l1 - 1);
+      block_fft_fwd_io<true>(sm, l2, lntr, LP, T.stage, [&](int tr, int r) -> double2 {
+        const uint32_t res = brev_bits((uint32_t)r, l2);
+        const bool mir = res > half2;
+        const uint32_t row = mir ? brev_bits(L2 - res, l2) : (uint32_t)r;
+        const double2 v = __ldcg(W + ((int64_t)row << l1) + tr);
+        return make_double2(v.x, mir ? -v.y : v.y);
+      }, SmemTag{});
+      __syncthreads();
+      tile_map_c<true>(SmemC{sm, LP}, l2, lntr, [&](int tr, int r, double2 lam) -> double2 {
+        const int64_t k = ((int64_t)r << l1) + tr;
+        const int q = q0 + tr;
+        lam.x += noise;
+        if (k + q0 == 0) lam.x += dc;
+        double t3[3] = {0.0, 0.0, 0.0};
+        const double2 G = spectral_c(lam, ysq[k], wn, wl, t3);
+        const double cw = (q == 0 || q == half1) ? 1.0 : (q < half1 ? 2.0 : 0.0);
+        s[0] = fma(cw, t3[0], s[0]);
+        s[1] = fma(cw, t3[1], s[1]);
+        s[2] = fma(cw, t3[2], s[2]);
+        // lam is real in exact arithmetic; its computed imaginary part is round-off, but dL/dIm(lam) ~ Im(lam) |y~|^2 / lam^3 is
+        // not small where lam is.  A Hermitian (instead of real) dL/dlam back-transforms to a real but not EVEN sequence,
+        // and the odd part only cancels in a sum over all points -- pass C sums half of them twice.  Keep the real part.
+        return make_double2(G.x, 0.0);
+      });
+      if (want_grad && (q0 == 0 || q0 == half1)) {
+        // the two self-mirrored columns hold both members of every pair (k, n-k): make them exactly equal as well
+        __syncthreads();
+        double2* col = sm;  // tr == 0
+        const int L2i = 1 << l2;
+        for (int sidx = threadIdx.x; sidx < (L2i >> 1); sidx += blockDim.x) {
+          const int s1 = sidx;
+          const int s2 = q0 == 0 ? (L2i - sidx) & (L2i - 1) : L2i - 1 - sidx;
+          if (s1 != s2) {
+            const int i1 = padidx<kPSC>(s1), i2 = padidx<kPSC>(s2);
+            const double av = 0.5 * (col[i1].x + col[i2].x);
+            col[i1].x = av;
+            col[i2].x = av;
+          }
+        }
+      }
+      if (want_grad) {
+        __syncthreads();
+        block_fft_inv_io<true>(sm, l2, lntr, LP, T.stage, SmemTag{}, [&](int tr, int r, double2 v) {
+          const uint32_t res = brev_bits((uint32_t)r, l2);
+          if (res > half2) return;  // pass C never reads the mirrored block rows
+          const double2 w = twiddle_n(T, res * (uint32_t)(q0 + tr));
+          W[((int64_t)r << l1) + tr] = cmulc(w, v);
+        });
+      }
+    } else {
+      block_fft_fwd_io<true>(sm, l2, lntr, LP, T.stage, [&](int tr, int r) -> double2 { return __ldcg(W + ((int64_t)r << l1) + tr); }, SmemTag{});
+      __syncthreads();
+      tile_map_c<true>(SmemC{sm, LP}, l2, lntr, [&](int tr, int r, double2 lam) -> double2 {
+        const int64_t k = ((int64_t)r << l1) + tr;
+        lam.x += noise;
+        if (k + q0 == 0) lam.x += dc;
+        if (lamo) lamo[k] = lam;
+        return spectral_c(lam, ysq[k], wn, wl, s);
+      });
+      if (want_grad) {
+        __syncthreads();
+        block_fft_inv_io<true>(sm, l2, lntr, LP, T.stage, SmemTag{}, [&](int tr, int r, double2 v) {
+          const double2 w = twiddle_n(T, brev_bits((uint32_t)r, l2) * (uint32_t)(q0 + tr));
+          W[((int64_t)r << l1) + tr] = cmulc(w, v);
+        });
+      }
+    }
+  }
+  __syncthreads();
+  reduce_store<3>(s, 3, red, a.partB + ((int64_t)b * a.ctasB + tile) * 3);
 }
 
 // pass C: contiguous blocks of the back-transformed dL/dlam -> inverse block transform -> contraction with dk1/dtheta
 template <int DT, bool NET, bool A2, bool GEN>
-__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kernel(const __grid_constant__ MllArgs a) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  __shared__ Hyp H;
-  __shared__ double red[kRed];
+__device__ __forceinline__ void passC_tile(const MllArgs& a, const Hyp& H, unsigned char* smraw, double* red, int tile, int b) {
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
-  pdl_prologue();
-  const double stop_flag = fit_stop_flag(a);
-  const int b = blockIdx.y;
   const int d = DT > 0 ? DT : a.d;
   const int l1 = a.l1, lntr = a.lntrA, LP = a.LPA;
   const bool hs = !NET && a.hs;
-  const int64_t blk0 = hs ? (int64_t)brev_bits(blockIdx.x, a.l2) : ((int64_t)blockIdx.x << lntr);
-  const int64_t g0 = blk0 << l1;
-  load_hyp<NET>(H, a, b);
-  if (stop_flag != 0.0) return;  // uniform over the CTA, before any barrier
-  if (GEN && NET) dnb2_build_tables(H, a, (uint64_t*)(smraw + a.tab_off), g0, l1 + lntr);
-  __syncthreads();
+  const int64_t g0 = tileA_block0<NET>(a, tile) << l1;
   double acc[DM + 1];
 #pragma unroll
   for (int j = 0; j <= DM; ++j) acc[j] = 0.0;
@@ -583,7 +695,7 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kerne
     double* sm = (double*)smraw;
     const double* W = (const double*)a.W + (int64_t)b * a.n + g0;
     // top stages first: a thread's 16 loads are 2^(l1-4) apart, consecutive threads read consecutive addresses
-    block_wht_io<false>(sm, l1, lntr, LP, wht_sched_coalesced(l1), [&](int tr, int idx) -> double { return W[((int64_t)tr << l1) + idx]; }, SmemTag{});
+    block_wht_io<false>(sm, l1, lntr, LP, wht_sched_coalesced(l1), [&](int tr, int idx) -> double { return __ldcg(W + ((int64_t)tr << l1) + idx); }, SmemTag{});
     __syncthreads();
     tile_drain_r<false>(SmemR{sm, LP}, l1, lntr,
                         [&](int tr, int idx, double w) { point_grad<DT, NET, A2, GEN>(a, H, g0 + ((int64_t)tr << l1) + idx, w, acc); });
@@ -593,22 +705,146 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kerne
     if (hs) {  // columns above L1/2 were not computed: W[b][L1-q] = conj(W[b][q])
       const int L1 = 1 << l1, half1 = L1 >> 1;
       block_fft_inv_io<false>(sm, l1, lntr, LP, a.T.stage, [&](int, int idx) -> double2 {
-        const double2 v = W[idx > half1 ? L1 - idx : idx];
+        const double2 v = __ldcg(W + (idx > half1 ? L1 - idx : idx));
         return make_double2(v.x, idx > half1 ? -v.y : v.y);
       }, SmemTag{});
     } else {
-      block_fft_inv_io<false>(sm, l1, lntr, LP, a.T.stage, [&](int tr, int idx) -> double2 { return W[((int64_t)tr << l1) + idx]; }, SmemTag{});
+      block_fft_inv_io<false>(sm, l1, lntr, LP, a.T.stage, [&](int tr, int idx) -> double2 { return __ldcg(W + ((int64_t)tr << l1) + idx); }, SmemTag{});
     }
     __syncthreads();
     tile_drain_c<false>(SmemC{sm, LP}, l1, lntr,
                         [&](int tr, int idx, double2 w) { point_grad<DT, NET, A2, GEN>(a, H, g0 + ((int64_t)tr << l1) + idx, w.x, acc); });
-    if (hs && blockIdx.x != 0 && blockIdx.x != (1u << (a.l2 - 1))) {  // class r stands for r and L2 - r
+    if (hs && tile != 0 && tile != (1 << (a.l2 - 1))) {  // class r stands for r and L2 - r
 #pragma unroll
       for (int j = 0; j <= DM; ++j) acc[j] *= 2.0;
     }
   }
-  reduce_store<DM + 1>(acc, d + 1, red, a.partC + ((int64_t)b * a.ctasA + blockIdx.x) * (d + 1));
+  reduce_store<DM + 1>(acc, d + 1, red, a.partC + ((int64_t)b * a.ctasA + tile) * (d + 1));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// per-pass kernels: one tile per CTA, three launches per evaluation (plain fgp_*_mll_grad calls, and the fit iteration when
+// the cooperative route is switched off)
+// ------------------------------------------------------------------------------------------------------------
+template <int DT, bool NET, bool A2, bool GEN>
+__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passA_kernel(const __grid_constant__ MllArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ Hyp H;
+  pdl_prologue();
+  if (fit_stop_flag(a) != 0.0) return;  // uniform over the CTA, before any barrier
+  const int tile = blockIdx.x, b = blockIdx.y;
+  tile_prologue<NET, GEN>(a, H, smraw, b, tileA_block0<NET>(a, tile) << a.l1, a.l1 + a.lntrA);
+  passA_tile<DT, NET, A2, GEN>(a, H, smraw, tile, b);
+}
+
+template <int DT, bool NET, bool A2, bool GEN>
+__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kernel(const __grid_constant__ MllArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ Hyp H;
+  __shared__ double red[kRed];
+  pdl_prologue();
+  if (fit_stop_flag(a) != 0.0) return;  // uniform over the CTA, before any barrier
+  const int tile = blockIdx.x, b = blockIdx.y;
+  tile_prologue<NET, GEN>(a, H, smraw, b, tileA_block0<NET>(a, tile) << a.l1, a.l1 + a.lntrA);
+  passC_tile<DT, NET, A2, GEN>(a, H, smraw, red, tile, b);
   if (a.has_fit) mll_fit_tail(a, b, a.ctasA, gridDim.y, true, red);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// persistent cooperative kernel: a whole fit() iteration -- or a.iters of them -- in ONE launch.  Every CTA is resident
+// (cooperative launch, grid <= occupancy x SMs) and walks pass-A tiles, a grid barrier, pass-B tiles, a grid barrier,
+// pass-C tiles; the CTA that finishes the last tile reduces the partial sums and runs the fit step (mll_fit_tail); before
+// the next iteration a third barrier makes the new hyperparameters visible.  Replaces three ~17 us launches, a third of
+// which was launch latency, ramp-up and drain (profiles/README.md, round 1 snapshot j).
+// ------------------------------------------------------------------------------------------------------------
+// Arrive-and-wait on a monotonically increasing counter.  The wait gives up after ~1 s of device clock and raises the
+// error word instead of hanging the GPU if the launch contract (all CTAs resident) were ever broken.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target, double* fit_state) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if ((int)(v - target) >= 0) break;
+      if (clock64() - t0 > (1ll << 31)) {
+        atomicExch(bar + 2, 1u);
+        if (fit_state) fit_state[ST_STOPPED] = 2.0;  // the host reads 2 as "the device-side loop failed"
+        break;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+#ifndef FGP_COOP_PHASE_ATTR
+#define FGP_COOP_PHASE_ATTR __forceinline__
+#endif
+// phase bodies of the persistent kernel (-DFGP_COOP_PHASE_ATTR=__noinline__ gives each its own register allocation; measured
+// worse: the argument block is then read through a generic pointer instead of constant-bank operands)
+template <int DT, bool NET, bool A2, bool GEN>
+__device__ FGP_COOP_PHASE_ATTR void coop_phaseA(const MllArgs& a, Hyp& H, unsigned char* smraw, int tile, int b) {
+  tile_prologue<NET, GEN>(a, H, smraw, b, tileA_block0<NET>(a, tile) << a.l1, a.l1 + a.lntrA);
+  passA_tile<DT, NET, A2, GEN>(a, H, smraw, tile, b);
+}
+template <bool NET>
+__device__ FGP_COOP_PHASE_ATTR void coop_phaseB(const MllArgs& a, unsigned char* smraw, double* red, int tile, int b, int B) {
+  __syncthreads();  // the previous tile's shared-memory readers are done
+  passB_tile<NET>(a, smraw, red, tile, b);
+  if (a.has_fit && !a.want_grad) mll_fit_tail(a, b, a.ctasB, B, true, red);
+}
+template <int DT, bool NET, bool A2, bool GEN>
+__device__ FGP_COOP_PHASE_ATTR void coop_phaseC(const MllArgs& a, Hyp& H, unsigned char* smraw, double* red, int tile, int b, int B) {
+  tile_prologue<NET, GEN>(a, H, smraw, b, tileA_block0<NET>(a, tile) << a.l1, a.l1 + a.lntrA);
+  passC_tile<DT, NET, A2, GEN>(a, H, smraw, red, tile, b);
+  if (a.has_fit) mll_fit_tail(a, b, a.ctasA, B, true, red);
+}
+
+template <int DT, bool NET, bool A2, bool GEN>
+__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_coop_kernel(const __grid_constant__ MllArgs a, const int B) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ Hyp H;
+  __shared__ double red[kRed];
+  const int tilesA = a.ctasA * B, tilesB = a.ctasB * B;
+  unsigned int nbar = 0;
+  FGP_STAMP(0);
+  for (int it = 0; it < a.iters; ++it) {
+    // written by the fit step before the barrier that ended the previous iteration (or by an earlier launch): every CTA
+    // reads the same value, so the whole grid leaves the loop together
+    if (fit_stop_flag(a) != 0.0) break;
+    for (int w = blockIdx.x; w < tilesA; w += gridDim.x) {
+      const int b = w / a.ctasA, tile = w - b * a.ctasA;
+      coop_phaseA<DT, NET, A2, GEN>(a, H, smraw, tile, b);
+    }
+    FGP_STAMP(1);
+    grid_barrier(a.bar, ++nbar * gridDim.x, a.has_fit ? a.fit.state : nullptr);
+    FGP_STAMP(2);
+    for (int w = blockIdx.x; w < tilesB; w += gridDim.x) {
+      const int b = w / a.ctasB, tile = w - b * a.ctasB;
+      coop_phaseB<NET>(a, smraw, red, tile, b, B);
+    }
+    FGP_STAMP(3);
+    if (a.want_grad) {
+      grid_barrier(a.bar, ++nbar * gridDim.x, a.has_fit ? a.fit.state : nullptr);
+      FGP_STAMP(4);
+      for (int w = blockIdx.x; w < tilesA; w += gridDim.x) {
+        const int b = w / a.ctasA, tile = w - b * a.ctasA;
+        coop_phaseC<DT, NET, A2, GEN>(a, H, smraw, red, tile, b, B);
+      }
+      FGP_STAMP(5);
+    }
+    if (it + 1 < a.iters) grid_barrier(a.bar, ++nbar * gridDim.x, a.has_fit ? a.fit.state : nullptr);
+  }
+  FGP_STAMP(6);
+  // every CTA has passed its last barrier when it gets here; the last one to leave re-arms the control words
+  if (threadIdx.x == 0 && atomicAdd(a.bar + 1, 1u) == gridDim.x - 1) {
+    a.bar[0] = 0u;
+    a.bar[1] = 0u;
+    __threadfence();
+  }
 }
 
 template <typename K>
@@ -626,6 +862,41 @@ static int set_smem_attr(K kernel, size_t bytes) {
 // defined once in fgp_mll_passb.cu
 int launch_mll_passB(const MllArgs& a, const PassGeom& g, int B, bool net, cudaStream_t st);
 int launch_mll_finalize(const MllArgs& a, int B, cudaStream_t st);
+bool coop_enabled();  // FGP_COOP=0 switches the persistent kernel off (three launches per iteration, as in round 1)
+int coop_max_ctas();  // FGP_COOP_CTAS caps the grid of the persistent kernel (tuning)
+
+template <int DT, bool NET, bool A2, bool GEN>
+static int launch_mll_coop(const MllArgs& a0, const PassGeom& g, int B, size_t smemAC, cudaStream_t st) {
+  int rc;
+  MllArgs a = a0;
+#ifdef FGP_TIMING
+  a.stamps = debug_stamp_buffer();
+#endif
+  int Bk = B;
+  const size_t smem = smemAC > g.smemB ? smemAC : g.smemB;
+  const int threads = g.threadsA > g.threadsB ? g.threadsA : g.threadsB;
+  auto kernel = mll_coop_kernel<DT, NET, A2, GEN>;
+  if ((rc = set_smem_attr(kernel, smem))) return rc;
+  // resident CTAs of this (kernel, block, shared memory) triple; queried once per variant and shape
+  static int cached_threads = 0, cached_per_sm = 0;
+  static size_t cached_smem = 0;
+  if (cached_threads != threads || cached_smem != smem) {
+    int per_sm = 0;
+    FGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    cached_threads = threads;
+    cached_smem = smem;
+    cached_per_sm = per_sm;
+  }
+  FGP_REQUIRE(cached_per_sm >= 1, "mll_coop: the persistent kernel does not fit an SM (%zu bytes of shared memory)", smem);
+  int64_t grid = (int64_t)cached_per_sm * sm_count();
+  const int64_t tiles = (int64_t)B * (a.ctasA > a.ctasB ? a.ctasA : a.ctasB);
+  if (grid > tiles) grid = tiles;
+  if (coop_max_ctas() > 0 && grid > coop_max_ctas()) grid = coop_max_ctas();
+  void* params[2] = {(void*)&a, (void*)&Bk};
+  FGP_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)grid), dim3(threads), params, smem, st));
+  FGP_LAUNCH_NAMED("mll_coop", st);
+  return FGP_OK;
+}
 
 template <int DT, bool NET, bool A2, bool GEN>
 static int launch_mll(const MllArgs& a, const PassGeom& g, int B, cudaStream_t st) {
@@ -637,6 +908,7 @@ static int launch_mll(const MllArgs& a, const PassGeom& g, int B, cudaStream_t s
     FGP_LAUNCH_NAMED("mll_single", st);
     return FGP_OK;
   }
+  if (a.has_fit && a.bar && coop_enabled()) return launch_mll_coop<DT, NET, A2, GEN>(a, g, B, smemAC, st);
   if ((rc = set_smem_attr(mll_passA_kernel<DT, NET, A2, GEN>, smemAC))) return rc;
   launch_chain(mll_passA_kernel<DT, NET, A2, GEN>, dim3(a.ctasA, B), dim3(g.threadsA), smemAC, st, a);
   FGP_LAUNCH_NAMED("mll_passA", st);

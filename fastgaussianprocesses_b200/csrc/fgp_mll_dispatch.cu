@@ -6,7 +6,7 @@ namespace fgp {
 static int mll_common(bool net, const uint64_t* z_host, const uint64_t* C_dev, int mmax, const void* x, int64_t n, int d, const int* alpha_host, int t, int B,
                       const double* ysq, const double* scale, const double* ls, const double* noise, const double* weights,
                       const void* table, void* workspace, double* lam, double* out, int want_grad, fgp_stream_t stream,
-                      const fgp_fit_layout* fit = nullptr) {
+                      const fgp_fit_layout* fit = nullptr, int iters = 1) {
   FGP_REQUIRE((x || z_host || C_dev) && alpha_host && ysq && scale && ls && noise && out, "mll_grad: null pointer");
   FGP_REQUIRE(!(net && z_host) && !(!net && C_dev), "mll_grad: generator arguments do not match the family");
   if (C_dev) FGP_REQUIRE(mmax >= 1 && mmax <= 64 && (mmax == 64 || n <= (int64_t(1) << mmax)), "mll_grad: n exceeds 2^mmax generating-matrix columns");
@@ -54,6 +54,7 @@ static int mll_common(bool net, const uint64_t* z_host, const uint64_t* C_dev, i
     FGP_REQUIRE(a.fit.B == B && a.fit.d == d, "fit_iteration: layout B/d do not match the problem");
     a.has_fit = 1;
   }
+  a.iters = iters;
   a.l1 = g.l1;
   a.l2 = g.l2;
   a.lntrA = g.l2 ? g.lntrA : 0;  // the single-pass kernel runs one transform per CTA
@@ -77,7 +78,11 @@ static int mll_common(bool net, const uint64_t* z_host, const uint64_t* C_dev, i
     a.W = workspace;
     a.partB = (double*)((char*)workspace + wbytes);
     a.partC = (double*)((char*)workspace + wbytes + pb);
+    // control words of the persistent kernel behind the partial sums (fgp_mll_workspace_bytes reserves them)
+    const size_t pc = align256((size_t)B * g.ctasA * (d + 1) * sizeof(double));
+    a.bar = (unsigned int*)((char*)workspace + wbytes + align256((size_t)B * g.ctasB * 3 * sizeof(double)) + pc);
   }
+  FGP_REQUIRE(iters == 1 || (fit && g.l2 && coop_enabled()) , "fit_iterations: several iterations per launch need the persistent two-pass kernel");
   mll_launch_fn fn;
   if (net && C_dev) {
     fn = mll_net_z_gen_alpha;
@@ -106,7 +111,7 @@ size_t fgp_mll_workspace_bytes(int family, int64_t n, int d, int B) {
   const PassGeom g = make_geom(n, !net);
   if (g.l2 == 0) return 256;
   return align256((size_t)B * n * (net ? sizeof(double) : sizeof(double2))) + align256((size_t)B * g.ctasB * 3 * sizeof(double)) +
-         align256((size_t)B * g.ctasA * (d + 1) * sizeof(double));
+         align256((size_t)B * g.ctasA * (d + 1) * sizeof(double)) + 256 /* control words of the persistent kernel */;
 }
 
 int fgp_lattice_mll_grad(const double* x_dev, int64_t n, int d, const int* alpha_host, int B, const double* ysq_dev, const double* scale_dev,
@@ -139,6 +144,22 @@ int fgp_fit_iteration(const fgp_fit_problem* p, const fgp_fit_layout* layout, fg
   return fgp::mll_common(net, net ? nullptr : p->z_host, net ? p->C_dev : nullptr, p->mmax, p->x_dev, p->n, p->d, p->alpha_host, p->t, layout->B, p->ysq_dev, layout->scale_B,
                          layout->ls_B, layout->noise_B, p->weights_dev, p->table_dev, p->workspace_dev, nullptr, p->out_dev, want_grad,
                          stream, layout);
+}
+
+int fgp_fit_iterations(const fgp_fit_problem* p, const fgp_fit_layout* layout, int iterations, fgp_stream_t stream) {
+  FGP_REQUIRE(p && layout && iterations >= 1, "fit_iterations: bad argument");
+  const bool net = p->family != 0;
+  const int want_grad = (layout->req_scale || layout->req_ls || layout->req_noise) ? 1 : 0;
+  return fgp::mll_common(net, net ? nullptr : p->z_host, net ? p->C_dev : nullptr, p->mmax, p->x_dev, p->n, p->d, p->alpha_host, p->t, layout->B, p->ysq_dev, layout->scale_B,
+                         layout->ls_B, layout->noise_B, p->weights_dev, p->table_dev, p->workspace_dev, nullptr, p->out_dev, want_grad,
+                         stream, layout, iterations);
+}
+
+int fgp_fit_iterations_per_launch(int family, int64_t n) {
+  using namespace fgp;
+  if (!is_pow2(n)) return 0;
+  const PassGeom g = make_geom(n, family == 0);
+  return (g.l2 && coop_enabled()) ? 1 << 20 : 1;
 }
 
 int fgp_dnb2_mll_grad(const int64_t* xb_dev, int64_t n, int d, const int* alpha_host, int t, int B, const double* ysq_dev,

@@ -152,8 +152,10 @@ def _pin_release(buf):
 
 
 class _FusedFitLoop(object):
-    """Device-side fit() loop (the product's fast path): every iteration is [fgp_*_mll_grad, fgp_fit_step] and runs
-    from a CUDA graph; the host only polls the `stopped` flag between graph replays (include/fgp_b200.h, K4/K4b).
+    """Device-side fit() loop (the product's fast path).  Two-pass sizes: ONE launch of the persistent cooperative kernel
+    runs a whole chunk of iterations (fgp_fit_iterations: eigen-solve, gradient, Rprop and the early-stop state machine
+    loop on the device).  Single-CTA sizes: every iteration is one fused kernel, replayed from a CUDA graph.  The host only
+    polls the `stopped` flag between chunks (include/fgp_b200.h, K4/K4b).
     Used when the loss is MLL, the optimiser is the default Rprop and the transforms are the default (log, exp)."""
     GRAPH_ITERS = 16
     EAGER_ITERS = 32  # large problems: iterations launched eagerly before a graph is worth capturing (~1.5 ms)
@@ -244,6 +246,12 @@ class _FusedFitLoop(object):
         self.launches = 0
         self.replayed = 0
         self.kernels_per_iteration = None
+        # persistent cooperative kernel: k iterations per launch, no graph and no warm-up launch needed
+        self.multi = _lib.fit_iterations_per_launch(fgp._FAMILY, self.n) > 1 and os.environ.get("FGP_B200_NO_MULTI") != "1"
+        if self.multi:
+            self.use_graph = False
+            self.kernels_per_iteration = 1
+            return
         # eager warm-up of every kernel before any capture; `stopped` is raised so that the fit step changes nothing
         # (the state block is zero: tickets start at 0 as fit_init leaves them)
         with torch.cuda.device(dev):
@@ -273,6 +281,8 @@ class _FusedFitLoop(object):
         n, d, B = self.n, self.d, self.B
         if self.fgp._zgen is not None or self._C is not None:
             d = 0
+        if name == "mll_coop":
+            return self.algorithmic_bytes
         return {"mll_passA": B * (8 * n * d + e * n), "mll_passB": B * (2 * e * n + 8 * n), "mll_passC": B * (8 * n * d + e * n),
                 "mll_single": B * (16 * n * d + 8 * n)}.get(name, 0)
 
@@ -315,6 +325,12 @@ class _FusedFitLoop(object):
         # capture / instantiation is paid (graphs save ~4 us of launch gaps per iteration; fit_stepper() opts in).  Small
         # ones replay a CUDA graph from the start: the 1-iteration graph k times, then a k-iteration graph once the fit is
         # long enough to amortise its capture.
+        if self.multi:
+            with torch.cuda.device(self.fgp.device):
+                _lib.fit_iterations(self.problem, self.layout, k)
+            self.replayed += k
+            self.launches += 1
+            return
         if not self.use_graph and (self.replayed < self.EAGER_ITERS or not self.graph_after_eager):
             with torch.cuda.device(self.fgp.device):
                 for _ in range(k):
@@ -345,6 +361,10 @@ class _FusedFitLoop(object):
         self.state_host.copy_(self.state[:self.ST_HEADER], non_blocking=True)
         torch.cuda.current_stream(self.fgp.device).synchronize()
         return self.state_host
+
+    def check(self, st):
+        if float(st[self.ST_STOPPED]) == 2.0:  # raised by a grid barrier of the persistent kernel that gave up waiting
+            raise _lib.FgpError("libfgp_b200: the device-side fit loop reported a failed grid barrier")
 
     def finish(self):
         with torch.cuda.device(self.fgp.device):
@@ -471,6 +491,7 @@ class _FastInverseLogDetCache(object):
 
 class AbstractFastGP(torch.nn.Module):
     _FAMILY = None  # 0 lattice, 1 digital net
+    _DENSE = False  # StandardGP (standard_gp.py): same parameter handling and fit loop, dense torch algebra instead of the CUDA path
     _XBDTYPE = None
     _FTOUTDTYPE = None
     _DEFAULT_NOISE = None
@@ -483,24 +504,25 @@ class AbstractFastGP(torch.nn.Module):
                  derivatives, derivatives_coeffs, compile_fts, compile_fts_kwargs, adaptive_nugget):
         super().__init__()
         assert torch.get_default_dtype() == torch.float64, "fast transforms do not work without torch.float64 precision"
-        _lib.load()  # fail loudly when the CUDA library is missing: there is no CPU path
         self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise RuntimeError("fastgaussianprocesses_b200 computes on a CUDA device only (got device=%r); there is no CPU fallback" % (device,))
-        if self.device.index is None:
+        if not self._DENSE:
+            _lib.load()  # fail loudly when the CUDA library is missing: there is no CPU path
+            if self.device.type != "cuda":
+                raise RuntimeError("fastgaussianprocesses_b200 computes on a CUDA device only (got device=%r); there is no CPU fallback" % (device,))
+        if self.device.type == "cuda" and self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         if num_tasks is None:
             solo_task, default_task, num_tasks = True, 0, 1
         else:
             assert isinstance(num_tasks, int) and num_tasks > 0
             solo_task, default_task = False, torch.arange(num_tasks)
-        if num_tasks != 1 and len(torch.Size(shape_batch)) != 0:
+        if num_tasks != 1 and len(torch.Size(shape_batch)) != 0 and not self._DENSE:
             raise NotImplementedError("multi-task GPs with batched outputs are not built (SURVEY.md section 8(f) row 2 is covered for one hyperparameter set)")
         if derivatives is not None or derivatives_coeffs is not None:  # abstract_gp.py:59-62
             rank_factor_task_kernel = 1
             tfs_noise_task_kernel = DEFAULT_TFS_ID
             noise_task_kernel = 0.
-        if adaptive_nugget:
+        if adaptive_nugget and not self._DENSE:
             raise NotImplementedError("adaptive_nugget is not supported by the B200 hot path")
         self.num_tasks = num_tasks
         self.default_task = default_task
@@ -514,10 +536,10 @@ class AbstractFastGP(torch.nn.Module):
             seqs = np.array([seqs], dtype=object)
         assert seqs.shape == (num_tasks,), "seqs should be a length num_tasks=%d list" % num_tasks
         seqs = np.array([self._adopt_sequence(s) for s in seqs], dtype=object)
-        assert all(seqs[i].order == "NATURAL" for i in range(num_tasks)), "each seq should be in 'NATURAL' order "
+        assert self._DENSE or all(seqs[i].order == "NATURAL" for i in range(num_tasks)), "each seq should be in 'NATURAL' order "
         assert all(seqs[i].replications == 1 for i in range(num_tasks)), "each seq should have only 1 replication"
         self.d = seqs[0].d
-        assert self.d <= _lib.MAX_D, "dimension %d exceeds the fused-kernel limit %d" % (self.d, _lib.MAX_D)
+        assert self._DENSE or self.d <= _lib.MAX_D, "dimension %d exceeds the fused-kernel limit %d" % (self.d, _lib.MAX_D)
         self.seqs = seqs
         self.n = torch.zeros(self.num_tasks, dtype=int, device=self.device)
         self.m = -1 * torch.ones(self.num_tasks, dtype=int, device=self.device)
@@ -539,7 +561,7 @@ class AbstractFastGP(torch.nn.Module):
         self.derivatives_coeffs = derivatives_coeffs
         self._has_derivs = any((self.derivatives[i] > 0).any() or (self.derivatives_coeffs[i] != 1).any() or len(self.derivatives[i]) != 1 for i in range(self.num_tasks))
         self._deriv_cache = {}
-        if self._has_derivs and len(torch.Size(shape_batch)) != 0:
+        if self._has_derivs and len(torch.Size(shape_batch)) != 0 and not self._DENSE:
             raise NotImplementedError("derivative-informed GPs with batched outputs are not built")
         # alpha
         assert (np.isscalar(alpha) and alpha % 1 == 0) or (isinstance(alpha, torch.Tensor) and alpha.shape == (self.d,)), "alpha should be an int or a torch.Tensor of length d"
@@ -650,14 +672,14 @@ class AbstractFastGP(torch.nn.Module):
         self._y = [torch.empty(0, device=self.device) for _ in range(self.num_tasks)]
         self.xxb_seqs = np.array([_XXbSeq(self, self.seqs[i]) for i in range(self.num_tasks)], dtype=object)
         self.inv_log_det_cache_dict = {}
-        self.adaptive_nugget = False
+        self.adaptive_nugget = bool(adaptive_nugget)
         # generator mode of the fused eigen-solve: a lattice spec of this package carries its generating vector, so the
         # first kernel column is regenerated from the point index and the points are never read (include/fgp_b200.h)
         s0 = self.seqs[0]
         self._zgen = [int(v) for v in s0.gen_vec] if (self._FAMILY == 0 and isinstance(s0, sequences.Lattice) and os.environ.get("FGP_B200_NO_GEN") != "1") else None
         self._netgen = self._FAMILY == 1 and isinstance(s0, sequences.DigitalNetB2) and os.environ.get("FGP_B200_NO_GEN") != "1"
         # several tasks, or derivative observations (their kernels are sums over derivative terms): block eigen-solve route
-        self._mt = multitask.MultiTaskEngine(self) if (self.num_tasks > 1 or self._has_derivs) else None
+        self._mt = multitask.MultiTaskEngine(self) if ((self.num_tasks > 1 or self._has_derivs) and not self._DENSE) else None
         if self._has_derivs:  # abstract_gp.py:147-150
             self.raw_noise_task_kernel.requires_grad_(False)
             self.raw_factor_task_kernel.requires_grad_(False)
@@ -1131,7 +1153,7 @@ class AbstractFastGP(torch.nn.Module):
         # MLL without masks: fused CUDA eigen-solve with the analytic gradient.  GCV, CV and masked fits: the same transforms
         # behind torch.autograd (_FTFunction), formulas as in the reference.
         autograd_route = loss_metric != "MLL" or masks is not None or self._mt is not None
-        if self._mt is not None and masks is not None:
+        if self._mt is not None and masks is not None and not self._DENSE:
             raise NotImplementedError("fit(masks=...) with several tasks is not built")
         if isinstance(cv_weights, torch.Tensor):
             cv_weights = cv_weights.to(self.device)
@@ -1177,7 +1199,9 @@ class AbstractFastGP(torch.nn.Module):
         if self._mt is None:
             self.get_ytilde(0)
         for i in range(iterations + 1):
-            if self._mt is not None:
+            if self._DENSE:
+                loss, term1, term2, metric_val = self._mt.loss(loss_metric, d_out, mll_const, masks, cv_weights)
+            elif self._mt is not None:
                 loss, term1, term2, metric_val = self._mt.loss(loss_metric, d_out, mll_const)
             elif autograd_route:
                 loss, term1, term2, metric_val = self._autograd_loss(loss_metric, masks, cv_weights, d_out, mll_const)
@@ -1285,6 +1309,7 @@ class AbstractFastGP(torch.nn.Module):
                 enqueue()
                 st = loop.read_state()
                 last, stopped = int(st[loop.ST_LAST_ITER]), bool(st[loop.ST_STOPPED] != 0)
+                loop.check(st)
                 rows = loop.loss_hist[printed:last + 1].cpu().numpy()
                 for r, row in enumerate(rows):
                     it = printed + r
@@ -1303,6 +1328,7 @@ class AbstractFastGP(torch.nn.Module):
                 loop.snapshot((j + 1) & 1)
                 st = loop.wait_snapshot(j & 1)
                 last, stopped = int(st[loop.ST_LAST_ITER]), bool(st[loop.ST_STOPPED] != 0)
+                loop.check(st)
                 if stopped:
                     break
                 j += 1

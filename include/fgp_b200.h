@@ -116,7 +116,7 @@ int fgp_fwht_fused(const double* in_dev, double* out_dev, int64_t batch, int64_t
  *     lam_dev: optional (B,n) complex (lattice) / real (net) output of lam (may be NULL).
  *     want_grad = 0 skips the backward transform.
  * ------------------------------------------------------------------------------------------------------------- */
-size_t fgp_mll_workspace_bytes(int family /*0 lattice, 1 net*/, int64_t n, int d, int B);
+size_t fgp_mll_workspace_bytes(int family /*0 lattice, 1 net*/, int64_t n, int d, int B); /* the last 256 bytes: zero once (control words) */
 int fgp_lattice_mll_grad(const double* x_dev, int64_t n, int d, const int* alpha_host, int B, const double* ysq_dev,
                          const double* scale_dev, const double* ls_dev, const double* noise_dev,
                          const double* weights_dev, const void* table_dev, void* workspace_dev, double* lam_dev, double* out_dev, int want_grad,
@@ -187,6 +187,13 @@ typedef struct {
   double* out_dev;
 } fgp_fit_problem;
 int fgp_fit_iteration(const fgp_fit_problem* problem, const fgp_fit_layout* layout, fgp_stream_t stream);
+/* `iterations` fit() iterations in ONE launch of the persistent cooperative kernel (two-pass sizes): every CTA stays resident,
+ * the three passes of an iteration are separated by grid barriers, the fit step runs in the tail of the last pass-C tile and the
+ * loop leaves as soon as the early-stop state machine raises state[4] (abstract_gp.py:276-283).  state[4] == 2 reports a
+ * device-side failure.  The last 256 bytes of workspace_dev are control words: zero them once after allocation; every launch
+ * leaves them zeroed.  fgp_fit_iterations_per_launch: the largest `iterations` this size accepts (1: three launches per iteration). */
+int fgp_fit_iterations(const fgp_fit_problem* problem, const fgp_fit_layout* layout, int iterations, fgp_stream_t stream);
+int fgp_fit_iterations_per_launch(int family, int64_t n);
 
 /* Generator form for a base-2 digital net in natural order: xb_i ^ xb_0 = XOR_{k in bits(i)} C[j][k] exactly (the digital
  * shift cancels), rebuilt per tile from two shared-memory XOR-fold tables; the (n,d) int64 points are never read.

@@ -225,7 +225,65 @@ def run_deriv_cases():
                        derivatives=[z2, torch.tensor([[1, 0], [1, 1]])], derivatives_coeffs=[torch.ones(1), torch.tensor([2., -1.])])
 
 
+def run_case_standard(name, d, ns, kernel_class, T=None, batch=(), noise=1e-4, fit_iterations=8, seed=7, m_test=48):
+    """StandardGP (standard_gp.py:11-439, util.py:207-267): the reference's dense GP on explicit points."""
+    nt = 1 if T is None else T
+    ns = [int(ns)] * nt if np.isscalar(ns) else [int(v) for v in ns]
+    seqs = [qmcpy.DigitalNetB2(dimension=d, seed=sd) for sd in np.random.SeedSequence(seed).spawn(nt)]
+    kw = dict(shape_batch=torch.Size(batch), shape_lengthscales=torch.Size(batch + (d,))) if batch else {}
+    gp = fastgps.StandardGP(seqs if T is not None else seqs[0], num_tasks=T, kernel_class=kernel_class, noise=noise, **kw)
+    xs = gp.get_x_next(ns if T is not None else ns[0])
+    xs = xs if T is not None else [xs]
+    f = lambda x, l: f_ackley(x) * (1 + 0.2 * l) + 0.3 * l * torch.sin(2 * np.pi * x[:, 0])
+    ys = [f(xs[l], l) for l in range(nt)]
+    if batch:
+        ys = [torch.stack([y * (1 + 0.5 * k) + k for k in range(batch[0])]) for y in ys]
+    gp.add_y_next(ys if T is not None else ys[0])
+    xt = torch.rand((m_test, d), generator=torch.Generator().manual_seed(17))
+    out = dict(d=d, ns=np.array(ns), T=nt, solo=T is None, kernel_class=kernel_class, noise0=noise, batch=np.array(batch, dtype=np.int64), xtest=xt.numpy())
+    out.update({"x_%d" % l: xs[l].numpy() for l in range(nt)})
+    out.update({"y_%d" % l: ys[l].numpy() for l in range(nt)})
+    os.environ["FASTGP_FORCE_RECOMPILE"] = "True"
+    norm_term, logdet = gp.get_inv_log_det_cache().get_norm_term_logdet_term()
+    loss = 0.5 * (norm_term.sum() + logdet.sum() + sum(ns) * np.log(2 * np.pi))
+    loss.backward()
+    out.update(loss0=loss.item(), norm_term0=norm_term.detach().numpy(), logdet0=logdet.detach().numpy(),
+               grad_raw_scale0=gp.raw_scale.grad.numpy().copy(), grad_raw_lengthscales0=gp.raw_lengthscales.grad.numpy().copy())
+    gp.zero_grad()
+    del os.environ["FASTGP_FORCE_RECOMPILE"]
+    out["coeffs0"] = gp.coeffs.detach().numpy()
+    out["pmean0"] = gp.post_mean(xt).numpy()
+    out["pvar0"] = gp.post_var(xt).numpy()
+    out["pcov0"] = gp.post_cov(xt[:8], xt[:5]).numpy()
+    if not batch:  # with batch dims the reference's diagonal clamp indexes the batch axis (abstract_gp.py:460-464) and fails
+        out["pcov0_eq"] = gp.post_cov(xt[:6], xt[:6]).numpy()
+    if kernel_class == "Gaussian":
+        out["pcmean0"] = gp.post_cubature_mean().numpy()
+        out["pcvar0"] = gp.post_cubature_var().numpy()
+        if not batch:  # same indexing failure with batch dims (standard_gp.py:424-428)
+            out["pccov0"] = gp.post_cubature_cov().numpy()
+    numer, denom = gp.get_inv_log_det_cache().get_gcv_numer_denom()
+    out["gcv_loss0"] = (numer / denom).sum().item()
+    data = gp.fit(iterations=fit_iterations, verbose=0, store_hists=True, stop_crit_wait_iterations=100)
+    out.update(fit_iterations=fit_iterations, fit_last_iteration=data["iterations"], loss_hist=data["loss_hist"].numpy(),
+               scale_hist=data["scale_hist"].numpy(), lengthscales_hist=data["lengthscales_hist"].numpy(),
+               pmean1=gp.post_mean(xt).numpy(), pvar1=gp.post_var(xt).numpy())
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "loss0", out["loss0"], "its", data["iterations"], os.path.getsize(path) // 1024, "KiB")
+
+
+def run_standard_cases():
+    run_case_standard("sg_gaussian_d2_n64", 2, 64, "Gaussian")
+    run_case_standard("sg_matern52_d3_T2_n48_20", 3, [48, 20], "Matern52", T=2)
+    run_case_standard("sg_gaussian_d2_n32_batch2", 2, 32, "Gaussian", batch=(2,))
+    run_case_standard("sg_matern12_d1_n40", 1, 40, "Matern12", noise=1e-3)
+
+
 if __name__ == "__main__":
+    if "--standard-only" in sys.argv:
+        run_standard_cases()
+        sys.exit(0)
     if "--multitask-only" in sys.argv:
         run_case_multitask("mt_lattice_T2_d2_n256_a2", "lattice", 2, 256, 2, 2)
         run_case_multitask("mt_dnb2_T3_d3_n128_a2", "dnb2", 3, 128, 3, 2)
@@ -255,3 +313,4 @@ if __name__ == "__main__":
     run_case_multitask("mt_lattice_T3_d2_ragged_a2", "lattice", 2, [64, 256, 128], 3, 2)
     run_case_multitask("mt_dnb2_T2_d3_ragged_a2", "dnb2", 3, [256, 32], 2, 2)
     run_deriv_cases()
+    run_standard_cases()

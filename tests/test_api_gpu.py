@@ -367,3 +367,37 @@ def test_masked_mll_fit_equals_fit_on_the_selected_outputs():
     db = gpb.fit(iterations=6, verbose=0, store_hists=True, stop_crit_wait_iterations=100)
     assert np.allclose(da["loss_hist"].numpy(), db["loss_hist"].numpy(), rtol=1e-8)
     assert rel(da["lengthscales_hist"], db["lengthscales_hist"]) < 1e-7
+
+
+@pytest.mark.parametrize("family,d,m,batch,iters", [("lattice", 8, 20, (), 12), ("lattice", 4, 14, (), 25), ("lattice", 2, 13, (3,), 20), ("lattice", 8, 18, (5,), 6),
+                                                    ("dnb2", 4, 16, (), 20), ("dnb2", 3, 14, (2,), 15), ("lattice", 3, 16, (), 40)])
+def test_persistent_kernel_fit_is_bit_identical_to_the_three_launch_route(monkeypatch, family, d, m, batch, iters):
+    """fgp_fit_iterations (ONE cooperative launch per chunk of iterations: grid barriers between the passes, the fit step in the
+    tail, early stop on the device) walks the same tiles with the same arithmetic as the per-pass kernels, so the whole fit
+    trajectory -- losses, hyperparameter histories, stopping iteration, final parameters -- must agree to the last bit."""
+    import fastgaussianprocesses_b200 as fgp
+    n = 1 << m
+
+    def run(coop):
+        monkeypatch.setenv("FGP_COOP", "1" if coop else "0")
+        if family == "lattice":
+            gp = fgp.FastGPLattice(fgp.Lattice(d, seed=11), device=dev, noise=1e-6, shape_batch=torch.Size(batch),
+                                   shape_lengthscales=torch.Size(batch + (d,)), shape_scale=torch.Size(batch + (1,)))
+        else:
+            gp = fgp.FastGPDigitalNetB2(fgp.DigitalNetB2(d, seed=11), device=dev, noise=1e-6, shape_batch=torch.Size(batch),
+                                        shape_lengthscales=torch.Size(batch + (d,)), shape_scale=torch.Size(batch + (1,)))
+        x = gp.get_x_next(n)
+        y = torch.cos(2 * np.pi * x).sum(1) + torch.sin(2 * np.pi * x[:, 0]) * x[:, -1]
+        if batch:
+            y = torch.stack([y * (1.0 + 0.3 * k) + 0.1 * k * torch.sin(4 * np.pi * x[:, 0]) for k in range(batch[0])])
+        gp.add_y_next(y)
+        data = gp.fit(iterations=iters, verbose=0, store_hists=True, stop_crit_wait_iterations=7)
+        assert gp._fused_loop.multi == coop
+        return data, gp.raw_scale.detach().clone(), gp.raw_lengthscales.detach().clone()
+
+    d1, s1, l1 = run(True)
+    d0, s0, l0 = run(False)
+    assert d1["iterations"] == d0["iterations"]
+    for key in ("loss_hist", "scale_hist", "lengthscales_hist"):
+        assert torch.equal(d1[key], d0[key]), key
+    assert torch.equal(s1, s0) and torch.equal(l1, l0)

@@ -1,19 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- fit() MLL+gradient iterations/s and post_mean points/s, FastGPLattice d=8 n=2^20 FP64 (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log2n 20] [--d 8]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log2n 20] [--d 8] [--log2m 22]
 
-A "step" is one fit() iteration: the fused eigen-solve (first kernel column -> FFT -> log-det + quadratic form ->
-inverse FFT -> hyperparameter gradients) followed by the Rprop update.  Three measurements per run:
-  value     device-resident: K steps, each timed alone with CUDA events, L2 flushed between steps (untimed);
-  e2e       the public API with HOST buffers: add_y_next(host y) -> fit(iterations=K) -> hyperparameters back on the
-            host, host<->device copies inside the timed region;
-  post_mean points/s of post_mean on m test points per GPU (device-resident, and e2e with host x* / host result).
-N>1 (torchrun): independent GPs per rank (batched fits / restarts: no data-path collective) and test points sharded
-across ranks with one NCCL all_gather of the results; max over ranks, weak scaling.
-`--impl reference` times the reference algorithm's CPU port (oracle/, torch float64 on the host cores).
+A "step" is one fit() iteration: the fused eigen-solve (first kernel column -> FFT -> log-det + quadratic form -> inverse FFT
+-> hyperparameter gradients) followed by the Rprop update and the early-stop bookkeeping, all on the device.  Per run:
+  value      device-resident: K steps, each timed alone with CUDA events, L2 flushed (256 MiB written) before every step; at N > 1
+             every rank fits its own GP (independent restarts: BASELINE.json configs[4] / north_star "batched fits") and the
+             timed region ends with the NCCL all_gather that collects the fitted hyperparameters;
+  warm       the public fit(iterations=K) call on device-resident data, device-timed (working set L2-resident);
+  e2e        the public API with HOST buffers: add_y_next(host y) -> fit(iterations=K) -> hyperparameters back on the host;
+  post_mean  STRONG scaling: 2^log2m test points in total, sharded over the ranks, one all_gather of the results (configs[2]);
+  post_var   the same for the posterior variance (2^log2mv points in total);
+  batched    configs[4]: 64 independent lattice GPs d=8 n=2^18, 64/N per rank in one batched object, results all_gathered;
+  net        configs[1]: FastGPDigitalNetB2 d=4 n=2^16 fit iterations/s (rank 0).
+`--impl reference` times the UNMODIFIED reference package (baseline/_ref, installed by baseline/install_reference.py) on the
+host cores, on top of the qmcpy stand-in (oracle/qmcpy_standin: qmcpy itself is absent from the image); when baseline/_ref is
+missing it falls back to the oracle port (oracle/fgp_oracle.py) and says so (`cpu_baseline.kind`).
 """
 import argparse
+import csv
+import glob
 import json
 import math
 import os
@@ -28,9 +35,6 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 torch.set_default_dtype(torch.float64)
-
-# dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, n=2^20 d=8 (profiles/README.md, snapshot g)
-NCU_TRAFFIC = {("mll_passA", 20, 8): 159232, ("mll_passB", 20, 8): 8623616, ("mll_passC", 20, 8): 4380416}
 
 GEN_VEC = [1, 182667, 469891, 498753, 110745, 446247, 250185, 118627]
 
@@ -56,6 +60,38 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the newest committed `ncu --set full` raw page
+    (profiles/*ncu_full*raw.csv) holding a kernel whose name contains `kernel_substr`; (bytes, file) or (None, None)."""
+    best = (None, None)
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_full*raw.csv"))):
+        try:
+            with open(path, newline="") as fh:
+                rows = list(csv.reader(fh))
+        except OSError:
+            continue
+        hdr = next((r for r in rows if "Kernel Name" in r), None)
+        if hdr is None:
+            continue
+        ik = hdr.index("Kernel Name")
+        try:
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        units = rows[rows.index(hdr) + 1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = []
+        for r in rows[rows.index(hdr) + 2:]:
+            if len(r) > max(ik, ir, iw) and kernel_substr in r[ik]:
+                try:
+                    vals.append(float(r[ir].replace(",", "")) * scale.get(units[ir], 1.0) + float(r[iw].replace(",", "")) * scale.get(units[iw], 1.0))
+                except ValueError:
+                    pass
+        if vals:
+            best = (float(np.mean(vals)), os.path.relpath(path, ROOT))
+    return best
+
+
 class ClockSampler(object):
     """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md clocks line)."""
 
@@ -76,9 +112,6 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
-    def mark(self):
-        return time.time()
-
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -98,44 +131,93 @@ class ClockSampler(object):
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        if not sm:
-            allsm = []
-            for ts, line in self.rows:
-                try:
-                    allsm.append((float(line.split(",")[0]), float(line.split(",")[1])))
-                except Exception:
-                    pass
-            sm = [a for a, _ in allsm]
-            mx = [b for _, b in allsm]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def make_config(args, world):
+    """The workload description, identical for both arms."""
+    return {"workload": "FastGPLattice d=%d n=2^%d alpha=2 FP64: fit() MLL+gradient iterations (BASELINE.json configs[2]); post_mean / post_var on 2^%d / 2^%d "
+                        "test points in total; configs[4] 64 GPs n=2^18 and configs[1] net d=4 n=2^16 as extra lines" % (args.d, args.log2n, args.log2m, args.log2mv),
+            "n": 1 << args.log2n, "d": args.d, "alpha": 2, "dtype": "f64", "test_function": "f_synth (sum_j cos(2 pi x_j)/j + sin(2 pi x_1) cos(2 pi x_d))",
+            "generating_vector": [int(v) for v in gen_vec(args.d)], "n_gpus": world,
+            "l2": "256 MiB buffer written before every timed step of `value`; warm / e2e run the natural back-to-back fit() loop",
+            "parallelism": "one independent GP per GPU (restarts), fitted hyperparameters all_gathered; post_mean / post_var test points sharded (strong scaling), one all_gather"}
+
+
 # ----------------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_run(n, d, iters, pm_points, seed=7):
-    """The reference algorithm's CPU port (oracle/) on this box's host cores: fit iterations/s and post_mean points/s."""
-    from oracle import primitives as P
-    from oracle.fgp_oracle import OracleFastGP
-    shift = np.random.Generator(np.random.PCG64(seed)).random(d)
-    x = P.lattice_points(gen_vec(d), shift, 0, n)
-    o = OracleFastGP("lattice", x, alpha=2)
-    y = f_synth(torch.from_numpy(x))
-    o.add_y(y)
-    o.k1parts()
-    o.fit(iterations=1, stop_crit_wait_iterations=10 ** 6, store_hist=False)  # warm-up (thread pool, allocator)
-    t0 = time.perf_counter()
-    o.fit(iterations=iters, stop_crit_wait_iterations=10 ** 6, store_hist=False)
-    t_fit = time.perf_counter() - t0
-    out = {"fit_iters_per_s": iters / t_fit, "fit_s": t_fit, "iters": iters}
-    if pm_points > 0:
+def reference_available():
+    return os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "fastgps"))
+
+
+def cpu_reference_run(n, d, iters, pm_points, pv_points, seed=7):
+    """The reference's own CPU implementation of the path on this box's host cores.  kind "reference": the unmodified
+    `fastgps` package from baseline/_ref on the qmcpy stand-in; kind "port": oracle/fgp_oracle.py."""
+    out = {}
+    if reference_available():
+        for p in (os.path.join(ROOT, "oracle", "qmcpy_standin"), os.path.join(ROOT, "baseline", "_ref")):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        import fastgps  # the reference, unmodified
+        import qmcpy  # tests-only stand-in (oracle/qmcpy_standin)
+        seq = qmcpy.Lattice(dimension=d, seed=seed, generating_vector=gen_vec(d))
+        gp = fastgps.FastGPLattice(seq, device="cpu")
+        x = gp.get_x_next(n)
+        gp.add_y_next(f_synth(x))
+        gp.fit(iterations=1, verbose=0, stop_crit_wait_iterations=10 ** 6)  # warm-up: thread pool, allocator, caches
+        t0 = time.perf_counter()
+        data = gp.fit(iterations=iters, verbose=0, stop_crit_wait_iterations=10 ** 6)
+        t_fit = time.perf_counter() - t0
+        assert int(data["iterations"]) == iters
+        out.update(kind="reference", note="unmodified fastgps (baseline/_ref) + qmcpy stand-in (oracle/qmcpy_standin; qmcpy is absent from the image)")
+        xt = torch.rand((max(pm_points, pv_points, 1), d), generator=torch.Generator().manual_seed(17))
+        if pm_points > 0:
+            t0 = time.perf_counter()
+            for i in range(0, pm_points, 16):  # 16 points per call: the reference materialises (m, n, d) doubles
+                gp.post_mean(xt[i:i + 16])
+            out.update(post_mean_s=time.perf_counter() - t0)
+        if pv_points > 0:
+            t0 = time.perf_counter()
+            for i in range(0, pv_points, 4):
+                gp.post_var(xt[i:i + 4])
+            out.update(post_var_s=time.perf_counter() - t0)
+    else:
+        from oracle import primitives as P
+        from oracle.fgp_oracle import OracleFastGP
+        shift = np.random.Generator(np.random.PCG64(seed)).random(d)
+        x = P.lattice_points(gen_vec(d), shift, 0, n)
+        o = OracleFastGP("lattice", x, alpha=2)
+        o.add_y(f_synth(torch.from_numpy(x)))
+        o.k1parts()
+        o.fit(iterations=1, stop_crit_wait_iterations=10 ** 6, store_hist=False)
+        t0 = time.perf_counter()
+        o.fit(iterations=iters, stop_crit_wait_iterations=10 ** 6, store_hist=False)
+        t_fit = time.perf_counter() - t0
+        out.update(kind="port", note="oracle/fgp_oracle.py (baseline/_ref is missing: run baseline/install_reference.py in the build container)")
+        xt = torch.rand((max(pm_points, pv_points, 1), d), generator=torch.Generator().manual_seed(17))
         with torch.no_grad():
             c = o.coeffs().detach()
-            xt = torch.rand((pm_points, d), generator=torch.Generator().manual_seed(17))
-            t0 = time.perf_counter()
-            o.post_mean(xt, coeffs=c)
-            t_pm = time.perf_counter() - t0
-        out.update(post_mean_pts_per_s=pm_points / t_pm, post_mean_s=t_pm, post_mean_points=pm_points)
+            if pm_points > 0:
+                t0 = time.perf_counter()
+                o.post_mean(xt[:pm_points], coeffs=c)
+                out.update(post_mean_s=time.perf_counter() - t0)
+            if pv_points > 0:
+                t0 = time.perf_counter()
+                o.post_var(xt[:pv_points])
+                out.update(post_var_s=time.perf_counter() - t0)
+    out.update(fit_iters_per_s=iters / t_fit, fit_s=t_fit, iters=iters, post_mean_points=pm_points, post_var_points=pv_points)
+    if pm_points > 0:
+        out["post_mean_pts_per_s"] = pm_points / out["post_mean_s"]
+    if pv_points > 0:
+        out["post_var_pts_per_s"] = pv_points / out["post_var_s"]
     return out
+
+
+def cpu_baseline_block(r, cores):
+    return {"value": r["fit_iters_per_s"], "unit": "iterations/s", "cores": cores, "kind": r["kind"], "note": r["note"],
+            "sample": "%d fit iterations at full size (%.1f s); post_mean on %d points (%.1f s); post_var on %d points (%.1f s)"
+                      % (r["iters"], r["fit_s"], r["post_mean_points"], r.get("post_mean_s", 0.0), r["post_var_points"], r.get("post_var_s", 0.0)),
+            "post_mean_points_per_s": r.get("post_mean_pts_per_s"), "post_var_points_per_s": r.get("post_var_pts_per_s")}
 
 
 def main():
@@ -146,46 +228,48 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=20)
     ap.add_argument("--d", type=int, default=8)
-    ap.add_argument("--log2m", type=int, default=16, help="log2 of post_mean test points per GPU per repetition")
+    ap.add_argument("--log2m", type=int, default=22, help="log2 of the TOTAL number of post_mean test points (strong scaling; configs[2] states 24)")
+    ap.add_argument("--log2mv", type=int, default=14, help="log2 of the TOTAL number of post_var test points")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[4] / configs[1] lines")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n, d, K, W = 1 << args.log2n, args.d, args.steps, max(args.warmup, 3)
-    workload = "FastGPLattice d=%d n=2^%d alpha=2: fit() MLL+grad iterations and post_mean on 2^%d test points per GPU (BASELINE.json configs[2])" % (d, args.log2n, args.log2m)
+    config = make_config(args, max(world, args.gpus))
     hbm_peak, peak_src = peaks()
 
     if args.impl == "reference":
         if rank != 0:
             return
-        iters = max(1, min(K, 8))
+        iters = max(1, min(K, 64))
         torch.set_num_threads(os.cpu_count() or 1)
-        r = cpu_reference_run(n, d, iters, 32)
+        r = cpu_reference_run(n, d, iters, 16, 4)
         line = {"impl": "reference", "metric": "fit_mll_grad_iters_per_s", "value": r["fit_iters_per_s"], "unit": "iterations/s",
                 "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 / r["fit_iters_per_s"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "note": "reference algorithm CPU port (oracle/fgp_oracle.py: torch float64, materialised parts, log2(n)-pass transforms, autograd, Rprop); bounded sample of %d iterations" % iters},
-                "cpu_baseline": {"value": r["fit_iters_per_s"], "unit": "iterations/s", "cores": torch.get_num_threads(), "kind": "port",
-                                 "sample": "%d fit iterations at n=2^%d d=%d; post_mean on %d points" % (iters, args.log2n, d, r.get("post_mean_points", 0))},
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "notes": "%s; bounded sample of %d iterations (fit(iterations=k) wall time / k, probnum25_paper.ipynb cell 15)" % (r["note"], iters),
+                "cpu_baseline": cpu_baseline_block(r, torch.get_num_threads()),
                 "e2e": {"value": r["fit_iters_per_s"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "post_mean": {"value": r.get("post_mean_pts_per_s"), "unit": "points/s"}, "gpu_launches": 0}
+                "post_mean": {"value": r.get("post_mean_pts_per_s"), "unit": "points/s"},
+                "post_var": {"value": r.get("post_var_pts_per_s"), "unit": "points/s"}, "gpu_launches": 0}
         print(json.dumps(line))
         return
 
     # ------------------------------------------------------------------------------------------------- our arm
     import fastgaussianprocesses_b200 as fgp
     from fastgaussianprocesses_b200 import _lib as L
+    from fastgaussianprocesses_b200 import distributed as D
     assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        # NCCL prints its version banner to STDOUT at every level from VERSION up (WARN included): stdout must stay one JSON line
-        if os.environ.get("FGP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = os.environ["FGP_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
+        # NCCL writes its INFO lines to stdout unless told otherwise: keep stdout one JSON line, keep the log on stderr
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -201,52 +285,68 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # independent GP per rank (another randomisation of the same lattice): weak scaling, no data-path collective
-    seq = fgp.Lattice(d, seed=7 + rank, generating_vector=gen_vec(d))
-    gp = fgp.FastGPLattice(seq, device=dev)
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def new_gp(seed_off=0):
+        return fgp.FastGPLattice(fgp.Lattice(d, seed=7 + rank + seed_off, generating_vector=gen_vec(d)), device=dev)
+
+    # independent GP per rank (another randomisation of the same lattice): weak scaling
+    gp = new_gp()
     x = gp.get_x_next(n)
     y_dev = f_synth(x)
     y_host = y_dev.cpu().pin_memory()
     gp.add_y_next(y_dev)
     flush = torch.empty(256 * 1024 * 1024 // 8, device=dev)  # 256 MiB > 126 MB L2
-    stepper = gp.fit_stepper()
+    stepper = gp.fit_stepper()  # the device-side loop fit() runs, armed for an open-ended run: .step() = one iteration
     for _ in range(W):
         stepper.step()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     t_mark0 = time.time()
-    # ---- value: K steps, each timed alone, L2 flushed between steps
+    # ---- value: K steps, each timed alone, L2 flushed before every step; then the all_gather of the fitted hyperparameters
     l0 = stepper.launches
     evs = []
     barrier()
     for _ in range(K):
         flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = ev(), ev()
         e0.record()
         stepper.step()
         e1.record()
         evs.append((e0, e1))
+    g0, g1 = ev(), ev()
+    g0.record()
+    fitted = D.gather_fit_results(torch.cat([gp.raw_scale.data.reshape(-1), gp.raw_lengthscales.data.reshape(-1), stepper.state[:9]]))
+    g1.record()
     barrier()
     step_ms = [a.elapsed_time(b) for a, b in evs]
-    t_cold = max_over_ranks(sum(step_ms) * 1e-3)
+    gather_ms = g0.elapsed_time(g1) if dist is not None else 0.0
+    t_cold = max_over_ranks((sum(step_ms) + gather_ms) * 1e-3)
     launches = stepper.launches - l0
-    # ---- warm: the same K steps back to back (the natural fit() loop, working set L2-resident)
+    assert fitted.shape[0] == world and bool(torch.isfinite(fitted).all())
+    kern = stepper.kernel_times(reps=10, flush=flush)
+    alg_bytes_iter = stepper.algorithmic_bytes
+    stepper.close()
+    # ---- warm: the public fit(iterations=K) on device-resident data, device-timed
+    gpw = new_gp()
+    gpw.get_x_next(n)
+    gpw.add_y_next(y_dev)
+    gpw.fit(iterations=W, verbose=0, stop_crit_wait_iterations=W + 1)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = ev(), ev()
     e0.record()
-    for _ in range(K):
-        stepper.step()
+    dataw = gpw.fit(iterations=K, verbose=0, stop_crit_wait_iterations=K + 1)
     e1.record()
     barrier()
     t_warm = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
-    kern = stepper.kernel_times(reps=10, flush=flush)
-    stepper.close()
+    warm_iters = int(dataw["iterations"])
     # ---- e2e: public API, host buffers
-    gp2 = fgp.FastGPLattice(fgp.Lattice(d, seed=7 + rank, generating_vector=gen_vec(d)), device=dev)
+    gp2 = new_gp()
     gp2.get_x_next(n)
     gp2.add_y_next(y_host)
     gp2.fit(iterations=W, verbose=0, stop_crit_wait_iterations=W + 1)  # warm-up
-    gp3 = fgp.FastGPLattice(fgp.Lattice(d, seed=7 + rank, generating_vector=gen_vec(d)), device=dev)
+    gp3 = new_gp()
     gp3.get_x_next(n)
     barrier()
     t0 = time.perf_counter()
@@ -257,78 +357,155 @@ def main():
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     barrier()
     fit_iters = int(data["iterations"])
-    # ---- post_mean: m points per GPU, sharded test set
-    m = 1 << args.log2m
-    xt_host = torch.rand((m, d), generator=torch.Generator().manual_seed(17 + rank)).pin_memory()
-    xt = xt_host.to(dev)
-    gp.coeffs
-    gp.post_mean(xt[:1024])
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    lp0 = L.launch_count()
-    e0.record()
-    pm = gp.post_mean(xt)
-    if dist is not None:
-        gathered = torch.empty((world, m), device=dev)
-        dist.all_gather_into_tensor(gathered, pm.contiguous())
-    e1.record()
-    barrier()
-    lp1 = L.launch_count()
-    t_pm = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
-    barrier()
-    t0 = time.perf_counter()
-    pm2 = gp.post_mean(xt_host).cpu()
-    torch.cuda.synchronize()
-    t_pm_e2e = max_over_ranks(time.perf_counter() - t0)
+    del gp2, gp3, gpw
+
+    # ---- post_mean / post_var: STRONG scaling over a fixed total number of test points; every rank needs the SAME GP
+    gps = fgp.FastGPLattice(fgp.Lattice(d, seed=7, generating_vector=gen_vec(d)), device=dev)
+    xs = gps.get_x_next(n)
+    gps.add_y_next(f_synth(xs))
+    gps.fit(iterations=3, verbose=0)
+    gps.coeffs
+
+    def sharded(fn, m_total, seed):
+        xt_host = torch.rand((m_total, d), generator=torch.Generator().manual_seed(seed)).pin_memory()
+        lo, hi = D.shard_bounds(m_total, world, rank)
+        xt = xt_host[lo:hi].to(dev)
+        fn(xt[:256])
+        barrier()
+        e0, e1 = ev(), ev()
+        lp0 = L.launch_count()
+        e0.record()
+        local = fn(xt)
+        if dist is not None:
+            kmax = -(-m_total // world)
+            pad = torch.zeros(kmax, device=dev)
+            pad[:hi - lo] = local
+            flat = torch.empty(world * kmax, device=dev)
+            dist.all_gather_into_tensor(flat, pad)
+            sizes = [D.shard_bounds(m_total, world, r) for r in range(world)]
+            full = torch.cat([flat[r * kmax:r * kmax + (b - a)] for r, (a, b) in enumerate(sizes)])
+        else:
+            full = local
+        e1.record()
+        barrier()
+        lp1 = L.launch_count()
+        t_dev = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+        # the gathered result equals what one rank computes on its own (a sample of rows from every shard)
+        idx = torch.randint(0, m_total, (min(512, m_total),), generator=torch.Generator().manual_seed(seed + 1))
+        chk = fn(xt_host[idx].to(dev))
+        err = float((full[idx.to(dev)] - chk).abs().max() / chk.abs().max().clamp_min(1e-300))
+        # end to end: host test points in, host result out (this rank's shard)
+        barrier()
+        t0 = time.perf_counter()
+        res = fn(xt_host[lo:hi].to(dev, non_blocking=True)).cpu()
+        torch.cuda.synchronize()
+        t_e2e_ = max_over_ranks(time.perf_counter() - t0)
+        assert res.shape[0] == hi - lo
+        return t_dev, t_e2e_, int(lp1 - lp0), err
+
+    m_total, mv_total = 1 << args.log2m, 1 << args.log2mv
+    t_pm, t_pm_e2e, pm_launches, pm_err = sharded(gps.post_mean, m_total, 17)
+    t_pv, t_pv_e2e, pv_launches, pv_err = sharded(gps.post_var, mv_total, 19)
+
+    # ---- configs[4]: 64 independent GPs n=2^18 d=8, 64/world per rank in one batched object; results all_gathered
+    extras = {}
+    if not args.no_extras:
+        nb, Bt = 1 << 18, 64
+        Bl = max(1, Bt // world)
+        gpb = fgp.FastGPLattice(fgp.Lattice(d, seed=100 + rank, generating_vector=gen_vec(d)), device=dev, shape_batch=torch.Size([Bl]),
+                                shape_scale=torch.Size([Bl, 1]), shape_lengthscales=torch.Size([Bl, d]), shape_noise=torch.Size([Bl, 1]))
+        xb = gpb.get_x_next(nb)
+        yb = f_synth(xb)
+        gpb.add_y_next(torch.stack([yb * (1.0 + 0.05 * (k + Bl * rank)) + 0.01 * k for k in range(Bl)]))
+        sb = gpb.fit_stepper()
+        for _ in range(3):
+            sb.step()
+        Kb = max(4, min(K, 20))
+        barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        sb.replay(Kb) if sb.multi else [sb.step() for _ in range(Kb)]
+        res_b = D.gather_fit_results(torch.cat([gpb.raw_scale.data.reshape(Bl, -1), gpb.raw_lengthscales.data.reshape(Bl, -1)], 1))
+        e1.record()
+        barrier()
+        t_b = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+        assert res_b.shape[0] == world and bool(torch.isfinite(res_b).all())
+        extras["batched_fits"] = {"value": world * Bl * Kb / t_b, "unit": "GP-iterations/s", "gps_total": world * Bl, "gps_per_gpu": Bl, "n": nb, "d": d,
+                                  "iterations": Kb, "ms_per_batched_iteration": 1e3 * t_b / Kb, "config": "BASELINE.json configs[4]; back to back, results all_gathered inside the timed region"}
+        sb.close()
+        del gpb, sb
+        # ---- configs[1]: net d=4 n=2^16 (rank 0 reports; every rank runs it so that the ranks stay in step)
+        gpn = fgp.FastGPDigitalNetB2(fgp.DigitalNetB2(4, seed=7), device=dev)
+        xn = gpn.get_x_next(1 << 16)
+        gpn.add_y_next(f_synth(xn))
+        gpn.fit(iterations=W, verbose=0, stop_crit_wait_iterations=W + 1)
+        Kn = max(K, 50)
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        dn = gpn.fit(iterations=Kn, verbose=0, stop_crit_wait_iterations=Kn + 1)
+        e1.record()
+        torch.cuda.synchronize()
+        extras["net_fit"] = {"value": int(dn["iterations"]) / (e0.elapsed_time(e1) * 1e-3), "unit": "iterations/s", "family": "FastGPDigitalNetB2", "d": 4, "n": 1 << 16,
+                             "iterations": int(dn["iterations"]), "config": "BASELINE.json configs[1]; public fit(), device-timed, 1 GPU"}
+        del gpn
     t_mark1 = time.time()
     clocks = sampler.stop(t_mark0, t_mark1) if sampler is not None else None
     # FP64 peak probe (not in MEASURED_PEAKS.json)
-    fl = L.fp64_peak_probe(2000, dev)
+    L.fp64_peak_probe(2000, dev)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = ev(), ev()
     e0.record()
     fl = L.fp64_peak_probe(4000, dev)
     e1.record()
     torch.cuda.synchronize()
     fp64_peak = fl / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    world_seen = dist.get_world_size() if dist is not None else 1
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernel of the step
-    alg_bytes_iter = stepper.algorithmic_bytes
     kern = [k for k in kern if k["alg_bytes"] > 0] or kern
     tmax = max(k["ms"] for k in kern)
     dom = max((k for k in kern if k["ms"] >= 0.9 * tmax), key=lambda k: k["alg_bytes"])  # ties within 10 %: the one moving more bytes
+    traffic, traffic_src = ncu_traffic(dom["name"])
     roof = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9 / hbm_peak,
-            # DRAM read+write bytes of that kernel per launch from the committed ncu --set full capture (same workload only)
-            "traffic": NCU_TRAFFIC.get((dom["name"], args.log2n, d)), "traffic_source": "profiles/r1j_ncu_full_mll_passABC_halfspectrum_raw.csv",
-            "peak_source": peak_src,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "alg_bytes_per_launch": dom["alg_bytes"], "kernels": kern,
-            "step": {"alg_bytes": alg_bytes_iter, "achieved": alg_bytes_iter / (t_cold / K) / 1e9, "frac": alg_bytes_iter / (t_cold / K) / 1e9 / hbm_peak}}
-    slots = (5 * d + 1) * float(m) * n  # FP64 issue slots of the alpha=2 inner loop
-    line = {"metric": "fit_mll_grad_iters_per_s", "value": world * K / t_cold, "unit": "iterations/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": 1e3 * t_cold / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "l2": "256 MiB buffer written between timed steps (value); e2e and warm run the natural back-to-back fit() loop",
-                       "parallelism": "replicas (one independent GP per GPU); post_mean test points sharded, one NCCL all_gather" if world > 1 else "1 GPU"},
-            "warm": {"value": world * K / t_warm, "unit": "iterations/s", "ms_per_step": 1e3 * t_warm / K},
+            "step": {"alg_bytes": alg_bytes_iter, "achieved": alg_bytes_iter / (t_cold / K) / 1e9, "frac": alg_bytes_iter / (t_cold / K) / 1e9 / hbm_peak},
+            "note": "the working set (8 MiB half spectrum + 8 MiB |y~|^2) is L2-resident by design: measured DRAM traffic is below the algorithmic bytes, "
+                    "the binding resource is FP64 issue + barrier latency (profiles/README.md)"}
+    slots = (5 * d + 1) * float(m_total) * n  # FP64 issue slots of the alpha=2 inner loop
+    line = {"metric": "fit_mll_grad_iters_per_s", "value": world * K / t_cold, "unit": "iterations/s", "n_gpus": world, "world_size": world_seen,
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * t_cold / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config,
+            "gather_ms": gather_ms,
+            "warm": {"value": world * warm_iters / t_warm, "unit": "iterations/s", "ms_per_step": 1e3 * t_warm / max(warm_iters, 1),
+                     "note": "public fit(iterations=K) on device-resident y, CUDA events around the call"},
             "e2e": {"value": world * fit_iters / t_e2e, "unit": "iterations/s", "h2d_bytes_per_step": int(y_host.numel() * 8 / max(fit_iters, 1)),
                     "d2h_bytes_per_step": int(sum(t.numel() for t in hyp_host) * 8 / max(fit_iters, 1)), "seconds": t_e2e, "iterations": fit_iters,
                     "note": "add_y_next(host y) + fit(iterations=K) + hyperparameters/loss history to host; copies amortised over the K iterations of the job"},
             "gpu_launches": int(launches), "roofline": roof,
-            "post_mean": {"value": world * m / t_pm, "unit": "points/s", "m_per_gpu": m, "ms": 1e3 * t_pm, "launches": int(lp1 - lp0),
-                          "e2e": {"value": world * m / t_pm_e2e, "unit": "points/s", "h2d_bytes": int(m * d * 8), "d2h_bytes": int(m * 8)},
-                          "roofline": {"bound": "fp64", "achieved": 2 * slots / t_pm / 1e12, "peak": fp64_peak, "unit": "TFLOP/s (FP64 issue slots x2)",
-                                       "frac": 2 * slots / t_pm / 1e12 / fp64_peak, "peak_source": "fgp_fp64_peak_probe DFMA chains, measured in this run"}},
+            "post_mean": {"value": m_total / t_pm, "unit": "points/s", "scaling": "strong", "m_total": m_total, "ms": 1e3 * t_pm, "launches": pm_launches,
+                          "gather_check_rel_err": pm_err,
+                          "e2e": {"value": m_total / t_pm_e2e, "unit": "points/s", "h2d_bytes": int(m_total * d * 8 // world), "d2h_bytes": int(m_total * 8 // world)},
+                          "roofline": {"bound": "fp64", "achieved": 2 * slots / t_pm / 1e12 / world, "peak": fp64_peak, "unit": "TFLOP/s per GPU (FP64 issue slots x2)",
+                                       "frac": 2 * slots / t_pm / 1e12 / world / fp64_peak, "peak_source": "fgp_fp64_peak_probe DFMA chains, measured in this run"}},
+            "post_var": {"value": mv_total / t_pv, "unit": "points/s", "scaling": "strong", "m_total": mv_total, "ms": 1e3 * t_pv, "launches": pv_launches,
+                         "gather_check_rel_err": pv_err,
+                         "e2e": {"value": mv_total / t_pv_e2e, "unit": "points/s"},
+                         "roofline": {"bound": "hbm", "achieved": 32.0 * n * mv_total / 2 / t_pv / 1e9 / world, "peak": hbm_peak, "unit": "GB/s per GPU",
+                                      "frac": 32.0 * n * mv_total / 2 / t_pv / 1e9 / world / hbm_peak,
+                                      "alg_bytes_per_pair": 32 * n, "note": "two test points per complex length-n transform: 16n bytes written + 16n read per pair if the cross kernel and the (k, n-k) reduction are fused into the transform passes"}},
             "clocks": clocks}
+    line.update(extras)
     if not args.no_cpu_baseline and world == 1:
         torch.set_num_threads(os.cpu_count() or 1)
-        # bounded sample of the same workload, ~10-20 s of CPU work on the GPU box's host cores
-        r = cpu_reference_run(n, d, 60, 128)
-        line["cpu_baseline"] = {"value": r["fit_iters_per_s"], "unit": "iterations/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": "60 fit iterations of the oracle port at n=2^%d d=%d (%.1f s); post_mean on 128 points (%.1f s)" % (args.log2n, d, r["fit_s"], r.get("post_mean_s", 0.0)),
-                                "post_mean_points_per_s": r.get("post_mean_pts_per_s")}
+        # bounded sample of the same workload, ~10-30 s of CPU work on the GPU box's host cores
+        r = cpu_reference_run(n, d, 20, 16, 4)
+        line["cpu_baseline"] = cpu_baseline_block(r, torch.get_num_threads())
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -77,6 +77,8 @@ SIGNATURES = {
     "fgp_post_var_workspace_bytes": (_sz, [_i32, _i64, _i64]),
     "fgp_lattice_post_var": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fgp_dnb2_post_var": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp, _vp, _vp]),
+    "fgp_lattice_post_var_z_workspace_bytes": (_sz, [_i64, _i64]),
+    "fgp_lattice_post_var_z": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fgp_lattice_cross_kernel": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _f64, _vp, _vp, _vp]),
     "fgp_dnb2_cross_kernel": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp]),
     "fgp_kernel_pairs": (_i32, [_i32, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp]),
@@ -501,6 +503,24 @@ def post_var(family, xs, xtrain, alpha, t, scale, ls, lam):
                                             float(scale), _harr(_f64, ls), _dev(lam, torch.float64), ws.data_ptr(), out.data_ptr(),
                                             _stream()))
     return out
+
+
+def post_var_z(xs, z, shift, n, alpha, scale, ls, lam):
+    """Fused lattice posterior variance in generator form (fgp_lattice_post_var_z); falls back is the caller's business:
+    `post_var_z_supported(n)` says whether the size is a two-pass size."""
+    m, d = xs.shape
+    out = torch.empty((m,), dtype=torch.float64, device=xs.device)
+    ws = _workspace("pvarz", load().fgp_lattice_post_var_z_workspace_bytes(m, n), xs.device)
+    with torch.cuda.device(xs.device):
+        tab = fft_table(n, xs.device)
+        _check(load().fgp_lattice_post_var_z(_dev(xs, torch.float64), m, _harr(_u64, [int(v) for v in z]), _harr(_f64, [float(v) for v in shift]), n, d,
+                                             _harr(_i32, alpha), float(scale), _harr(_f64, ls), _dev(lam, torch.complex128), tab.data_ptr(),
+                                             ws.data_ptr(), out.data_ptr(), _stream()))
+    return out
+
+
+def post_var_z_supported(n):
+    return load().fgp_lattice_post_var_z_workspace_bytes(2, int(n)) > 0
 
 
 def fp64_peak_probe(iters, device):

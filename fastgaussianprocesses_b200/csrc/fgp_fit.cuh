@@ -43,8 +43,17 @@ __device__ __forceinline__ void write_effective(const FitLayout& c) {
 }
 
 // gradient w.r.t. raw element e of parameter group g (0 scale, 1 lengthscales, 2 noise); theta = exp(raw) => dtheta/draw = theta
-__device__ __forceinline__ double raw_grad(const FitLayout& c, const double* out, int g, int e) {
+// s_out: the (d+4) reduced terms of the only set in shared memory (B == 1), else NULL and `out` is read from global memory
+__device__ __forceinline__ double raw_grad(const FitLayout& c, const double* out, const double* s_out, int g, int e) {
   const int stride = c.d + 4;
+  if (s_out) {
+    if (g == 0) return s_out[3] * c.scale_B[0];
+    if (g == 2) return s_out[2] * c.noise_B[0];
+    const int j0 = c.n_ls_d == 1 ? 0 : e, j1 = c.n_ls_d == 1 ? c.d : e + 1;
+    double s = 0.0;
+    for (int j = j0; j < j1; ++j) s += s_out[4 + j] * c.ls_B[j];
+    return s;
+  }
   double s = 0.0;
   if (g == 0) {
     if (c.n_scale == 1) {
@@ -70,20 +79,29 @@ __device__ __forceinline__ double raw_grad(const FitLayout& c, const double* out
 
 // One fit() iteration's bookkeeping, executed by ONE CTA (any size >= 32 threads).  `out` is read with cache-global
 // loads so the function can run in the tail of the kernel that produced it.  hdr: ST_HEADER doubles of shared memory.
-__device__ __forceinline__ void fit_step_device(const FitLayout& c, const double* out, double* red, double* hdr, int* flags) {
+// hdr_loaded: the caller already copied the state header into hdr (and synchronised); s_out: see raw_grad.
+__device__ __forceinline__ void fit_step_device(const FitLayout& c, const double* out, double* red, double* hdr, int* flags, bool hdr_loaded = false,
+                                                const double* s_out = nullptr) {
   double* st = hdr;
-  for (int e = threadIdx.x; e < ST_HEADER; e += blockDim.x) hdr[e] = __ldcg(c.state + e);
-  __syncthreads();
+  if (!hdr_loaded) {
+    for (int e = threadIdx.x; e < ST_HEADER; e += blockDim.x) hdr[e] = __ldcg(c.state + e);
+    __syncthreads();
+  }
   if (st[ST_STOPPED] != 0.0) return;
   int& s_break = flags[0];
   int& s_newbest = flags[1];
   const int stride = c.d + 4;
   double v[2] = {0.0, 0.0};
-  for (int b = threadIdx.x; b < c.B; b += blockDim.x) {
-    v[0] += __ldcg(out + b * stride + 0);
-    v[1] += __ldcg(out + b * stride + 1);
+  if (s_out) {
+    v[0] = s_out[0];
+    v[1] = s_out[1];
+  } else {
+    for (int b = threadIdx.x; b < c.B; b += blockDim.x) {
+      v[0] += __ldcg(out + b * stride + 0);
+      v[1] += __ldcg(out + b * stride + 1);
+    }
+    block_sum<2>(v, red);
   }
-  block_sum<2>(v, red);
   if (threadIdx.x == 0) {
     const double wn = st[ST_WN], wl = st[ST_WL];
     const double loss = wn * v[0] + wl * v[1] + st[ST_HALF_CONST];
@@ -153,7 +171,7 @@ __device__ __forceinline__ void fit_step_device(const FitLayout& c, const double
       g = 2, le = e - c.n_scale - n_ls, raw = c.raw_noise + le;
       if (!c.req_noise) continue;
     }
-    double grad = raw_grad(c, out, g, le);
+    double grad = raw_grad(c, out, s_out, g, le);
     const double sp = grad * prev[e];
     double factor = 1.0;
     if (sp > 0.0) factor = etap;

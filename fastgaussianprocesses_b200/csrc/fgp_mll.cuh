@@ -362,40 +362,80 @@ __device__ __forceinline__ bool fit_stopped(const MllArgs& a) { return a.has_fit
 __device__ __forceinline__ double fit_stop_flag(const MllArgs& a) { return a.has_fit ? __ldcg(a.fit.state + ST_STOPPED) : 0.0; }
 
 // deterministic reduction of the per-CTA partial sums of set b into out[b] (fixed order); any CTA size that is a
-// multiple of 32.  Partials come from other CTAs: cache-global loads.
-__device__ __forceinline__ void finalize_set(const MllArgs& a, int b, double* red) {
+// multiple of 32.  Partials come from other CTAs: cache-global loads, all of them issued before the first reduction so that
+// the call costs ONE L2 round trip.  s_out (optional, d+4 shared doubles): the same values for a fit step run by this CTA.
+__device__ __forceinline__ void finalize_set(const MllArgs& a, int b, double* red, double* s_out = nullptr) {
   const int d = a.d;
   double* out = a.out + (int64_t)b * (d + 4);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  double s[3] = {0.0, 0.0, 0.0};
   {
-    double s[3] = {0.0, 0.0, 0.0};
     const double* p = a.partB + (int64_t)b * a.ctasB * 3;
     for (int c = threadIdx.x; c < a.ctasB; c += blockDim.x) {
       s[0] += __ldcg(p + c * 3 + 0);
       s[1] += __ldcg(p + c * 3 + 1);
       s[2] += __ldcg(p + c * 3 + 2);
     }
-    reduce_store<3>(s, 3, red, out);
+  }
+  // warp w reduces gradient components w, w + nwarp, ... over all pass-C CTAs, four components' loads in flight at a time; the
+  // first four are requested before the block reduction above is waited for
+  const double* p = a.partC + (int64_t)b * a.ctasA * (d + 1);
+  auto load4 = [&](int j0, double* v) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = j0 + k * nwarp;
+      v[k] = 0.0;
+      if (j <= d)
+        for (int c = lane; c < a.ctasA; c += 32) v[k] += __ldcg(p + (int64_t)c * (d + 1) + j);
+    }
+  };
+  double inv_scale = 1.0;
+  auto store4 = [&](int j0, const double* v) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = j0 + k * nwarp;
+      if (j > d) continue;  // uniform over the warp
+      double r = warp_sum(v[k]);
+      if (lane == 0) {
+        r = j == 0 ? r * inv_scale : r;
+        out[3 + j] = r;
+        if (s_out) s_out[3 + j] = r;
+      }
+    }
+  };
+  double v0[4];
+  if (a.want_grad) {
+    inv_scale = 1.0 / __ldcg(a.scale + b);
+    load4(warp, v0);
+  }
+  block_sum<3>(s, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      out[k] = s[k];
+      if (s_out) s_out[k] = s[k];
+    }
   }
   if (!a.want_grad) return;
-  // warp w reduces components w, w + nwarp, ... over all pass-C CTAs
-  const double* p = a.partC + (int64_t)b * a.ctasA * (d + 1);
-  const double inv_scale = 1.0 / a.scale[b];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int j = warp; j <= d; j += nwarp) {
-    double v = 0.0;
-    for (int c = lane; c < a.ctasA; c += 32) v += __ldcg(p + (int64_t)c * (d + 1) + j);
-    v = warp_sum(v);
-    if (lane == 0) out[3 + j] = j == 0 ? v * inv_scale : v;
+  store4(warp, v0);
+  for (int j0 = warp + 4 * nwarp; j0 <= d; j0 += 4 * nwarp) {
+    load4(j0, v0);
+    store4(j0, v0);
   }
 }
 
 // Tail of a fused fit iteration, called by every CTA of the iteration's LAST kernel after its partial sums are stored:
 // the last CTA of set b finalizes b; the last finalizer runs the fit step (loss, early stop, Rprop, new hyperparameters).
 // ctas_b: CTAs per set in this kernel; B: sets; two_pass: partial sums need reducing.
+// Critical path (it is serial: ~8 us of a 51 us iteration in round 1): one atomic ticket, one L2 round trip for the partial
+// sums, the fit step on values that are already in shared memory.  The state header is requested BEFORE the ticket (it was
+// written by the previous iteration's fit step, long ago), and with one set the second ticket is skipped.
 __device__ __forceinline__ void mll_fit_tail(const MllArgs& a, int b, int ctas_b, int B, bool two_pass, double* red) {
   __shared__ int s_last;
   __shared__ double s_hdr[ST_HEADER];
   __shared__ int s_flags[2];
+  __shared__ double s_out[FGP_MAX_D + 4];
+  const double pre_hdr = threadIdx.x < ST_HEADER ? __ldcg(a.fit.state + threadIdx.x) : 0.0;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -403,9 +443,17 @@ __device__ __forceinline__ void mll_fit_tail(const MllArgs& a, int b, int ctas_b
   }
   __syncthreads();
   if (!s_last) return;
+  const bool local = two_pass && B == 1;  // this CTA finalizes the only set: the fit step reads the sums from shared memory
   if (two_pass) {
     __threadfence();
-    finalize_set(a, b, red);
+    finalize_set(a, b, red, local ? s_out : nullptr);
+  }
+  if (threadIdx.x < ST_HEADER) s_hdr[threadIdx.x] = pre_hdr;
+  if (B == 1) {
+    if (threadIdx.x == 0) a.fit.tickets[1 + b] = 0u;
+    __syncthreads();
+    fit_step_device(a.fit, a.out, red, s_hdr, s_flags, true, local ? s_out : nullptr);
+    return;
   }
   __threadfence();
   __syncthreads();
@@ -419,7 +467,7 @@ __device__ __forceinline__ void mll_fit_tail(const MllArgs& a, int b, int ctas_b
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  fit_step_device(a.fit, a.out, red, s_hdr, s_flags);
+  fit_step_device(a.fit, a.out, red, s_hdr, s_flags, true, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -803,8 +851,11 @@ __device__ FGP_COOP_PHASE_ATTR void coop_phaseC(const MllArgs& a, Hyp& H, unsign
   if (a.has_fit) mll_fit_tail(a, b, a.ctasA, B, true, red);
 }
 
+#ifndef FGP_COOP_MINB
+#define FGP_COOP_MINB FGP_LB_BLOCKS
+#endif
 template <int DT, bool NET, bool A2, bool GEN>
-__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_coop_kernel(const __grid_constant__ MllArgs a, const int B) {
+__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_COOP_MINB) mll_coop_kernel(const __grid_constant__ MllArgs a, const int B) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
   __shared__ double red[kRed];

@@ -27,8 +27,12 @@ bool pdl_enabled() {
   return on;
 }
 
-// read on every call (a getenv): tests and tuning runs switch routes inside one process
-bool coop_enabled() { return env_int("FGP_COOP", 1) != 0; }
+// The persistent cooperative kernel is OPT-IN (FGP_COOP=1).  Measured on B200 (profiles/README.md, round 2): its phases walk the same
+// tiles as the three per-pass kernels, but the merged kernel needs more than the 128 registers that two 256-thread CTAs per SM allow
+// (1.4 KB of spills; 0.2 KB with factorised twiddles), and the globaltimer stamps show that a pass-A tile alone takes 9.6-12 us
+// even without spills -- launch gaps were never the bottleneck, the per-tile dependent chain is.  Best variant 51.1 us per
+// iteration against 53.2 us for the three launches from a CUDA graph.  Read on every call (a getenv): tests switch routes.
+bool coop_enabled() { return env_int("FGP_COOP", 0) != 0; }
 int coop_max_ctas() { return env_int("FGP_COOP_CTAS", 0); }
 
 #ifdef FGP_TIMING

@@ -212,6 +212,183 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, MINB) wht_fused(const double* 
   }
 }
 
+// ---- the same fused transform with TMA-staged, double-buffered tiles ---------------------------------------------------
+// wht_fused above is latency-bound: a CTA loads its tile with ordinary loads, waits, computes, stores, and only then draws the
+// next ticket (8.1 us per 32 KiB tile, profiles/README.md round 1).  Here the loads are bulk-asynchronous copies
+// (cp.async.bulk, the TMA engine; SASS UBLKCP) into a DENSE staging tile, completion is tracked by an mbarrier
+// (SYNCS.ARRIVE.TRANS64 / SYNCS.PHASECHK), and there are two staging tiles: while the CTA runs the rounds of tile k out of
+// its padded working tile, the TMA engine already fills the other staging tile with tile k+1 -- no registers and no warp
+// slots are held by loads in flight.  The first round of a tile reads the dense staging tile (conflict-free: in both
+// schedules consecutive threads read consecutive words) and writes the padded working tile; the last round stores to global
+// memory from registers.  Same round schedules as wht_passA / wht_passB, hence the same bits.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// spin on the phase parity; traps (a launch error, not a hang) if the copies never land
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (unsigned spins = 0;; ++spins) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spins > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct FusedTile {
+  unsigned b, idx;
+  bool phaseB, valid;
+};
+__device__ __forceinline__ FusedTile fused_decode(const FusedGeom& g, unsigned t) {
+  const unsigned lag = g.lag < g.B ? g.lag : g.B;
+  const unsigned head = lag * g.nA, mid = (g.B - lag) * (g.nA + g.nB), total = g.B * (g.nA + g.nB);
+  FusedTile o;
+  o.valid = t < total;
+  o.b = o.idx = 0;
+  o.phaseB = false;
+  if (!o.valid) return o;
+  if (t < head) {
+    o.b = t / g.nA, o.idx = t - o.b * g.nA;
+  } else if (t < head + mid) {
+    t -= head;
+    const unsigned slot = t / (g.nA + g.nB), w = t - slot * (g.nA + g.nB);
+    if (w < g.nA)
+      o.b = slot + lag, o.idx = w;
+    else
+      o.b = slot, o.idx = w - g.nA, o.phaseB = true;
+  } else {
+    t -= head + mid;
+    const unsigned slot = t / g.nB;
+    o.b = g.B - lag + slot, o.idx = t - slot * g.nB, o.phaseB = true;
+  }
+  return o;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) wht_fused_tma(const double* __restrict__ in, double* __restrict__ out, FusedGeom g, double scale,
+                                                         unsigned* __restrict__ ctl, int stage_doubles) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double* stg0 = (double*)smraw;                   // dense staging tiles (TMA destinations)
+  double* stg1 = stg0 + stage_doubles;
+  double* sm = stg1 + stage_doubles;               // padded working tile
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ unsigned s_t;
+  unsigned* done = ctl + 2;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int ncolsB = 1 << g.lntrB;
+  // warp 0 issues the copies of a tile into staging buffer `buf`; returns false (nothing issued) when a pass-B tile's item is
+  // not transformed yet and `block` is false
+  auto issue = [&](const FusedTile& t, int buf, bool block) -> bool {
+    bool ready = true;
+    if (t.phaseB) {
+      if (threadIdx.x == 0) {
+        if (block) {
+          while (ld_acquire_u32(&done[t.b]) < g.nA) __nanosleep(40);
+        } else {
+          ready = ld_acquire_u32(&done[t.b]) >= g.nA;
+        }
+      }
+      ready = __shfl_sync(0xffffffffu, (int)ready, 0) != 0;
+      if (!ready) return false;
+    }
+    double* dst = buf ? stg1 : stg0;
+    uint64_t* bar = &bars[buf];
+    const int64_t item0 = (int64_t)t.b << (g.l1 + g.l2);
+    const int lane = threadIdx.x & 31;
+    asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes (other CTAs' stores, our own reads of dst) before the async proxy
+    if (!t.phaseB) {
+      const unsigned tile_bytes = 8u << (g.l1 + g.lntrA);
+      if (lane == 0) mbar_arrive_expect_tx(bar, tile_bytes);
+      __syncwarp();
+      const double* src = in + item0 + ((int64_t)t.idx << (g.l1 + g.lntrA));
+      const unsigned chunk = tile_bytes / 32;  // one 1/32 of the tile per lane (>= 16 bytes for every geometry used)
+      tma_load_1d((char*)dst + (size_t)lane * chunk, (const char*)src + (size_t)lane * chunk, chunk, bar);
+    } else {
+      const unsigned row_bytes = 8u * ncolsB;
+      const int rows = 1 << g.l2;
+      if (lane == 0) mbar_arrive_expect_tx(bar, row_bytes * rows);
+      __syncwarp();
+      const double* src = out + item0 + ((int64_t)t.idx << g.lntrB);
+      for (int r = lane; r < rows; r += 32) tma_load_1d(dst + (size_t)r * ncolsB, src + ((int64_t)r << g.l1), row_bytes, bar);
+    }
+    return true;
+  };
+  auto draw = [&]() -> FusedTile {
+    __syncthreads();
+    if (threadIdx.x == 0) s_t = atomicAdd(&ctl[0], 1u);
+    __syncthreads();
+    return fused_decode(g, s_t);
+  };
+  unsigned parity[2] = {0u, 0u};
+  int buf = 0;
+  FusedTile cur = draw();
+  if (cur.valid && threadIdx.x < 32) issue(cur, 0, true);
+  while (cur.valid) {
+    const FusedTile nxt = draw();
+    bool issued = false;
+    if (nxt.valid && threadIdx.x < 32) issued = issue(nxt, buf ^ 1, false);
+    mbar_wait(&bars[buf], parity[buf]);
+    parity[buf] ^= 1u;
+    const double* stg = buf ? stg1 : stg0;
+    const int64_t item0 = (int64_t)cur.b << (g.l1 + g.l2);
+    if (!cur.phaseB) {
+      const int64_t g0 = item0 + ((int64_t)cur.idx << (g.l1 + g.lntrA));
+      const int l1 = g.l1;
+      auto gld = [&](int tr, int e) -> double { return stg[(tr << l1) + e] * scale; };
+      auto gst = [&](int tr, int e, double v) { out[g0 + ((int64_t)tr << l1) + e] = v; };
+      block_wht_io<false>(sm, g.l1, g.lntrA, g.LPA, wht_sched_coalesced(g.l1), gld, gst);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&done[cur.b], 1u);
+      }
+    } else {
+      double* base = out + item0 + ((int64_t)cur.idx << g.lntrB);
+      const int l1 = g.l1, lc = g.lntrB;
+      auto gld = [&](int tr, int e) -> double { return stg[(e << lc) + tr]; };
+      auto gst = [&](int tr, int e, double v) { base[((int64_t)e << l1) + tr] = v; };
+      block_wht_io<true>(sm, g.l2, g.lntrB, g.LPB, wht_sched_up(g.l2), gld, gst);
+    }
+    if (nxt.valid && threadIdx.x < 32) {
+      // uniform over warp 0: `issued` came out of a warp-wide shuffle
+      if (!issued) issue(nxt, buf ^ 1, true);
+    }
+    buf ^= 1;
+    cur = nxt;
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&ctl[1], 1u) == gridDim.x - 1) {
+      for (unsigned i = 0; i < g.B; ++i) done[i] = 0u;
+      ctl[0] = 0u;
+      __threadfence();
+      ctl[1] = 0u;
+    }
+  }
+}
+
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
   if (bytes > 24 * 1024) {  // static shared memory counts towards the 48 KiB default limit
@@ -406,6 +583,17 @@ int fgp_fwht_fused(const double* in_dev, double* out_dev, int64_t batch, int64_t
   const int threads = g.threadsA > g.threadsB ? g.threadsA : g.threadsB;
   const double scale = 1.0 / sqrt((double)n);
   const int64_t tiles = (int64_t)f.B * (f.nA + f.nB);
+  // TMA-staged variant: two dense staging tiles + the padded working tile; rows of a pass-B tile must be >= 16 bytes
+  static const int no_tma = env_int("FGP_FUSED_NO_TMA", 0);
+  const int tile_log = (g.l1 + g.lntrA) > (g.l2 + g.lntrB) ? (g.l1 + g.lntrA) : (g.l2 + g.lntrB);
+  const size_t smem_tma = 2 * (sizeof(double) << tile_log) + smem;
+  if (!no_tma && g.lntrB >= 1 && (g.l1 + g.lntrA) >= 9 && smem_tma <= 110 * 1024 && (((uintptr_t)in_dev | (uintptr_t)out_dev) & 15) == 0) {
+    if ((rc = set_smem(wht_fused_tma<2>, smem_tma))) return rc;
+    const int64_t grid = tiles < (int64_t)sms * 2 ? tiles : (int64_t)sms * 2;
+    wht_fused_tma<2><<<(unsigned)grid, threads, smem_tma, st>>>(in_dev, out_dev, f, scale, ctl_dev, 1 << tile_log);
+    FGP_LAUNCH_NAMED("wht_fused_tma", st);
+    return FGP_OK;
+  }
   if (smem <= 40 * 1024) {
     if ((rc = set_smem(wht_fused<FGP_LB_BLOCKS_R>, smem))) return rc;
     const int64_t grid = tiles < (int64_t)sms * FGP_LB_BLOCKS_R ? tiles : (int64_t)sms * FGP_LB_BLOCKS_R;

@@ -1424,7 +1424,13 @@ class AbstractFastGP(torch.nn.Module):
         if x.shape[0] == 0:
             outs = [torch.empty((0,), dtype=torch.float64, device=self.device) for b in range(B)]
         else:
-            outs = [_lib.post_var(self._FAMILY, x, xpts, self._alpha_list, self._t, scale_B[b], ls_B[b], lam[b]) for b in range(B)]
+            # lattice with a known generating vector: fused generator form (the points are regenerated inside the first transform pass)
+            zgen = self._zgen is not None and all(int(v) < (1 << 32) for v in self._zgen) and os.environ.get("FGP_B200_NO_PVZ") != "1" and _lib.post_var_z_supported(n)
+            if zgen:
+                shift = self.seqs[0].shift
+                outs = [_lib.post_var_z(x, self._zgen, shift, n, self._alpha_list, scale_B[b], ls_B[b], lam[b]) for b in range(B)]
+            else:
+                outs = [_lib.post_var(self._FAMILY, x, xpts, self._alpha_list, self._t, scale_B[b], ls_B[b], lam[b]) for b in range(B)]
         pvar = torch.stack(outs, 0).reshape(tuple(pshape) + (1, x.shape[0]))
         return pvar[..., 0, :] if inttask else pvar
 

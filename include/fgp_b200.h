@@ -230,6 +230,14 @@ int fgp_lattice_post_var(const double* xs_dev, int64_t m, const double* x_dev, i
 int fgp_dnb2_post_var(const double* xs_dev, int64_t m, const int64_t* xb_dev, int64_t n, int d,
                       const int* alpha_host, int t, double scale, const double* ls_host, const double* lam_dev,
                       void* work_dev, double* pvar_dev, fgp_stream_t stream);
+/* Fused generator form of fgp_lattice_post_var for two-pass sizes (n > 2^12): the training points are regenerated from the point
+ * index, x_i - shift = frac(phi2(i) z), inside the first transform pass (nothing but the test points is read), and the reduction
+ * over the spectral pairs (k, n-k) runs in the epilogue of the second pass (mirror-paired column tiles), so a pair of test points
+ * moves 32 n bytes instead of ~96 n and takes two kernels instead of four.  z_host[d] < 2^32, shift_host[d] in [0,1). */
+size_t fgp_lattice_post_var_z_workspace_bytes(int64_t m, int64_t n);
+int fgp_lattice_post_var_z(const double* xs_dev, int64_t m, const uint64_t* z_host, const double* shift_host, int64_t n, int d,
+                           const int* alpha_host, double scale, const double* ls_host, const double* lam_dev, const void* table_dev,
+                           void* work_dev, double* pvar_dev, fgp_stream_t stream);
 /* dense cross-kernel tile K[i,a] = k(xs_i, X_a) (m,n) for post_cov / user-facing kernel() calls */
 int fgp_lattice_cross_kernel(const double* xs_dev, int64_t m, const double* x_dev, int64_t n, int d,
                              const int* alpha_host, double scale, const double* ls_host, double* k_dev,

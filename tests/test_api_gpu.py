@@ -56,33 +56,35 @@ def test_api_matches_reference_fixture(case, path, monkeypatch):
     assert pm.shape == (xt.shape[0],)
     ymax = float(np.abs(g["y"]).max())
     # pmean = sum of n terms of size |coeffs| ~ |y|/noise cancelling down to |y|: compare on the scale of y
-    assert float((pm.cpu() - torch.from_numpy(g["pmean0"])).abs().max()) < 1e-8 * ymax
+    # achieved (profiles/PARITY_r02.json, norm-wise relative): pmean <= 3.3e-11, pvar <= 9.3e-11, both on lattice_d2_n1024_a2 whose
+    # spectrum spans 11 decades (reference self-spread there: 8.3e-12 / 1.4e-11, profiles/r2_reference_spread.json)
+    assert rel(pm, g["pmean0"]) < 1e-10
     pv = gp.post_var(xt)
     sc = float(g["scale0"][0])
-    assert float((pv.cpu() - torch.from_numpy(g["pvar0"])).abs().max()) < 1e-8 * max(float(np.abs(g["pvar0"]).max()), sc * 1e-6) + 1e-9 * sc
+    assert rel(pv, g["pvar0"]) < 2e-10
     mcov = g["pcov0"].shape[0]
     pc = gp.post_cov(xt[:mcov], xt[:mcov // 2])
     assert pc.shape == g["pcov0"].shape
-    assert float((pc.cpu() - torch.from_numpy(g["pcov0"])).abs().max()) < 1e-7 * sc
+    assert rel(pc, g["pcov0"]) < 2e-10  # achieved <= 7.4e-11
     pcs = gp.post_cov(xt[:mcov], xt[:mcov])
     assert (pcs.diagonal() >= 0).all()
     assert torch.allclose(pcs.diagonal(), pv[:mcov], atol=1e-7 * sc)
     assert abs(float(gp.post_cubature_mean()) - float(g["pcmean0"])) < 1e-8 * ymax
     assert abs(float(gp.post_cubature_var()) - float(g["pcvar0"])) < 1e-8 * sc
     pvf = gp.post_var(xt[:64], n=2 * n)
-    assert float((pvf.cpu() - torch.from_numpy(g["pvar0_future"])).abs().max()) < 1e-8 * sc
+    assert rel(pvf, g["pvar0_future"]) < 2e-9  # achieved 6.0e-10 on lattice_d2_n1024_a2 (spectrum of the doubled point set), <= 4.2e-11 elsewhere
     # fit: same loss trajectory, same stopping iteration, same hyperparameters
     data = gp.fit(iterations=int(g["fit_iterations"]), verbose=0, store_hists=True)
     assert data["iterations"] == int(g["fit_last_iteration"])
-    assert np.allclose(data["loss_hist"].numpy(), g["loss_hist"], rtol=1e-8, atol=0)
-    assert rel(data["scale_hist"], g["scale_hist"]) < 1e-8
-    assert rel(data["lengthscales_hist"], g["lengthscales_hist"]) < 1e-8
-    assert rel(gp.scale, g["scale1"]) < 1e-8
-    assert rel(gp.lengthscales, g["lengthscales1"]) < 1e-8
-    assert float((gp.post_mean(xt).cpu() - torch.from_numpy(g["pmean1"])).abs().max()) < 1e-6 * ymax
-    pv1 = gp.post_var(xt)
-    sc1 = float(g["scale1"][0])
-    assert float((pv1.cpu() - torch.from_numpy(g["pvar1"])).abs().max()) < 1e-6 * max(float(np.abs(g["pvar1"]).max()), sc1 * 1e-6) + 1e-8 * sc1
+    # achieved: loss trajectory <= 7.7e-11, hyperparameter trajectories <= 2e-16 (Rprop only uses the sign of the gradient),
+    # posterior after the fit <= 2.5e-11 / 9.7e-11
+    assert rel(data["loss_hist"], g["loss_hist"]) < 1e-10
+    assert rel(data["scale_hist"], g["scale_hist"]) < 1e-10
+    assert rel(data["lengthscales_hist"], g["lengthscales_hist"]) < 1e-10
+    assert rel(gp.scale, g["scale1"]) < 1e-10
+    assert rel(gp.lengthscales, g["lengthscales1"]) < 1e-10
+    assert rel(gp.post_mean(xt), g["pmean1"]) < 1e-10
+    assert rel(gp.post_var(xt), g["pvar1"]) < 2e-10
 
 
 @pytest.mark.parametrize("case", ["lattice_d2_n1024_a2", "dnb2_d2_n1024_a2"])
@@ -371,10 +373,11 @@ def test_masked_mll_fit_equals_fit_on_the_selected_outputs():
 
 @pytest.mark.parametrize("family,d,m,batch,iters", [("lattice", 8, 20, (), 12), ("lattice", 4, 14, (), 25), ("lattice", 2, 13, (3,), 20), ("lattice", 8, 18, (5,), 6),
                                                     ("dnb2", 4, 16, (), 20), ("dnb2", 3, 14, (2,), 15), ("lattice", 3, 16, (), 40)])
-def test_persistent_kernel_fit_is_bit_identical_to_the_three_launch_route(monkeypatch, family, d, m, batch, iters):
+def test_persistent_kernel_fit_matches_the_three_launch_route(monkeypatch, family, d, m, batch, iters):
     """fgp_fit_iterations (ONE cooperative launch per chunk of iterations: grid barriers between the passes, the fit step in the
-    tail, early stop on the device) walks the same tiles with the same arithmetic as the per-pass kernels, so the whole fit
-    trajectory -- losses, hyperparameter histories, stopping iteration, final parameters -- must agree to the last bit."""
+    tail, early stop on the device) walks the same tiles with the same arithmetic as the per-pass kernels; only the number of
+    threads that share a tile's partial sums can differ (the persistent kernel runs every pass with one block size), so the
+    whole fit trajectory -- losses, hyperparameter histories, stopping iteration, final parameters -- agrees to round-off."""
     import fastgaussianprocesses_b200 as fgp
     n = 1 << m
 
@@ -392,12 +395,12 @@ def test_persistent_kernel_fit_is_bit_identical_to_the_three_launch_route(monkey
             y = torch.stack([y * (1.0 + 0.3 * k) + 0.1 * k * torch.sin(4 * np.pi * x[:, 0]) for k in range(batch[0])])
         gp.add_y_next(y)
         data = gp.fit(iterations=iters, verbose=0, store_hists=True, stop_crit_wait_iterations=7)
-        assert gp._fused_loop.multi == coop
+        assert gp._fused_loop.multi == coop  # FGP_COOP=1 opts into the persistent kernel (the default is three launches per iteration)
         return data, gp.raw_scale.detach().clone(), gp.raw_lengthscales.detach().clone()
 
     d1, s1, l1 = run(True)
     d0, s0, l0 = run(False)
     assert d1["iterations"] == d0["iterations"]
     for key in ("loss_hist", "scale_hist", "lengthscales_hist"):
-        assert torch.equal(d1[key], d0[key]), key
-    assert torch.equal(s1, s0) and torch.equal(l1, l0)
+        assert rel(d1[key], d0[key]) < 1e-12, key
+    assert rel(s1, s0) < 1e-12 and rel(l1, l0) < 1e-12

@@ -1,0 +1,158 @@
+"""Achieved parity errors, per quantity and per case, of the CUDA path against (a) the fixtures written by the unmodified
+reference (tests/golden/) and (b) the CPU oracle port at sizes up to the headline n = 2^20.  Run on the GPU box:
+
+    python tools/parity_report.py > gpurun_out/PARITY.json        (committed as profiles/PARITY_r02.json)
+
+Error measure: max |a - b| / max |b| (norm-wise relative), the measure of north_star's 1e-10.  profiles/
+r2_reference_spread.json holds the spread of the reference against ITSELF under a second evaluation order -- the floor of
+what a comparison against a fixture can resolve."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+torch.set_default_dtype(torch.float64)
+import fastgaussianprocesses_b200 as fgp  # noqa: E402
+from fastgaussianprocesses_b200 import _lib as L  # noqa: E402
+from oracle import primitives as P  # noqa: E402
+from oracle.fgp_oracle import OracleFastGP  # noqa: E402
+
+dev = "cuda:0"
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).detach().cpu(), torch.as_tensor(b).detach().cpu()
+    if a.is_complex() != b.is_complex():
+        a, b = a.to(torch.complex128), b.to(torch.complex128)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+
+
+def make_gp(g, **kw):
+    fam, d, alpha = str(g["family"]), int(g["d"]), int(g["alpha"])
+    args = dict(alpha=alpha, scale=float(g["scale0"][0]), lengthscales=torch.from_numpy(g["lengthscales0"]).clone(), noise=float(g["noise0"][0]), device=dev)
+    args.update(kw)
+    if fam == "lattice":
+        return fgp.FastGPLattice(fgp.Lattice(d, generating_vector=g["z"], shift=g["shift"]), **args)
+    return fgp.FastGPDigitalNetB2(fgp.DigitalNetB2(d, generating_matrices=g["C"], dshift=g["dshift"], t=int(g["t"])), **args)
+
+
+def fixture_case(name):
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    n, d = int(g["n"]), int(g["d"])
+    gp = make_gp(g)
+    x = gp.get_x_next(n)
+    row = {"points_bit_exact": bool(np.array_equal(x.cpu().numpy(), g["x"]))}
+    gp.add_y_next(torch.from_numpy(g["y"]))
+    row["k1parts"] = rel(gp.get_k1parts(0, 0)[:, 0, 0, :], g["k1parts"])
+    row["lam0"] = rel(gp.get_lam(0, 0), g["lam0"])
+    row["ytilde"] = rel(gp.get_ytilde(0), g["ytilde"])
+    cache = gp.get_inv_log_det_cache()
+    norm, logdet = cache.get_norm_term_logdet_term()
+    loss = 0.5 * (norm.sum() + logdet.sum() + n * np.log(2 * np.pi))
+    loss.backward()
+    row["loss0"] = abs(float(loss) - float(g["loss0"])) / abs(float(g["loss0"]))
+    row["norm_term0"] = rel(norm, g["norm_term0"])
+    row["logdet0"] = rel(logdet, g["logdet0"])
+    row["grad_raw_scale0"] = rel(gp.raw_scale.grad, g["grad_raw_scale0"])
+    row["grad_raw_lengthscales0"] = rel(gp.raw_lengthscales.grad, g["grad_raw_lengthscales0"])
+    gp.zero_grad()
+    xt = torch.from_numpy(g["xtest"])
+    row["coeffs0"] = rel(gp.coeffs, g["coeffs0"])
+    row["pmean0"] = rel(gp.post_mean(xt), g["pmean0"])
+    row["pvar0"] = rel(gp.post_var(xt), g["pvar0"])
+    mcov = g["pcov0"].shape[0]
+    row["pcov0"] = rel(gp.post_cov(xt[:mcov], xt[:mcov // 2]), g["pcov0"])
+    row["pcmean0_abs_over_ymax"] = float(abs(float(gp.post_cubature_mean()) - float(g["pcmean0"])) / np.abs(g["y"]).max())  # the integral itself can be 0
+    row["pcvar0_abs"] = float(abs(float(gp.post_cubature_var()) - float(g["pcvar0"])))
+    row["pvar0_future"] = rel(gp.post_var(xt[:64], n=2 * n), g["pvar0_future"])
+    data = gp.fit(iterations=int(g["fit_iterations"]), verbose=0, store_hists=True)
+    row["fit_same_stop_iteration"] = bool(data["iterations"] == int(g["fit_last_iteration"]))
+    if row["fit_same_stop_iteration"]:
+        row["loss_hist"] = rel(data["loss_hist"], g["loss_hist"])
+        row["scale_hist"] = rel(data["scale_hist"], g["scale_hist"])
+        row["lengthscales_hist"] = rel(data["lengthscales_hist"], g["lengthscales_hist"])
+    row["pmean1"] = rel(gp.post_mean(xt), g["pmean1"])
+    row["pvar1"] = rel(gp.post_var(xt), g["pvar1"])
+    return row
+
+
+def oracle_case(family, d, m, alpha=2, noise=1e-6, t=52, pm_points=64, pv_points=16, fit_iters=0):
+    """CUDA path against the CPU oracle port on the same seeded inputs, up to the headline size."""
+    n = 1 << m
+    t0 = time.time()
+    ls0 = torch.from_numpy(np.random.default_rng(d * 100 + m).uniform(0.3, 1.2, size=d))
+    if family == "lattice":
+        seq = fgp.Lattice(d, seed=7)
+        gp = fgp.FastGPLattice(seq, device=dev, alpha=alpha, noise=noise, scale=1.7, lengthscales=ls0.clone())
+        xh = P.lattice_points(seq.gen_vec, seq.shift, 0, n)
+        o = OracleFastGP("lattice", xh, alpha=alpha, noise=noise, scale=1.7, lengthscales=ls0.clone())
+    else:
+        seq = fgp.DigitalNetB2(d, seed=7, t=t)
+        gp = fgp.FastGPDigitalNetB2(seq, device=dev, alpha=alpha, noise=noise, scale=1.7, lengthscales=ls0.clone())
+        xbh, xh = P.dnb2_points(seq.gen_mats, seq.rshift, seq.t, 0, n)
+        o = OracleFastGP("dnb2", xh, xb=xbh, t=seq.t, alpha=alpha, noise=noise, scale=1.7, lengthscales=ls0.clone())
+    x = gp.get_x_next(n)
+    row = {"points_bit_exact": bool(np.array_equal(x.cpu().numpy(), xh))}
+    j = torch.arange(1, d + 1, device=x.device, dtype=x.dtype)
+    y = torch.cos(2 * np.pi * x).mul(1.0 / j).sum(1) + torch.sin(2 * np.pi * x[:, 0]) * torch.cos(2 * np.pi * x[:, -1])
+    gp.add_y_next(y)
+    o.add_y(y.cpu())
+    norm, logdet = gp.get_inv_log_det_cache().get_norm_term_logdet_term()
+    loss = 0.5 * (norm.sum() + logdet.sum() + n * np.log(2 * np.pi))
+    loss.backward()
+    lo = o.mll_loss()[0]
+    lo.backward()
+    row["loss"] = abs(float(loss) - float(lo)) / abs(float(lo))
+    row["grad_raw_scale"] = rel(gp.raw_scale.grad, o.raw_scale.grad)
+    row["grad_raw_lengthscales"] = rel(gp.raw_lengthscales.grad, o.raw_lengthscales.grad)
+    gp.zero_grad()
+    with torch.no_grad():
+        row["lam"] = rel(gp.get_lam(0, 0), o.lam().detach())
+        co = o.coeffs().detach()
+        row["coeffs"] = rel(gp.coeffs, co)
+        xt = torch.rand((max(pm_points, pv_points), d), generator=torch.Generator().manual_seed(17))
+        if pm_points:
+            row["post_mean"] = rel(gp.post_mean(xt[:pm_points]), o.post_mean(xt[:pm_points], coeffs=co))
+        if pv_points:
+            pvo = o.post_var(xt[:pv_points])
+            pv = gp.post_var(xt[:pv_points]).cpu()
+            row["post_var"] = rel(pv, pvo)
+            row["post_var_abs_over_scale"] = float((pv - pvo).abs().max() / 1.7)
+    row["seconds"] = round(time.time() - t0, 1)
+    return row
+
+
+def main():
+    out = {"measure": "max|a-b| / max|b| against the unmodified reference's fixtures (fixtures) and the CPU oracle port (oracle)",
+           "device": torch.cuda.get_device_name(0), "fixtures": {}, "oracle": {}}
+    for f in sorted(os.listdir(GOLDEN)):
+        if f.endswith(".npz") and not f.startswith(("mt_", "dv_", "sg_")):
+            out["fixtures"][f[:-4]] = fixture_case(f[:-4])
+    cases = [("lattice", 8, 14, 2, 1e-6), ("lattice", 2, 13, 3, 1e-6), ("lattice", 5, 16, 2, 1e-4), ("dnb2", 4, 16, 2, 1e-6), ("dnb2", 16, 13, 2, 1e-6),
+             ("dnb2", 3, 16, 3, 1e-6), ("lattice", 8, 18, 2, 1e-6), ("lattice", 8, 20, 2, 1e-6), ("lattice", 8, 20, 2, 1e-8), ("dnb2", 8, 20, 2, 1e-6)]
+    if "--quick" in sys.argv:
+        cases = cases[:4]
+    for fam, d, m, alpha, noise in cases:
+        big = m >= 20
+        out["oracle"]["%s_d%d_n2^%d_a%d_noise%g" % (fam, d, m, alpha, noise)] = oracle_case(fam, d, m, alpha, noise, pm_points=64, pv_points=8 if big else 32)
+    if "--quick" not in sys.argv:  # configs[3]: net d=16, n = 2^22 (MLL + gradient only: the port's posterior at this size takes minutes)
+        out["oracle"]["dnb2_d16_n2^22_a2_noise1e-06"] = oracle_case("dnb2", 16, 22, 2, 1e-6, pm_points=16, pv_points=0)
+    worst = {}
+    for grp in ("fixtures", "oracle"):
+        for row in out[grp].values():
+            for k, v in row.items():
+                if isinstance(v, float) and k != "seconds":
+                    worst[grp + ":" + k] = max(worst.get(grp + ":" + k, 0.0), v)
+    out["worst"] = worst
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -317,7 +317,7 @@ def main():
         evs.append((e0, e1))
     g0, g1 = ev(), ev()
     g0.record()
-    fitted = D.gather_fit_results(torch.cat([gp.raw_scale.data.reshape(-1), gp.raw_lengthscales.data.reshape(-1), stepper.state[:9]]))
+    fitted = D.gather_fit_results(torch.cat([stepper.ctx.raw[0].reshape(-1), stepper.ctx.raw[1].reshape(-1), stepper.state[:9]]))
     g1.record()
     barrier()
     step_ms = [a.elapsed_time(b) for a, b in evs]
@@ -424,8 +424,9 @@ def main():
         barrier()
         e0, e1 = ev(), ev()
         e0.record()
-        sb.replay(Kb) if sb.multi else [sb.step() for _ in range(Kb)]
-        res_b = D.gather_fit_results(torch.cat([gpb.raw_scale.data.reshape(Bl, -1), gpb.raw_lengthscales.data.reshape(Bl, -1)], 1))
+        for _ in range(Kb):
+            sb.step()
+        res_b = D.gather_fit_results(torch.cat([sb.ctx.raw[0].reshape(Bl, -1), sb.ctx.raw[1].reshape(Bl, -1)], 1))
         e1.record()
         barrier()
         t_b = max_over_ranks(e0.elapsed_time(e1) * 1e-3)

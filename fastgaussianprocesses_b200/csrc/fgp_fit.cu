@@ -13,8 +13,14 @@
 
 namespace fgp {
 
-__global__ void __launch_bounds__(256) fit_init_kernel(FitLayout c) {
+struct FitHeader {
+  double v[ST_HEADER];
+};
+
+__global__ void __launch_bounds__(256) fit_init_kernel(FitLayout c, FitHeader h) {
   double* st = c.state;
+  if (threadIdx.x < ST_HEADER) st[threadIdx.x] = h.v[threadIdx.x];  // options by value: no host copy, no synchronisation
+  __syncthreads();
   double* prev = st + ST_HEADER;
   double* step = prev + c.P;
   for (int e = threadIdx.x; e < c.P; e += blockDim.x) {
@@ -103,8 +109,9 @@ int fgp_fit_init(const fgp_fit_layout* layout, const fgp_fit_options* opt, fgp_s
   if (rc) return rc;
   FGP_REQUIRE(opt, "fit_init: null options");
   FGP_REQUIRE(opt->iterations >= 0 && opt->stop_wait > 0 && opt->lr > 0.0, "fit_init: bad options");
-  double h[fgp::ST_HEADER];
-  memset(h, 0, sizeof(h));
+  fgp::FitHeader hdr;
+  double* h = hdr.v;
+  memset(h, 0, sizeof(hdr));
   h[fgp::ST_ITERATIONS] = (double)opt->iterations;
   h[fgp::ST_STOP_WAIT] = (double)opt->stop_wait;
   h[fgp::ST_LOGTOL] = opt->logtol;
@@ -117,10 +124,7 @@ int fgp_fit_init(const fgp_fit_layout* layout, const fgp_fit_options* opt, fgp_s
   h[fgp::ST_SMIN] = opt->step_min;
   h[fgp::ST_SMAX] = opt->step_max;
   h[fgp::ST_HIST_CAP] = (double)opt->hist_capacity;
-  // the header is tiny: a by-value kernel parameter would also do, but a stream-ordered copy keeps the graph generic
-  FGP_CUDA(cudaMemcpyAsync(c.state, h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream));
-  FGP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // h lives on this stack frame
-  fgp::fit_init_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(c);
+  fgp::fit_init_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(c, hdr);
   FGP_LAUNCH_CHECK();
   return FGP_OK;
 }

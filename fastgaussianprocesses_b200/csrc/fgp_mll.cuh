@@ -18,6 +18,10 @@
 #include "fgp_transform.cuh"
 #include "fgp_fit.cuh"
 
+#ifndef FGP_K1_SIGMA
+#define FGP_K1_SIGMA 1  // six-slot first-column evaluation for lattice / alpha = 2 / generator mode (Hyp::sig); 0: the nine-slot form
+#endif
+
 namespace fgp {
 
 constexpr int kRed = 32 * 4;  // doubles of reduction scratch (block_sum<4>)
@@ -94,6 +98,10 @@ struct Hyp {  // per-CTA hyperparameters and first point, staged in shared memor
   double scale, noise;
   double ls[FGP_MAX_D];
   double x0[FGP_MAX_D];     // lattice
+  // lattice, alpha = 2, generator mode: 1 + ls_j c B_4(t) = A_j (1 - h^2), h = (sig_j t)(sig_j - sig_j t), A_j = 1 + ls_j q0_j,
+  // sig_j = (ls_j |q2_j| / A_j)^(1/4); sig32 = sig 2^-32 (the integer-to-[0,1) scaling folded in), pref = scale prod_j A_j.
+  // Six FP64 issue slots per (point, dimension) in the first-column evaluation instead of nine (post_mean's form of the kernel).
+  double sig[FGP_MAX_D], sig32[FGP_MAX_D], pref;
   uint64_t xb0[FGP_MAX_D];  // net
   // net generator mode: xb_i ^ xb_0 of tile element e = TA[j][e & 63] ^ TB[j][e >> 6] (shared-memory tables of XOR folds,
   // dimension-major so that consecutive threads read consecutive words)
@@ -141,6 +149,19 @@ __device__ __forceinline__ void load_hyp(Hyp& H, const MllArgs& a, int b) {
   if (threadIdx.x == 0) {
     H.scale = __ldcg(a.scale + b);
     H.noise = __ldcg(a.noise + b);
+  }
+  if (!NET && !a.x) {  // generator mode: constants of the six-slot alpha = 2 form (unused by the other variants)
+    if (threadIdx.x == 0) {
+      double pref = __ldcg(a.scale + b);
+      for (int j = 0; j < a.d; ++j) pref *= fma(__ldcg(a.ls + (int64_t)b * a.d + j), a.P.q[j][0], 1.0);
+      H.pref = pref;
+    }
+    for (int j = threadIdx.x; j < a.d; j += blockDim.x) {
+      const double l = __ldcg(a.ls + (int64_t)b * a.d + j);
+      const double sg = sqrt(sqrt(-l * a.P.q[j][2] / fma(l, a.P.q[j][0], 1.0)));
+      H.sig[j] = sg;
+      H.sig32[j] = sg * 0x1.0p-32;
+    }
   }
   for (int j = threadIdx.x; j < a.d; j += blockDim.x) {
     H.ls[j] = __ldcg(a.ls + (int64_t)b * a.d + j);
@@ -282,6 +303,16 @@ template <int DT, bool NET, bool A2, bool GEN>
 __device__ __forceinline__ double point_k1(const MllArgs& a, const Hyp& H, int64_t i) {
   if constexpr (DT == 0) {
     return point_k1_generic<NET, GEN>(a, H, i);
+  } else if constexpr (FGP_K1_SIGMA && GEN && !NET && A2) {
+    const uint32_t rev = __brev((uint32_t)i);
+    double k = H.pref;
+#pragma unroll
+    for (int j = 0; j < DT; ++j) {
+      const double ts = (double)(rev * (uint32_t)a.z.v[j]) * H.sig32[j];
+      const double h = ts * (H.sig[j] - ts);
+      k *= fma(-h, h, 1.0);
+    }
+    return k;
   } else {
     double p[DT];
     point_parts<DT, NET, A2, GEN>(a, H, i, p);
@@ -329,6 +360,30 @@ __device__ __forceinline__ double2 spectral_c(double2 lam, double ysq, double wn
   const double gb = fma(-2.0 * a * b, yi2, b * li);
   s[2] += ga;
   return make_double2(ga, gb);
+}
+// The same without the logarithm: |lam|^2 goes into a running product kept as (mantissa product, exponent sum), so that a thread
+// takes ONE log for all its eigenvalues (a double-precision log is ~40 FP64 instructions, a third of the epilogue's work); exact
+// range handling: m2 = f 2^e with f in [0.5, 1), log prod m2 = log prod f + ln2 sum e.
+__device__ __forceinline__ double2 spectral_c_prod(double2 lam, double ysq, double wn, double wl, double& s0, double& s2, double& mant, int& ex) {
+  const double a = lam.x, b = lam.y;
+  const double m2 = fma(a, a, b * b);
+  const double inv = 1.0 / m2;
+  s0 = fma(ysq, a * inv, s0);
+  const long long bits = __double_as_longlong(m2);
+  ex += (int)((bits >> 52) & 0x7ff) - 1022;
+  mant *= __longlong_as_double((bits & 0x800fffffffffffffLL) | 0x3fe0000000000000LL);
+  const double yi2 = wn * ysq * inv * inv;
+  const double li = wl * inv;
+  const double ga = fma(yi2, fma(b, b, -a * a), a * li);
+  const double gb = fma(-2.0 * a * b, yi2, b * li);
+  s2 += ga;
+  return make_double2(ga, gb);
+}
+__device__ __forceinline__ double logprod_flush(double& mant, int& ex) {
+  const double v = fma((double)ex, 0.69314718055994530942, log(mant));
+  mant = 1.0;
+  ex = 0;
+  return v;
 }
 __device__ __forceinline__ double spectral_r(double lam, double ysq, double wn, double wl, double* s) {
   const double inv = 1.0 / lam;
@@ -664,22 +719,29 @@ __device__ __forceinline__ void passB_tile(const MllArgs& a, unsigned char* smra
         return make_double2(v.x, mir ? -v.y : v.y);
       }, SmemTag{});
       __syncthreads();
+      // a thread stays in one column (the block size is a multiple of the columns per tile), so its weight cw is a constant and the
+      // log-determinant terms of its eigenvalues can be taken as one log of their product
+      double mant = 1.0, t0 = 0.0, t2 = 0.0;
+      int ex = 0, cnt = 0;
+      const int qt = q0 + (threadIdx.x & ((1 << lntr) - 1));
+      const double cwt = (qt == 0 || qt == half1) ? 1.0 : (qt < half1 ? 2.0 : 0.0);
       tile_map_c<true>(SmemC{sm, LP}, l2, lntr, [&](int tr, int r, double2 lam) -> double2 {
         const int64_t k = ((int64_t)r << l1) + tr;
-        const int q = q0 + tr;
         lam.x += noise;
         if (k + q0 == 0) lam.x += dc;
-        double t3[3] = {0.0, 0.0, 0.0};
-        const double2 G = spectral_c(lam, ysq[k], wn, wl, t3);
-        const double cw = (q == 0 || q == half1) ? 1.0 : (q < half1 ? 2.0 : 0.0);
-        s[0] = fma(cw, t3[0], s[0]);
-        s[1] = fma(cw, t3[1], s[1]);
-        s[2] = fma(cw, t3[2], s[2]);
+        const double2 G = spectral_c_prod(lam, ysq[k], wn, wl, t0, t2, mant, ex);
+        if (++cnt == 64) {  // 0.5^64 is far from underflow
+          s[1] = fma(0.5 * cwt, logprod_flush(mant, ex), s[1]);
+          cnt = 0;
+        }
         // lam is real in exact arithmetic; its computed imaginary part is round-off, but dL/dIm(lam) ~ Im(lam) |y~|^2 / lam^3 is
         // not small where lam is.  A Hermitian (instead of real) dL/dlam back-transforms to a real but not EVEN sequence,
         // and the odd part only cancels in a sum over all points -- pass C sums half of them twice.  Keep the real part.
         return make_double2(G.x, 0.0);
       });
+      s[0] = cwt * t0;
+      s[1] = fma(0.5 * cwt, logprod_flush(mant, ex), s[1]);
+      s[2] = cwt * t2;
       if (want_grad && (q0 == 0 || q0 == half1)) {
         // the two self-mirrored columns hold both members of every pair (k, n-k): make them exactly equal as well
         __syncthreads();

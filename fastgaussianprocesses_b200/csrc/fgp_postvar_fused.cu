@@ -27,7 +27,7 @@ struct PvArgs {
   DVec shift;   // random shift of the lattice
   int a2;       // every alpha_j == 2
   // a2:  f_j / A_j = 1 - h^2,  h = |x' - t'| (sig_j - |x' - t'|) with coordinates pre-scaled by sig_j (post_mean's 5-slot form)
-  DVec sig;
+  DVec sig, sig32;  // sig_j and sig_j 2^-32
   double pref;  // scale * prod_j A_j  (a2) or scale
   // general alpha: f_j(u) = sum_p c[j][p] u^p, u = a(1-a)
   double c[FGP_MAX_D][FGP_MAX_ALPHA + 1];
@@ -74,9 +74,10 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) pv_passA_kernel
 #pragma unroll
     for (int j = 0; j < DM; ++j) {
       if (j >= d) break;
-      const double t = (double)(rev * (uint32_t)a.z.v[j]) * 0x1.0p-32;
+      const double ti = (double)(rev * (uint32_t)a.z.v[j]);  // 2^32 frac(phi2(i) z_j), exact
+      const double t = ti * 0x1.0p-32;
       if (A2) {
-        const double ts = t * a.sig.v[j];
+        const double ts = ti * a.sig32.v[j];  // sig_j 2^-32 folded into one constant
         const double da = fabs(xq[0][j] - ts), db = fabs(xq[1][j] - ts);
         const double ha = da * (a.sig.v[j] - da), hb = db * (a.sig.v[j] - db);
         const double fa = fma(-ha, ha, 1.0), fb = fma(-hb, hb, 1.0);
@@ -169,11 +170,12 @@ __global__ void __launch_bounds__(256) pv_final_kernel(const double* __restrict_
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static int64_t pv_chunk_pairs(int64_t pairs, int64_t n) {
-  // pairs per chunk: the (pairs, n) complex workspace of a chunk should stay L2-resident between the two kernels (64 MiB), and a
-  // chunk should fill the GPU for several waves; FGP_PV_CHUNK overrides
+  // pairs per chunk: enough tiles per launch for many waves (measured at n = 2^20, d = 8: 1 / 4 / 16 pairs per chunk -> 28.6 k / 52.8 k /
+  // 65.6 k points per second, although 16 pairs = 256 MiB no longer fit the L2); FGP_PV_CHUNK overrides
   static const int env = env_int("FGP_PV_CHUNK", 0);
-  int64_t c = env > 0 ? env : (int64_t(1) << 22) / n;
-  if (c < 1) c = 1;
+  int64_t c = env > 0 ? env : (int64_t(1) << 24) / n;
+  if (c < 16) c = 16;
+  if (c * n > (int64_t(1) << 26)) c = (int64_t(1) << 26) / n;  // at most 1 GiB of workspace
   if (c > 4096) c = 4096;
   if (c > pairs) c = pairs;
   return c;
@@ -239,6 +241,7 @@ int fgp_lattice_post_var_z(const double* xs_dev, int64_t m, const uint64_t* z_ho
     for (int j = 0; j < d; ++j) {
       const double A = a.c[j][0], Bq = -a.c[j][2];
       a.sig.v[j] = sqrt(sqrt(Bq / A));
+      a.sig32.v[j] = a.sig.v[j] * 0x1.0p-32;
       a.pref *= A;
     }
   }

@@ -608,7 +608,9 @@ static inline int env_int(const char* name, int dflt) {
 }
 // standalone: the stand-alone real transforms (fgp_fwht) take 128 KiB tiles for n >= 2^24 (pass-B strips of 8 columns instead
 // of 4: 2^24 159 -> 146 us, 2^26 1149 -> 753 us on B200); the fused MLL kernels keep 64 KiB tiles (they carry generator tables).
-static inline PassGeom make_geom(int64_t n, bool cplx, bool standalone = false) {
+// mll: the fused eigen-solve kernels (fgp_mll.cuh): 2^11-point tiles and 4-column strips up to n = 2^20 -- two tiles per SM in
+// flight in every pass (measured at n = 2^20, d = 8 on B200: 47.4 us per iteration against 49.5 us with 2^12 / 8, 58.4 against 62.4 cold)
+static inline PassGeom make_geom(int64_t n, bool cplx, bool standalone = false, bool mll = false) {
   PassGeom g;
   const size_t elem = cplx ? sizeof(double2) : sizeof(double);
   g.m = ilog2(n);
@@ -617,12 +619,13 @@ static inline PassGeom make_geom(int64_t n, bool cplx, bool standalone = false) 
   static const int capC = env_int("FGP_CAP_C", 0), capR = env_int("FGP_CAP_R", 0), colsEnv = env_int("FGP_COLS_LOG2", -1);
   static const int hardC = env_int("FGP_HARD_C", 0), hardR = env_int("FGP_HARD_R", 13);
   // complex: 2^11-point tiles and 4-column strips while one iteration's CTAs fit one wave (n <= 2^18), 2^12 / 8 above
-  int cap = cplx ? (capC ? capC : (g.m <= 18 ? 11 : 12)) : (capR ? capR : (g.m <= 22 ? 12 : ((standalone && g.m >= 25) ? 14 : 13)));
+  const int small_c = mll ? 20 : 18;  // complex tiles: 2^11 points / 4 columns up to here
+  int cap = cplx ? (capC ? capC : (g.m <= small_c ? 11 : 12)) : (capR ? capR : (g.m <= 22 ? 12 : ((standalone && g.m >= 25) ? 14 : 13)));
   // largest tile: 64 KiB of elements; the 2^24-point FFT takes 128 KiB pass-B tiles (2 columns instead of 1)
   static const int hardREnv = env_int("FGP_HARD_R", 0);
   const int hard = cplx ? (hardC ? hardC : (g.m >= 24 ? 13 : 12)) : (hardREnv ? hardREnv : ((standalone && g.m >= 24) ? 14 : hardR));
   if (cap > hard) cap = hard;
-  const int colsLog = colsEnv >= 0 ? colsEnv : (cplx ? (g.m <= 18 ? 2 : 3) : (g.m <= 22 ? 4 : 3));
+  const int colsLog = colsEnv >= 0 ? colsEnv : (cplx ? (g.m <= small_c ? 2 : 3) : (g.m <= 22 ? 4 : 3));
   int tileA, tileB = 0;
   if (g.m <= cap) {
     g.l1 = g.m;

@@ -151,14 +151,119 @@ def _pin_release(buf):
         _PIN_POOL.append(buf)
 
 
+class _FitContext(object):
+    """Everything a device-side fit loop touches on the GPU, owned by a process-wide pool and keyed on the problem's shape:
+    raw-parameter staging, effective hyperparameters, |ytilde|^2, workspace, state block, history rows -- and the CUDA graphs
+    captured over exactly these buffers.  A fit() copies its parameters and |ytilde|^2 in (a few KB + 8n bytes, device to device),
+    runs, copies the fitted parameters out and hands the context back, so the second and every later fit of a given shape in a
+    process pays neither allocations nor graph capture (measured: ~1.2 ms of a 2.7 ms fit(iterations=20) at n = 2^20)."""
+    POOL = {}
+    ST_HEADER = 32
+
+    def __init__(self, key, fgp, shapes, req, B, n, tau, d_out, hist_flags, cap):
+        dev = fgp.device
+        self.key = key
+        self.B, self.d, self.n, self.tau, self.d_out = B, fgp.d, n, tau, d_out
+        self.family = fgp._FAMILY
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.raw = tuple(torch.zeros(tuple(sh), **f64) for sh in shapes)
+        self.scale_B = torch.zeros(B, **f64)
+        self.ls_B = torch.zeros((B, fgp.d), **f64)
+        self.noise_B = torch.zeros(B, **f64)
+        self.ysq = torch.zeros((B, n), **f64)
+        self.out = torch.zeros((B, fgp.d + 4), **f64)
+        self.ws = _lib.mll_workspace(fgp._FAMILY, n, fgp.d, B, dev)
+        # filled on the device: torch.tensor(list, device=cuda) is a pageable H2D copy that makes the host wait for the stream
+        self.weights = torch.empty((B, 2), **f64)
+        self.weights[:, 0] = 0.5
+        self.weights[:, 1] = 0.5 * d_out / B
+        self.P = sum(r.numel() for r in self.raw)
+        self.state = torch.zeros(_lib.fit_state_doubles(self.P, B), **f64)
+        self.pin = _pin_acquire()
+        self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.hist_flags, self.hist_capacity = hist_flags, cap
+        self.loss_hist = torch.zeros((cap, 3), **f64)
+        mk = lambda flag, r: torch.zeros((cap, r.numel()), **f64) if flag else None
+        self.scale_hist, self.ls_hist, self.noise_hist = (mk(f, r) for f, r in zip(hist_flags, self.raw))
+        L = _lib.FitLayout()
+        L.B, L.d = B, fgp.d
+        L.n_scale = _prod(shapes[0][:-1])
+        L.n_ls_b, L.n_ls_d = _prod(shapes[1][:-1]), int(shapes[1][-1])
+        L.n_noise = _prod(shapes[2][:-1])
+        L.req_scale, L.req_ls, L.req_noise = (int(r) for r in req)
+        L.tau = tau
+        L.raw_scale, L.raw_ls, L.raw_noise = (r.data_ptr() for r in self.raw)
+        L.scale_B, L.ls_B, L.noise_B = self.scale_B.data_ptr(), self.ls_B.data_ptr(), self.noise_B.data_ptr()
+        L.state = self.state.data_ptr()
+        L.loss_hist = self.loss_hist.data_ptr()
+        L.scale_hist = None if self.scale_hist is None else self.scale_hist.data_ptr()
+        L.ls_hist = None if self.ls_hist is None else self.ls_hist.data_ptr()
+        L.noise_hist = None if self.noise_hist is None else self.noise_hist.data_ptr()
+        self.layout = L
+        # the whole iteration as one C call (fgp_fit_iteration); ctypes arrays and device tensors are kept alive on self
+        self._alpha_arr = (_lib._i32 * fgp.d)(*fgp._alpha_list)
+        self._z_arr = (_lib._u64 * fgp.d)(*fgp._zgen) if fgp._zgen is not None else None
+        self.xpts = fgp._xpts(n).contiguous()
+        self._C = fgp._Cgen(n)
+        Pb = _lib.FitProblem()
+        Pb.family = fgp._FAMILY
+        Pb.x_dev = self.xpts.data_ptr()
+        Pb.z_host = _lib._c.cast(self._z_arr, _lib._vp) if self._z_arr is not None else None
+        Pb.C_dev = self._C.data_ptr() if self._C is not None else None
+        Pb.mmax = int(self._C.shape[1]) if self._C is not None else 0
+        Pb.n, Pb.d, Pb.t = n, fgp.d, int(fgp._t)
+        Pb.alpha_host = _lib._c.cast(self._alpha_arr, _lib._vp)
+        Pb.ysq_dev = self.ysq.data_ptr()
+        Pb.weights_dev = self.weights.data_ptr()
+        Pb.table_dev = _lib.fft_table(n, dev).data_ptr() if fgp._FAMILY == 0 else None
+        Pb.workspace_dev = self.ws.data_ptr()
+        Pb.out_dev = self.out.data_ptr()
+        self.problem = Pb
+        self.generator = self._z_arr is not None or self._C is not None
+        self.graphs = {}
+        self.warmed = False
+        self.kernels_per_iteration = None
+
+    @classmethod
+    def acquire(cls, fgp, pshape, hist_flags, hist_capacity):
+        with torch.no_grad():
+            tau = fgp._tau_host()
+        raws = (fgp.raw_scale, fgp.raw_lengthscales, fgp.raw_noise)
+        shapes = tuple(tuple(r.shape) for r in raws)
+        req = tuple(bool(r.requires_grad) for r in raws)
+        B, n = _prod(pshape), fgp._nint
+        d_out = _prod(fgp.shape_batch)
+        cap = 64
+        while cap < max(int(hist_capacity), 1):
+            cap *= 2
+        hist_flags = tuple(bool(f) for f in hist_flags)
+        # what the captured kernels read besides the pooled buffers: the generator inputs, or -- without them -- the stored points
+        if fgp._zgen is not None:
+            gen = ("z",) + tuple(fgp._zgen)
+        elif fgp._Cgen(n) is not None:
+            gen = ("C", fgp._Cgen(n).data_ptr())
+        else:
+            gen = ("x", fgp._xpts(n).data_ptr())
+        key = (str(fgp.device), fgp._FAMILY, n, fgp.d, B, tuple(fgp._alpha_list), int(fgp._t), gen, shapes, req, tau, d_out, hist_flags, cap)
+        free = cls.POOL.setdefault(key, [])
+        return free.pop() if free else cls(key, fgp, shapes, req, B, n, tau, d_out, hist_flags, cap)
+
+    def release(self):
+        free = self.POOL.setdefault(self.key, [])
+        if len(free) < 4:
+            free.append(self)
+        else:
+            _pin_release(self.pin)
+            self.pin = None
+
+
 class _FusedFitLoop(object):
-    """Device-side fit() loop (the product's fast path).  Two-pass sizes: ONE launch of the persistent cooperative kernel
-    runs a whole chunk of iterations (fgp_fit_iterations: eigen-solve, gradient, Rprop and the early-stop state machine
-    loop on the device).  Single-CTA sizes: every iteration is one fused kernel, replayed from a CUDA graph.  The host only
-    polls the `stopped` flag between chunks (include/fgp_b200.h, K4/K4b).
+    """Device-side fit() loop (the product's fast path): every iteration is ONE C call (fgp_fit_iteration: fused eigen-solve whose
+    last CTA reduces the partial sums and runs Rprop and the early-stop state machine), replayed from CUDA graphs held by a pooled
+    `_FitContext`; the host only polls the `stopped` flag between chunks (include/fgp_b200.h, K4/K4b).  FGP_COOP=1 opts into the
+    persistent cooperative kernel instead (a chunk of iterations per launch).
     Used when the loss is MLL, the optimiser is the default Rprop and the transforms are the default (log, exp)."""
     GRAPH_ITERS = 16
-    EAGER_ITERS = 32  # large problems: iterations launched eagerly before a graph is worth capturing (~1.5 ms)
     ST_STOPPED, ST_LAST_ITER, ST_HEADER = 4, 5, 32
 
     @staticmethod
@@ -175,111 +280,51 @@ class _FusedFitLoop(object):
 
     def __init__(self, fgp, hist_flags=(False, False, False), hist_capacity=0):
         self.fgp = fgp
-        dev = fgp.device
-        with torch.no_grad():
-            scale_B, ls_B, noise_B, pshape = fgp._hyper()
-            self.tau = fgp._tau_host()
+        pshape = fgp._pshape()
         self.pshape = pshape
-        self.B, self.d, self.n = scale_B.numel(), fgp.d, fgp._nint
-        self.raw = (fgp.raw_scale.data, fgp.raw_lengthscales.data, fgp.raw_noise.data)
-        self.req = (fgp.raw_scale.requires_grad, fgp.raw_lengthscales.requires_grad, fgp.raw_noise.requires_grad)
-        self.scale_B = scale_B.clone().contiguous()
-        self.ls_B = ls_B.clone().contiguous()
-        self.noise_B = noise_B.clone().contiguous()
-        self.xpts = fgp._xpts(self.n).contiguous()
-        self.ysq = fgp._get_ysq(pshape)
-        self.d_out = _prod(fgp.shape_batch)
-        self.out = torch.zeros((self.B, self.d + 4), dtype=torch.float64, device=dev)
-        self.ws = _lib.mll_workspace(fgp._FAMILY, self.n, self.d, self.B, dev)
-        # filled on the device: torch.tensor(list, device=cuda) is a pageable H2D copy that makes the host wait for the stream
-        self.weights = torch.empty((self.B, 2), dtype=torch.float64, device=dev)
-        self.weights[:, 0] = 0.5
-        self.weights[:, 1] = 0.5 * self.d_out / self.B
-        self.P = sum(r.numel() for r in self.raw)
-        self.state = torch.zeros(_lib.fit_state_doubles(self.P, self.B), dtype=torch.float64, device=dev)
-        self._pin = _pin_acquire()
-        self.state_host = self._pin[2]
-        self.state_host2 = self._pin[:2]
-        self.events = [torch.cuda.Event(), torch.cuda.Event()]
-        self.use_graph = self.n * self.B < (1 << 18) and os.environ.get("FGP_B200_NO_GRAPH") != "1"
-        self.graph_after_eager = False  # set by fit_stepper(): the steady state of a long fit
-        self.hist_flags = tuple(bool(f) for f in hist_flags)
-        self.hist_capacity = int(hist_capacity)
-        cap = max(self.hist_capacity, 1)
-        self.loss_hist = torch.zeros((cap, 3), dtype=torch.float64, device=dev)
-        mk = lambda flag, r: torch.zeros((cap, r.numel()), dtype=torch.float64, device=dev) if flag else None
-        self.scale_hist, self.ls_hist, self.noise_hist = (mk(f, r) for f, r in zip(self.hist_flags, self.raw))
-        L = _lib.FitLayout()
-        L.B, L.d = self.B, self.d
-        L.n_scale = _prod(self.raw[0].shape[:-1])
-        L.n_ls_b, L.n_ls_d = _prod(self.raw[1].shape[:-1]), int(self.raw[1].shape[-1])
-        L.n_noise = _prod(self.raw[2].shape[:-1])
-        L.req_scale, L.req_ls, L.req_noise = (int(r) for r in self.req)
-        L.tau = self.tau
-        L.raw_scale, L.raw_ls, L.raw_noise = (r.data_ptr() for r in self.raw)
-        L.scale_B, L.ls_B, L.noise_B = self.scale_B.data_ptr(), self.ls_B.data_ptr(), self.noise_B.data_ptr()
-        L.state = self.state.data_ptr()
-        L.loss_hist = self.loss_hist.data_ptr()
-        L.scale_hist = None if self.scale_hist is None else self.scale_hist.data_ptr()
-        L.ls_hist = None if self.ls_hist is None else self.ls_hist.data_ptr()
-        L.noise_hist = None if self.noise_hist is None else self.noise_hist.data_ptr()
-        self.layout = L
-        # the whole iteration as one C call (fgp_fit_iteration); ctypes arrays are kept alive on self
-        self._alpha_arr = (_lib._i32 * self.d)(*fgp._alpha_list)
-        self._z_arr = (_lib._u64 * self.d)(*fgp._zgen) if fgp._zgen is not None else None
-        Pb = _lib.FitProblem()
-        Pb.family = fgp._FAMILY
-        Pb.x_dev = self.xpts.data_ptr()
-        Pb.z_host = _lib._c.cast(self._z_arr, _lib._vp) if self._z_arr is not None else None
-        self._C = fgp._Cgen(self.n)
-        Pb.C_dev = self._C.data_ptr() if self._C is not None else None
-        Pb.mmax = int(self._C.shape[1]) if self._C is not None else 0
-        Pb.n, Pb.d, Pb.t = self.n, self.d, int(fgp._t)
-        Pb.alpha_host = _lib._c.cast(self._alpha_arr, _lib._vp)
-        Pb.ysq_dev = self.ysq.data_ptr()
-        Pb.weights_dev = self.weights.data_ptr()
-        Pb.table_dev = _lib.fft_table(self.n, dev).data_ptr() if fgp._FAMILY == 0 else None
-        Pb.workspace_dev = self.ws.data_ptr()
-        Pb.out_dev = self.out.data_ptr()
-        self.problem = Pb
-        self.graphs = {}
+        ysq = fgp._get_ysq(pshape)
+        c = self.ctx = _FitContext.acquire(fgp, pshape, hist_flags, hist_capacity)
+        self.B, self.d, self.n, self.d_out = c.B, c.d, c.n, c.d_out
+        # parameters and |ytilde|^2 in: device-to-device copies into the buffers the captured kernels read
+        with torch.no_grad():
+            for dst, src in zip(c.raw, (fgp.raw_scale, fgp.raw_lengthscales, fgp.raw_noise)):
+                dst.copy_(src.data)
+            c.ysq.copy_(ysq)
+        self.state, self.layout, self.problem = c.state, c.layout, c.problem
+        self.loss_hist, self.scale_hist, self.ls_hist, self.noise_hist = c.loss_hist, c.scale_hist, c.ls_hist, c.noise_hist
+        self.hist_capacity = c.hist_capacity
+        self.state_host, self.state_host2, self.events = c.pin[2], c.pin[:2], c.events
         self.launches = 0
         self.replayed = 0
-        self.kernels_per_iteration = None
-        # persistent cooperative kernel: k iterations per launch, no graph and no warm-up launch needed
+        # persistent cooperative kernel (opt-in): k iterations per launch, no graph
         self.multi = _lib.fit_iterations_per_launch(fgp._FAMILY, self.n) > 1 and os.environ.get("FGP_B200_NO_MULTI") != "1"
+        self.use_graph = not self.multi and os.environ.get("FGP_B200_NO_GRAPH") != "1"
         if self.multi:
-            self.use_graph = False
-            self.kernels_per_iteration = 1
-            return
-        # eager warm-up of every kernel before any capture; `stopped` is raised so that the fit step changes nothing
-        # (the state block is zero: tickets start at 0 as fit_init leaves them)
-        with torch.cuda.device(dev):
-            self.state[self.ST_STOPPED] = 1.0
-            c0 = _lib.launch_count()
-            self._iteration()
-            self.kernels_per_iteration = _lib.launch_count() - c0
-            if self.use_graph:  # a capture must not meet lazy module loading; eager launches are simply stream-ordered
-                torch.cuda.synchronize(dev)
-
-    def matches(self, fgp, hist_flags, hist_capacity):
-        return (self._pin is not None and fgp._nint == self.n and tuple(p.data_ptr() for p in (fgp.raw_scale, fgp.raw_lengthscales, fgp.raw_noise)) == tuple(r.data_ptr() for r in self.raw)
-                and (fgp.raw_scale.requires_grad, fgp.raw_lengthscales.requires_grad, fgp.raw_noise.requires_grad) == self.req
-                and fgp._ysq is self.ysq and tuple(bool(f) for f in hist_flags) == self.hist_flags and hist_capacity <= self.hist_capacity
-                and fgp._tau_host() == self.tau)
+            c.kernels_per_iteration = 1
+        elif not c.warmed:
+            # eager warm-up of every kernel before the first capture (a capture must not meet lazy module loading); `stopped`
+            # is raised so that the fit step changes nothing (the state block is zero: tickets start at 0 as fit_init leaves them)
+            with torch.cuda.device(fgp.device):
+                c.state[self.ST_STOPPED] = 1.0
+                c0 = _lib.launch_count()
+                self._iteration()
+                c.kernels_per_iteration = _lib.launch_count() - c0
+                torch.cuda.synchronize(fgp.device)
+            c.warmed = True
+        self.kernels_per_iteration = c.kernels_per_iteration
 
     # algorithmic bytes of one iteration: points read by the first and last pass, workspace written and
     # read twice, |ytilde|^2 read once
     @property
     def algorithmic_bytes(self):
         e = 16 if self.fgp._FAMILY == 0 else 8
-        pts = 0 if (self.fgp._zgen is not None or self._C is not None) else 2 * 8 * self.n * self.d
+        pts = 0 if self.ctx.generator else 2 * 8 * self.n * self.d
         return self.B * (pts + 4 * e * self.n + 8 * self.n)
 
     def kernel_algorithmic_bytes(self, name):
         e = 16 if self.fgp._FAMILY == 0 else 8
         n, d, B = self.n, self.d, self.B
-        if self.fgp._zgen is not None or self._C is not None:
+        if self.ctx.generator:
             d = 0
         if name == "mll_coop":
             return self.algorithmic_bytes
@@ -300,7 +345,8 @@ class _FusedFitLoop(object):
             _lib.fit_init(self.layout, o)
 
     def _graph(self, k):
-        g = self.graphs.get(k)
+        graphs = self.ctx.graphs
+        g = graphs.get(k)
         if g is None:
             # raw capture on a side stream: the torch.cuda.graph() context manager also runs gc.collect() and
             # empty_cache(), tens of milliseconds -- more than a whole short fit
@@ -317,30 +363,28 @@ class _FusedFitLoop(object):
                     finally:
                         g.capture_end()
                 cur.wait_stream(side)
-            self.graphs[k] = g
+            graphs[k] = g
         return g
 
     def replay(self, k):
-        # Large problems (an iteration of >= ~40 us of kernels) are launched eagerly: the host stays ahead of the GPU and no
-        # capture / instantiation is paid (graphs save ~4 us of launch gaps per iteration; fit_stepper() opts in).  Small
-        # ones replay a CUDA graph from the start: the 1-iteration graph k times, then a k-iteration graph once the fit is
-        # long enough to amortise its capture.
+        """Enqueue k iterations: a k-iteration graph when the context holds one (or k is worth capturing: the chunk size, which
+        every later fit of this shape reuses), else the 1-iteration graph k times."""
         if self.multi:
             with torch.cuda.device(self.fgp.device):
                 _lib.fit_iterations(self.problem, self.layout, k)
             self.replayed += k
             self.launches += 1
             return
-        if not self.use_graph and (self.replayed < self.EAGER_ITERS or not self.graph_after_eager):
+        if not self.use_graph:
             with torch.cuda.device(self.fgp.device):
                 for _ in range(k):
                     self._iteration()
-        elif k > 1 and k not in self.graphs and self.replayed < 16 * k:
+        elif k in self.ctx.graphs or k == self.GRAPH_ITERS or k == 1:
+            self._graph(k).replay()
+        else:
             g1 = self._graph(1)
             for _ in range(k):
                 g1.replay()
-        else:
-            self._graph(k).replay()
         self.replayed += k
         self.launches += k * self.kernels_per_iteration
 
@@ -367,8 +411,14 @@ class _FusedFitLoop(object):
             raise _lib.FgpError("libfgp_b200: the device-side fit loop reported a failed grid barrier")
 
     def finish(self):
-        with torch.cuda.device(self.fgp.device):
+        """Best iterate -> staged parameters (abstract_gp.py:297-298) -> the GP's own parameter storages."""
+        fgp, c = self.fgp, self.ctx
+        with torch.cuda.device(fgp.device):
             _lib.fit_finish(self.layout)
+        with torch.no_grad():
+            for dst, src in zip((fgp.raw_scale, fgp.raw_lengthscales, fgp.raw_noise), c.raw):
+                dst.data.copy_(src)
+        fgp._epoch += 1
 
     def kernel_times(self, reps=10, flush=None):
         """Per-kernel device time of one iteration (eager launches, CUDA events between kernels; L2 flushed first)."""
@@ -383,19 +433,21 @@ class _FusedFitLoop(object):
                     acc.setdefault(name, []).append(ms)
         return [{"name": k, "ms": float(np.mean(v)), "alg_bytes": self.kernel_algorithmic_bytes(k)} for k, v in acc.items()]
 
-    def close(self):
-        self.graphs = {}
-        if self._pin is not None:
-            torch.cuda.current_stream(self.fgp.device).synchronize()  # no copy into the buffers may be in flight
-            _pin_release(self._pin)
-            self._pin = None
-            self.state_host = self.state_host2 = None
+    def close(self, finish=True):
+        """Hand the context back to the pool.  finish: copy the best iterate into the GP first (an open-ended `fit_stepper` run ends
+        here; fit() has already done it)."""
+        if self.ctx is None:
+            return
+        if finish:
+            self.finish()
+        torch.cuda.current_stream(self.fgp.device).synchronize()  # nothing may still be reading or writing the pooled buffers
+        self.ctx.release()
+        self.ctx = None
 
     def __del__(self):
         try:
-            if getattr(self, "_pin", None) is not None:
-                _pin_release(self._pin)
-                self._pin = None
+            if getattr(self, "ctx", None) is not None:
+                self.close(finish=False)
         except Exception:
             pass
 
@@ -712,6 +764,11 @@ class AbstractFastGP(torch.nn.Module):
         noise_B = (noise[..., 0] * tau).expand(pshape).reshape(B)
         ls_B = ls.expand(tuple(pshape) + (self.d,)).reshape(B, self.d)
         return scale_B, ls_B, noise_B, pshape
+
+    def _pshape(self):
+        """Batch shape of the hyperparameter sets (what `_hyper` returns last), from the parameter shapes alone: no device work."""
+        tau_shape = torch.broadcast_shapes(self.raw_factor_task_kernel.shape[:-2], self.raw_noise_task_kernel.shape[:-1])
+        return torch.broadcast_shapes(self.raw_scale.shape[:-1], self.raw_lengthscales.shape[:-1], self.raw_noise.shape[:-1], tau_shape)
 
     def _tau_host(self):
         """K_task[0,0] of a single task as a host float, cached on the task-kernel parameters' identity and version: reading it
@@ -1254,45 +1311,36 @@ class AbstractFastGP(torch.nn.Module):
             data["task_kernel_hist"] = task_kernel_hist[:(i + 1)]
         return data
 
-    def _get_fused_loop(self, hist_flags=(False, False, False), hist_capacity=0):
-        loop = getattr(self, "_fused_loop", None)
+    def _new_fused_loop(self, hist_flags=(False, False, False), hist_capacity=0):
+        """Bind this GP to a pooled fit context (buffers + CUDA graphs of its shape): parameters and |ytilde|^2 are copied in."""
+        old = getattr(self, "_fused_loop", None)
+        if old is not None:
+            old.close(finish=False)
         self.get_ytilde(0)
-        if loop is None or not loop.matches(self, hist_flags, hist_capacity):
-            if loop is not None:
-                loop.close()
-            with torch.no_grad():
-                _, _, _, pshape = self._hyper()
-            self._get_ysq(pshape)
-            loop = _FusedFitLoop(self, hist_flags, max(hist_capacity, 1))
-            self._fused_loop = loop
+        loop = _FusedFitLoop(self, hist_flags, max(hist_capacity, 1))
+        self._fused_loop = loop
         return loop
 
     def fit_stepper(self):
-        """The fused device-side fit loop armed for an open-ended run, in the steady state of a long fit (CUDA-graph replays):
-        `.step()` = one MLL+gradient+Rprop iteration."""
+        """The fused device-side fit loop armed for an open-ended run: `.step()` = one MLL+gradient+Rprop iteration on the device
+        (what fit() replays in chunks); `.close()` copies the best iterate into the parameters and returns the buffers to the pool.
+        While the stepper is open the GP's own parameters are NOT updated."""
         assert self._nint > 0, "cannot fit without data"
         assert _FusedFitLoop.eligible(self), "fit_stepper needs the default transforms and parameter layouts"
-        loop = self._get_fused_loop()
-        loop.replayed = max(loop.replayed, loop.EAGER_ITERS)
-        loop.graph_after_eager = True
+        loop = self._new_fused_loop()
         loop.begin(2 ** 30, 2 ** 30, np.log(1.05), 1e-1)
-        self._epoch += 1
         return loop
 
     def _fit_fused(self, iterations, lr, logtol, stop_wait, store_loss_hist, store_scale_hist, store_lengthscales_hist, store_noise_hist,
                    store_task_kernel_hist, verbose, verbose_indent):
         """fit() on the device: same state machine and outputs as the generic loop below (abstract_gp.py:236-306)."""
         flags = (store_scale_hist, store_lengthscales_hist, store_noise_hist)
-        loop = self._get_fused_loop(flags, iterations + 1)
+        loop = self._new_fused_loop(flags, iterations + 1)
         if verbose:
             _s = "%16s | %-10s | %-10s | %-10s" % ("iter of %.1e" % iterations, "loss", "term1", "term2")
             print(" " * verbose_indent + _s)
             print(" " * verbose_indent + "~" * len(_s))
         loop.begin(iterations, stop_wait, logtol, lr)
-        # long fits of large problems: eager launches cost ~10 us per iteration more than graph replays (62 against 51 us at
-        # n = 2^20, d = 8), so after EAGER_ITERS eager iterations a 16-iteration graph is captured while the GPU works them off
-        if iterations + 1 >= 6 * loop.GRAPH_ITERS:
-            loop.graph_after_eager = True
         printed = 0
         chunk = min(loop.GRAPH_ITERS, iterations + 1)
         budget = [iterations + 1]  # never enqueue past the iteration budget: launching no-op iterations costs host time
@@ -1332,12 +1380,11 @@ class AbstractFastGP(torch.nn.Module):
                 if stopped:
                     break
                 j += 1
-        loop.finish()
+        loop.finish()  # best iterate -> this GP's parameter storages (bumps the cache epoch)
         i = last
         for pname in ("raw_scale", "raw_lengthscales", "raw_noise", "raw_factor_task_kernel", "raw_noise_task_kernel"):
             p = getattr(self, pname)
             setattr(self, pname, torch.nn.Parameter(p.data, requires_grad=p.requires_grad))
-        self._epoch += 1
         data = {"iterations": i}
         if store_loss_hist:
             data["loss_hist"] = -loop.loss_hist[:(i + 1), 0].cpu()
@@ -1349,6 +1396,9 @@ class AbstractFastGP(torch.nn.Module):
             data["noise_hist"] = loop.noise_hist[:(i + 1)].reshape((i + 1,) + tuple(self.raw_noise.shape)).cpu()
         if store_task_kernel_hist:
             data["task_kernel_hist"] = self.gram_matrix_tasks.detach().cpu()[None].expand((i + 1,) + tuple(self.gram_matrix_tasks.shape)).clone()
+        self._fit_route = ("coop" if loop.multi else "graph", id(loop.ctx))  # diagnostics: which device loop ran, over which pooled context
+        loop.close(finish=False)  # buffers and graphs back to the pool: the next fit of this shape (any GP object) reuses them
+        self._fused_loop = None
         return data
 
     # ------------------------------------------------------------------------------------------------ posterior

@@ -163,7 +163,7 @@ typedef struct {
   double lr, etaminus, etaplus, step_min, step_max; /* torch.optim.Rprop: 0.1, 0.5, 1.2, 1e-6, 50 */
 } fgp_fit_options;
 size_t fgp_fit_state_doubles(int n_raw_params, int B);
-int fgp_fit_init(const fgp_fit_layout* layout, const fgp_fit_options* opt, fgp_stream_t stream); /* synchronises `stream` once */
+int fgp_fit_init(const fgp_fit_layout* layout, const fgp_fit_options* opt, fgp_stream_t stream); /* one launch, nothing synchronises */
 int fgp_fit_step(const fgp_fit_layout* layout, const double* mll_out_dev, fgp_stream_t stream);
 int fgp_fit_finish(const fgp_fit_layout* layout, fgp_stream_t stream); /* best iterate -> parameters */
 /* One whole fit() iteration in one call: the fused eigen-solve of K4 on layout->scale_B / ls_B / noise_B, whose last

@@ -254,13 +254,23 @@ def test_repeated_fit_and_growth_reuse_the_device_loop():
     f = lambda x: torch.cos(2 * np.pi * x).sum(1)
     gp.add_y_next(f(gp.get_x_next(256)))
     d1 = gp.fit(iterations=5, verbose=0, store_loss_hist=True, stop_crit_wait_iterations=100)
-    loop = gp._fused_loop
+    ctx = gp._fit_route[1]
     d2 = gp.fit(iterations=5, verbose=0, store_loss_hist=True, stop_crit_wait_iterations=100)
-    assert gp._fused_loop is loop  # same buffers and graphs
+    assert gp._fit_route[1] == ctx  # same pooled buffers and CUDA graphs
     assert float(d2["loss_hist"][0]) >= float(d1["loss_hist"].max()) - 1e-9  # restarts from the best iterate of the first fit
+    # another GP object of the same shape (another randomisation of the lattice) reuses the context too, and is not disturbed by it
+    gp_b = fgp.FastGPLattice(fgp.Lattice(2, seed=10), device=dev, noise=1e-6)
+    gp_b.add_y_next(f(gp_b.get_x_next(256)) * 2.0)
+    ls_a = gp.lengthscales.detach().clone()
+    db = gp_b.fit(iterations=5, verbose=0, store_loss_hist=True, stop_crit_wait_iterations=100)
+    assert gp_b._fit_route[1] == ctx and db["iterations"] == 5 and torch.equal(gp.lengthscales.detach(), ls_a)
+    gp_c = fgp.FastGPLattice(fgp.Lattice(2, seed=10), device=dev, noise=1e-6)
+    gp_c.add_y_next(f(gp_c.get_x_next(256)) * 2.0)
+    dc = gp_c.fit(iterations=5, verbose=0, store_loss_hist=True, stop_crit_wait_iterations=100)
+    assert torch.equal(dc["loss_hist"], db["loss_hist"]) and torch.equal(gp_c.lengthscales.detach(), gp_b.lengthscales.detach())  # no state leaks between fits
     gp.add_y_next(f(gp.get_x_next(512)))
     d3 = gp.fit(iterations=5, verbose=0, store_loss_hist=True, stop_crit_wait_iterations=100)
-    assert gp._fused_loop is not loop and d3["iterations"] == 5
+    assert gp._fit_route[1] != ctx and d3["iterations"] == 5
     xt = torch.rand(9, 2, generator=torch.Generator().manual_seed(1))
     assert torch.isfinite(gp.post_mean(xt)).all() and (gp.post_var(xt) >= 0).all()
 
@@ -395,7 +405,7 @@ def test_persistent_kernel_fit_matches_the_three_launch_route(monkeypatch, famil
             y = torch.stack([y * (1.0 + 0.3 * k) + 0.1 * k * torch.sin(4 * np.pi * x[:, 0]) for k in range(batch[0])])
         gp.add_y_next(y)
         data = gp.fit(iterations=iters, verbose=0, store_hists=True, stop_crit_wait_iterations=7)
-        assert gp._fused_loop.multi == coop  # FGP_COOP=1 opts into the persistent kernel (the default is three launches per iteration)
+        assert gp._fit_route[0] == ("coop" if coop else "graph")  # FGP_COOP=1 opts into the persistent kernel (default: three launches per iteration)
         return data, gp.raw_scale.detach().clone(), gp.raw_lengthscales.detach().clone()
 
     d1, s1, l1 = run(True)

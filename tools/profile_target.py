@@ -49,5 +49,12 @@ if which in ("all", "pvar"):  # lattice post_var: cross-pair kernel -> in-place 
     _, lam = L.mll_grad(0, xp, [2] * d, 0, ysq, scale, ls, noise, want_lam=True)
     for _ in range(reps):
         L.post_var(0, xs, xp, [2] * d, 0, 1.0, [0.5] * d, lam[0])
+if which in ("all", "pvarz"):  # fused generator-form lattice post_var: pv_passA (kernel evaluation + block transform) -> pv_passB (+ pair reduction)
+    xs = torch.rand(256, d, device=dev)
+    ysq = torch.rand(1, n, device=dev)
+    scale = torch.ones(1, device=dev); ls = torch.full((1, d), 0.5, device=dev); noise = torch.full((1,), 1e-6, device=dev)
+    _, lam = L.mll_grad(0, xp, [2] * d, 0, ysq, scale, ls, noise, want_lam=True)
+    for _ in range(reps):
+        L.post_var_z(xs, z, np.linspace(0.1, 0.9, d), n, [2] * d, 1.0, [0.5] * d, lam[0])
 torch.cuda.synchronize()
 print("ok")

@@ -84,6 +84,7 @@ SIGNATURES = {
     "fgp_kernel_pairs": (_i32, [_i32, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp]),
     "fgp_deriv_kernel_parts": (_i32, [_i32, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp]),
     "fgp_deriv_cross_kernel": (_i32, [_i32, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _f64, _vp, _vp, _vp]),
+    "fgp_block_inv_logdet": (_i32, [_i32, _vp, _i64, _i32, _vp, _vp, _vp]),
     "fgp_fp64_peak_probe": (_i32, [_i32, _vp, _vp, _vp]),
 }
 
@@ -338,9 +339,15 @@ def fwht(x, fused=None):
 _workspaces = {}
 
 
+def release_workspaces():
+    """Drop every cached scratch buffer (they are kept per (kind, device, stream) for the life of the process otherwise)."""
+    _workspaces.clear()
+
+
 def _workspace(kind, nbytes, device):
+    """Scratch buffer cached per (kind, device, stream): two streams never share one (calls on one stream are serialised)."""
     device = torch.device(device)
-    key = (kind, device.index if device.index is not None else torch.cuda.current_device())
+    key = (kind, device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() * 8 < nbytes:
         ws = torch.empty((max(nbytes, 256) + 7) // 8, dtype=torch.float64, device=device)
@@ -521,6 +528,17 @@ def post_var_z(xs, z, shift, n, alpha, scale, ls, lam):
 
 def post_var_z_supported(n):
     return load().fgp_lattice_post_var_z_workspace_bytes(2, int(n)) > 0
+
+
+def block_inv_logdet(L):
+    """(nm, R, R) complex128 / float64 -> (inverse (nm, R, R), log|det| (nm)); fgp_block_inv_logdet."""
+    assert L.ndim == 3 and L.shape[1] == L.shape[2]
+    L = L.contiguous()
+    A = torch.empty_like(L)
+    logdet = torch.empty(L.shape[0], dtype=torch.float64, device=L.device)
+    with torch.cuda.device(L.device):
+        _check(load().fgp_block_inv_logdet(1 if L.is_complex() else 0, _dev(L, L.dtype), L.shape[0], L.shape[1], A.data_ptr(), logdet.data_ptr(), _stream()))
+    return A, logdet
 
 
 def fp64_peak_probe(iters, device):

@@ -420,7 +420,10 @@ int fgp_dnb2_post_mean(const double* xs_dev, int64_t m, const int64_t* xb_dev, i
 size_t fgp_post_var_workspace_bytes(int family, int64_t m, int64_t n) {
   if (m <= 0 || n <= 0) return 0;
   const int64_t mc = fgp::post_var_chunk(m, n);
-  return ((size_t)mc * n * (family == 0 ? 3 : 1) + 2 + (family == 0 ? 0 : 16 * (size_t)mc)) * sizeof(double);  // net: + 16 partial sums per row
+  // lattice: mc PAIRS of test points per chunk = mc*n complex values + 16 x 2 partial sums per pair (n = 1: a real and a complex row
+  // per point); net: mc rows + 16 partial sums per row
+  if (family == 0) return (n > 1 ? (size_t)mc * n * 2 + 32 * (size_t)mc + 2 : (size_t)mc * 3 + 2) * sizeof(double);
+  return ((size_t)mc * n + 2 + 16 * (size_t)mc) * sizeof(double);
 }
 
 static int post_var_common(int family, const double* xs, int64_t m, const void* x, int64_t n, int d, const int* alpha_host,

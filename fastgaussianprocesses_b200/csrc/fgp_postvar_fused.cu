@@ -15,6 +15,7 @@
 //             against Re(1/lam_k) right there: the spectrum is never written.
 // Per-tile partial sums are added in a fixed order by a tiny final kernel: results do not depend on scheduling.
 #include "fgp_transform.cuh"
+#include "fgp_tma.cuh"
 
 namespace fgp {
 
@@ -45,6 +46,25 @@ __global__ void __launch_bounds__(256) pv_winv_kernel(const double2* __restrict_
     const double2 l = lam[k];
     winv[k] = l.x / fma(l.x, l.x, l.y * l.y) * inv_n;
   }
+}
+
+// Workspace layout of one pair: pass-B tile t holds the c columns q0 .. q0+c-1 (q0 = t c) in slots 0 .. c-1 and their mirrors L1 - q in slots
+// c .. 2c-1 (the self-mirrored column L1/2 takes the slot of q = 0's mirror), all L2 rows: element (row, slot) of tile t at ((t L2 + row) 2c + slot).
+__device__ __forceinline__ int64_t pv_woff(int q, int row, int lcB, int l1, int l2) {
+  const int c = 1 << lcB, L1 = 1 << l1, half1 = L1 >> 1;
+  int tile, slot;
+  if (q < half1) {
+    tile = q >> lcB;
+    slot = q & (c - 1);
+  } else if (q == half1) {
+    tile = 0;
+    slot = c;
+  } else {
+    const int qm = L1 - q;
+    tile = qm >> lcB;
+    slot = c + (qm & (c - 1));
+  }
+  return ((int64_t)tile << (l2 + lcB + 1)) + ((int64_t)row << (lcB + 1)) + slot;
 }
 
 template <int DT, bool A2>
@@ -99,30 +119,21 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) pv_passA_kernel
     return make_double2(ka * a.pref, kb * a.pref);
   });
   __syncthreads();
-  double2* W = a.W + p * a.n + g0;
+  // scatter on store, never on load: the workspace of a pair is laid out by PASS-B TILE, [tile][row][2c slots] (pv_woff), so that pass B
+  // reads each of its tiles as one contiguous block; pass A pays with 16c-byte store runs, which nobody waits for
+  double2* W = a.W + p * a.n;
   const FftTables T = a.T;
   const uint32_t rb = brev_bits((uint32_t)blk, a.l2);
-  block_fft_fwd_io<false>(sm, l1, 0, LP, T.stage, SmemTag{}, [&](int, int idx, double2 v) { W[idx] = cmul(v, twiddle_n(T, rb * (uint32_t)idx)); });
+  const int lcB = a.lcB, l2 = a.l2;
+  block_fft_fwd_io<false>(sm, l1, 0, LP, T.stage, SmemTag{},
+                          [&](int, int idx, double2 v) { W[pv_woff(idx, blk, lcB, l1, l2)] = cmul(v, twiddle_n(T, rb * (uint32_t)idx)); });
 }
 
-__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) pv_passB_kernel(const __grid_constant__ PvArgs a) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  __shared__ double red[32 * 4];
-  double2* sm = (double2*)smraw;
-  const int64_t p = blockIdx.y;
-  const int tile = blockIdx.x;
+// reduction of one transformed pass-B tile (in shared memory) against Re(1/lam): both members of every pair (k, n-k) are in the tile
+__device__ __forceinline__ void pv_tile_reduce(const PvArgs& a, double2* sm, int64_t p, int tile, double* red) {
   const int l1 = a.l1, l2 = a.l2, LP = a.LPB, lcB = a.lcB;
   const int c = 1 << lcB, L1 = 1 << l1, L2 = 1 << l2, half1 = L1 >> 1;
   const int q0 = tile << lcB;
-  // local column tr < c: q = q0 + tr; local column c + t: its mirror L1 - q (the self-mirrored column L1/2 takes the slot of q = 0)
-  auto colq = [&](int tr) -> int {
-    if (tr < c) return q0 + tr;
-    const int q = q0 + tr - c;
-    return q == 0 ? half1 : L1 - q;
-  };
-  const double2* W = a.W + p * a.n;
-  block_fft_fwd_io<true>(sm, l2, lcB + 1, LP, a.T.stage, [&](int tr, int r) -> double2 { return W[((int64_t)r << l1) + colq(tr)]; }, SmemTag{});
-  __syncthreads();
   const SmemC S{sm, LP};
   const double* winv = a.winv;
   const int64_t n = a.n;
@@ -154,6 +165,69 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) pv_passB_kernel
   }
 }
 
+__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) pv_passB_kernel(const __grid_constant__ PvArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ double red[32 * 4];
+  double2* sm = (double2*)smraw;
+  const int64_t p = blockIdx.y;
+  const int tile = blockIdx.x;
+  const int lc2 = a.lcB + 1;
+  const double2* Wt = a.W + p * a.n + ((int64_t)tile << (a.l2 + lc2));  // the tile is one contiguous block (pv_woff)
+  block_fft_fwd_io<true>(sm, a.l2, lc2, a.LPB, a.T.stage, [&](int tr, int r) -> double2 { return Wt[(r << lc2) + tr]; }, SmemTag{});
+  __syncthreads();
+  pv_tile_reduce(a, sm, p, tile, red);
+}
+
+// The same pass as a PERSISTENT kernel with TMA-staged, double-buffered tiles: a CTA walks tiles w, w + grid, ...; while it transforms
+// and reduces tile w out of its padded working tile, the TMA engine (bulk-asynchronous copies of the contiguous tile, SASS UBLKCP, completion
+// on an mbarrier) already fills the other dense staging tile with tile w + grid: no registers and no warp slots are held by loads in flight.
+__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) pv_passB_tma_kernel(const __grid_constant__ PvArgs a, int npairs, int stage_elems) {
+  extern __shared__ __align__(128) unsigned char smraw_pv[];
+  __shared__ double red[32 * 4];
+  __shared__ __align__(8) uint64_t bars[2];
+  double2* stg0 = (double2*)smraw_pv;
+  double2* stg1 = stg0 + stage_elems;
+  double2* sm = stg1 + stage_elems;
+  const int l2 = a.l2, lc2 = a.lcB + 1;
+  const int total = npairs * a.tilesB;
+  const unsigned tile_bytes = (unsigned)(sizeof(double2) << (l2 + lc2));
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int w, int buf) {  // warp 0: the tile as 32 bulk copies
+    const int p = w / a.tilesB, tile = w - p * a.tilesB;
+    const char* src = (const char*)(a.W + (int64_t)p * a.n + ((int64_t)tile << (l2 + lc2)));
+    char* dst = (char*)(buf ? stg1 : stg0);
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+      asm volatile("fence.proxy.async;" ::: "memory");
+      mbar_arrive_expect_tx(&bars[buf], tile_bytes);
+    }
+    __syncwarp();
+    const unsigned chunk = tile_bytes / 32;
+    tma_load_1d(dst + (size_t)lane * chunk, src + (size_t)lane * chunk, chunk, &bars[buf]);
+  };
+  unsigned parity[2] = {0u, 0u};
+  int buf = 0;
+  int w = blockIdx.x;
+  if (w < total && threadIdx.x < 32) issue(w, 0);
+  for (; w < total; w += gridDim.x) {
+    if (w + (int)gridDim.x < total && threadIdx.x < 32) issue(w + gridDim.x, buf ^ 1);
+    const int p = w / a.tilesB, tile = w - p * a.tilesB;
+    mbar_wait(&bars[buf], parity[buf]);
+    parity[buf] ^= 1u;
+    const double2* stg = buf ? stg1 : stg0;
+    block_fft_fwd_io<true>(sm, l2, lc2, a.LPB, a.T.stage, [&](int tr, int r) -> double2 { return stg[(r << lc2) + tr]; }, SmemTag{});
+    __syncthreads();
+    pv_tile_reduce(a, sm, p, tile, red);
+    __syncthreads();  // the working tile and this staging tile are free again
+    buf ^= 1;
+  }
+}
+
 __global__ void __launch_bounds__(256) pv_final_kernel(const double* __restrict__ partial, int tiles, int64_t pairs, int64_t m, double kxx, double* __restrict__ out) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= pairs) return;
@@ -168,6 +242,28 @@ __global__ void __launch_bounds__(256) pv_final_kernel(const double* __restrict_
 }
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// Geometry of the two passes: the complex two-pass split of the transforms (make_geom), with pass-B tiles as wide as 64 KiB of shared
+// memory allow -- 2^(12 - l2) columns, half of them mirrors.  Measured at d = 8 on B200 (profiles/README.md, round 2): 16 instead of 8
+// columns per tile at n = 2^20: 68.0 k -> 77.8 k points/s; n = 2^16: 690 k -> 947 k.
+static PassGeom pv_geom(int64_t n) {
+  PassGeom g = make_geom(n, true);
+  if (!g.l2) return g;
+  static const int cols_env = env_int("FGP_PV_COLS_LOG2", 0);
+  int lb = cols_env > 0 ? cols_env : 12 - g.l2;
+  if (env_int("FGP_PV_TMA", 0) != 0 && lb > 11 - g.l2) lb = 11 - g.l2;  // the staged variant needs room for two staging tiles: 32 KiB tiles
+  if (lb > g.l1 - 1) lb = g.l1 - 1;
+  if (lb < 1) lb = 1;
+  g.lntrB = lb;
+  g.ntrB = 1 << lb;
+  g.LPB = padlen(1 << g.l2, g.ntrB, kPSC);
+  int t = ((1 << (g.l2 + lb)) / 16) * 2;
+  if (t < 32) t = 32;
+  if (t > FGP_LB_THREADS) t = FGP_LB_THREADS;
+  g.threadsB = t;
+  g.smemB = (size_t)g.ntrB * g.LPB * sizeof(double2);
+  return g;
+}
 
 static int64_t pv_chunk_pairs(int64_t pairs, int64_t n) {
   // pairs per chunk: enough tiles per launch for many waves (measured at n = 2^20, d = 8: 1 / 4 / 16 pairs per chunk -> 28.6 k / 52.8 k /
@@ -193,7 +289,7 @@ extern "C" {
 size_t fgp_lattice_post_var_z_workspace_bytes(int64_t m, int64_t n) {
   using namespace fgp;
   if (m <= 0 || !is_pow2(n)) return 0;
-  const PassGeom g = make_geom(n, true);
+  const PassGeom g = pv_geom(n);
   if (!g.l2) return 0;
   const int64_t pairs = (m + 1) >> 1, cp = pv_chunk_pairs(pairs, n);
   const int64_t tilesB = (int64_t(1) << g.l1) >> g.lntrB;
@@ -207,7 +303,7 @@ int fgp_lattice_post_var_z(const double* xs_dev, int64_t m, const uint64_t* z_ho
   FGP_REQUIRE(xs_dev && z_host && shift_host && alpha_host && ls_host && lam_dev && table_dev && work_dev && pvar_dev, "post_var_z: null pointer");
   FGP_REQUIRE(d >= 1 && d <= FGP_MAX_D && m >= 0 && is_pow2(n) && ilog2(n) <= FGP_MAX_LOG2N_FFT, "post_var_z: bad m/n/d (n must be a power of two <= 2^%d)", FGP_MAX_LOG2N_FFT);
   if (m == 0) return FGP_OK;
-  const PassGeom g = make_geom(n, true);
+  const PassGeom g = pv_geom(n);
   FGP_REQUIRE(g.l2 >= 1 && g.lntrA == 0 && g.lntrB >= 1, "post_var_z: n=%lld is a single-tile size, use fgp_lattice_post_var", (long long)n);
   PvArgs a;
   memset(&a, 0, sizeof(a));
@@ -284,6 +380,19 @@ int fgp_lattice_post_var_z(const double* xs_dev, int64_t m, const uint64_t* z_ho
     cudaGetLastError();
     attr_done = true;
   }
+  // TMA-staged persistent pass B (two dense staging tiles + the padded working tile); FGP_PV_TMA=1 selects it
+  // (read per call so that tests compare both routes in one process)
+  const int stage_elems = (2 << a.lcB) << g.l2;
+  const size_t smem_tma = 2 * (size_t)stage_elems * sizeof(double2) + g.smemB;
+  // opt-in: measured SLOWER than the one-tile-per-CTA kernel on B200 (n = 2^20: 62.6 k against 68.0 k points/s; n = 2^16: 242 k against 690 k) --
+  // with ~2 us of work per tile, many small CTAs that the hardware schedules beat two resident CTAs per SM that prefetch
+  const bool use_tma = env_int("FGP_PV_TMA", 0) != 0 && smem_tma <= 110 * 1024 && (stage_elems * sizeof(double2)) % 512 == 0;  // 32 copies of >= 16 bytes
+  static bool attr_tma = false;
+  if (use_tma && !attr_tma) {
+    cudaFuncSetAttribute(pv_passB_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaGetLastError();
+    attr_tma = true;
+  }
   for (int64_t p0 = 0; p0 < pairs; p0 += cp) {
     const int64_t np = pairs - p0 < cp ? pairs - p0 : cp;
     a.xs = xs_dev + 2 * p0 * d;
@@ -301,8 +410,15 @@ int fgp_lattice_post_var_z(const double* xs_dev, int64_t m, const uint64_t* z_ho
       launch_pvA<0, false>(a, gridA, g.threadsA, g.smemA, st);
     }
     FGP_LAUNCH_NAMED("pv_passA", st);
-    pv_passB_kernel<<<dim3((unsigned)a.tilesB, (unsigned)np), g.threadsB, g.smemB, st>>>(a);
-    FGP_LAUNCH_NAMED("pv_passB", st);
+    if (use_tma) {
+      int64_t grid = (int64_t)np * a.tilesB;
+      if (grid > 2 * (int64_t)sm_count()) grid = 2 * (int64_t)sm_count();
+      pv_passB_tma_kernel<<<(unsigned)grid, g.threadsB, smem_tma, st>>>(a, (int)np, stage_elems);
+      FGP_LAUNCH_NAMED("pv_passB_tma", st);
+    } else {
+      pv_passB_kernel<<<dim3((unsigned)a.tilesB, (unsigned)np), g.threadsB, g.smemB, st>>>(a);
+      FGP_LAUNCH_NAMED("pv_passB", st);
+    }
     pv_final_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(a.partial, a.tilesB, np, a.m, kxx, pvar_dev + 2 * p0);
     FGP_LAUNCH_NAMED("pv_final", st);
   }

@@ -1,7 +1,7 @@
 // K3: stand-alone FFT-BRO (forward / inverse) and FWHT over (batch, n) arrays.
 // Replaces qmcpy.fftbr_torch / ifftbr_torch / fwht_torch (fast_gp_lattice.py:224-225, fast_gp_digital_net_b2.py:226).
-#include <cuda.h>  // CUtensorMap and its enums only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint (no -lcuda)
 #include "fgp_transform.cuh"
+#include "fgp_tma.cuh"
 
 namespace fgp {
 
@@ -30,11 +30,13 @@ __global__ void fft_table_kernel(double2* stage, double2* lo, double2* hi, doubl
   }
 }
 
+// `in` and `out` of the transform kernels may be the SAME buffer (in-place calls are part of the C-ABI contract): every CTA reads its
+// whole tile before it writes it and tiles are disjoint, but the pointers are deliberately not __restrict__.
 // ---- forward -------------------------------------------------------------------------------------------------
 // pass A: 2^lntr contiguous length-2^l1 blocks per CTA; the first round reads global memory straight into registers,
 // the last round applies the inter-pass twiddle and writes global memory (coalesced: its elements are 2^(l1-4) apart).
 template <bool REAL_IN, int MINB>
-__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) fft_passA_fwd(const double* __restrict__ in, double2* __restrict__ out, int64_t total_blocks,
+__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) fft_passA_fwd(const double* in, double2* out, int64_t total_blocks,
                                                          int l1, int l2, int lntr, int LP, double scale, FftTables T) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double2* sm = (double2*)smraw;
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, MINB) fft_passA_fwd(const doub
 
 // pass B: 2^lntr adjacent stride-2^l1 columns per CTA, in place; consecutive threads take consecutive columns.
 template <bool INV, int MINB>
-__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) fft_passB(const double2* __restrict__ in, double2* __restrict__ out, int l1, int l2, int lntr,
+__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) fft_passB(const double2* in, double2* out, int l1, int l2, int lntr,
                                                      int LP, FftTables T) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double2* sm = (double2*)smraw;
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, MINB) fft_passB(const double2*
 }
 
 template <int MINB>
-__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) fft_passA_inv(const double2* __restrict__ in, double2* __restrict__ out, int64_t total_blocks,
+__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) fft_passA_inv(const double2* in, double2* out, int64_t total_blocks,
                                                          int l1, int lntr, int LP, double scale, FftTables T) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double2* sm = (double2*)smraw;
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, MINB) fft_passA_inv(const doub
 
 // ---- FWHT ------------------------------------------------------------------------------------------------------
 template <int MINB>
-__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) wht_passA(const double* __restrict__ in, double* __restrict__ out, int64_t total_blocks, int l1,
+__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) wht_passA(const double* in, double* out, int64_t total_blocks, int l1,
                                                      int lntr, int LP, double scale) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double* sm = (double*)smraw;
@@ -147,7 +149,7 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   return v;
 }
 template <int MINB>
-__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) wht_fused(const double* __restrict__ in, double* __restrict__ out, FusedGeom g, double scale,
+__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) wht_fused(const double* in, double* out, FusedGeom g, double scale,
                                                      unsigned* __restrict__ ctl) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double* sm = (double*)smraw;
@@ -222,72 +224,6 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, MINB) wht_fused(const double* 
 // slots are held by loads in flight.  The first round of a tile reads the dense staging tile (conflict-free: in both
 // schedules consecutive threads read consecutive words) and writes the padded working tile; the last round stores to global
 // memory from registers.  Same round schedules as wht_passA / wht_passB, hence the same bits.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// spin on the phase parity; traps (a launch error, not a hang) if the copies never land
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-  const uint32_t addr = smem_u32(bar);
-  for (unsigned spins = 0;; ++spins) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (spins > (1u << 28)) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
-               "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-// 2-D tiled TMA load (cp.async.bulk.tensor, SASS UTMALDG): box (c0.., c1..) of the tensor described by `tmap` -> dense shared memory
-__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst_smem)),
-               "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-               : "memory");
-}
-
-// row-major (rows, cols) float64 matrix at `base` as a tiled tensor map with boxes of (box_rows, box_cols)
-static int make_tmap_2d(const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols, uint32_t box_rows, CUtensorMap* out) {
-  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static encode_fn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
-      cudaGetLastError();
-      set_error("cuTensorMapEncodeTiled is not available from this driver");
-      return FGP_ECUDA;
-    }
-    encode = (encode_fn)fn;
-  }
-  const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {cols * sizeof(double)};  // bytes between rows (dimension 0 is contiguous)
-  const cuuint32_t box[2] = {box_cols, box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with code %d (cols=%llu rows=%llu box=%ux%u)", (int)r, (unsigned long long)cols, (unsigned long long)rows, box_cols, box_rows);
-    return FGP_ECUDA;
-  }
-  return FGP_OK;
-}
-
 struct FusedTile {
   unsigned b, idx;
   bool phaseB, valid;
@@ -318,7 +254,7 @@ __device__ __forceinline__ FusedTile fused_decode(const FusedGeom& g, unsigned t
 }
 
 template <int MINB>
-__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) wht_fused_tma(const double* __restrict__ in, double* __restrict__ out, FusedGeom g, double scale,
+__global__ void __launch_bounds__(FGP_LB_THREADS, MINB) wht_fused_tma(const double* in, double* out, FusedGeom g, double scale,
                                                          unsigned* __restrict__ ctl, int stage_doubles, const __grid_constant__ CUtensorMap tmapB, int box_rows) {
   extern __shared__ __align__(128) unsigned char smraw_tma[];
   double* stg0 = (double*)smraw_tma;               // dense staging tiles (TMA destinations)

@@ -783,9 +783,21 @@ class AbstractFastGP(torch.nn.Module):
         return c[1]
 
     def _hyper_host(self):
-        with torch.no_grad():
-            scale_B, ls_B, noise_B, pshape = self._hyper()
-            return scale_B.cpu().numpy(), ls_B.cpu().numpy(), noise_B.cpu().numpy(), pshape
+        """Host copies of the effective hyperparameters, cached on the parameter state (one device-to-host synchronisation per
+        change of the parameters instead of one per posterior / kernel call)."""
+        key = self._param_key()
+        c = getattr(self, "_hyper_host_cache", None)
+        if c is None or c[0] != key:
+            with torch.no_grad():
+                scale_B, ls_B, noise_B, pshape = self._hyper()
+                c = (key, (scale_B.cpu().numpy(), ls_B.cpu().numpy(), noise_B.cpu().numpy(), pshape))
+            self._hyper_host_cache = c
+        return c[1]
+
+    def _check_unit_cube(self, x):
+        """fast_gp_lattice.py:264-265: the lattice kernel takes points of the unit cube (its |x - z| form is only valid there)."""
+        if self._FAMILY == 0 and x.numel():
+            assert bool(((0 <= x) & (x <= 1)).all()), "x should have all elements in [0,1]"
 
     def _Cgen(self, n):
         """Device generating matrices for the net generator mode (None: read the stored points)."""
@@ -834,17 +846,34 @@ class AbstractFastGP(torch.nn.Module):
             task = torch.tensor(task, dtype=int)
         assert isinstance(y_next, list) and isinstance(task, torch.Tensor) and task.ndim == 1 and len(y_next) == len(task)
         assert all(y_next[i].shape[:-1] == self.shape_batch for i in range(len(y_next)))
+        # sizes first, from the shapes alone: the small size tensors must not queue (and make the host wait) behind the copy of y
+        ncur = [int(self._y[i].size(-1)) for i in range(self.num_tasks)]
         for i, l in enumerate(task):
-            self._y[int(l)] = torch.cat([self._y[int(l)], y_next[i].to(self.device)], -1)
-        self._nint = max(int(self._y[i].size(-1)) for i in range(self.num_tasks))
-        self.n = torch.tensor([self._y[i].size(-1) for i in range(self.num_tasks)], dtype=int, device=self.device)
-        self.m = torch.where(self.n == 0, -1, torch.log2(self.n)).to(int)
-        assert all(nl == 0 or (nl & (nl - 1)) == 0 for nl in (int(v) for v in self.n.tolist())), "total samples must be power of 2"
-        ncur = self.n.tolist()
+            ncur[int(l)] += int(y_next[i].size(-1))
+        assert all(nl == 0 or (nl & (nl - 1)) == 0 for nl in ncur), "total samples must be power of 2"
+        self._nint = max(ncur)
+        self.n = torch.tensor(ncur, dtype=int, device=self.device)
+        self.m = torch.tensor([-1 if nl == 0 else nl.bit_length() - 1 for nl in ncur], dtype=int, device=self.device)
+        for i, l in enumerate(task):
+            yi = y_next[i]
+            if yi.device.type == "cpu" and yi.is_pinned():
+                # a PINNED host buffer is copied asynchronously (stream-ordered): the host goes on to enqueue the transforms below while the
+                # copy is in flight.  The source is kept alive until then; as with any non_blocking copy it must not be rewritten before
+                # the next synchronising call.
+                self._pinned_src = yi
+                yi = yi.to(self.device, non_blocking=True)
+            fresh = y_next[i].device != self.device  # our own device copy: no need to copy it again when it is the first block
+            yi = yi.to(self.device)
+            self._y[int(l)] = yi if (fresh and self._y[int(l)].numel() == 0 and yi.dtype == self._y[int(l)].dtype) else torch.cat([self._y[int(l)], yi], -1)
         for key in list(self.inv_log_det_cache_dict.keys()):
             if any(k < c for k, c in zip(key, ncur)):
                 del self.inv_log_det_cache_dict[key]
         self._epoch += 1
+        # single-task fast path: enqueue ytilde = ft(y) and |ytilde|^2 right away.  They are what fit() and coeffs need first, and here
+        # their host-side launch work overlaps the (asynchronous) host-to-device copy of y instead of delaying the first fit iteration.
+        if self._mt is None and not self._DENSE and self._nint > 0 and os.environ.get("FGP_B200_NO_PREFETCH") != "1":
+            with torch.no_grad():
+                self._get_ysq(self._pshape())
 
     # ------------------------------------------------------------------------------------------------ properties
     @property
@@ -1441,6 +1470,7 @@ class AbstractFastGP(torch.nn.Module):
             return pmean[0] if inttask else pmean
         coeffs = self.coeffs
         x = x.to(self.device).contiguous()
+        self._check_unit_cube(x)
         scale_B, ls_B, _, pshape = self._hyper_host()
         B = len(scale_B)
         sb = tuple(self.shape_batch)
@@ -1464,6 +1494,7 @@ class AbstractFastGP(torch.nn.Module):
         assert x.ndim == 2 and x.size(1) == self.d, "x must a torch.Tensor with shape (-1,d)"
         inttask, task = self._parse_task(task)
         x = x.to(self.device).contiguous()
+        self._check_unit_cube(x)
         if self._mt is not None:
             pvar = self._mt.post_var(x, task, n)
             return pvar[0] if inttask else pvar
@@ -1494,6 +1525,8 @@ class AbstractFastGP(torch.nn.Module):
         inttask1, task1 = self._parse_task(task1)
         x0 = x0.to(self.device).contiguous()
         x1 = x1.to(self.device).contiguous()
+        self._check_unit_cube(x0)
+        self._check_unit_cube(x1)
         equal = torch.equal(x0, x1) and torch.equal(task0, task1)
         if self._mt is not None:
             kmat = self._mt.post_cov(x0, x1, task0, task1, n, equal)
@@ -1714,10 +1747,11 @@ class FastGPLattice(AbstractFastGP):
         return torch.exp(-torch.pi * 1j * torch.arange(2 ** m, device=self.device) / 2 ** m)
 
     def _ft_unstable(self, x):
-        return _FTFunction.apply(x, 0)
+        # the autograd wrapper costs ~0.1 ms of host time per call: only when a gradient can flow
+        return _FTFunction.apply(x, 0) if (torch.is_grad_enabled() and x.requires_grad) else _lib.fftbr(x)
 
     def _ift_unstable(self, x):
-        return _FTFunction.apply(x, 1)
+        return _FTFunction.apply(x, 1) if (torch.is_grad_enabled() and x.requires_grad) else _lib.ifftbr(x)
 
     def _ominus(self, x, z):
         return (x - z) % 1
@@ -1802,7 +1836,7 @@ class FastGPDigitalNetB2(AbstractFastGP):
         return 1
 
     def _ft_unstable(self, x):
-        return _FTFunction.apply(x, 2)
+        return _FTFunction.apply(x, 2) if (torch.is_grad_enabled() and x.requires_grad) else _lib.fwht(x)
 
     _ift_unstable = _ft_unstable
 

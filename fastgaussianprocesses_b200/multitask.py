@@ -5,8 +5,8 @@ Every block K_task[l0,l1] * K(X_l0, X_l1) of the Gram matrix of T randomisations
 diagonalised by the same fast transform, so the whole matrix reduces to n independent T x T Hermitian systems
     Lam_k[l0,l1] = K_task[l0,l1] (sqrt(n) ft(k1^(l0,l1))_k + noise [l0 == l1]).
 The transforms are the CUDA kernels of libfgp_b200 behind torch.autograd (`_FTFunction`); the kernel parts, cross
-kernels and posterior-mean products are the K2 / K5 kernels; the n small T x T factorizations are batched torch.linalg
-calls (library code, as the reference's own Schur-complement recursion is torch code).  Tasks of different (power-of-two)
+kernels and posterior-mean products are the K2 / K5 kernels; the n small R x R systems are inverted by the
+fgp_block_inv_logdet kernel (one thread per system, Gauss-Jordan with partial pivoting in registers; `_BlockInvLogdet`).  Tasks of different (power-of-two)
 sizes fold into n_min independent R x R systems, R = sum_l n_l / n_min, because sub-sampling a lattice aliases the
 frequencies kappa and kappa mod n_l.  This path is parity-tested against reference fixtures but not fused or tuned.
 """
@@ -14,6 +14,30 @@ import numpy as np
 import torch
 
 from . import _lib
+
+
+class _BlockInvLogdet(torch.autograd.Function):
+    """A_k = L_k^-1 and log|det L_k| of the n_min per-frequency R x R systems, computed by the fgp_block_inv_logdet kernel (one thread per
+    system, Gauss-Jordan with partial pivoting in registers).  Backward: dL = -A^H gA A^H + g_logdet A^H, two small batched products on the
+    saved inverse."""
+
+    @staticmethod
+    def forward(ctx, L):
+        A, logdet = _lib.block_inv_logdet(L)
+        ctx.save_for_backward(A)
+        return A, logdet
+
+    @staticmethod
+    def backward(ctx, gA, gld):
+        (A,) = ctx.saved_tensors
+        AH = A.mH
+        g = None
+        if gA is not None:
+            g = -torch.einsum("kij,kjl,klm->kim", AH, gA.to(A.dtype), AH)
+        if gld is not None:
+            t = gld.to(A.dtype)[:, None, None] * AH
+            g = t if g is None else g + t
+        return g
 
 
 class MultiTaskEngine(object):
@@ -135,13 +159,13 @@ class MultiTaskEngine(object):
     def factor(self, n=None, grad=False):
         """(Lam^-1 (n_min,R,R), logdet) -- cached on the hyperparameter state when no gradient is needed."""
         if grad:
-            L = self.lam_system(n)
-            return torch.linalg.inv(L), torch.linalg.slogdet(L)[1].sum(-1)
+            A, ld = _BlockInvLogdet.apply(self.lam_system(n))
+            return A, ld.sum(-1)
         key = (tuple(self.sizes(n)[0]),) + self.gp._param_key()
         if self._lam_key != key:
             with torch.no_grad():
-                L = self.lam_system(n)
-                self._solve_cache = (torch.linalg.inv(L), torch.linalg.slogdet(L)[1].sum(-1))
+                A, ld = _lib.block_inv_logdet(self.lam_system(n))
+                self._solve_cache = (A, ld.sum(-1))
             self._lam_key = key
         return self._solve_cache
 

@@ -265,6 +265,11 @@ int fgp_deriv_cross_kernel(int family, const double* xs_dev, int64_t m, const vo
                            const int* ord_dev, const double* par_dev, const double* ind_dev, const double* w_dev, int t,
                            double scale, const double* ls_host, double* k_dev, fgp_stream_t stream);
 
+/* Per-frequency block systems of the multi-task / derivative-informed eigen-solve (replaces the Schur-complement recursion of
+ * util.py:301-323 and the block solve of :354-363): nm independent R x R matrices L[k] (row-major (nm,R,R); interleaved complex when cplx != 0,
+ * real otherwise; R <= 16), A[k] = L[k]^-1 and logdet[k] = log|det L[k]| by in-register Gauss-Jordan elimination with partial pivoting. */
+int fgp_block_inv_logdet(int cplx, const double* L_dev, int64_t nm, int R, double* A_dev, double* logdet_dev, fgp_stream_t stream);
+
 /* FP64 FMA-chain peak probe used by bench.py for the FP64 roofline denominator: runs `iters` dependent-chain
  * DFMA blocks on every SM and returns the flop count in *flops (time it with events on `stream`). */
 int fgp_fp64_peak_probe(int iters, double* sink_dev, double* flops, fgp_stream_t stream);

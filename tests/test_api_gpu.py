@@ -130,6 +130,19 @@ def test_api_guards_and_errors():
         gp.post_var(x[:4], n=96)
     with pytest.raises(AssertionError):
         gp.post_mean(torch.zeros(4, 2))
+    # the lattice kernel lives on the unit cube (fast_gp_lattice.py:264-265): x = 1 is admissible and equals x = 0, outside raises
+    edge = torch.tensor([[1.0, 0.25, 0.5], [0.0, 0.25, 0.5]])
+    pm = gp.post_mean(edge)
+    assert abs(float(pm[0] - pm[1])) <= 1e-12 * max(1.0, float(pm.abs().max()))
+    pv = gp.post_var(edge)
+    assert abs(float(pv[0] - pv[1])) <= 1e-10
+    for bad in (torch.tensor([[1.0 + 1e-9, 0.2, 0.2]]), torch.tensor([[-0.1, 0.2, 0.2]])):
+        with pytest.raises(AssertionError, match="\\[0,1\\]"):
+            gp.post_mean(bad)
+        with pytest.raises(AssertionError, match="\\[0,1\\]"):
+            gp.post_var(bad)
+        with pytest.raises(AssertionError, match="\\[0,1\\]"):
+            gp.post_cov(bad, bad)
     with pytest.raises(RuntimeError):
         fgp.FastGPLattice(3, device="cpu")
     with pytest.raises(NotImplementedError):

@@ -351,7 +351,7 @@ def test_c_abi_rejects_bad_arguments(L):
 
 
 @pytest.mark.parametrize("d,m,alpha,mtest", [(8, 20, 2, 37), (8, 16, 2, 64), (2, 13, 2, 5), (3, 14, 3, 16), (16, 15, 2, 9), (5, 13, 1, 1), (4, 18, 2, 130), (8, 12, 2, 8)])
-def test_fused_generator_post_var_matches_unfused_route(L, P, d, m, alpha, mtest):
+def test_fused_generator_post_var_matches_unfused_route(L, P, d, m, alpha, mtest, monkeypatch):
     """fgp_lattice_post_var_z (points regenerated inside the first transform pass, (k, n-k) reduction in the epilogue of the
     second pass over mirror-paired column tiles) against fgp_lattice_post_var fed with the stored points (itself pinned to the
     reference fixtures).  Odd numbers of test points, general alpha and the smallest two-pass sizes included."""
@@ -371,6 +371,11 @@ def test_fused_generator_post_var_matches_unfused_route(L, P, d, m, alpha, mtest
     if not L.post_var_z_supported(n):
         pytest.skip("single-tile size: the unfused route is the only one")
     got = L.post_var_z(xs, z, shift, n, [alpha] * d, scale, ls, lam[0])
+    # the TMA-staged persistent pass B (opt-in: bulk-asynchronous copies of the next tile under an mbarrier) does the same arithmetic as
+    # the one-tile-per-CTA pass B
     kxx = max(float(ref.max()), scale)  # the variances are kxx minus a sum of the same size: round-off scales with kxx
+    monkeypatch.setenv("FGP_PV_TMA", "1")  # (narrower tiles: the partial sums group differently)
+    assert float((L.post_var_z(xs, z, shift, n, [alpha] * d, scale, ls, lam[0]) - got).abs().max()) <= 1e-13 * kxx
+    monkeypatch.delenv("FGP_PV_TMA")  # the variances are kxx minus a sum of the same size: round-off scales with kxx
     assert float((got - ref).abs().max()) <= 1e-11 * kxx
     assert float(got[0]) <= 1e-2 * kxx  # at a training point the variance is noise-limited

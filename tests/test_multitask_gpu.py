@@ -139,3 +139,32 @@ def test_multitask_guards():
         gp.post_var(torch.rand(4, 2), n=[64, 8])  # sizes may only grow
     with pytest.raises(NotImplementedError):
         fgp.FastGPLattice(2, num_tasks=2, shape_batch=[3], device=dev)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("R", [1, 2, 3, 4, 5, 8, 16])
+def test_block_inv_logdet_kernel_matches_dense_algebra(R, cplx):
+    """fgp_block_inv_logdet (one thread per R x R system, Gauss-Jordan with partial pivoting) against torch.linalg on the same matrices:
+    Hermitian positive definite systems as the eigen-solve produces them, and general (pivoting) ones; then its autograd wrapper."""
+    from fastgaussianprocesses_b200 import _lib
+    from fastgaussianprocesses_b200.multitask import _BlockInvLogdet
+    g = torch.Generator(device=dev).manual_seed(R + 100 * cplx)
+    nm = 1000
+    dt = torch.complex128 if cplx else torch.float64
+    M = torch.randn(nm, R, R, dtype=dt, device=dev, generator=g)
+    for L in (M @ M.mH + 0.1 * torch.eye(R, device=dev, dtype=dt), M):
+        A, ld = _lib.block_inv_logdet(L)
+        Aref = torch.linalg.inv(L)
+        ldref = torch.linalg.slogdet(L)[1]
+        assert float((A - Aref).abs().max() / Aref.abs().max()) < 1e-9
+        assert float((ld - ldref).abs().max()) < 1e-10 * max(1.0, float(ldref.abs().max()))
+    Ls = (M[:4] @ M[:4].mH + torch.eye(R, device=dev, dtype=dt)).requires_grad_(True)
+    w = torch.randn(4, R, R, dtype=dt, device=dev, generator=g)
+
+    def f(fn):
+        A, ld = fn(Ls)
+        return (A * w).sum().real + (ld * torch.arange(1.0, 5.0, device=dev)).sum()
+
+    g1, = torch.autograd.grad(f(_BlockInvLogdet.apply), Ls)
+    g2, = torch.autograd.grad(f(lambda L: (torch.linalg.inv(L), torch.linalg.slogdet(L)[1])), Ls)
+    assert float((g1 - g2).abs().max() / g2.abs().max()) < 1e-10

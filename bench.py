@@ -265,11 +265,16 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
+    out_fd = None
     if world > 1:
-        # NCCL writes its INFO lines to stdout unless told otherwise: keep stdout one JSON line, keep the log on stderr
+        # NCCL prints its version banner and its INFO lines on STDOUT (file descriptor 1), whatever Python's sys.stdout is: point fd 1 at
+        # stderr for the whole run -- the communicator lines (nranks, NVLS, rings) stay visible to the driver there -- and write the one
+        # JSON line to the saved descriptor at the end
+        sys.stdout.flush()
+        out_fd = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -338,13 +343,16 @@ def main():
     gpw0.add_y_next(y_dev)
     gpw0.fit(iterations=K, verbose=0, stop_crit_wait_iterations=K + 1)
     del gpw0
-    barrier()
-    e0, e1 = ev(), ev()
-    e0.record()
-    dataw = gpw.fit(iterations=K, verbose=0, stop_crit_wait_iterations=K + 1)
-    e1.record()
-    barrier()
-    t_warm = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    warm_ts = []
+    for _ in range(3):  # median of three calls (each restarts from the previous best iterate)
+        barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        dataw = gpw.fit(iterations=K, verbose=0, stop_crit_wait_iterations=K + 1)
+        e1.record()
+        barrier()
+        warm_ts.append(max_over_ranks(e0.elapsed_time(e1) * 1e-3))
+    t_warm = float(np.median(warm_ts))
     warm_iters = int(dataw["iterations"])
     # ---- e2e: public API, host buffers
     gp2 = new_gp()
@@ -513,7 +521,11 @@ def main():
         # bounded sample of the same workload, ~10-30 s of CPU work on the GPU box's host cores
         r = cpu_reference_run(n, d, 20, 16, 4)
         line["cpu_baseline"] = cpu_baseline_block(r, torch.get_num_threads())
-    print(json.dumps(line))
+    if out_fd is not None:
+        sys.stdout.flush()
+        os.write(out_fd, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 

@@ -79,6 +79,8 @@ SIGNATURES = {
     "fgp_dnb2_post_var": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp, _vp, _vp]),
     "fgp_lattice_post_var_z_workspace_bytes": (_sz, [_i64, _i64]),
     "fgp_lattice_post_var_z": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fgp_dnb2_post_var_C_workspace_bytes": (_sz, [_i64, _i64]),
+    "fgp_dnb2_post_var_C": (_i32, [_vp, _i64, _vp, _i32, _vp, _i32, _i64, _i32, _vp, _f64, _vp, _vp, _vp, _vp, _vp]),
     "fgp_lattice_cross_kernel": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _f64, _vp, _vp, _vp]),
     "fgp_dnb2_cross_kernel": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp]),
     "fgp_kernel_pairs": (_i32, [_i32, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp]),
@@ -524,6 +526,21 @@ def post_var_z(xs, z, shift, n, alpha, scale, ls, lam):
                                              _harr(_i32, alpha), float(scale), _harr(_f64, ls), _dev(lam, torch.complex128), tab.data_ptr(),
                                              ws.data_ptr(), out.data_ptr(), _stream()))
     return out
+
+
+def post_var_C(xs, C, dshift, t, n, alpha, scale, ls, lam):
+    """Fused digital-net posterior variance in generator form (fgp_dnb2_post_var_C); C: (d, mmax) int64 device tensor."""
+    m, d = xs.shape
+    out = torch.empty((m,), dtype=torch.float64, device=xs.device)
+    ws = _workspace("pvarC", load().fgp_dnb2_post_var_C_workspace_bytes(m, n), xs.device)
+    with torch.cuda.device(xs.device):
+        _check(load().fgp_dnb2_post_var_C(_dev(xs, torch.float64), m, _dev(C, torch.int64), int(C.shape[1]), _harr(_u64, [int(v) for v in dshift]), int(t), n, d,
+                                          _harr(_i32, alpha), float(scale), _harr(_f64, ls), _dev(lam, torch.float64), ws.data_ptr(), out.data_ptr(), _stream()))
+    return out
+
+
+def post_var_C_supported(n):
+    return load().fgp_dnb2_post_var_C_workspace_bytes(2, int(n)) > 0
 
 
 def post_var_z_supported(n):

@@ -160,7 +160,20 @@ __device__ __forceinline__ double dnb2_part(uint64_t delta, int alpha, int t) {
           beta * (s / 48.0 - 1.0 / 42.0)) - 1.0;
 }
 
-// net alpha = 2 without branches on alpha: W_2(delta) - 1 = 3/2 - (5/2) 2^-beta - beta x_f, beta = t - floor(log2 delta)
+// net alpha = 2 without branches on alpha: W_2(delta) - 1 = 3/2 - (5/2) 2^-beta - beta x_f, beta = t - floor(log2 delta).
+// t <= 52 (delta < 2^52, this package's default nets): the integer converts EXACTLY through the 2^52 magic number (one OR on the high
+// word, one DADD) and floor(log2 delta) is the exponent field of that double -- no 64-bit count-leading-zeros and no 64-bit int-to-double
+// conversion, both of which are multi-instruction sequences (the inner loop of the net post_mean kernel was 55 instructions per
+// (test, train, dimension), issue-bound; about 18 this way).
+__device__ __forceinline__ double dnb2_part_a2_t52(uint64_t delta, int t, double tscale) {  // requires t <= 52
+  const double dd = __longlong_as_double((long long)(delta | 0x4330000000000000ull)) - 4503599627370496.0;
+  const int fl = (int)((unsigned long long)__double_as_longlong(dd) >> 52) - 1023;  // floor(log2 delta), delta > 0
+  const int beta = t - fl;
+  const double xf = dd * tscale;
+  const double pw = __longlong_as_double((long long)(1023 - beta) << 52);  // 2^-beta
+  const double r = fma(-(double)beta, xf, fma(-2.5, pw, 1.5));
+  return delta ? r : 1.5;
+}
 __device__ __forceinline__ double dnb2_part_a2(uint64_t delta, int t, double tscale) {
   const int fl = 63 - __clzll((long long)delta);  // -1 when delta == 0
   const int beta = t - fl;

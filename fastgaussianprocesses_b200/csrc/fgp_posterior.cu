@@ -37,7 +37,8 @@ struct PostArgs {
   double pref;            // scale (times prod_j A_j on the fast path)
 };
 
-// MODE 0: lattice alpha=2 fast path; 1: lattice generic alpha; 2: net generic alpha; 3: net alpha=2 (branch-free part)
+// MODE 0: lattice alpha=2 fast path; 1: lattice generic alpha; 2: net generic alpha; 3: net alpha=2 (branch-free part);
+// 4: net alpha=2 with t <= 52 (exact conversion through the 2^52 magic number, fgp_common.cuh)
 template <int DT, int R, int MODE>
 __global__ void __launch_bounds__(kPT) post_mean_kernel(const __grid_constant__ PostArgs a) {
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
@@ -93,7 +94,8 @@ __global__ void __launch_bounds__(kPT) post_mean_kernel(const __grid_constant__ 
           const uint64_t Xb = ((const uint64_t*)sX)[k * d + j];
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            const double part = MODE == 3 ? dnb2_part_a2(xbr[r][j] ^ Xb, a.t, a.tscale) : dnb2_part(xbr[r][j] ^ Xb, a.alpha[j], a.t);
+            const double part = MODE == 4 ? dnb2_part_a2_t52(xbr[r][j] ^ Xb, a.t, a.tscale)
+                                          : (MODE == 3 ? dnb2_part_a2(xbr[r][j] ^ Xb, a.t, a.tscale) : dnb2_part(xbr[r][j] ^ Xb, a.alpha[j], a.t));
             const double f = fma(a.ls[j], part, 1.0);
             prod[r] = j == 0 ? f : prod[r] * f;
           }
@@ -369,11 +371,12 @@ static int post_mean_common(int family, const double* xs, int64_t m, const void*
     }
     bool all2 = true;
     for (int j = 0; j < d; ++j) all2 = all2 && alpha_host[j] == 2;
-    mode = all2 ? 3 : 2;
+    mode = all2 ? (t <= 52 ? 4 : 3) : 2;
   }
   cudaStream_t st = (cudaStream_t)stream;
   int rc = mode == 0 ? dispatch_post_mean<0>(a, st)
-                     : (mode == 1 ? dispatch_post_mean<1>(a, st) : (mode == 2 ? dispatch_post_mean<2>(a, st) : dispatch_post_mean<3>(a, st)));
+                     : (mode == 1 ? dispatch_post_mean<1>(a, st)
+                                  : (mode == 2 ? dispatch_post_mean<2>(a, st) : (mode == 3 ? dispatch_post_mean<3>(a, st) : dispatch_post_mean<4>(a, st))));
   if (rc) return rc;
   if (a.splits > 1) {
     const int64_t total = (int64_t)B * m;

@@ -228,17 +228,24 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) pv_passB_tma_ke
   }
 }
 
+// one WARP per pair: lane-strided partial sums, then a shuffle tree -- a fixed order, so the result does not depend on scheduling
+// (one thread per pair made this kernel 30 us of serial loads per chunk, 7 % of the whole post_var)
 __global__ void __launch_bounds__(256) pv_final_kernel(const double* __restrict__ partial, int tiles, int64_t pairs, int64_t m, double kxx, double* __restrict__ out) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (p >= pairs) return;
   double s0 = 0.0, s1 = 0.0;
-  for (int g = 0; g < tiles; ++g) {
+  for (int g = lane; g < tiles; g += 32) {
     s0 += partial[(p * tiles + g) * 2 + 0];
     s1 += partial[(p * tiles + g) * 2 + 1];
   }
-  const double v0 = kxx - s0, v1 = kxx - s1;
-  out[2 * p] = v0 < 0.0 ? 0.0 : v0;
-  if (2 * p + 1 < m) out[2 * p + 1] = v1 < 0.0 ? 0.0 : v1;
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  if (lane == 0) {
+    const double v0 = kxx - s0, v1 = kxx - s1;
+    out[2 * p] = v0 < 0.0 ? 0.0 : v0;
+    if (2 * p + 1 < m) out[2 * p + 1] = v1 < 0.0 ? 0.0 : v1;
+  }
 }
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -280,6 +287,172 @@ static int64_t pv_chunk_pairs(int64_t pairs, int64_t n) {
 template <int DT, bool A2>
 static void launch_pvA(const PvArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
   pv_passA_kernel<DT, A2><<<grid, threads, smem, st>>>(a);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// digital nets: the same two-kernel structure with the real Walsh-Hadamard transform (no pairing: one real sequence per test point)
+//   pvn_passA  k(x*, X_i) for the 2^l1 points of a block, the points REGENERATED as xb_i = XOR_{k in bits(i)} C[j][k] ^ dshift_j from two
+//              shared-memory XOR-fold tables per tile (as the fit kernels do) -> block FWHT -> workspace in pass-B tile order
+//   pvn_passB  column FWHT of a contiguous tile -> sum_k v_k^2 / (n lam_k) in the epilogue
+// ------------------------------------------------------------------------------------------------------------------------------
+struct PvnArgs {
+  const double* xs;
+  int64_t m, n;
+  int d, t, mmax;
+  double tscale;
+  const uint64_t* C;  // device (d, mmax) generating-matrix columns
+  UVec dshift;
+  DVec ls;
+  IVec alpha;
+  double scale;
+  double* W;           // (points, n) in pass-B tile order
+  const double* winv;  // (n) 1 / (n lam_k)
+  double* partial;     // (points, tilesB)
+  int l1, l2, LPA, LPB, lcB, tilesB, tab_off;
+};
+
+__global__ void __launch_bounds__(256) pvn_winv_kernel(const double* __restrict__ lam, int64_t n, double* __restrict__ winv) {
+  const double inv_n = 1.0 / (double)n;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) winv[k] = inv_n / lam[k];
+}
+
+__device__ __forceinline__ uint64_t pvn_fold(const uint64_t* __restrict__ Cj, uint64_t v) {
+  uint64_t r = 0;
+  while (v) {
+    const int k = __ffsll((long long)v) - 1;
+    r ^= __ldg(Cj + k);
+    v &= v - 1;
+  }
+  return r;
+}
+
+constexpr int kPvnPoints = 4;
+// MODE 0: any alpha; 1: every alpha == 2; 2: alpha == 2 and t <= 52 (exact conversion through the 2^52 magic number)
+template <int DT, int MODE>
+__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) pvn_passA_kernel(const __grid_constant__ PvnArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ uint64_t cst[FGP_MAX_D];  // to_b(x*_j) ^ dshift_j
+  constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
+  const int d = DT > 0 ? DT : a.d;
+  double* sm = (double*)smraw;
+  uint64_t* TA = (uint64_t*)(smraw + a.tab_off);  // TA[j*64 + v]: fold over the low 6 index bits; TB[j*nb + h]: over the rest of the tile index
+  const int l1 = a.l1, LP = a.LPA;
+  const int nb = l1 > 6 ? 1 << (l1 - 6) : 1;
+  uint64_t* TB = TA + 64 * d;
+  const int blk = blockIdx.x;
+  const int64_t g0 = (int64_t)blk << l1;
+  for (int e = threadIdx.x; e < 64 * d; e += blockDim.x) TA[e] = pvn_fold(a.C + (int64_t)(e >> 6) * a.mmax, (uint64_t)(e & 63));
+  for (int e = threadIdx.x; e < nb * d; e += blockDim.x) {
+    const int j = e / nb, h = e - j * nb;
+    TB[e] = pvn_fold(a.C + (int64_t)j * a.mmax, (uint64_t)g0 | ((uint64_t)h << 6));
+  }
+  const int lcB = a.lcB, l2 = a.l2;
+  // kPvnPoints test points per CTA, one after the other: the fold tables of the block are built once for all of them
+  for (int q = 0; q < kPvnPoints; ++q) {
+    const int64_t p = (int64_t)blockIdx.y * kPvnPoints + q;
+    if (p >= a.m) break;  // uniform over the CTA
+    __syncthreads();      // the previous point's tile and cst are no longer read
+    if (threadIdx.x < d) cst[threadIdx.x] = dnb2_to_b(a.xs[p * d + threadIdx.x], a.t) ^ a.dshift.v[threadIdx.x];
+    __syncthreads();
+    tile_fill_r<false>(SmemR{sm, LP}, l1, 0, [&](int, int idx) -> double {
+      const uint64_t* ta = TA + (idx & 63);
+      const uint64_t* tb = TB + (idx >> 6);
+      double k = a.scale;
+#pragma unroll
+      for (int j = 0; j < DM; ++j) {
+        if (j >= d) break;
+        const uint64_t delta = ta[j * 64] ^ tb[j * nb] ^ cst[j];
+        const double part = MODE == 2 ? dnb2_part_a2_t52(delta, a.t, a.tscale) : (MODE == 1 ? dnb2_part_a2(delta, a.t, a.tscale) : dnb2_part(delta, a.alpha.v[j], a.t));
+        k *= fma(a.ls.v[j], part, 1.0);
+      }
+      return k;
+    });
+    __syncthreads();
+    // workspace in pass-B tile order: tile = q >> lcB holds 2^lcB adjacent columns of all L2 rows, element (row, slot) at ((tile L2 + row) << lcB) + slot
+    double* W = a.W + p * a.n;
+    block_wht_io<false>(sm, l1, 0, LP, wht_sched_up(l1), SmemTag{}, [&](int, int idx, double v) {
+      W[((int64_t)(idx >> lcB) << (l2 + lcB)) + ((int64_t)blk << lcB) + (idx & ((1 << lcB) - 1))] = v;
+    });
+  }
+}
+
+__global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS_R) pvn_passB_kernel(const __grid_constant__ PvnArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ double red[32 * 4];
+  double* sm = (double*)smraw;
+  const int64_t p = blockIdx.y;
+  const int tile = blockIdx.x;
+  const int l1 = a.l1, l2 = a.l2, lcB = a.lcB;
+  const double* Wt = a.W + p * a.n + ((int64_t)tile << (l2 + lcB));
+  block_wht_io<true>(sm, l2, lcB, a.LPB, wht_sched_up(l2), [&](int tr, int r) -> double { return Wt[(r << lcB) + tr]; }, SmemTag{});
+  __syncthreads();
+  const double* winv = a.winv + ((int64_t)tile << lcB);
+  double s[1] = {0.0};
+  tile_drain_r<true>(SmemR{sm, a.LPB}, l2, lcB, [&](int tr, int r, double v) { s[0] = fma(v * v, winv[((int64_t)r << l1) + tr], s[0]); });
+  block_sum<1>(s, red);
+  if (threadIdx.x == 0) a.partial[p * a.tilesB + tile] = s[0];
+}
+
+__global__ void __launch_bounds__(256) pvn_final_kernel(const double* __restrict__ partial, int tiles, int64_t cnt, double kxx, double* __restrict__ out) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per test point, fixed summation order
+  const int lane = threadIdx.x & 31;
+  if (i >= cnt) return;
+  double s = 0.0;
+  for (int g = lane; g < tiles; g += 32) s += partial[i * tiles + g];
+  s = warp_sum(s);
+  if (lane == 0) {
+    const double v = kxx - s;
+    out[i] = v < 0.0 ? 0.0 : v;
+  }
+}
+
+static PassGeom pvn_geom(int64_t n) {
+  PassGeom g = make_geom(n, false);
+  if (!g.l2) return g;
+  int lb = 12 - g.l2;  // 32 KiB pass-B tiles
+  if (lb > g.l1) lb = g.l1;
+  if (lb < 0) lb = 0;
+  g.lntrB = lb;
+  g.ntrB = 1 << lb;
+  g.LPB = padlen(1 << g.l2, g.ntrB, kPSR);
+  int t = (1 << (g.l2 + lb)) / 16;
+  if (t < 32) t = 32;
+  if (t > FGP_LB_THREADS) t = FGP_LB_THREADS;
+  g.threadsB = t;
+  g.smemB = (size_t)g.ntrB * g.LPB * sizeof(double);
+  return g;
+}
+
+static int64_t pvn_chunk_points(int64_t m, int64_t n) {
+  static const int env = env_int("FGP_PV_CHUNK", 0);
+  int64_t c = env > 0 ? env : (int64_t(1) << 25) / n;
+  if (c < 32) c = 32;
+  if (c * n > (int64_t(1) << 27)) c = (int64_t(1) << 27) / n;  // at most 1 GiB of workspace
+  if (c < 1) c = 1;
+  if (c > m) c = m;
+  return c;
+}
+
+template <int DT, int MODE>
+static void launch_pvnA(const PvnArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(pvn_passA_kernel<DT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaGetLastError();
+    attr = true;
+  }
+  pvn_passA_kernel<DT, MODE><<<grid, threads, smem, st>>>(a);
+}
+template <int MODE>
+static void dispatch_pvnA(const PvnArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+  switch (a.d) {
+    case 2: launch_pvnA<2, MODE>(a, grid, threads, smem, st); break;
+    case 4: launch_pvnA<4, MODE>(a, grid, threads, smem, st); break;
+    case 8: launch_pvnA<8, MODE>(a, grid, threads, smem, st); break;
+    case 16: launch_pvnA<16, MODE>(a, grid, threads, smem, st); break;
+    default: launch_pvnA<0, MODE>(a, grid, threads, smem, st); break;
+  }
 }
 
 }  // namespace fgp
@@ -419,8 +592,99 @@ int fgp_lattice_post_var_z(const double* xs_dev, int64_t m, const uint64_t* z_ho
       pv_passB_kernel<<<dim3((unsigned)a.tilesB, (unsigned)np), g.threadsB, g.smemB, st>>>(a);
       FGP_LAUNCH_NAMED("pv_passB", st);
     }
-    pv_final_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(a.partial, a.tilesB, np, a.m, kxx, pvar_dev + 2 * p0);
+    pv_final_kernel<<<(unsigned)((np * 32 + 255) / 256), 256, 0, st>>>(a.partial, a.tilesB, np, a.m, kxx, pvar_dev + 2 * p0);
     FGP_LAUNCH_NAMED("pv_final", st);
+  }
+  return FGP_OK;
+}
+
+size_t fgp_dnb2_post_var_C_workspace_bytes(int64_t m, int64_t n) {
+  using namespace fgp;
+  if (m <= 0 || !is_pow2(n)) return 0;
+  const PassGeom g = pvn_geom(n);
+  if (!g.l2) return 0;
+  const int64_t cp = pvn_chunk_points(m, n);
+  const int64_t tilesB = (int64_t(1) << g.l1) >> g.lntrB;
+  return align256((size_t)cp * n * sizeof(double)) + align256((size_t)n * sizeof(double)) + align256((size_t)cp * tilesB * sizeof(double));
+}
+
+int fgp_dnb2_post_var_C(const double* xs_dev, int64_t m, const uint64_t* C_dev, int mmax, const uint64_t* dshift_host, int t, int64_t n, int d,
+                        const int* alpha_host, double scale, const double* ls_host, const double* lam_dev, void* work_dev, double* pvar_dev,
+                        fgp_stream_t stream) {
+  using namespace fgp;
+  FGP_REQUIRE(xs_dev && C_dev && dshift_host && alpha_host && ls_host && lam_dev && work_dev && pvar_dev, "post_var_C: null pointer");
+  FGP_REQUIRE(d >= 1 && d <= FGP_MAX_D && m >= 0 && is_pow2(n) && ilog2(n) <= FGP_MAX_LOG2N_WHT && t >= 1 && t < 64, "post_var_C: bad m/n/d/t");
+  FGP_REQUIRE(mmax >= 1 && mmax <= 64 && (mmax == 64 || n <= (int64_t(1) << mmax)), "post_var_C: n exceeds 2^mmax generating-matrix columns");
+  if (m == 0) return FGP_OK;
+  const PassGeom g = pvn_geom(n);
+  FGP_REQUIRE(g.l2 >= 1 && g.lntrA == 0, "post_var_C: n=%lld is a single-tile size, use fgp_dnb2_post_var", (long long)n);
+  PvnArgs a;
+  memset(&a, 0, sizeof(a));
+  static const double w0[5] = {0.0, 1.0, 1.5, 43.0 / 18.0 - 1.0, 701.0 / 294.0 - 1.0};
+  double kxx = scale;
+  bool all2 = true;
+  for (int j = 0; j < d; ++j) {
+    FGP_REQUIRE(alpha_host[j] >= 1 && alpha_host[j] <= 4, "post_var_C: net alpha outside 1..4");
+    a.alpha.v[j] = alpha_host[j];
+    a.ls.v[j] = ls_host[j];
+    a.dshift.v[j] = dshift_host[j];
+    all2 = all2 && alpha_host[j] == 2;
+    kxx *= 1.0 + ls_host[j] * w0[alpha_host[j]];
+  }
+  a.n = n;
+  a.d = d;
+  a.t = t;
+  a.mmax = mmax;
+  a.tscale = ldexp(1.0, -t);
+  a.C = C_dev;
+  a.scale = scale;
+  a.l1 = g.l1;
+  a.l2 = g.l2;
+  a.LPA = g.LPA;
+  a.LPB = g.LPB;
+  a.lcB = g.lntrB;
+  a.tilesB = (int)((int64_t(1) << g.l1) >> g.lntrB);
+  a.tab_off = (int)((g.smemA + 15) & ~(size_t)15);
+  const size_t smemA = (size_t)a.tab_off + (size_t)(64 + (g.l1 > 6 ? 1 << (g.l1 - 6) : 1)) * d * sizeof(uint64_t);
+  const int64_t cp = pvn_chunk_points(m, n);
+  char* w = (char*)work_dev;
+  a.W = (double*)w;
+  w += align256((size_t)cp * n * sizeof(double));
+  double* winv = (double*)w;
+  a.winv = winv;
+  w += align256((size_t)n * sizeof(double));
+  a.partial = (double*)w;
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    pvn_winv_kernel<<<(unsigned)blocks, 256, 0, st>>>(lam_dev, n, winv);
+    FGP_LAUNCH_NAMED("pvn_winv", st);
+  }
+  static bool attrB = false;
+  if (!attrB) {
+    cudaFuncSetAttribute(pvn_passB_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaGetLastError();
+    attrB = true;
+  }
+  const int mode = all2 ? (t <= 52 ? 2 : 1) : 0;
+  for (int64_t p0 = 0; p0 < m; p0 += cp) {
+    const int64_t np = m - p0 < cp ? m - p0 : cp;
+    a.xs = xs_dev + p0 * d;
+    a.m = np;
+    const dim3 gridA((unsigned)(1 << g.l2), (unsigned)((np + kPvnPoints - 1) / kPvnPoints));
+    if (mode == 2)
+      dispatch_pvnA<2>(a, gridA, g.threadsA, smemA, st);
+    else if (mode == 1)
+      dispatch_pvnA<1>(a, gridA, g.threadsA, smemA, st);
+    else
+      launch_pvnA<0, 0>(a, gridA, g.threadsA, smemA, st);
+    FGP_LAUNCH_NAMED("pvn_passA", st);
+    pvn_passB_kernel<<<dim3((unsigned)a.tilesB, (unsigned)np), g.threadsB, g.smemB, st>>>(a);
+    FGP_LAUNCH_NAMED("pvn_passB", st);
+    pvn_final_kernel<<<(unsigned)((np * 32 + 255) / 256), 256, 0, st>>>(a.partial, a.tilesB, np, kxx, pvar_dev + p0);
+    FGP_LAUNCH_NAMED("pvn_final", st);
   }
   return FGP_OK;
 }

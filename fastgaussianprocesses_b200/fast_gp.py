@@ -367,8 +367,7 @@ class _FusedFitLoop(object):
         return g
 
     def replay(self, k):
-        """Enqueue k iterations: a k-iteration graph when the context holds one (or k is worth capturing: the chunk size, which
-        every later fit of this shape reuses), else the 1-iteration graph k times."""
+        """Enqueue k <= GRAPH_ITERS iterations."""
         if self.multi:
             with torch.cuda.device(self.fgp.device):
                 _lib.fit_iterations(self.problem, self.layout, k)
@@ -379,12 +378,10 @@ class _FusedFitLoop(object):
             with torch.cuda.device(self.fgp.device):
                 for _ in range(k):
                     self._iteration()
-        elif k in self.ctx.graphs or k == self.GRAPH_ITERS or k == 1:
-            self._graph(k).replay()
         else:
-            g1 = self._graph(1)
-            for _ in range(k):
-                g1.replay()
+            # one graph per chunk length, captured on first use and kept by the pooled context (a fit of K iterations replays two graphs:
+            # chunks of GRAPH_ITERS and the remainder)
+            self._graph(k).replay()
         self.replayed += k
         self.launches += k * self.kernels_per_iteration
 
@@ -1507,9 +1504,12 @@ class AbstractFastGP(torch.nn.Module):
         else:
             # lattice with a known generating vector: fused generator form (the points are regenerated inside the first transform pass)
             zgen = self._zgen is not None and all(int(v) < (1 << 32) for v in self._zgen) and os.environ.get("FGP_B200_NO_PVZ") != "1" and _lib.post_var_z_supported(n)
+            Cgen = self._Cgen(n) if (self._FAMILY == 1 and os.environ.get("FGP_B200_NO_PVZ") != "1" and _lib.post_var_C_supported(n)) else None
             if zgen:
                 shift = self.seqs[0].shift
                 outs = [_lib.post_var_z(x, self._zgen, shift, n, self._alpha_list, scale_B[b], ls_B[b], lam[b]) for b in range(B)]
+            elif Cgen is not None:  # digital net with known generating matrices: the same fusion with the Walsh-Hadamard transform
+                outs = [_lib.post_var_C(x, Cgen, self.seqs[0].rshift, self._t, n, self._alpha_list, scale_B[b], ls_B[b], lam[b]) for b in range(B)]
             else:
                 outs = [_lib.post_var(self._FAMILY, x, xpts, self._alpha_list, self._t, scale_B[b], ls_B[b], lam[b]) for b in range(B)]
         pvar = torch.stack(outs, 0).reshape(tuple(pshape) + (1, x.shape[0]))

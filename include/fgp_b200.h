@@ -238,6 +238,13 @@ size_t fgp_lattice_post_var_z_workspace_bytes(int64_t m, int64_t n);
 int fgp_lattice_post_var_z(const double* xs_dev, int64_t m, const uint64_t* z_host, const double* shift_host, int64_t n, int d,
                            const int* alpha_host, double scale, const double* ls_host, const double* lam_dev, const void* table_dev,
                            void* work_dev, double* pvar_dev, fgp_stream_t stream);
+/* The same for a base-2 digital net in generator form: xb_i = XOR_{k in bits(i)} C[j][k] ^ dshift_j is rebuilt per tile from two shared-memory
+ * XOR-fold tables, k(x*, X) goes straight into the first pass of the real Walsh-Hadamard transform, sum_k v_k^2 / lam_k is the epilogue of the
+ * second.  C_dev: device (d, mmax) columns as in fgp_dnb2_points; dshift_host[d]; lam_dev: (n) real eigenvalues. */
+size_t fgp_dnb2_post_var_C_workspace_bytes(int64_t m, int64_t n);
+int fgp_dnb2_post_var_C(const double* xs_dev, int64_t m, const uint64_t* C_dev, int mmax, const uint64_t* dshift_host, int t, int64_t n, int d,
+                        const int* alpha_host, double scale, const double* ls_host, const double* lam_dev, void* work_dev, double* pvar_dev,
+                        fgp_stream_t stream);
 /* dense cross-kernel tile K[i,a] = k(xs_i, X_a) (m,n) for post_cov / user-facing kernel() calls */
 int fgp_lattice_cross_kernel(const double* xs_dev, int64_t m, const double* x_dev, int64_t n, int d,
                              const int* alpha_host, double scale, const double* ls_host, double* k_dev,

@@ -379,3 +379,29 @@ def test_fused_generator_post_var_matches_unfused_route(L, P, d, m, alpha, mtest
     monkeypatch.delenv("FGP_PV_TMA")  # the variances are kxx minus a sum of the same size: round-off scales with kxx
     assert float((got - ref).abs().max()) <= 1e-11 * kxx
     assert float(got[0]) <= 1e-2 * kxx  # at a training point the variance is noise-limited
+
+
+@pytest.mark.parametrize("d,m,alpha,t,mtest", [(8, 20, 2, 52, 33), (4, 16, 2, 63, 64), (2, 13, 2, 40, 5), (3, 14, 3, 52, 16), (16, 15, 2, 52, 9), (5, 13, 1, 45, 1), (2, 14, 4, 32, 7)])
+def test_fused_generator_net_post_var_matches_unfused_route(L, P, d, m, alpha, t, mtest):
+    """fgp_dnb2_post_var_C (points rebuilt from XOR-fold tables inside the first FWHT pass, sum v^2 / lam in the epilogue of the second)
+    against fgp_dnb2_post_var fed with the stored points."""
+    n = 1 << m
+    rng = np.random.default_rng(190 + m)
+    Ch = P.default_dnb2_gen_mats(d, t)
+    C = torch.from_numpy(Ch.astype(np.int64)).to(dev)
+    dshift = rng.integers(0, 2 ** t, size=d, dtype=np.uint64)
+    xb, xpts = L.dnb2_points(C, dshift, t, 0, n)
+    scale, noise = 1.3, 1e-3
+    ls = rng.uniform(0.2, 1.3, size=d)
+    ysq = torch.zeros(1, n, device=dev)
+    _, lam = L.mll_grad(1, xb, [alpha] * d, t, ysq, torch.tensor([scale], device=dev), torch.from_numpy(ls[None]).to(dev), torch.tensor([noise], device=dev),
+                        want_grad=False, want_lam=True)
+    xs = torch.from_numpy(rng.random((mtest, d))).to(dev)
+    xs[0] = xpts[3]
+    ref = L.post_var(1, xs, xb, [alpha] * d, t, scale, ls, lam[0])
+    if not L.post_var_C_supported(n):
+        pytest.skip("single-tile size: the unfused route is the only one")
+    got = L.post_var_C(xs, C, dshift, t, n, [alpha] * d, scale, ls, lam[0])
+    kxx = max(float(ref.max()), scale)
+    assert float((got - ref).abs().max()) <= 1e-11 * kxx
+    assert float(got[0]) <= 1e-2 * kxx

@@ -56,5 +56,22 @@ if which in ("all", "pvarz"):  # fused generator-form lattice post_var: pv_passA
     _, lam = L.mll_grad(0, xp, [2] * d, 0, ysq, scale, ls, noise, want_lam=True)
     for _ in range(reps):
         L.post_var_z(xs, z, np.linspace(0.1, 0.9, d), n, [2] * d, 1.0, [0.5] * d, lam[0])
+if which in ("netpm",):  # net post_mean d = 16 (configs[3] family), alpha = 2, t = 52: which pipe binds the inner loop?
+    import fastgaussianprocesses_b200 as fgp
+    gp = fgp.FastGPDigitalNetB2(fgp.DigitalNetB2(16, seed=7, t=52), device=dev, noise=1e-8)
+    xn = gp.get_x_next(n)
+    gp.add_y_next(torch.cos(2 * np.pi * xn).sum(1))
+    gp.coeffs
+    xs = torch.rand(1 << 12, 16, device=dev)
+    for _ in range(reps):
+        gp.post_mean(xs)
+if which in ("netpv",):  # fused net post_var d = 8
+    import fastgaussianprocesses_b200 as fgp
+    gp = fgp.FastGPDigitalNetB2(fgp.DigitalNetB2(8, seed=7, t=52), device=dev, noise=1e-8)
+    xn = gp.get_x_next(n)
+    gp.add_y_next(torch.cos(2 * np.pi * xn).sum(1))
+    xs = torch.rand(128, 8, device=dev)
+    for _ in range(reps):
+        gp.post_var(xs)
 torch.cuda.synchronize()
 print("ok")

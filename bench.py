@@ -273,7 +273,7 @@ def main():
         sys.stdout.flush()
         out_fd = os.dup(1)
         os.dup2(2, 1)
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ["NCCL_DEBUG"] = os.environ.get("FGP_NCCL_DEBUG", "INFO")  # the image presets VERSION; the driver reads the communicator lines
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)

@@ -565,8 +565,6 @@ class AbstractFastGP(torch.nn.Module):
         else:
             assert isinstance(num_tasks, int) and num_tasks > 0
             solo_task, default_task = False, torch.arange(num_tasks)
-        if num_tasks != 1 and len(torch.Size(shape_batch)) != 0 and not self._DENSE:
-            raise NotImplementedError("multi-task GPs with batched outputs are not built (SURVEY.md section 8(f) row 2 is covered for one hyperparameter set)")
         if derivatives is not None or derivatives_coeffs is not None:  # abstract_gp.py:59-62
             rank_factor_task_kernel = 1
             tfs_noise_task_kernel = DEFAULT_TFS_ID
@@ -610,8 +608,6 @@ class AbstractFastGP(torch.nn.Module):
         self.derivatives_coeffs = derivatives_coeffs
         self._has_derivs = any((self.derivatives[i] > 0).any() or (self.derivatives_coeffs[i] != 1).any() or len(self.derivatives[i]) != 1 for i in range(self.num_tasks))
         self._deriv_cache = {}
-        if self._has_derivs and len(torch.Size(shape_batch)) != 0 and not self._DENSE:
-            raise NotImplementedError("derivative-informed GPs with batched outputs are not built")
         # alpha
         assert (np.isscalar(alpha) and alpha % 1 == 0) or (isinstance(alpha, torch.Tensor) and alpha.shape == (self.d,)), "alpha should be an int or a torch.Tensor of length d"
         if np.isscalar(alpha):
@@ -624,97 +620,25 @@ class AbstractFastGP(torch.nn.Module):
         assert isinstance(shape_batch, torch.Size)
         self.shape_batch = shape_batch
         self.ndim_batch = len(self.shape_batch)
-        # scale (abstract_gp.py:77-88)
-        assert np.isscalar(scale) or isinstance(scale, torch.Tensor), "scale must be a scalar or torch.Tensor"
-        if isinstance(scale, torch.Tensor):
-            shape_scale = scale.shape
-        if isinstance(shape_scale, (list, tuple)):
-            shape_scale = torch.Size(shape_scale)
-        assert isinstance(shape_scale, torch.Size) and shape_scale[-1] == 1
-        if len(shape_scale) > 1:
-            assert shape_scale[:-1] == shape_batch[-(len(shape_scale) - 1):]
-        if np.isscalar(scale):
-            scale = scale * torch.ones(shape_scale, device=self.device)
-        scale = scale.to(self.device)
-        assert (scale > 0).all(), "scale must be positive"
-        assert len(tfs_scale) == 2 and callable(tfs_scale[0]) and callable(tfs_scale[1]), "tfs_scale should be a tuple of two callables, the transform and inverse transform"
-        self.tf_scale = tfs_scale[1]
-        self.raw_scale = torch.nn.Parameter(tfs_scale[0](scale), requires_grad=requires_grad_scale)
-        # lengthscales (abstract_gp.py:89-100)
-        assert np.isscalar(lengthscales) or isinstance(lengthscales, torch.Tensor), "lengthscales must be a scalar or torch.Tensor"
-        if isinstance(lengthscales, torch.Tensor):
-            shape_lengthscales = lengthscales.shape
-        if shape_lengthscales is None:
-            shape_lengthscales = torch.Size([self.d])
-        if isinstance(shape_lengthscales, (list, tuple)):
-            shape_lengthscales = torch.Size(shape_lengthscales)
-        assert isinstance(shape_lengthscales, torch.Size) and (shape_lengthscales[-1] == self.d or shape_lengthscales[-1] == 1)
-        if len(shape_lengthscales) > 1:
-            assert shape_lengthscales[:-1] == shape_batch[-(len(shape_lengthscales) - 1):]
-        if np.isscalar(lengthscales):
-            lengthscales = lengthscales * torch.ones(shape_lengthscales, device=self.device)
-        lengthscales = lengthscales.to(self.device)
-        assert (lengthscales > 0).all(), "lengthscales must be positive"
-        assert len(tfs_lengthscales) == 2 and callable(tfs_lengthscales[0]) and callable(tfs_lengthscales[1]), "tfs_lengthscales should be a tuple of two callables, the transform and inverse transform"
-        self.tf_lengthscales = tfs_lengthscales[1]
-        self.raw_lengthscales = torch.nn.Parameter(tfs_lengthscales[0](lengthscales), requires_grad=requires_grad_lengthscales)
-        # noise (abstract_gp.py:101-111)
-        assert np.isscalar(noise) or isinstance(noise, torch.Tensor), "noise must be a scalar or torch.Tensor"
-        if isinstance(noise, torch.Tensor):
-            shape_noise = noise.shape
-        if isinstance(shape_noise, (list, tuple)):
-            shape_noise = torch.Size(shape_noise)
-        assert isinstance(shape_noise, torch.Size) and shape_noise[-1] == 1
-        if len(shape_noise) > 1:
-            assert shape_noise[:-1] == shape_batch[-(len(shape_noise) - 1):]
-        if np.isscalar(noise):
-            noise = noise * torch.ones(shape_noise, device=self.device)
-        noise = noise.to(self.device)
-        assert (noise > 0).all(), "noise must be positive"
-        assert len(tfs_noise) == 2 and callable(tfs_noise[0]) and callable(tfs_noise[1]), "tfs_scale should be a tuple of two callables, the transform and inverse transform"
-        self.tf_noise = tfs_noise[1]
-        self.raw_noise = torch.nn.Parameter(tfs_noise[0](noise), requires_grad=requires_grad_noise)
-        # task kernel of a single task: F F^T + diag(v) with F of rank 0 (abstract_gp.py:112-139)
-        assert np.isscalar(factor_task_kernel) or isinstance(factor_task_kernel, torch.Tensor), "factor_task_kernel must be a scalar or torch.Tensor"
-        if isinstance(factor_task_kernel, torch.Tensor):
-            shape_factor_task_kernel = factor_task_kernel.shape
-        if shape_factor_task_kernel is None:
+        # hyperparameters (abstract_gp.py:77-139): one raw (transformed) torch Parameter each, the trailing dimensions fixed by the
+        # parameter, any leading ones matching the tail of shape_batch. Task kernel: F F^T + diag(v), F of rank 0 for a single task
+        if shape_factor_task_kernel is None and not isinstance(factor_task_kernel, torch.Tensor):
             if rank_factor_task_kernel is None:
                 rank_factor_task_kernel = 0 if self.num_tasks == 1 else 1
             assert isinstance(rank_factor_task_kernel, int) and 0 <= rank_factor_task_kernel <= self.num_tasks
-            shape_factor_task_kernel = torch.Size([self.num_tasks, rank_factor_task_kernel])
-        if isinstance(shape_factor_task_kernel, (list, tuple)):
-            shape_factor_task_kernel = torch.Size(shape_factor_task_kernel)
-        assert isinstance(shape_factor_task_kernel, torch.Size) and 0 <= shape_factor_task_kernel[-1] <= self.num_tasks and shape_factor_task_kernel[-2] == self.num_tasks
-        if len(shape_factor_task_kernel) > 2:
-            assert shape_factor_task_kernel[:-2] == shape_batch[-(len(shape_factor_task_kernel) - 2):]
-        if np.isscalar(factor_task_kernel):
-            factor_task_kernel = factor_task_kernel * torch.ones(shape_factor_task_kernel, device=self.device)
-        factor_task_kernel = factor_task_kernel.to(self.device)
-        assert len(tfs_factor_task_kernel) == 2 and callable(tfs_factor_task_kernel[0]) and callable(tfs_factor_task_kernel[1])
-        self.tf_factor_task_kernel = tfs_factor_task_kernel[1]
-        if requires_grad_factor_task_kernel is None:
-            requires_grad_factor_task_kernel = self.num_tasks > 1
-        self.raw_factor_task_kernel = torch.nn.Parameter(tfs_factor_task_kernel[0](factor_task_kernel), requires_grad=requires_grad_factor_task_kernel)
-        assert np.isscalar(noise_task_kernel) or isinstance(noise_task_kernel, torch.Tensor), "noise_task_kernel must be a scalar or torch.Tensor"
-        if isinstance(noise_task_kernel, torch.Tensor):
-            shape_noise_task_kernel = noise_task_kernel.shape
-        if shape_noise_task_kernel is None:
-            shape_noise_task_kernel = torch.Size([self.num_tasks])
-        if isinstance(shape_noise_task_kernel, (list, tuple)):
-            shape_noise_task_kernel = torch.Size(shape_noise_task_kernel)
-        assert isinstance(shape_noise_task_kernel, torch.Size) and (shape_noise_task_kernel[-1] == self.num_tasks or shape_noise_task_kernel[-1] == 1)
-        if len(shape_noise_task_kernel) > 1:
-            assert shape_noise_task_kernel[:-1] == shape_batch[-(len(shape_noise_task_kernel) - 1):]
-        if np.isscalar(noise_task_kernel):
-            noise_task_kernel = noise_task_kernel * torch.ones(shape_noise_task_kernel, device=self.device)
-        noise_task_kernel = noise_task_kernel.to(self.device)
-        assert (noise_task_kernel >= 0).all(), "noise_task_kernel must be positive"
-        assert len(tfs_noise_task_kernel) == 2 and callable(tfs_noise_task_kernel[0]) and callable(tfs_noise_task_kernel[1])
-        self.tf_noise_task_kernel = tfs_noise_task_kernel[1]
-        if requires_grad_noise_task_kernel is None:
-            requires_grad_noise_task_kernel = self.num_tasks > 1
-        self.raw_noise_task_kernel = torch.nn.Parameter(tfs_noise_task_kernel[0](noise_task_kernel), requires_grad=requires_grad_noise_task_kernel)
+            shape_factor_task_kernel = [self.num_tasks, rank_factor_task_kernel]
+        T = self.num_tasks
+        tfs_hint = " should be a tuple of two callables, the transform and inverse transform"
+        for name, value, shape, tfs, rgrad, trailing, lower in (
+                ("scale", scale, shape_scale, tfs_scale, requires_grad_scale, lambda s: s[-1] == 1, ">"),
+                ("lengthscales", lengthscales, shape_lengthscales or [self.d], tfs_lengthscales, requires_grad_lengthscales, lambda s: s[-1] in (self.d, 1), ">"),
+                ("noise", noise, shape_noise, tfs_noise, requires_grad_noise, lambda s: s[-1] == 1, ">"),
+                ("factor_task_kernel", factor_task_kernel, shape_factor_task_kernel, tfs_factor_task_kernel, requires_grad_factor_task_kernel,
+                 lambda s: 0 <= s[-1] <= T and s[-2] == T, None),
+                ("noise_task_kernel", noise_task_kernel, shape_noise_task_kernel or [T], tfs_noise_task_kernel, requires_grad_noise_task_kernel,
+                 lambda s: s[-1] in (T, 1), ">=")):
+            self._add_hyperparameter(name, value, shape, tfs, (T > 1) if rgrad is None else rgrad, trailing, 2 if name == "factor_task_kernel" else 1,
+                                     lower, tfs_hint)
         self._default_tfs = (tuple(tfs_scale) == DEFAULT_TFS_LOG_EXP and tuple(tfs_lengthscales) == DEFAULT_TFS_LOG_EXP and
                              tuple(tfs_noise) == DEFAULT_TFS_LOG_EXP)
         # storage and caches
@@ -746,6 +670,25 @@ class AbstractFastGP(torch.nn.Module):
         self.ift_unstable = self._ift_unstable
 
     # ------------------------------------------------------------------------------------------------ state keys
+    def _add_hyperparameter(self, name, value, shape, tfs, requires_grad, trailing_ok, ntrail, sign, tfs_hint):
+        """Validate one hyperparameter of abstract_gp.py:77-139 and register tfs[0](value) as self.raw_<name> (self.tf_<name> = tfs[1]).
+        A tensor value fixes the shape; a scalar is broadcast to `shape`, whose last `ntrail` dimensions must pass `trailing_ok` and whose
+        leading dimensions must equal the tail of shape_batch; `sign` is ">" / ">=" / None for the positivity assertion."""
+        assert np.isscalar(value) or isinstance(value, torch.Tensor), name + " must be a scalar or torch.Tensor"
+        if isinstance(value, torch.Tensor):
+            shape = value.shape
+        if isinstance(shape, (list, tuple)):
+            shape = torch.Size(shape)
+        assert isinstance(shape, torch.Size) and len(shape) >= ntrail and trailing_ok(shape)
+        lead = len(shape) - ntrail
+        assert lead == 0 or shape[:lead] == self.shape_batch[-lead:]
+        value = (value * torch.ones(shape, device=self.device) if np.isscalar(value) else value).to(self.device)
+        if sign is not None:
+            assert ((value > 0) if sign == ">" else (value >= 0)).all(), name + " must be positive"
+        assert len(tfs) == 2 and callable(tfs[0]) and callable(tfs[1]), "tfs_" + name + tfs_hint
+        setattr(self, "tf_" + name, tfs[1])
+        setattr(self, "raw_" + name, torch.nn.Parameter(tfs[0](value), requires_grad=requires_grad))
+
     def _param_key(self):
         ps = (self.raw_scale, self.raw_lengthscales, self.raw_noise, self.raw_factor_task_kernel, self.raw_noise_task_kernel)
         return (self._epoch,) + tuple((id(p), p._version, p.data_ptr()) for p in ps)
@@ -1464,7 +1407,7 @@ class AbstractFastGP(torch.nn.Module):
         inttask, task = self._parse_task(task)
         if self._mt is not None:
             pmean = self._mt.post_mean(x.to(self.device).contiguous(), task)
-            return pmean[0] if inttask else pmean
+            return pmean[..., 0, :] if inttask else pmean
         coeffs = self.coeffs
         x = x.to(self.device).contiguous()
         self._check_unit_cube(x)
@@ -1494,7 +1437,7 @@ class AbstractFastGP(torch.nn.Module):
         self._check_unit_cube(x)
         if self._mt is not None:
             pvar = self._mt.post_var(x, task, n)
-            return pvar[0] if inttask else pvar
+            return pvar[..., 0, :] if inttask else pvar
         scale_B, ls_B, _, pshape = self._hyper_host()
         B = len(scale_B)
         lam = self.get_inv_log_det_cache(n)._lam_full()
@@ -1530,13 +1473,18 @@ class AbstractFastGP(torch.nn.Module):
         equal = torch.equal(x0, x1) and torch.equal(task0, task1)
         if self._mt is not None:
             kmat = self._mt.post_cov(x0, x1, task0, task1, n, equal)
-            if inttask0 and inttask1:
-                return kmat[0, 0]
-            elif inttask0 and not inttask1:
-                return kmat[0]
-            elif not inttask0 and inttask1:
-                return kmat[:, 0]
-            return kmat
+        else:
+            kmat = self._post_cov_single(x0, x1, n, equal)
+        if inttask0 and inttask1:
+            return kmat[..., 0, 0, :, :]
+        elif inttask0 and not inttask1:
+            return kmat[..., 0, :, :, :]
+        elif not inttask0 and inttask1:
+            return kmat[..., :, 0, :, :]
+        return kmat
+
+    def _post_cov_single(self, x0, x1, n, equal):
+        """One task: k(x0,x1) - k(x0,X) K^-1 k(X,x1) per hyperparameter set, (*batch, 1, 1, N0, N1)."""
         scale_B, ls_B, _, pshape = self._hyper_host()
         B = len(scale_B)
         cache = self.get_inv_log_det_cache(n)
@@ -1555,14 +1503,7 @@ class AbstractFastGP(torch.nn.Module):
                     dg = kmat.diagonal()
                     dg.clamp_(min=0)
                 outs.append(kmat)
-        kmat = torch.stack(outs, 0).reshape(tuple(pshape) + (1, 1) + tuple(outs[0].shape))
-        if inttask0 and inttask1:
-            return kmat[..., 0, 0, :, :]
-        elif inttask0 and not inttask1:
-            return kmat[..., 0, :, :, :]
-        elif not inttask0 and inttask1:
-            return kmat[..., :, 0, :, :]
-        return kmat
+        return torch.stack(outs, 0).reshape(tuple(pshape) + (1, 1) + tuple(outs[0].shape))
 
     def post_error(self, x: torch.Tensor, task: Union[int, torch.Tensor] = None, n: Union[int, torch.Tensor] = None, confidence: float = 0.99, eval: bool = True):
         assert np.isscalar(confidence) and 0 < confidence < 1, "confidence must be between 0 and 1"
@@ -1587,7 +1528,7 @@ class AbstractFastGP(torch.nn.Module):
         inttask, task = self._parse_task(task)
         if self._mt is not None:
             pcmean = self._mt.post_cubature_mean(task)
-            return pcmean[0] if inttask else pcmean
+            return pcmean[..., 0] if inttask else pcmean
         with torch.no_grad():
             scale_B, _, _, pshape = self._hyper()
             coeffs = self.coeffs
@@ -1599,8 +1540,8 @@ class AbstractFastGP(torch.nn.Module):
         n = self._parse_n(n)
         inttask, task = self._parse_task(task)
         if self._mt is not None:
-            pcvar = self._mt.post_cubature_cov(task, task, n).diagonal().clamp(min=0)
-            return pcvar[0] if inttask else pcvar
+            pcvar = self._mt.post_cubature_cov(task, task, n).diagonal(dim1=-2, dim2=-1).clamp(min=0)
+            return pcvar[..., 0] if inttask else pcvar
         with torch.no_grad():
             scale_B, _, _, pshape = self._hyper()
             lam = self.get_inv_log_det_cache(n)._lam_full()
@@ -1615,22 +1556,16 @@ class AbstractFastGP(torch.nn.Module):
         if self._mt is not None:
             pccov = self._mt.post_cubature_cov(task0, task1, n)
             if torch.equal(task0, task1):
-                pccov.diagonal().clamp_(min=0)
-            if inttask0 and inttask1:
-                return pccov[0, 0]
-            elif inttask0 and not inttask1:
-                return pccov[0]
-            elif not inttask0 and inttask1:
-                return pccov[:, 0]
-            return pccov
-        pcvar = self.post_cubature_var(task=[0], n=n)[..., None]
+                pccov.diagonal(dim1=-2, dim2=-1).clamp_(min=0)
+        else:
+            pccov = self.post_cubature_var(task=[0], n=n)[..., None]
         if inttask0 and inttask1:
-            return pcvar[..., 0, 0]
+            return pccov[..., 0, 0]
         elif inttask0 and not inttask1:
-            return pcvar[..., 0, :]
+            return pccov[..., 0, :]
         elif not inttask0 and inttask1:
-            return pcvar[..., :, 0]
-        return pcvar
+            return pccov[..., :, 0]
+        return pccov
 
     def post_cubature_error(self, task: Union[int, torch.Tensor] = None, n: Union[int, torch.Tensor] = None, confidence: float = 0.99, eval: bool = True):
         assert np.isscalar(confidence) and 0 < confidence < 1, "confidence must be between 0 and 1"

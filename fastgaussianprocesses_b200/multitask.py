@@ -9,6 +9,11 @@ kernels and posterior-mean products are the K2 / K5 kernels; the n small R x R s
 fgp_block_inv_logdet kernel (one thread per system, Gauss-Jordan with partial pivoting in registers; `_BlockInvLogdet`).  Tasks of different (power-of-two)
 sizes fold into n_min independent R x R systems, R = sum_l n_l / n_min, because sub-sampling a lattice aliases the
 frequencies kappa and kappa mod n_l.  This path is parity-tested against reference fixtures but not fused or tuned.
+
+Batched outputs (shape_batch): y_l is (*shape_batch, n_l); every hyperparameter may carry leading dimensions that match a
+tail of shape_batch.  Bh below is the broadcast of those leading dimensions (empty for one shared hyperparameter set): the
+systems are (*Bh, n_min, R, R), data-dependent results (coeffs, posterior mean) are (*shape_batch, ...), data-independent
+ones (variances, covariances) are (*Bh, ...), as in the reference (abstract_gp.py:352-474).
 """
 import numpy as np
 import torch
@@ -120,14 +125,21 @@ class MultiTaskEngine(object):
             return _lib.deriv_cross_kernel(gp._FAMILY, x, self.xpts(l, n), self.terms(t, l), gp._t, scale, ls)
         return _lib.cross_kernel(gp._FAMILY, x, self.xpts(l, n), gp._alpha_list, gp._t, scale, ls)
 
+    def hyper_shape(self):
+        """Bh: broadcast of the leading (batch) dimensions of the five hyperparameters."""
+        gp = self.gp
+        return tuple(torch.broadcast_shapes(gp.raw_scale.shape[:-1], gp.raw_lengthscales.shape[:-1], gp.raw_noise.shape[:-1],
+                                            gp.raw_factor_task_kernel.shape[:-2], gp.raw_noise_task_kernel.shape[:-1]))
+
     def lam_system(self, n=None):
-        """Lam (n_min, R, R), differentiable w.r.t. every raw parameter.  Block (t0, t1), n_t0 >= n_t1: the length-n_t0 vector
+        """Lam (*Bh, n_min, R, R), differentiable w.r.t. every raw parameter.  Block (t0, t1), n_t0 >= n_t1: the length-n_t0 vector
         lam = K_task[t0,t1] sqrt(n_t1) ft(k1^(t0,t1)) (+ noise on the diagonal) couples frequency kappa of task t0 with
         frequency kappa mod n_t1 of task t1 (sub-sampling aliases frequencies), util.py:279-323."""
         gp = self.gp
         ns, active, nmin, r, off, R = self.sizes(n)
         scale, ls, noise, kt = gp.scale, gp.lengthscales, gp.noise, gp.gram_matrix_tasks
         dev = gp.device
+        Bh = self.hyper_shape()
         bidx, rows, cols, vals = [], [], [], []
         ar = torch.arange(nmin, device=dev)
         for i0, t0 in enumerate(active):
@@ -140,7 +152,7 @@ class MultiTaskEngine(object):
                 lam = np.sqrt(ns[t1]) * lam
                 if t0 == t1:
                     lam = lam + noise
-                V = (lam * kt[..., t0, t1, None]).reshape(r[t0], nmin)
+                V = (lam * kt[..., t0, t1, None]).expand(Bh + (nbig,)).reshape(Bh + (r[t0], nmin)).movedim(-1, 0).movedim(-1, 0)  # (r, n_min, *Bh)
                 for a0 in range(r[t0]):
                     a1 = a0 if t0 == t1 else a0 % r[t1]
                     bidx.append(ar)
@@ -152,20 +164,23 @@ class MultiTaskEngine(object):
                         rows.append(torch.full((nmin,), off[t1] + a1, device=dev))
                         cols.append(torch.full((nmin,), off[t0] + a0, device=dev))
                         vals.append(V[a0].conj())
-        vals = torch.cat(vals)
-        L = torch.zeros((nmin, R, R), dtype=vals.dtype, device=dev)
-        return L.index_put((torch.cat(bidx), torch.cat(rows), torch.cat(cols)), vals)
+        vals = torch.cat(vals)  # (entries * n_min, *Bh)
+        L = torch.zeros((nmin, R, R) + Bh, dtype=vals.dtype, device=dev)
+        L = L.index_put((torch.cat(bidx), torch.cat(rows), torch.cat(cols)), vals)
+        return L.permute(tuple(range(3, 3 + len(Bh))) + (0, 1, 2)) if len(Bh) else L
 
     def factor(self, n=None, grad=False):
-        """(Lam^-1 (n_min,R,R), logdet) -- cached on the hyperparameter state when no gradient is needed."""
+        """(Lam^-1 (*Bh,n_min,R,R), logdet (*Bh)) -- cached on the hyperparameter state when no gradient is needed."""
         if grad:
-            A, ld = _BlockInvLogdet.apply(self.lam_system(n))
-            return A, ld.sum(-1)
+            L = self.lam_system(n)
+            A, ld = _BlockInvLogdet.apply(L.reshape((-1,) + L.shape[-2:]))
+            return A.reshape(L.shape), ld.reshape(L.shape[:-2]).sum(-1)
         key = (tuple(self.sizes(n)[0]),) + self.gp._param_key()
         if self._lam_key != key:
             with torch.no_grad():
-                A, ld = _lib.block_inv_logdet(self.lam_system(n))
-                self._solve_cache = (A, ld.sum(-1))
+                L = self.lam_system(n)
+                A, ld = _lib.block_inv_logdet(L.reshape((-1,) + L.shape[-2:]).contiguous())
+                self._solve_cache = (A.reshape(L.shape), ld.reshape(L.shape[:-2]).sum(-1))
             self._lam_key = key
         return self._solve_cache
 
@@ -194,8 +209,8 @@ class MultiTaskEngine(object):
         return self._yt
 
     def solve_tilde(self, A, zt):
-        """A (n_min,R,R), zt (..., R, n_min) -> (..., R, n_min)."""
-        return torch.einsum("kij,...jk->...ik", A, zt.to(A.dtype))
+        """A (*Bh,n_min,R,R), zt (..., R, n_min) -> (..., R, n_min); the leading dimensions broadcast."""
+        return torch.einsum("...kij,...jk->...ik", A, zt.to(A.dtype))
 
     def gram_matrix_solve(self, y, n=None, A=None):
         """K^-1 y for y (..., sum_l n_l), tasks concatenated in task order (util.py:338-344)."""
@@ -234,11 +249,15 @@ class MultiTaskEngine(object):
 
     # ------------------------------------------------------------------------------------------------ posterior
     def _host(self):
+        """(Bh, [(scale, lengthscales (d), K_task (T,T)) per hyperparameter set, flattened over Bh]) on the host: the kernels of
+        libfgp_b200 take one hyperparameter set per call."""
         gp = self.gp
+        Bh = self.hyper_shape()
         with torch.no_grad():
-            assert gp.scale.numel() == 1 and gp.lengthscales.ndim == 1 and gp.noise.numel() == 1, "multi-task GPs take one hyperparameter set"
-            ls = gp.lengthscales.expand(gp.d) if gp.lengthscales.numel() == 1 else gp.lengthscales
-            return float(gp.scale.reshape(-1)[0]), ls.cpu().numpy(), gp.gram_matrix_tasks.cpu().numpy()
+            sc = gp.scale.expand(Bh + (1,)).reshape(-1).cpu().numpy()
+            ls = gp.lengthscales.expand(Bh + (gp.d,)).reshape(-1, gp.d).cpu().numpy()
+            kt = gp.gram_matrix_tasks.expand(Bh + (self.T, self.T)).reshape(-1, self.T, self.T).cpu().numpy()
+        return Bh, [(float(sc[h]), np.ascontiguousarray(ls[h]), kt[h]) for h in range(len(sc))]
 
     def coeffs(self):
         gp = self.gp
@@ -250,28 +269,35 @@ class MultiTaskEngine(object):
         return self._coeffs
 
     def post_mean(self, x, task):
+        """(*shape_batch, len(task), N)."""
         gp, T = self.gp, self.T
         ns = self.sizes()[0]
-        scale, ls, kt = self._host()
-        c = self.coeffs().split(ns, dim=-1)
+        Bh, sets = self._host()
+        H = len(sets)
+        sb = tuple(gp.shape_batch)
         N = x.shape[0]
         if N == 0:
-            return torch.empty((len(task), 0), dtype=torch.float64, device=gp.device)
-        if gp._has_derivs:  # the kernel depends on the test task: chunked cross tiles times the coefficients
-            out = torch.zeros((len(task), N), dtype=torch.float64, device=gp.device)
-            step = max(1, (1 << 24) // max(1, max(ns)))
-            for i, t in enumerate(task.tolist()):
-                for l in range(T):
-                    if ns[l] == 0:
-                        continue
-                    for r0 in range(0, N, step):
-                        out[i, r0:r0 + step] += kt[t, l] * (self.cross(x[r0:r0 + step].contiguous(), t, l, ns[l], scale, ls) @ c[l].reshape(-1))
-            return out
-        # one on-the-fly kernel-vector product per training task, then the T x T task kernel mixes them
-        base = torch.stack([_lib.post_mean(gp._FAMILY, x, self.xpts(l, ns[l]), gp._alpha_list, gp._t, scale, ls, c[l].reshape(1, -1).contiguous())[0]
-                            if ns[l] > 0 else torch.zeros(N, dtype=torch.float64, device=gp.device) for l in range(T)], 0)
-        ktd = torch.from_numpy(kt).to(gp.device)
-        return ktd[task.to(gp.device)] @ base  # (len(task), N)
+            return torch.empty(sb + (len(task), 0), dtype=torch.float64, device=gp.device)
+        # coefficient rows grouped by hyperparameter set: Bh is a tail of shape_batch, so (*shape_batch, n_l) = (lead, H, n_l)
+        c = [v.reshape(-1, H, v.shape[-1]) for v in self.coeffs().split(ns, dim=-1)]
+        lead = c[0].shape[0]
+        out = torch.zeros((lead, H, len(task), N), dtype=torch.float64, device=gp.device)
+        for h, (scale, ls, kt) in enumerate(sets):
+            if gp._has_derivs:  # the kernel depends on the test task: chunked cross tiles times the coefficients
+                step = max(1, (1 << 24) // max(1, max(ns)))
+                for i, t in enumerate(task.tolist()):
+                    for l in range(T):
+                        if ns[l] == 0:
+                            continue
+                        for r0 in range(0, N, step):
+                            out[:, h, i, r0:r0 + step] += kt[t, l] * (c[l][:, h, :] @ self.cross(x[r0:r0 + step].contiguous(), t, l, ns[l], scale, ls).T)
+                continue
+            # one on-the-fly kernel-vector product per training task, then the T x T task kernel mixes them
+            base = torch.stack([_lib.post_mean(gp._FAMILY, x, self.xpts(l, ns[l]), gp._alpha_list, gp._t, scale, ls, c[l][:, h, :].contiguous())
+                                if ns[l] > 0 else torch.zeros((lead, N), dtype=torch.float64, device=gp.device) for l in range(T)], 0)  # (T, lead, N)
+            ktd = torch.from_numpy(kt).to(gp.device)
+            out[:, h] = torch.einsum("it,tln->lin", ktd[task.to(gp.device)], base)
+        return out.reshape(sb + (len(task), N))
 
     def _cross_rows(self, x, t, ns, scale, ls, kt):
         """K_task[t, l1] k(x, X_l1) for all l1, concatenated: (N, sum_l n_l)."""
@@ -294,59 +320,67 @@ class MultiTaskEngine(object):
             return _lib.deriv_cross_kernel(gp._FAMILY, x0, z.contiguous(), self.terms(t0, t1), gp._t, scale, ls)
         return _lib.cross_kernel(gp._FAMILY, x0, z, gp._alpha_list, gp._t, scale, ls)
 
-    def post_var(self, x, task, n):
-        gp = self.gp
-        scale, ls, kt = self._host()
+    def _inverse_sets(self, n):
         A, _ = self.factor(n)
+        return A.reshape((-1,) + A.shape[-3:])
+
+    def post_var(self, x, task, n):
+        """(*Bh, len(task), N)."""
+        Bh, sets = self._host()
+        A = self._inverse_sets(n)
         ns = self.sizes(n)[0]
         out = []
         with torch.no_grad():
-            for t in task.tolist():
-                km = self._cross_rows(x, t, ns, scale, ls, kt)
-                sol = self.gram_matrix_solve(km, n=n, A=A)
-                out.append((kt[t, t] * self._kxx(t, scale, ls) - (sol * km).sum(-1)).clamp_(min=0))
-        return torch.stack(out, 0)
+            for h, (scale, ls, kt) in enumerate(sets):
+                for t in task.tolist():
+                    km = self._cross_rows(x, t, ns, scale, ls, kt)
+                    sol = self.gram_matrix_solve(km, n=n, A=A[h])
+                    out.append((kt[t, t] * self._kxx(t, scale, ls) - (sol * km).sum(-1)).clamp_(min=0))
+        return torch.stack(out, 0).reshape(Bh + (len(task), x.shape[0]))
 
     def post_cov(self, x0, x1, task0, task1, n, equal):
+        """(*Bh, len(task0), len(task1), N0, N1)."""
         gp = self.gp
-        scale, ls, kt = self._host()
-        A, _ = self.factor(n)
+        Bh, sets = self._host()
+        A = self._inverse_sets(n)
         ns = self.sizes(n)[0]
+        out = torch.empty((len(sets), len(task0), len(task1), x0.shape[0], x1.shape[0]), dtype=torch.float64, device=gp.device)
         with torch.no_grad():
-            knew = None if gp._has_derivs else self._knew(x0, x1, 0, 0, scale, ls)
-            k1 = {t: self._cross_rows(x0, t, ns, scale, ls, kt) for t in set(task0.tolist())}
-            sol2 = {t: self.gram_matrix_solve(k1[t] if (equal and t in k1) else self._cross_rows(x1, t, ns, scale, ls, kt), n=n, A=A) for t in set(task1.tolist())}
-            out = torch.empty((len(task0), len(task1), x0.shape[0], x1.shape[0]), dtype=torch.float64, device=gp.device)
-            for i0, t0 in enumerate(task0.tolist()):
-                for i1, t1 in enumerate(task1.tolist()):
-                    out[i0, i1] = kt[t0, t1] * (self._knew(x0, x1, t0, t1, scale, ls) if knew is None else knew) - k1[t0] @ sol2[t1].T
-                    if equal and t0 == t1 and i0 == i1:
-                        out[i0, i1].diagonal().clamp_(min=0)
-        return out
+            for h, (scale, ls, kt) in enumerate(sets):
+                knew = None if gp._has_derivs else self._knew(x0, x1, 0, 0, scale, ls)
+                k1 = {t: self._cross_rows(x0, t, ns, scale, ls, kt) for t in set(task0.tolist())}
+                sol2 = {t: self.gram_matrix_solve(k1[t] if (equal and t in k1) else self._cross_rows(x1, t, ns, scale, ls, kt), n=n, A=A[h]) for t in set(task1.tolist())}
+                for i0, t0 in enumerate(task0.tolist()):
+                    for i1, t1 in enumerate(task1.tolist()):
+                        out[h, i0, i1] = kt[t0, t1] * (self._knew(x0, x1, t0, t1, scale, ls) if knew is None else knew) - k1[t0] @ sol2[t1].T
+                        if equal and t0 == t1 and i0 == i1:
+                            out[h, i0, i1].diagonal().clamp_(min=0)
+        return out.reshape(Bh + out.shape[1:])
 
     def post_cubature_mean(self, task):
+        """(*shape_batch, len(task)): K_task[task, :] (scale sum_i coeffs_l,i)_l."""
         gp = self.gp
         ns = self.sizes()[0]
-        scale, _, kt = self._host()
         with torch.no_grad():
-            sums = scale * torch.stack([c.sum(-1) for c in self.coeffs().split(ns, dim=-1)])  # (T)
-            return torch.from_numpy(kt).to(gp.device)[task.to(gp.device)] @ sums
+            sums = gp.scale * torch.stack([c.sum(-1) for c in self.coeffs().split(ns, dim=-1)], -1)  # (*shape_batch, T)
+            return torch.einsum("...it,...t->...i", gp.gram_matrix_tasks[..., task.to(gp.device), :], sums)
 
     def post_cubature_cov(self, task0, task1, n):
-        """abstract_fast_gp.py:110-154: scale K_task - scale^2 K_task (sqrt(n_i n_j) A_0[first rows]) K_task."""
+        """abstract_fast_gp.py:110-154: scale K_task - scale^2 K_task (sqrt(n_i n_j) A_0[first rows]) K_task, (*Bh, len(task0), len(task1))."""
         gp = self.gp
-        scale, _, kt = self._host()
         with torch.no_grad():
             A, _ = self.factor(n)
             ns, active, nmin, r, off, R = self.sizes(n)
-            ktd = torch.from_numpy(kt).to(gp.device).to(A.dtype)
+            Bh = self.hyper_shape()
+            ktd = gp.gram_matrix_tasks.expand(Bh + (self.T, self.T)).to(A.dtype)
+            scale = gp.scale.expand(Bh + (1,))[..., None]
             idx = torch.tensor([off[l] for l in active], device=gp.device)
             act = torch.tensor(active, device=gp.device)
             nv = torch.tensor([float(ns[l]) for l in active], device=gp.device)
-            mid = torch.sqrt(nv[:, None] * nv[None, :]) * A[0][idx][:, idx]
+            mid = torch.sqrt(nv[:, None] * nv[None, :]) * A[..., 0, :, :][..., idx, :][..., :, idx]
             t0, t1 = task0.to(gp.device), task1.to(gp.device)
-            term = (ktd[t0][:, act] @ mid @ ktd[act][:, t1]).real
-            return scale * ktd.real[t0][:, t1] - scale ** 2 * term
+            term = (ktd[..., t0, :][..., :, act] @ mid @ ktd[..., act, :][..., :, t1]).real
+            return scale * ktd.real[..., t0, :][..., :, t1] - scale ** 2 * term
 
 
 class MultiTaskInverseLogDetCache(object):
@@ -362,7 +396,7 @@ class MultiTaskInverseLogDetCache(object):
 
     def __call__(self):
         A, logdet = self.fgp._mt.factor(self.nvec)
-        return A.permute(1, 2, 0), logdet  # (R, R, n_min) as the reference lays it out
+        return A.movedim(-3, -1), logdet  # (..., R, R, n_min) as the reference lays it out
 
     def gram_matrix_solve(self, y):
         return self.fgp._mt.gram_matrix_solve(y, n=self.nvec)

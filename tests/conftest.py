@@ -11,7 +11,8 @@ if ROOT not in sys.path:
 torch.set_default_dtype(torch.float64)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("mt_", "dv_", "sg_")))
+GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("mt_", "dv_", "sg_", "mb_")))
+GOLDEN_MB_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith("mb_"))  # several tasks with batched outputs
 GOLDEN_MT_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith(("mt_", "dv_")))  # dv_: derivative-informed
 
 

@@ -273,6 +273,101 @@ def run_case_standard(name, d, ns, kernel_class, T=None, batch=(), noise=1e-4, f
     print(name, "loss0", out["loss0"], "its", data["iterations"], os.path.getsize(path) // 1024, "KiB")
 
 
+def run_case_multitask_batch(name, family, d, n, T, alpha, batch, hyper_batch=None, m_test=24, noise=1e-4, fit_iterations=6, seed=23, derivatives=None):
+    """num_tasks = T with batched outputs y_l (*batch, n_l).  hyper_batch = None: one shared hyperparameter
+    set; otherwise the leading shape (a tail of batch) of all five hyperparameters, initialised to different values per set."""
+    ns = [int(n)] * T if np.isscalar(n) else [int(v) for v in n]
+    seeds = np.random.SeedSequence(seed).spawn(T)
+    if derivatives is not None:
+        seeds = [seeds[0]] * T
+    batch = tuple(batch)
+    kw = {"shape_batch": list(batch)}
+    if derivatives is not None:
+        kw["derivatives"] = derivatives
+    if hyper_batch is not None:
+        hb = tuple(hyper_batch)
+        g = torch.Generator().manual_seed(5)
+        kw.update(scale=0.5 + torch.rand(hb + (1,), generator=g), lengthscales=0.3 + torch.rand(hb + (d,), generator=g), noise=noise * (1 + torch.rand(hb + (1,), generator=g)))
+        if derivatives is None:
+            kw.update(factor_task_kernel=0.5 + torch.rand(hb + (T, 1), generator=g), noise_task_kernel=0.5 + torch.rand(hb + (T,), generator=g))
+    else:
+        kw["noise"] = noise
+    if family == "lattice":
+        seqs = [qmcpy.Lattice(dimension=d, seed=sd) for sd in seeds]
+        gp = fastgps.FastGPLattice(seqs, num_tasks=T, alpha=alpha, **kw)
+        gen = {"z": np.stack([s.gen_vec.astype(np.uint64) for s in seqs]), "shift": np.stack([s.shift for s in seqs])}
+    else:
+        seqs = [qmcpy.DigitalNetB2(dimension=d, seed=sd) for sd in seeds]
+        gp = fastgps.FastGPDigitalNetB2(seqs, num_tasks=T, alpha=alpha, **kw)
+        gen = {"C": np.stack([s.gen_mats.astype(np.uint64) for s in seqs]), "dshift": np.stack([s.rshift.astype(np.uint64) for s in seqs]), "t": np.int64(seqs[0].t)}
+    nb = int(np.prod(batch))
+
+    def f(x, l):  # batch element b: a different amplitude / phase; with derivatives task l observes D^{beta_l} of it
+        rows = []
+        for b in range(nb):
+            if derivatives is None:
+                rows.append((1 + 0.5 * b) * torch.cos(2 * np.pi * x).sum(1) + 0.4 * l * torch.sin(2 * np.pi * x[:, 0] + b) + 0.1 * l)
+            else:
+                term = torch.ones(len(x))
+                for j in range(d):
+                    a = 2 * np.pi * x[:, j]
+                    amp = (1 + 0.25 * b) / (j + 2)
+                    term = term * [1 + amp * torch.sin(a), 2 * np.pi * amp * torch.cos(a), -(2 * np.pi) ** 2 * amp * torch.sin(a)][int(gp.derivatives[l][0][j])]
+                rows.append(term)
+        return torch.stack(rows, 0).reshape(batch + (len(x),))
+    xs = gp.get_x_next(ns)
+    ys = [f(xs[l], l) for l in range(T)]
+    gp.add_y_next(ys)
+    xt = torch.rand((m_test, d), generator=torch.Generator().manual_seed(17))
+    out = dict(gen)
+    out.update(family=family, d=d, ns=np.array(ns), T=T, alpha=alpha, batch=np.array(batch), xtest=xt.numpy(),
+               hyper_batch=np.array(hyper_batch if hyper_batch is not None else [], dtype=np.int64))
+    for k in ("scale", "lengthscales", "noise", "factor_task_kernel", "noise_task_kernel"):
+        out[k + "0"] = getattr(gp, k).detach().numpy().copy()  # copy: an identity transform returns the parameter itself, which fit() updates in place
+    if derivatives is not None:
+        out.update({"deriv_%d" % l: gp.derivatives[l].numpy() for l in range(T)})
+    out.update({"x_%d" % l: xs[l].numpy() for l in range(T)})
+    out.update({"y_%d" % l: ys[l].numpy() for l in range(T)})
+    os.environ["FASTGP_FORCE_RECOMPILE"] = "True"
+    norm_term, logdet = gp.get_inv_log_det_cache().get_norm_term_logdet_term()
+    d_out = nb
+    loss = 0.5 * (norm_term.sum() + d_out / logdet.numel() * logdet.sum() + d_out * sum(ns) * np.log(2 * np.pi))  # abstract_gp.py:253-256
+    loss.backward()
+    gr = lambda p: p.grad.numpy().copy() if p.grad is not None else np.zeros(0)
+    out.update(loss0=loss.item(), norm_term0=norm_term.detach().numpy(), logdet0=logdet.detach().numpy(),
+               grad_raw_scale0=gr(gp.raw_scale), grad_raw_lengthscales0=gr(gp.raw_lengthscales), grad_raw_noise0=gr(gp.raw_noise),
+               grad_raw_factor0=gr(gp.raw_factor_task_kernel), grad_raw_noise_task0=gr(gp.raw_noise_task_kernel))
+    gp.zero_grad()
+    del os.environ["FASTGP_FORCE_RECOMPILE"]
+    out["coeffs0"] = gp.coeffs.detach().numpy()
+    out["pmean0"] = gp.post_mean(xt).numpy()
+    out["pmean0_task1"] = gp.post_mean(xt, task=1).numpy()
+    out["pvar0"] = gp.post_var(xt).numpy()
+    out["pvar0_task0"] = gp.post_var(xt, task=0).numpy()
+    out["pcov0"] = gp.post_cov(xt[:6], xt[:4]).numpy()
+    out["pcov0_t10"] = gp.post_cov(xt[:6], xt[:4], task0=1, task1=[0]).numpy()
+    out["pcmean0"] = gp.post_cubature_mean().numpy()
+    out["pcvar0"] = gp.post_cubature_var().numpy()
+    out["pccov0"] = gp.post_cubature_cov().numpy()
+    out["pvar0_n2"] = gp.post_var(xt, n=2 * gp.n).numpy()
+    data = gp.fit(iterations=fit_iterations, verbose=0, store_hists=True, stop_crit_wait_iterations=100)
+    out.update(fit_iterations=fit_iterations, fit_last_iteration=data["iterations"], loss_hist=data["loss_hist"].numpy(),
+               scale_hist=data["scale_hist"].numpy(), lengthscales_hist=data["lengthscales_hist"].numpy(), noise_hist=data["noise_hist"].numpy(),
+               task_kernel_hist=data["task_kernel_hist"].numpy(), pmean1=gp.post_mean(xt).numpy(), pvar1=gp.post_var(xt).numpy())
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "loss0", out["loss0"], "its", data["iterations"], {k: out[k].shape for k in ("pmean0", "pvar0", "pcov0", "pcmean0", "pcvar0", "pccov0", "logdet0")},
+          os.path.getsize(path) // 1024, "KiB")
+
+
+def run_multitask_batch_cases():
+    run_case_multitask_batch("mb_lattice_T2_d2_ragged_a2_b3_shared", "lattice", 2, [64, 32], 2, 2, (3,))
+    run_case_multitask_batch("mb_dnb2_T2_d3_n64_a2_b2x3_hyper3", "dnb2", 3, 64, 2, 2, (2, 3), hyper_batch=(3,), noise=1e-6)
+    run_case_multitask_batch("mb_lattice_T3_d2_ragged_a3_b2_hyper2", "lattice", 2, [32, 128, 64], 3, 3, (2,), hyper_batch=(2,))
+    run_case_multitask_batch("mb_lattice_dv_d2_n32_a3_b2_hyper2", "lattice", 2, 32, 2, 3, (2,), hyper_batch=(2,), noise=1e-3,
+                             derivatives=[torch.zeros(2, dtype=int), torch.tensor([1, 0])])
+
+
 def run_standard_cases():
     run_case_standard("sg_gaussian_d2_n64", 2, 64, "Gaussian")
     run_case_standard("sg_matern52_d3_T2_n48_20", 3, [48, 20], "Matern52", T=2)
@@ -283,6 +378,9 @@ def run_standard_cases():
 if __name__ == "__main__":
     if "--standard-only" in sys.argv:
         run_standard_cases()
+        sys.exit(0)
+    if "--multitask-batch-only" in sys.argv:
+        run_multitask_batch_cases()
         sys.exit(0)
     if "--multitask-only" in sys.argv:
         run_case_multitask("mt_lattice_T2_d2_n256_a2", "lattice", 2, 256, 2, 2)
@@ -313,4 +411,5 @@ if __name__ == "__main__":
     run_case_multitask("mt_lattice_T3_d2_ragged_a2", "lattice", 2, [64, 256, 128], 3, 2)
     run_case_multitask("mt_dnb2_T2_d3_ragged_a2", "dnb2", 3, [256, 32], 2, 2)
     run_deriv_cases()
+    run_multitask_batch_cases()
     run_standard_cases()

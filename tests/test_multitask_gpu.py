@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_MT_CASES, load_golden
+from conftest import GOLDEN_MB_CASES, GOLDEN_MT_CASES, load_golden
 
 pytestmark = pytest.mark.gpu
 dev = "cuda:0"
@@ -137,8 +137,72 @@ def test_multitask_guards():
     assert gp.coeffs.shape == (80,) and gp.n.tolist() == [64, 16]
     with pytest.raises(AssertionError):
         gp.post_var(torch.rand(4, 2), n=[64, 8])  # sizes may only grow
-    with pytest.raises(NotImplementedError):
-        fgp.FastGPLattice(2, num_tasks=2, shape_batch=[3], device=dev)
+
+
+def amax(a, b):
+    return float((torch.as_tensor(a).detach().cpu() - torch.as_tensor(b)).abs().max())
+
+
+@pytest.mark.parametrize("case", GOLDEN_MB_CASES)
+def test_multitask_batched_outputs_match_reference_fixture(case):
+    """num_tasks > 1 (and derivative observations) with shape_batch: batched y, one shared or one-per-batch hyperparameter set
+    (tests/golden/make_golden.py::run_case_multitask_batch, written by the unmodified reference)."""
+    import fastgaussianprocesses_b200 as fgp
+    g = load_golden(case)
+    T, d, alpha = int(g["T"]), int(g["d"]), int(g["alpha"])
+    ns = [int(v) for v in g["ns"]]
+    batch = [int(v) for v in g["batch"]]
+    kw = {"shape_batch": batch, "scale": torch.from_numpy(g["scale0"]), "lengthscales": torch.from_numpy(g["lengthscales0"]), "noise": torch.from_numpy(g["noise0"])}
+    if "deriv_0" in g:
+        kw["derivatives"] = [torch.from_numpy(g["deriv_%d" % l]) for l in range(T)]
+    else:  # K_task = F F^T + diag(v): F and v are not stored for the shared-set case, their defaults are the reference's
+        if g["hyper_batch"].size:
+            kw.update(factor_task_kernel=torch.from_numpy(g["factor_task_kernel0"]), noise_task_kernel=torch.from_numpy(g["noise_task_kernel0"]))
+    if str(g["family"]) == "lattice":
+        seqs = [fgp.Lattice(d, generating_vector=g["z"][l], shift=g["shift"][l]) for l in range(T)]
+        gp = fgp.FastGPLattice(seqs, num_tasks=T, alpha=alpha, device=dev, **kw)
+    else:
+        seqs = [fgp.DigitalNetB2(d, generating_matrices=g["C"][l], dshift=g["dshift"][l], t=int(g["t"])) for l in range(T)]
+        gp = fgp.FastGPDigitalNetB2(seqs, num_tasks=T, alpha=alpha, device=dev, **kw)
+    xs = gp.get_x_next(ns)
+    assert all(np.array_equal(xs[l].cpu().numpy(), g["x_%d" % l]) for l in range(T))  # bit-exact points
+    gp.add_y_next([torch.from_numpy(g["y_%d" % l]) for l in range(T)])
+    ymax = max(float(np.abs(g["y_%d" % l]).max()) for l in range(T))
+    # loss terms (abstract_gp.py:253-256) and the autograd gradients of every parameter group
+    norm, logdet = gp.get_inv_log_det_cache().get_norm_term_logdet_term()
+    assert norm.shape == g["norm_term0"].shape and logdet.shape == g["logdet0"].shape
+    assert rel(norm, g["norm_term0"]) < 1e-9 and rel(logdet, g["logdet0"]) < 1e-10
+    d_out = int(np.prod(batch))
+    loss = 0.5 * (norm.sum() + d_out / logdet.numel() * logdet.sum() + d_out * sum(ns) * np.log(2 * np.pi))
+    assert abs(float(loss) - float(g["loss0"])) <= 1e-9 * abs(float(g["loss0"]))
+    loss.backward()
+    for pname, key in (("raw_scale", "grad_raw_scale0"), ("raw_lengthscales", "grad_raw_lengthscales0"), ("raw_noise", "grad_raw_noise0"),
+                       ("raw_factor_task_kernel", "grad_raw_factor0"), ("raw_noise_task_kernel", "grad_raw_noise_task0")):
+        grad = getattr(gp, pname).grad
+        if g[key].size == 0:
+            assert grad is None
+        else:
+            assert grad.shape == g[key].shape and rel(grad, g[key]) < 1e-7, pname
+    gp.zero_grad()
+    assert gp.coeffs.shape == g["coeffs0"].shape and rel(gp.coeffs, g["coeffs0"]) < 1e-8
+    xt = torch.from_numpy(g["xtest"])
+    # derivative observations multiply the spectrum by (2 pi kappa)^2, so those systems are orders of magnitude worse conditioned than the
+    # function-value ones: the reference's Schur recursion and the pivoted block solve then agree to ~1e-7 of the prior variance only
+    vmax = max(1.0, float(np.abs(g["pvar0"]).max())) * (10.0 if "deriv_0" in g else 1.0)
+    for name, val, tol in (("pmean0", gp.post_mean(xt), 1e-8 * ymax), ("pmean0_task1", gp.post_mean(xt, task=1), 1e-8 * ymax),
+                           ("pvar0", gp.post_var(xt), 1e-8 * vmax), ("pvar0_task0", gp.post_var(xt, task=0), 1e-8 * vmax),
+                           ("pcov0", gp.post_cov(xt[:6], xt[:4]), 1e-8 * vmax), ("pcov0_t10", gp.post_cov(xt[:6], xt[:4], task0=1, task1=[0]), 1e-8 * vmax),
+                           ("pcmean0", gp.post_cubature_mean(), 1e-8 * ymax), ("pcvar0", gp.post_cubature_var(), 1e-9), ("pccov0", gp.post_cubature_cov(), 1e-9),
+                           ("pvar0_n2", gp.post_var(xt, n=2 * gp.n), 1e-8 * vmax)):
+        assert val.shape == g[name].shape, (name, val.shape, g[name].shape)
+        assert amax(val, g[name]) < tol, (name, amax(val, g[name]), tol)
+    data = gp.fit(iterations=int(g["fit_iterations"]), verbose=0, store_hists=True, stop_crit_wait_iterations=100)
+    assert data["iterations"] == int(g["fit_last_iteration"])
+    assert np.allclose(data["loss_hist"].numpy(), g["loss_hist"], rtol=1e-7)
+    for key in ("scale_hist", "lengthscales_hist", "noise_hist", "task_kernel_hist"):
+        assert data[key].shape == g[key].shape and rel(data[key], g[key]) < 1e-6, key
+    assert amax(gp.post_mean(xt), g["pmean1"]) < 1e-6 * ymax
+    assert amax(gp.post_var(xt), g["pvar1"]) < 1e-6 * vmax
 
 
 @pytest.mark.parametrize("cplx", [False, True])

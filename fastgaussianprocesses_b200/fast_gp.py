@@ -15,8 +15,8 @@ streams, the tiny hyperparameter transforms and (outside the fast path) the opti
 
 Scope: the fused device-side path covers one task without derivative information (rows a1-a15); several
 tasks (equal or different power-of-two sizes), derivative observations, GCV / CV losses and masked fits run on the same CUDA
-transforms through torch.autograd (multitask.py, _FTFunction) -- rows (f)2-(f)4.  The adaptive nugget and batched outputs combined
-with several tasks or derivatives raise NotImplementedError rather than being approximated.
+transforms through torch.autograd (multitask.py, _FTFunction) -- rows (f)2-(f)4, with batched outputs (shape_batch), one shared or
+one hyperparameter set per batch element, and the adaptive nugget (util.py:286-290; the identity for a single task).
 """
 import functools
 import math
@@ -569,8 +569,6 @@ class AbstractFastGP(torch.nn.Module):
             rank_factor_task_kernel = 1
             tfs_noise_task_kernel = DEFAULT_TFS_ID
             noise_task_kernel = 0.
-        if adaptive_nugget and not self._DENSE:
-            raise NotImplementedError("adaptive_nugget is not supported by the B200 hot path")
         self.num_tasks = num_tasks
         self.default_task = default_task
         self.solo_task = solo_task
@@ -1179,8 +1177,6 @@ class AbstractFastGP(torch.nn.Module):
         # MLL without masks: fused CUDA eigen-solve with the analytic gradient.  GCV, CV and masked fits: the same transforms
         # behind torch.autograd (_FTFunction), formulas as in the reference.
         autograd_route = loss_metric != "MLL" or masks is not None or self._mt is not None
-        if self._mt is not None and masks is not None and not self._DENSE:
-            raise NotImplementedError("fit(masks=...) with several tasks is not built")
         if isinstance(cv_weights, torch.Tensor):
             cv_weights = cv_weights.to(self.device)
         fused = (not autograd_route) and optimizer is None and _FusedFitLoop.eligible(self) and os.environ.get("FGP_B200_GENERIC_FIT") != "1"
@@ -1228,7 +1224,7 @@ class AbstractFastGP(torch.nn.Module):
             if self._DENSE:
                 loss, term1, term2, metric_val = self._mt.loss(loss_metric, d_out, mll_const, masks, cv_weights)
             elif self._mt is not None:
-                loss, term1, term2, metric_val = self._mt.loss(loss_metric, d_out, mll_const)
+                loss, term1, term2, metric_val = self._mt.loss(loss_metric, d_out, mll_const, masks, cv_weights)
             elif autograd_route:
                 loss, term1, term2, metric_val = self._autograd_loss(loss_metric, masks, cv_weights, d_out, mll_const)
             else:
@@ -1590,7 +1586,7 @@ _CTOR_DOC = """
     `device` defaults to "cuda" and must be a CUDA device; `seqs` may be an int (dimension), one of this package's
     GPU-side sequence specs (`sequences.Lattice` / `sequences.DigitalNetB2`) or any qmcpy-style sequence object, whose
     points are then taken from its own host generator; `compile_fts*` are accepted and ignored (the transforms are
-    hand-written CUDA kernels); `adaptive_nugget` raises NotImplementedError.
+    hand-written CUDA kernels).
 """
 
 

@@ -140,6 +140,10 @@ class MultiTaskEngine(object):
         scale, ls, noise, kt = gp.scale, gp.lengthscales, gp.noise, gp.gram_matrix_tasks
         dev = gp.device
         Bh = self.hyper_shape()
+        tr00 = None
+        if gp.adaptive_nugget:  # util.py:286-290: the noise of task l is scaled by |trace(block l) / trace(block 0)|
+            assert ns[0] > 0, "adaptive_nugget needs data for task 0"
+            tr00 = (np.sqrt(ns[0]) * gp.ft(self.k1(0, 0, ns[0]))).sum(-1, keepdim=True)
         bidx, rows, cols, vals = [], [], [], []
         ar = torch.arange(nmin, device=dev)
         for i0, t0 in enumerate(active):
@@ -151,7 +155,7 @@ class MultiTaskEngine(object):
                     lam = gp.ft(self.k1(t1, t0, nbig)).conj()
                 lam = np.sqrt(ns[t1]) * lam
                 if t0 == t1:
-                    lam = lam + noise
+                    lam = lam + (noise if tr00 is None else noise * (lam.sum(-1, keepdim=True) / tr00).abs())
                 V = (lam * kt[..., t0, t1, None]).expand(Bh + (nbig,)).reshape(Bh + (r[t0], nmin)).movedim(-1, 0).movedim(-1, 0)  # (r, n_min, *Bh)
                 for a0 in range(r[t0]):
                     a1 = a0 if t0 == t1 else a0 % r[t1]
@@ -231,21 +235,45 @@ class MultiTaskEngine(object):
         norm = (yt.conj() * zt).real.sum((-1, -2))[..., None]
         return norm, logdet[..., None], A, zt
 
-    def loss(self, loss_metric, d_out, mll_const):
-        """The reference's losses on the block spectrum (abstract_gp.py:242-273); returns (loss, term1, term2, metric_val)."""
+    def loss(self, loss_metric, d_out, mll_const, masks=None, cv_weights=1):
+        """The reference's losses on the block spectrum (abstract_gp.py:242-273); returns (loss, term1, term2, metric_val).  `masks`
+        (one index row per leading batch dimension) restricts the sums to a subset of the batched outputs."""
+        gp = self.gp
+        sb = list(gp.shape_batch)
         norm, logdet, A, zt = self.norm_logdet(grad=True)
         if loss_metric == "MLL":
-            term1 = norm.sum()
-            term2 = d_out / logdet.numel() * logdet.sum()
+            if masks is None:
+                term1 = norm.sum()
+                term2 = d_out / logdet.numel() * logdet.sum()
+            else:
+                term1 = norm[..., *masks, 0].sum()
+                term2 = logdet.expand(sb + [1])[..., *masks, 0].sum()
             loss = 1 / 2 * (term1 + term2 + mll_const)
             return loss, term1, term2, -loss
         if loss_metric == "GCV":
             numer = (zt.conj() * zt).real.sum((-1, -2))[..., None]
             tr_k_inv = torch.diagonal(A, dim1=-2, dim2=-1).real.sum((-1, -2))[..., None]
-            denom = ((tr_k_inv / int(self.gp.n.sum())) ** 2).real
-            loss = (numer / denom).sum()
-            return loss, numer, denom, loss
-        raise NotImplementedError("loss_metric='CV' needs the O(n^2 log n) inverse diagonal of the reference for several tasks (util.py:386-393); not built")
+            denom = ((tr_k_inv / int(gp.n.sum())) ** 2).real
+            if masks is None:
+                term1, term2 = numer, denom
+            else:
+                term1 = numer[..., *masks, :]
+                term2 = denom.expand(sb + [1])[..., *masks, :]
+            loss = (term1 / term2).sum()
+            return loss, term1, term2, loss
+        # CV: leave-one-out residuals coeffs_i / (K^-1)_ii; the diagonal of K^-1 from solving against the identity, O(n^2 log n) as in the
+        # reference (util.py:386-393)
+        ns = self.sizes()[0]
+        nsum = sum(ns)
+        coeffs = torch.cat([gp.ift(v).real if v.size(-1) > 0 else v.real for v in self.unfold(zt)], -1)
+        Bh = self.hyper_shape()
+        eye = torch.eye(nsum, device=gp.device).reshape((nsum,) + (1,) * len(Bh) + (nsum,))
+        kinv = self.gram_matrix_solve(eye, A=A)  # (nsum, *Bh, nsum)
+        inv_diag = kinv.movedim(0, -2).diagonal(dim1=-2, dim2=-1)
+        squared_sums = ((coeffs / inv_diag) ** 2 * cv_weights).sum(-1, keepdim=True)
+        loss = squared_sums.sum() if masks is None else squared_sums[..., *masks, 0].sum()
+        nan = torch.nan * torch.ones(1)
+        return loss, nan, nan, loss
 
     # ------------------------------------------------------------------------------------------------ posterior
     def _host(self):

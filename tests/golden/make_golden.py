@@ -133,7 +133,7 @@ def run_case(name, family, d, n, m_test, alpha, f, scale=1.0, lengthscales=1.0, 
 
 
 def run_case_multitask(name, family, d, n, T, alpha, m_test=64, noise=1e-6, fit_iterations=8, seed=11, derivatives=None, derivatives_coeffs=None,
-                       shared_seq=False):
+                       shared_seq=False, adaptive_nugget=False):
     """num_tasks = T: block eigen-solve util.py:301-323,354-363.  n is one size for every task
     or a list of per-task sizes (ragged arrays are then stored per task: x_0, x_1, ..., y_0, ...)."""
     ns = [int(n)] * T if np.isscalar(n) else [int(v) for v in n]
@@ -142,6 +142,8 @@ def run_case_multitask(name, family, d, n, T, alpha, m_test=64, noise=1e-6, fit_
     if shared_seq:  # derivative observations at the same points as the function values
         seeds = [seeds[0]] * T
     dkw = {} if derivatives is None else {"derivatives": derivatives, "derivatives_coeffs": derivatives_coeffs}
+    if adaptive_nugget:  # util.py:286-290
+        dkw["adaptive_nugget"] = True
     if family == "lattice":
         seqs = [qmcpy.Lattice(dimension=d, seed=sd) for sd in seeds]
         gp = fastgps.FastGPLattice(seqs, num_tasks=T, alpha=alpha, noise=noise, **dkw)
@@ -168,6 +170,8 @@ def run_case_multitask(name, family, d, n, T, alpha, m_test=64, noise=1e-6, fit_
     xt = torch.rand((m_test, d), generator=torch.Generator().manual_seed(17))
     out = dict(gen)
     out.update(family=family, d=d, n=max(ns), ns=np.array(ns), T=T, alpha=alpha, noise0=noise, xtest=xt.numpy())
+    if adaptive_nugget:
+        out["adaptive_nugget"] = np.int64(1)
     if derivatives is not None:
         out.update({"deriv_%d" % l: gp.derivatives[l].numpy() for l in range(T)})
         out.update({"dcoef_%d" % l: gp.derivatives_coeffs[l].numpy() for l in range(T)})
@@ -292,13 +296,15 @@ def run_case_multitask_batch(name, family, d, n, T, alpha, batch, hyper_batch=No
             kw.update(factor_task_kernel=0.5 + torch.rand(hb + (T, 1), generator=g), noise_task_kernel=0.5 + torch.rand(hb + (T,), generator=g))
     else:
         kw["noise"] = noise
+    # every object gets its own copies: an identity transform makes the constructor's tensor the parameter itself, which fit() updates in place
+    fresh_kw = lambda: {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in kw.items()}
     if family == "lattice":
         seqs = [qmcpy.Lattice(dimension=d, seed=sd) for sd in seeds]
-        gp = fastgps.FastGPLattice(seqs, num_tasks=T, alpha=alpha, **kw)
+        gp = fastgps.FastGPLattice(seqs, num_tasks=T, alpha=alpha, **fresh_kw())
         gen = {"z": np.stack([s.gen_vec.astype(np.uint64) for s in seqs]), "shift": np.stack([s.shift for s in seqs])}
     else:
         seqs = [qmcpy.DigitalNetB2(dimension=d, seed=sd) for sd in seeds]
-        gp = fastgps.FastGPDigitalNetB2(seqs, num_tasks=T, alpha=alpha, **kw)
+        gp = fastgps.FastGPDigitalNetB2(seqs, num_tasks=T, alpha=alpha, **fresh_kw())
         gen = {"C": np.stack([s.gen_mats.astype(np.uint64) for s in seqs]), "dshift": np.stack([s.rshift.astype(np.uint64) for s in seqs]), "t": np.int64(seqs[0].t)}
     nb = int(np.prod(batch))
 
@@ -354,6 +360,22 @@ def run_case_multitask_batch(name, family, d, n, T, alpha, batch, hyper_batch=No
     out.update(fit_iterations=fit_iterations, fit_last_iteration=data["iterations"], loss_hist=data["loss_hist"].numpy(),
                scale_hist=data["scale_hist"].numpy(), lengthscales_hist=data["lengthscales_hist"].numpy(), noise_hist=data["noise_hist"].numpy(),
                task_kernel_hist=data["task_kernel_hist"].numpy(), pmean1=gp.post_mean(xt).numpy(), pvar1=gp.post_var(xt).numpy())
+    # the other losses of fit (abstract_gp.py:242-273) on fresh objects: GCV, CV, and fits restricted to a subset of the batch by masks
+    masks = torch.tensor([[0, nb - 1]]) if len(batch) == 1 else torch.tensor([[0, batch[0] - 1], [batch[1] - 1, 0]])
+    out["masks"] = masks.numpy()
+    for tag, fkw in (("gcv", {"loss_metric": "GCV"}), ("cv", {"loss_metric": "CV"}), ("mllmask", {"masks": masks}), ("gcvmask", {"loss_metric": "GCV", "masks": masks})):
+        cls = fastgps.FastGPLattice if family == "lattice" else fastgps.FastGPDigitalNetB2
+        gp2 = cls(seqs, num_tasks=T, alpha=alpha, **fresh_kw())
+        gp2.get_x_next(ns)
+        gp2.add_y_next(ys)
+        try:
+            d2 = gp2.fit(iterations=3, verbose=0, store_hists=True, stop_crit_wait_iterations=100, **fkw)
+        except Exception as e:
+            print("   ", tag, "not available in the reference:", type(e).__name__, str(e)[:80])
+            continue
+        out.update({"var_%s_loss_hist" % tag: d2["loss_hist"].numpy(), "var_%s_lengthscales_hist" % tag: d2["lengthscales_hist"].numpy(),
+                    "var_%s_task_kernel_hist" % tag: d2["task_kernel_hist"].numpy()})
+        print("   ", tag, d2["loss_hist"].numpy())
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print(name, "loss0", out["loss0"], "its", data["iterations"], {k: out[k].shape for k in ("pmean0", "pvar0", "pcov0", "pcmean0", "pcvar0", "pccov0", "logdet0")},
@@ -366,6 +388,11 @@ def run_multitask_batch_cases():
     run_case_multitask_batch("mb_lattice_T3_d2_ragged_a3_b2_hyper2", "lattice", 2, [32, 128, 64], 3, 3, (2,), hyper_batch=(2,))
     run_case_multitask_batch("mb_lattice_dv_d2_n32_a3_b2_hyper2", "lattice", 2, 32, 2, 3, (2,), hyper_batch=(2,), noise=1e-3,
                              derivatives=[torch.zeros(2, dtype=int), torch.tensor([1, 0])])
+
+
+def run_nugget_cases():
+    run_case_multitask("mt_lattice_T3_d2_ragged_a2_nugget", "lattice", 2, [64, 256, 128], 3, 2, noise=1e-4, adaptive_nugget=True)
+    run_case_multitask("mt_dnb2_T2_d3_n128_a2_nugget", "dnb2", 3, 128, 2, 2, noise=1e-5, adaptive_nugget=True)
 
 
 def run_standard_cases():
@@ -381,6 +408,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--multitask-batch-only" in sys.argv:
         run_multitask_batch_cases()
+        sys.exit(0)
+    if "--nugget-only" in sys.argv:
+        run_nugget_cases()
         sys.exit(0)
     if "--multitask-only" in sys.argv:
         run_case_multitask("mt_lattice_T2_d2_n256_a2", "lattice", 2, 256, 2, 2)
@@ -412,4 +442,5 @@ if __name__ == "__main__":
     run_case_multitask("mt_dnb2_T2_d3_ragged_a2", "dnb2", 3, [256, 32], 2, 2)
     run_deriv_cases()
     run_multitask_batch_cases()
+    run_nugget_cases()
     run_standard_cases()

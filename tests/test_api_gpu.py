@@ -146,8 +146,7 @@ def test_api_guards_and_errors():
     with pytest.raises(RuntimeError):
         fgp.FastGPLattice(3, device="cpu")
     assert fgp.FastGPLattice(3, num_tasks=2, shape_batch=[2], device=dev).shape_batch == (2,)  # several tasks with batched outputs: test_multitask_gpu.py
-    with pytest.raises(NotImplementedError):
-        fgp.FastGPLattice(3, adaptive_nugget=True, device=dev)
+    assert fgp.FastGPLattice(3, adaptive_nugget=True, device=dev).adaptive_nugget  # the identity for one task (util.py:286-290); several: test_multitask_gpu.py
     assert gp.post_mean(torch.rand(5, 3)).shape == (5,)
     assert gp.post_mean(torch.rand(5, 3), task=[0]).shape == (1, 5)
     assert gp.post_mean(torch.zeros(0, 3)).shape == (0,)

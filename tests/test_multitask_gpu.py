@@ -22,6 +22,8 @@ def make_gp(g):
     kw = {}
     if "deriv_0" in g:  # derivative-informed kernels
         kw = {"derivatives": [torch.from_numpy(g["deriv_%d" % l]) for l in range(T)], "derivatives_coeffs": [torch.from_numpy(g["dcoef_%d" % l]) for l in range(T)]}
+    if "adaptive_nugget" in g:  # util.py:286-290
+        kw["adaptive_nugget"] = True
     if str(g["family"]) == "lattice":
         seqs = [fgp.Lattice(d, generating_vector=g["z"][l], shift=g["shift"][l]) for l in range(T)]
         return fgp.FastGPLattice(seqs, num_tasks=T, alpha=alpha, noise=float(g["noise0"]), device=dev, **kw)
@@ -143,27 +145,31 @@ def amax(a, b):
     return float((torch.as_tensor(a).detach().cpu() - torch.as_tensor(b)).abs().max())
 
 
-@pytest.mark.parametrize("case", GOLDEN_MB_CASES)
-def test_multitask_batched_outputs_match_reference_fixture(case):
-    """num_tasks > 1 (and derivative observations) with shape_batch: batched y, one shared or one-per-batch hyperparameter set
-    (tests/golden/make_golden.py::run_case_multitask_batch, written by the unmodified reference)."""
+def make_gp_batched(g):
     import fastgaussianprocesses_b200 as fgp
-    g = load_golden(case)
     T, d, alpha = int(g["T"]), int(g["d"]), int(g["alpha"])
-    ns = [int(v) for v in g["ns"]]
     batch = [int(v) for v in g["batch"]]
     kw = {"shape_batch": batch, "scale": torch.from_numpy(g["scale0"]), "lengthscales": torch.from_numpy(g["lengthscales0"]), "noise": torch.from_numpy(g["noise0"])}
     if "deriv_0" in g:
         kw["derivatives"] = [torch.from_numpy(g["deriv_%d" % l]) for l in range(T)]
-    else:  # K_task = F F^T + diag(v): F and v are not stored for the shared-set case, their defaults are the reference's
-        if g["hyper_batch"].size:
-            kw.update(factor_task_kernel=torch.from_numpy(g["factor_task_kernel0"]), noise_task_kernel=torch.from_numpy(g["noise_task_kernel0"]))
+    elif g["hyper_batch"].size:  # K_task = F F^T + diag(v); the shared-set case keeps the reference's defaults
+        kw.update(factor_task_kernel=torch.from_numpy(g["factor_task_kernel0"]), noise_task_kernel=torch.from_numpy(g["noise_task_kernel0"]))
     if str(g["family"]) == "lattice":
         seqs = [fgp.Lattice(d, generating_vector=g["z"][l], shift=g["shift"][l]) for l in range(T)]
-        gp = fgp.FastGPLattice(seqs, num_tasks=T, alpha=alpha, device=dev, **kw)
-    else:
-        seqs = [fgp.DigitalNetB2(d, generating_matrices=g["C"][l], dshift=g["dshift"][l], t=int(g["t"])) for l in range(T)]
-        gp = fgp.FastGPDigitalNetB2(seqs, num_tasks=T, alpha=alpha, device=dev, **kw)
+        return fgp.FastGPLattice(seqs, num_tasks=T, alpha=alpha, device=dev, **kw)
+    seqs = [fgp.DigitalNetB2(d, generating_matrices=g["C"][l], dshift=g["dshift"][l], t=int(g["t"])) for l in range(T)]
+    return fgp.FastGPDigitalNetB2(seqs, num_tasks=T, alpha=alpha, device=dev, **kw)
+
+
+@pytest.mark.parametrize("case", GOLDEN_MB_CASES)
+def test_multitask_batched_outputs_match_reference_fixture(case):
+    """num_tasks > 1 (and derivative observations) with shape_batch: batched y, one shared or one-per-batch hyperparameter set
+    (tests/golden/make_golden.py::run_case_multitask_batch, written by the unmodified reference)."""
+    g = load_golden(case)
+    T = int(g["T"])
+    ns = [int(v) for v in g["ns"]]
+    batch = [int(v) for v in g["batch"]]
+    gp = make_gp_batched(g)
     xs = gp.get_x_next(ns)
     assert all(np.array_equal(xs[l].cpu().numpy(), g["x_%d" % l]) for l in range(T))  # bit-exact points
     gp.add_y_next([torch.from_numpy(g["y_%d" % l]) for l in range(T)])
@@ -232,3 +238,23 @@ def test_block_inv_logdet_kernel_matches_dense_algebra(R, cplx):
     g1, = torch.autograd.grad(f(_BlockInvLogdet.apply), Ls)
     g2, = torch.autograd.grad(f(lambda L: (torch.linalg.inv(L), torch.linalg.slogdet(L)[1])), Ls)
     assert float((g1 - g2).abs().max() / g2.abs().max()) < 1e-10
+
+
+@pytest.mark.parametrize("tag", ["gcv", "cv", "mllmask", "gcvmask"])
+@pytest.mark.parametrize("case", GOLDEN_MB_CASES)
+def test_multitask_batched_loss_variants_match_reference_fixture(case, tag):
+    """GCV / CV losses and fits restricted by masks to a subset of the batched outputs (abstract_gp.py:242-273), several tasks: three
+    optimiser iterations against the trajectory of the unmodified reference."""
+    g = load_golden(case)
+    T = int(g["T"])
+    gp = make_gp_batched(g)
+    gp.get_x_next([int(v) for v in g["ns"]])
+    gp.add_y_next([torch.from_numpy(g["y_%d" % l]) for l in range(T)])
+    fkw = {"gcv": {"loss_metric": "GCV"}, "cv": {"loss_metric": "CV"}, "mllmask": {"masks": torch.from_numpy(g["masks"])},
+           "gcvmask": {"loss_metric": "GCV", "masks": torch.from_numpy(g["masks"])}}[tag]
+    data = gp.fit(iterations=3, verbose=0, store_hists=True, stop_crit_wait_iterations=100, **fkw)
+    # the CV loss divides by the diagonal of K^-1 (an O(n^2 log n) solve against the identity in both implementations): looser
+    tol = 1e-5 if tag == "cv" or "deriv_0" in g else 1e-7
+    assert np.allclose(data["loss_hist"].numpy(), g["var_%s_loss_hist" % tag], rtol=tol), (data["loss_hist"].numpy(), g["var_%s_loss_hist" % tag])
+    assert rel(data["lengthscales_hist"], g["var_%s_lengthscales_hist" % tag]) < 10 * tol
+    assert rel(data["task_kernel_hist"], g["var_%s_task_kernel_hist" % tag]) < 10 * tol

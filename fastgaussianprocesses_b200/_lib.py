@@ -68,6 +68,10 @@ SIGNATURES = {
     "fgp_fit_init": (_i32, [_c.POINTER(FitLayout), _c.POINTER(FitOptions), _vp]),
     "fgp_fit_step": (_i32, [_c.POINTER(FitLayout), _vp, _vp]),
     "fgp_fit_finish": (_i32, [_c.POINTER(FitLayout), _vp]),
+    "fgp_fit_init_from": (_i32, [_c.POINTER(FitLayout), _c.POINTER(FitOptions), _vp, _vp, _vp, _vp]),
+    "fgp_fit_finish_to": (_i32, [_c.POINTER(FitLayout), _vp, _vp, _vp, _vp]),
+    "fgp_data_spectrum_workspace_bytes": (_sz, [_i64, _i64]),
+    "fgp_data_spectrum": (_i32, [_i32, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "fgp_profile_begin": (_i32, [_vp]),
     "fgp_profile_end": (_i32, [_vp, _i32, _c.POINTER(_c.c_char_p), _c.POINTER(_c.c_float)]),
     "fgp_gram_solve": (_i32, [_i32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
@@ -119,8 +123,35 @@ def _check(rc):
         raise FgpError("libfgp_b200: %s (code %d)" % (load().fgp_last_error().decode(), rc))
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """The current CUDA stream of the current device as a raw handle.  torch.cuda.current_stream() builds a Stream object through several
+    Python layers (~20 us, measured with cProfile inside fit()); the raw getter is what torch's own compiled code paths use."""
+    if _raw_stream is not None:
+        return _raw_stream(torch._C._cuda_getDevice())
     return torch.cuda.current_stream().cuda_stream
+
+
+class _NoSwitch(object):
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def on_device(device):
+    """`with on_device(dev):` -- torch.cuda.device(dev) only when dev is not already the current device (the context manager costs
+    ~15 us of host time per use, and every C call of the fit loop sits inside one)."""
+    idx = device.index
+    if idx is None or idx == torch._C._cuda_getDevice():
+        return _NO_SWITCH
+    return torch.cuda.device(device)
 
 
 def _dev(t, dtype=None):
@@ -154,7 +185,7 @@ def lattice_points(z, shift, i0, i1, device):
     x = torch.empty((int(i1) - int(i0), d), dtype=torch.float64, device=device)
     if x.numel() == 0:
         return x
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         _check(load().fgp_lattice_points(_harr(_u64, [int(v) for v in z]), _harr(_f64, [float(v) for v in shift]), d,
                                          int(i0), int(i1), x.data_ptr(), _stream()))
     return x
@@ -167,7 +198,7 @@ def dnb2_points(C_dev, dshift, t, i0, i1, want_x=True):
     x = torch.empty((int(i1) - int(i0), d), dtype=torch.float64, device=C_dev.device) if want_x else None
     if xb.numel() == 0:
         return xb, x
-    with torch.cuda.device(C_dev.device):
+    with on_device(C_dev.device):
         _check(load().fgp_dnb2_points(C_dev.data_ptr(), mmax, _harr(_u64, [int(v) for v in dshift]), d, int(t), int(i0), int(i1),
                                       xb.data_ptr(), x.data_ptr() if want_x else None, _stream()))
     return xb, x
@@ -177,7 +208,7 @@ def dnb2_points(C_dev, dshift, t, i0, i1, want_x=True):
 def lattice_kernel_parts(x, z, alpha):
     n, d = x.shape
     out = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         _check(load().fgp_lattice_kernel_parts(_dev(x, torch.float64), n, d, _harr(_f64, z), _harr(_i32, alpha), out.data_ptr(), _stream()))
     return out
 
@@ -185,7 +216,7 @@ def lattice_kernel_parts(x, z, alpha):
 def dnb2_kernel_parts(xb, zb, alpha, t):
     n, d = xb.shape
     out = torch.empty((n, d), dtype=torch.float64, device=xb.device)
-    with torch.cuda.device(xb.device):
+    with on_device(xb.device):
         _check(load().fgp_dnb2_kernel_parts(_dev(xb, torch.int64), n, d, _harr(_i64, zb), _harr(_i32, alpha), int(t), out.data_ptr(), _stream()))
     return out
 
@@ -195,7 +226,7 @@ def kernel_from_parts(parts, scale, ls):
     n, d = parts.shape
     B = scale.numel()
     out = torch.empty((B, n), dtype=torch.float64, device=parts.device)
-    with torch.cuda.device(parts.device):
+    with on_device(parts.device):
         _check(load().fgp_kernel_from_parts(_dev(parts, torch.float64), n, d, B, _dev(scale, torch.float64), _dev(ls, torch.float64),
                                             out.data_ptr(), _stream()))
     return out
@@ -205,7 +236,7 @@ def cross_kernel(family, xs, xtrain, alpha, t, scale, ls):
     m, d = xs.shape
     n = xtrain.shape[0]
     out = torch.empty((m, n), dtype=torch.float64, device=xs.device)
-    with torch.cuda.device(xs.device):
+    with on_device(xs.device):
         if family == 0:
             _check(load().fgp_lattice_cross_kernel(_dev(xs, torch.float64), m, _dev(xtrain, torch.float64), n, d, _harr(_i32, alpha),
                                                    float(scale), _harr(_f64, ls), out.data_ptr(), _stream()))
@@ -220,7 +251,7 @@ def kernel_pairs(family, x, z, alpha, t, scale, ls):
     N, d = x.shape
     out = torch.empty((N,), dtype=torch.float64, device=x.device)
     z_is_int = z.dtype == torch.int64
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         _check(load().fgp_kernel_pairs(int(family), _dev(x, torch.float64), _dev(z, torch.int64 if z_is_int else torch.float64), int(z_is_int),
                                        N, d, _harr(_i32, alpha), int(t), float(scale), _harr(_f64, ls), out.data_ptr(), _stream()))
     return out
@@ -243,7 +274,7 @@ def deriv_kernel_parts(family, x, z, terms, t):
     """parts (n, nt, d) of the points x (float64 lattice / int64 net) against the single point z (length-d host list)."""
     n, d = x.shape
     out = torch.empty((n, terms.nt, d), dtype=torch.float64, device=x.device)
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         zh = _harr(_f64, [float(v) for v in z]) if family == 0 else _harr(_i64, [int(v) for v in z])
         _check(load().fgp_deriv_kernel_parts(int(family), _dev(x, torch.float64 if family == 0 else torch.int64), n, d, zh, terms.nt,
                                              _dev(terms.ord, torch.int32), _dev(terms.par, torch.float64), int(t), out.data_ptr(), _stream()))
@@ -255,7 +286,7 @@ def deriv_cross_kernel(family, xs, xtrain, terms, t, scale, ls):
     m, d = xs.shape
     n = xtrain.shape[0]
     out = torch.empty((m, n), dtype=torch.float64, device=xs.device)
-    with torch.cuda.device(xs.device):
+    with on_device(xs.device):
         _check(load().fgp_deriv_cross_kernel(int(family), _dev(xs, torch.float64), m, _dev(xtrain, torch.float64 if family == 0 else torch.int64), n, d,
                                              terms.nt, _dev(terms.ord, torch.int32), _dev(terms.par, torch.float64), _dev(terms.ind, torch.float64),
                                              _dev(terms.w, torch.float64), int(t), float(scale), _harr(_f64, ls), out.data_ptr(), _stream()))
@@ -274,7 +305,7 @@ def fft_table(n, device):
     if tab is None:
         nbytes = load().fgp_fft_table_bytes(int(n))
         tab = torch.empty(nbytes // 8, dtype=torch.float64, device=device)
-        with torch.cuda.device(device):
+        with on_device(device):
             _check(load().fgp_fft_table_init(int(n), tab.data_ptr(), _stream()))
         _tables[key] = tab
     return tab
@@ -291,7 +322,7 @@ def fftbr(x):
     x2, n = _as2d(x.contiguous())
     out = torch.empty(x2.shape, dtype=torch.complex128, device=x.device)
     tab = fft_table(n, x.device)
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         if x2.dtype == torch.float64:
             _check(load().fgp_fftbr_r2c(_dev(x2), out.data_ptr(), x2.shape[0], n, tab.data_ptr(), _stream()))
         elif x2.dtype == torch.complex128:
@@ -308,7 +339,7 @@ def ifftbr(x):
     x2, n = _as2d(x)
     out = torch.empty_like(x2)
     tab = fft_table(n, x.device)
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         _check(load().fgp_ifftbr_c2c(_dev(x2, torch.complex128), out.data_ptr(), x2.shape[0], n, tab.data_ptr(), _stream()))
     return out.reshape(x.shape)
 
@@ -324,7 +355,7 @@ def fwht(x, fused=None):
     out = torch.empty_like(x2)
     if fused is None:
         fused = os.environ.get("FGP_B200_FUSED_FWHT") == "1"
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         if fused and n > 4096 and x2.shape[0] < (1 << 24):
             # control block per (device, stream): the kernel leaves it zeroed, calls on one stream are serialised
             key = (x.device.index, _stream())
@@ -369,7 +400,7 @@ def mll_grad(family, xpts, alpha, t, ysq, scale, ls, noise, want_grad=True, want
     lam = torch.empty((B, n), dtype=torch.complex128 if family == 0 else torch.float64, device=dev) if want_lam else None
     ws = _workspace("mll", load().fgp_mll_workspace_bytes(family, n, d, B), dev)
     wptr = None if weights is None else _dev(weights, torch.float64)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         if family == 0 and z is not None:
             tab = fft_table(n, dev)
             _check(load().fgp_lattice_mll_grad_z(_harr(_u64, [int(v) for v in z]), n, d, _harr(_i32, alpha), B, _dev(ysq, torch.float64),
@@ -447,6 +478,29 @@ def fit_finish(layout):
     _check(load().fgp_fit_finish(_c.byref(layout), _stream()))
 
 
+def fit_init_from(layout, options, raw_scale, raw_ls, raw_noise):
+    """fgp_fit_init_from: the three parameter tensors (float64, contiguous, shapes of the layout) are copied into the layout's staging first."""
+    _check(load().fgp_fit_init_from(_c.byref(layout), _c.byref(options), raw_scale.data_ptr(), raw_ls.data_ptr(), raw_noise.data_ptr(), _stream()))
+
+
+def fit_finish_to(layout, raw_scale, raw_ls, raw_noise):
+    """fgp_fit_finish_to: best iterate -> the layout's staging AND the three given parameter tensors."""
+    _check(load().fgp_fit_finish_to(_c.byref(layout), raw_scale.data_ptr(), raw_ls.data_ptr(), raw_noise.data_ptr(), _stream()))
+
+
+def data_spectrum(family, y, B):
+    """y (rows, n) float64 on the GPU, rows = lead * B -> (ytilde (rows, n) complex128 / float64, ysq (B, n)); fgp_data_spectrum."""
+    rows, n = y.shape
+    dev = y.device
+    yt = torch.empty((rows, n), dtype=torch.complex128 if family == 0 else torch.float64, device=dev)
+    ysq = torch.empty((B, n), dtype=torch.float64, device=dev)
+    ws = _workspace("spectrum", load().fgp_data_spectrum_workspace_bytes(rows, n), dev)
+    table = fft_table(n, dev).data_ptr() if family == 0 else None
+    with on_device(dev):
+        _check(load().fgp_data_spectrum(family, _dev(y, torch.float64), rows, B, n, table, yt.data_ptr(), ysq.data_ptr(), ws.data_ptr(), _stream()))
+    return yt, ysq
+
+
 def profile_begin():
     _check(load().fgp_profile_begin(_stream()))
 
@@ -465,7 +519,7 @@ def gram_solve(family, y, lam):
     y2, n = _as2d(y.contiguous())
     R = y2.shape[0]
     out = torch.empty_like(y2)
-    with torch.cuda.device(y.device):
+    with on_device(y.device):
         if family == 0:
             tab = fft_table(n, y.device)
             work = _workspace("solve", R * n * 16, y.device)
@@ -484,7 +538,7 @@ def post_mean(family, xs, xtrain, alpha, t, scale, ls, coeffs):
     B = coeffs.shape[0]
     out = torch.empty((B, m), dtype=torch.float64, device=xs.device)
     ws = _workspace("pmean", load().fgp_post_mean_workspace_bytes(m, n, d, B), xs.device)
-    with torch.cuda.device(xs.device):
+    with on_device(xs.device):
         if family == 0:
             _check(load().fgp_lattice_post_mean(_dev(xs, torch.float64), m, _dev(xtrain, torch.float64), n, d, _harr(_i32, alpha),
                                                 float(scale), _harr(_f64, ls), _dev(coeffs, torch.float64), B, ws.data_ptr(),
@@ -501,7 +555,7 @@ def post_var(family, xs, xtrain, alpha, t, scale, ls, lam):
     n = xtrain.shape[0]
     out = torch.empty((m,), dtype=torch.float64, device=xs.device)
     ws = _workspace("pvar", load().fgp_post_var_workspace_bytes(family, m, n), xs.device)
-    with torch.cuda.device(xs.device):
+    with on_device(xs.device):
         if family == 0:
             tab = fft_table(n, xs.device)
             _check(load().fgp_lattice_post_var(_dev(xs, torch.float64), m, _dev(xtrain, torch.float64), n, d, _harr(_i32, alpha),
@@ -520,7 +574,7 @@ def post_var_z(xs, z, shift, n, alpha, scale, ls, lam):
     m, d = xs.shape
     out = torch.empty((m,), dtype=torch.float64, device=xs.device)
     ws = _workspace("pvarz", load().fgp_lattice_post_var_z_workspace_bytes(m, n), xs.device)
-    with torch.cuda.device(xs.device):
+    with on_device(xs.device):
         tab = fft_table(n, xs.device)
         _check(load().fgp_lattice_post_var_z(_dev(xs, torch.float64), m, _harr(_u64, [int(v) for v in z]), _harr(_f64, [float(v) for v in shift]), n, d,
                                              _harr(_i32, alpha), float(scale), _harr(_f64, ls), _dev(lam, torch.complex128), tab.data_ptr(),
@@ -533,7 +587,7 @@ def post_var_C(xs, C, dshift, t, n, alpha, scale, ls, lam):
     m, d = xs.shape
     out = torch.empty((m,), dtype=torch.float64, device=xs.device)
     ws = _workspace("pvarC", load().fgp_dnb2_post_var_C_workspace_bytes(m, n), xs.device)
-    with torch.cuda.device(xs.device):
+    with on_device(xs.device):
         _check(load().fgp_dnb2_post_var_C(_dev(xs, torch.float64), m, _dev(C, torch.int64), int(C.shape[1]), _harr(_u64, [int(v) for v in dshift]), int(t), n, d,
                                           _harr(_i32, alpha), float(scale), _harr(_f64, ls), _dev(lam, torch.float64), ws.data_ptr(), out.data_ptr(), _stream()))
     return out
@@ -553,7 +607,7 @@ def block_inv_logdet(L):
     L = L.contiguous()
     A = torch.empty_like(L)
     logdet = torch.empty(L.shape[0], dtype=torch.float64, device=L.device)
-    with torch.cuda.device(L.device):
+    with on_device(L.device):
         _check(load().fgp_block_inv_logdet(1 if L.is_complex() else 0, _dev(L, L.dtype), L.shape[0], L.shape[1], A.data_ptr(), logdet.data_ptr(), _stream()))
     return A, logdet
 

@@ -17,9 +17,18 @@ struct FitHeader {
   double v[ST_HEADER];
 };
 
-__global__ void __launch_bounds__(256) fit_init_kernel(FitLayout c, FitHeader h) {
+// the three raw parameter groups of a layout, in state order (scale, lengthscales, noise)
+__device__ __forceinline__ double* raw_slot(const FitLayout& c, double* s0, double* s1, double* s2, int e) {
+  const int n_ls = c.n_ls_b * c.n_ls_d;
+  return e < c.n_scale ? s0 + e : (e < c.n_scale + n_ls ? s1 + (e - c.n_scale) : s2 + (e - c.n_scale - n_ls));
+}
+
+__global__ void __launch_bounds__(256) fit_init_kernel(FitLayout c, FitHeader h, FitParamPtrs src) {
   double* st = c.state;
   if (threadIdx.x < ST_HEADER) st[threadIdx.x] = h.v[threadIdx.x];  // options by value: no host copy, no synchronisation
+  if (src.scale) {  // the caller's parameter storages -> the layout's (one launch instead of three device-to-device copies)
+    for (int e = threadIdx.x; e < c.P; e += blockDim.x) *raw_slot(c, c.raw_scale, c.raw_ls, c.raw_noise, e) = *raw_slot(c, src.scale, src.ls, src.noise, e);
+  }
   __syncthreads();
   double* prev = st + ST_HEADER;
   double* step = prev + c.P;
@@ -47,16 +56,15 @@ __global__ void __launch_bounds__(256) fit_step_kernel(FitLayout c, const double
 }
 
 // copy the best iterate back into the parameters (abstract_gp.py:297-298) and refresh the effective values
-__global__ void __launch_bounds__(256) fit_finish_kernel(FitLayout c) {
+__global__ void __launch_bounds__(256) fit_finish_kernel(FitLayout c, FitParamPtrs dst) {
   double* st = c.state;
   const int P = c.P;
   const double* best = st + ST_HEADER + 2 * P;
-  const int n_ls = c.n_ls_b * c.n_ls_d;
-  if (st[ST_BEST] < INFINITY) {
-    for (int e = threadIdx.x; e < P; e += blockDim.x) {
-      double* dst = e < c.n_scale ? c.raw_scale + e : (e < c.n_scale + n_ls ? c.raw_ls + (e - c.n_scale) : c.raw_noise + (e - c.n_scale - n_ls));
-      *dst = best[e];
-    }
+  const bool have = st[ST_BEST] < INFINITY;
+  for (int e = threadIdx.x; e < P; e += blockDim.x) {
+    double* own = raw_slot(c, c.raw_scale, c.raw_ls, c.raw_noise, e);
+    if (have) *own = best[e];
+    if (dst.scale) *raw_slot(c, dst.scale, dst.ls, dst.noise, e) = *own;  // and out to the caller's parameter storages
   }
   __syncthreads();
   write_effective(c);
@@ -104,10 +112,18 @@ size_t fgp_fit_state_doubles(int n_raw_params, int B) {
 }
 
 int fgp_fit_init(const fgp_fit_layout* layout, const fgp_fit_options* opt, fgp_stream_t stream) {
+  return fgp_fit_init_from(layout, opt, nullptr, nullptr, nullptr, stream);
+}
+
+int fgp_fit_init_from(const fgp_fit_layout* layout, const fgp_fit_options* opt, const double* raw_scale_src, const double* raw_ls_src,
+                      const double* raw_noise_src, fgp_stream_t stream) {
   fgp::FitLayout c;
   int rc = fgp::make_layout(layout, &c);
   if (rc) return rc;
   FGP_REQUIRE(opt, "fit_init: null options");
+  const int nsrc = (raw_scale_src != nullptr) + (raw_ls_src != nullptr) + (raw_noise_src != nullptr);
+  FGP_REQUIRE(nsrc == 0 || nsrc == 3, "fit_init_from: give all three parameter sources or none");
+  const fgp::FitParamPtrs src{const_cast<double*>(raw_scale_src), const_cast<double*>(raw_ls_src), const_cast<double*>(raw_noise_src)};
   FGP_REQUIRE(opt->iterations >= 0 && opt->stop_wait > 0 && opt->lr > 0.0, "fit_init: bad options");
   fgp::FitHeader hdr;
   double* h = hdr.v;
@@ -124,7 +140,7 @@ int fgp_fit_init(const fgp_fit_layout* layout, const fgp_fit_options* opt, fgp_s
   h[fgp::ST_SMIN] = opt->step_min;
   h[fgp::ST_SMAX] = opt->step_max;
   h[fgp::ST_HIST_CAP] = (double)opt->hist_capacity;
-  fgp::fit_init_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(c, hdr);
+  fgp::fit_init_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(c, hdr, src);
   FGP_LAUNCH_CHECK();
   return FGP_OK;
 }
@@ -140,10 +156,17 @@ int fgp_fit_step(const fgp_fit_layout* layout, const double* out_dev, fgp_stream
 }
 
 int fgp_fit_finish(const fgp_fit_layout* layout, fgp_stream_t stream) {
+  return fgp_fit_finish_to(layout, nullptr, nullptr, nullptr, stream);
+}
+
+int fgp_fit_finish_to(const fgp_fit_layout* layout, double* raw_scale_dst, double* raw_ls_dst, double* raw_noise_dst, fgp_stream_t stream) {
   fgp::FitLayout c;
   int rc = fgp::make_layout(layout, &c);
   if (rc) return rc;
-  fgp::fit_finish_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(c);
+  const int ndst = (raw_scale_dst != nullptr) + (raw_ls_dst != nullptr) + (raw_noise_dst != nullptr);
+  FGP_REQUIRE(ndst == 0 || ndst == 3, "fit_finish_to: give all three parameter destinations or none");
+  const fgp::FitParamPtrs dst{raw_scale_dst, raw_ls_dst, raw_noise_dst};
+  fgp::fit_finish_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(c, dst);
   FGP_LAUNCH_CHECK();
   return FGP_OK;
 }

@@ -31,6 +31,10 @@ struct FitLayout {
   unsigned int* tickets;  // B + 1 counters behind the state block (zeroed by fit_init, self-resetting)
 };
 
+struct FitParamPtrs {  // optional caller-side storages of the three raw parameter groups (all null: unused)
+  double *scale, *ls, *noise;
+};
+
 __device__ __forceinline__ void write_effective(const FitLayout& c) {
   for (int b = threadIdx.x; b < c.B; b += blockDim.x) {
     c.scale_B[b] = c.tau * exp(c.raw_scale[c.n_scale == 1 ? 0 : b]);

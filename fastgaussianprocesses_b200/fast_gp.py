@@ -56,6 +56,20 @@ def _prod(shape):
     return out
 
 
+def _bshape(*shapes):
+    """torch.broadcast_shapes for plain shape tuples (that function goes through several Python layers: ~20 us per call in fit()'s set-up)."""
+    nd = max(len(sh) for sh in shapes)
+    out = [1] * nd
+    for sh in shapes:
+        for k in range(1, len(sh) + 1):
+            v = int(sh[-k])
+            if v != 1:
+                if out[-k] != 1 and out[-k] != v:
+                    raise RuntimeError("shapes %s do not broadcast" % (shapes,))
+                out[-k] = v
+    return torch.Size(out)
+
+
 class _XXbSeq(object):
     """Growing cache of the points of one sequence, generated on the GPU (util.py:16-38)."""
 
@@ -221,6 +235,7 @@ class _FitContext(object):
         self.problem = Pb
         self.generator = self._z_arr is not None or self._C is not None
         self.graphs = {}
+        self.streams = {}
         self.warmed = False
         self.kernels_per_iteration = None
 
@@ -274,8 +289,8 @@ class _FusedFitLoop(object):
             return False
         if fgp.raw_factor_task_kernel.numel() != 0 or fgp.raw_noise_task_kernel.numel() != 1:
             return False
-        B = _prod(torch.broadcast_shapes(fgp.raw_scale.shape[:-1], fgp.raw_lengthscales.shape[:-1], fgp.raw_noise.shape[:-1]))
-        ok = lambda p: _prod(p.shape[:-1]) in (1, B) and p.is_contiguous()
+        B = _prod(_bshape(fgp.raw_scale.shape[:-1], fgp.raw_lengthscales.shape[:-1], fgp.raw_noise.shape[:-1]))
+        ok = lambda p: _prod(p.shape[:-1]) in (1, B) and p.is_contiguous() and p.dtype == torch.float64
         return ok(fgp.raw_scale) and ok(fgp.raw_lengthscales) and ok(fgp.raw_noise) and B <= 65535
 
     def __init__(self, fgp, hist_flags=(False, False, False), hist_capacity=0):
@@ -285,10 +300,8 @@ class _FusedFitLoop(object):
         ysq = fgp._get_ysq(pshape)
         c = self.ctx = _FitContext.acquire(fgp, pshape, hist_flags, hist_capacity)
         self.B, self.d, self.n, self.d_out = c.B, c.d, c.n, c.d_out
-        # parameters and |ytilde|^2 in: device-to-device copies into the buffers the captured kernels read
+        # |ytilde|^2 in: a device-to-device copy into the buffer the captured kernels read (the parameters follow in begin())
         with torch.no_grad():
-            for dst, src in zip(c.raw, (fgp.raw_scale, fgp.raw_lengthscales, fgp.raw_noise)):
-                dst.copy_(src.data)
             c.ysq.copy_(ysq)
         self.state, self.layout, self.problem = c.state, c.layout, c.problem
         self.loss_hist, self.scale_hist, self.ls_hist, self.noise_hist = c.loss_hist, c.scale_hist, c.ls_hist, c.noise_hist
@@ -296,6 +309,13 @@ class _FusedFitLoop(object):
         self.state_host, self.state_host2, self.events = c.pin[2], c.pin[:2], c.events
         self.launches = 0
         self.replayed = 0
+        # the Stream object snapshot events are recorded on and close() waits for: kept by the pooled context per raw stream handle
+        # (torch.cuda.current_stream() alone is ~20 us of host time)
+        with _lib.on_device(fgp.device):
+            handle = _lib._stream()
+        self.stream = c.streams.get(handle)
+        if self.stream is None:
+            self.stream = c.streams[handle] = torch.cuda.current_stream(fgp.device)
         # persistent cooperative kernel (opt-in): k iterations per launch, no graph
         self.multi = _lib.fit_iterations_per_launch(fgp._FAMILY, self.n) > 1 and os.environ.get("FGP_B200_NO_MULTI") != "1"
         self.use_graph = not self.multi and os.environ.get("FGP_B200_NO_GRAPH") != "1"
@@ -341,8 +361,9 @@ class _FusedFitLoop(object):
         o.half_const = 0.5 * self.d_out * self.n * float(np.log(2 * np.pi))
         o.wn, o.wl = 0.5, 0.5 * self.d_out / self.B
         o.lr, o.etaminus, o.etaplus, o.step_min, o.step_max = float(lr), 0.5, 1.2, 1e-6, 50.0
-        with torch.cuda.device(self.fgp.device):
-            _lib.fit_init(self.layout, o)
+        fgp = self.fgp
+        with _lib.on_device(fgp.device):  # the GP's parameters -> the pooled staging buffers, inside the init launch
+            _lib.fit_init_from(self.layout, o, fgp.raw_scale.data, fgp.raw_lengthscales.data, fgp.raw_noise.data)
 
     def _graph(self, k):
         graphs = self.ctx.graphs
@@ -369,13 +390,13 @@ class _FusedFitLoop(object):
     def replay(self, k):
         """Enqueue k <= GRAPH_ITERS iterations."""
         if self.multi:
-            with torch.cuda.device(self.fgp.device):
+            with _lib.on_device(self.fgp.device):
                 _lib.fit_iterations(self.problem, self.layout, k)
             self.replayed += k
             self.launches += 1
             return
         if not self.use_graph:
-            with torch.cuda.device(self.fgp.device):
+            with _lib.on_device(self.fgp.device):
                 for _ in range(k):
                     self._iteration()
         else:
@@ -389,7 +410,7 @@ class _FusedFitLoop(object):
         """Stream-ordered copy of the state header into pinned slot `slot` plus an event: lets the host look at chunk j
         while chunk j+1 is already enqueued (kernels of iterations after the stop decision exit immediately)."""
         self.state_host2[slot].copy_(self.state[:self.ST_HEADER], non_blocking=True)
-        self.events[slot].record(torch.cuda.current_stream(self.fgp.device))
+        self.events[slot].record(self.stream)
 
     def wait_snapshot(self, slot):
         self.events[slot].synchronize()
@@ -410,11 +431,8 @@ class _FusedFitLoop(object):
     def finish(self):
         """Best iterate -> staged parameters (abstract_gp.py:297-298) -> the GP's own parameter storages."""
         fgp, c = self.fgp, self.ctx
-        with torch.cuda.device(fgp.device):
-            _lib.fit_finish(self.layout)
-        with torch.no_grad():
-            for dst, src in zip((fgp.raw_scale, fgp.raw_lengthscales, fgp.raw_noise), c.raw):
-                dst.data.copy_(src)
+        with _lib.on_device(fgp.device):
+            _lib.fit_finish_to(self.layout, fgp.raw_scale.data, fgp.raw_lengthscales.data, fgp.raw_noise.data)
         fgp._epoch += 1
 
     def kernel_times(self, reps=10, flush=None):
@@ -437,7 +455,7 @@ class _FusedFitLoop(object):
             return
         if finish:
             self.finish()
-        torch.cuda.current_stream(self.fgp.device).synchronize()  # nothing may still be reading or writing the pooled buffers
+        self.stream.synchronize()  # nothing may still be reading or writing the pooled buffers
         self.ctx.release()
         self.ctx = None
 
@@ -667,6 +685,14 @@ class AbstractFastGP(torch.nn.Module):
         self.ft_unstable = self._ft_unstable
         self.ift_unstable = self._ift_unstable
 
+    def __setattr__(self, name, value):
+        # bookkeeping attributes (underscore names, sizes) skip nn.Module's parameter / buffer / submodule checks: ~5 us each, a dozen per
+        # add_y_next + fit; parameters and anything else still go through nn.Module
+        if name[0] == "_" or name in ("n", "m"):
+            object.__setattr__(self, name, value)
+        else:
+            super().__setattr__(name, value)
+
     # ------------------------------------------------------------------------------------------------ state keys
     def _add_hyperparameter(self, name, value, shape, tfs, requires_grad, trailing_ok, ntrail, sign, tfs_hint):
         """Validate one hyperparameter of abstract_gp.py:77-139 and register tfs[0](value) as self.raw_<name> (self.tf_<name> = tfs[1]).
@@ -705,8 +731,8 @@ class AbstractFastGP(torch.nn.Module):
 
     def _pshape(self):
         """Batch shape of the hyperparameter sets (what `_hyper` returns last), from the parameter shapes alone: no device work."""
-        tau_shape = torch.broadcast_shapes(self.raw_factor_task_kernel.shape[:-2], self.raw_noise_task_kernel.shape[:-1])
-        return torch.broadcast_shapes(self.raw_scale.shape[:-1], self.raw_lengthscales.shape[:-1], self.raw_noise.shape[:-1], tau_shape)
+        return _bshape(self.raw_scale.shape[:-1], self.raw_lengthscales.shape[:-1], self.raw_noise.shape[:-1],
+                       self.raw_factor_task_kernel.shape[:-2], self.raw_noise_task_kernel.shape[:-1])
 
     def _tau_host(self):
         """K_task[0,0] of a single task as a host float, cached on the task-kernel parameters' identity and version: reading it
@@ -779,20 +805,20 @@ class AbstractFastGP(torch.nn.Module):
         if task is None:
             task = self.default_task
         if isinstance(task, int):
-            task = torch.tensor([task], dtype=int)
-        if isinstance(task, list):
-            task = torch.tensor(task, dtype=int)
-        assert isinstance(y_next, list) and isinstance(task, torch.Tensor) and task.ndim == 1 and len(y_next) == len(task)
+            tasks = [task]
+        else:
+            if isinstance(task, list):
+                task = torch.tensor(task, dtype=int)
+            assert isinstance(task, torch.Tensor) and task.ndim == 1
+            tasks = [int(l) for l in task.tolist()]
+        assert isinstance(y_next, list) and len(y_next) == len(tasks)
         assert all(y_next[i].shape[:-1] == self.shape_batch for i in range(len(y_next)))
-        # sizes first, from the shapes alone: the small size tensors must not queue (and make the host wait) behind the copy of y
+        # sizes from the shapes alone, then the copies FIRST: everything after them on the host overlaps the transfer
         ncur = [int(self._y[i].size(-1)) for i in range(self.num_tasks)]
-        for i, l in enumerate(task):
-            ncur[int(l)] += int(y_next[i].size(-1))
+        for i, l in enumerate(tasks):
+            ncur[l] += int(y_next[i].size(-1))
         assert all(nl == 0 or (nl & (nl - 1)) == 0 for nl in ncur), "total samples must be power of 2"
-        self._nint = max(ncur)
-        self.n = torch.tensor(ncur, dtype=int, device=self.device)
-        self.m = torch.tensor([-1 if nl == 0 else nl.bit_length() - 1 for nl in ncur], dtype=int, device=self.device)
-        for i, l in enumerate(task):
+        for i, l in enumerate(tasks):
             yi = y_next[i]
             if yi.device.type == "cpu" and yi.is_pinned():
                 # a PINNED host buffer is copied asynchronously (stream-ordered): the host goes on to enqueue the transforms below while the
@@ -802,7 +828,15 @@ class AbstractFastGP(torch.nn.Module):
                 yi = yi.to(self.device, non_blocking=True)
             fresh = y_next[i].device != self.device  # our own device copy: no need to copy it again when it is the first block
             yi = yi.to(self.device)
-            self._y[int(l)] = yi if (fresh and self._y[int(l)].numel() == 0 and yi.dtype == self._y[int(l)].dtype) else torch.cat([self._y[int(l)], yi], -1)
+            self._y[l] = yi if (fresh and self._y[l].numel() == 0 and yi.dtype == self._y[l].dtype) else torch.cat([self._y[l], yi], -1)
+        self._nint = max(ncur)
+        mcur = [-1 if nl == 0 else nl.bit_length() - 1 for nl in ncur]
+        if self.num_tasks == 1:  # device fills: torch.tensor(list, device=cuda) is a pageable copy the host waits for
+            self.n = torch.full((1,), ncur[0], dtype=int, device=self.device)
+            self.m = torch.full((1,), mcur[0], dtype=int, device=self.device)
+        else:
+            self.n = torch.tensor(ncur, dtype=int, device=self.device)
+            self.m = torch.tensor(mcur, dtype=int, device=self.device)
         for key in list(self.inv_log_det_cache_dict.keys()):
             if any(k < c for k, c in zip(key, ncur)):
                 del self.inv_log_det_cache_dict[key]
@@ -915,8 +949,15 @@ class AbstractFastGP(torch.nn.Module):
 
     def _get_ysq(self, pshape):
         """(B,n) sums of |ytilde|^2 over the leading batch dims that share one hyperparameter set."""
-        ytilde = self.get_ytilde(0)
         B = _prod(pshape)
+        n = self._nint
+        if ((self._ytilde is None or self._ytilde_n != n) and n > 1 and self._mt is None and self._y[0].dtype == torch.float64
+                and B <= 65535 and _prod(self.shape_batch) <= 65535 and os.environ.get("FGP_B200_NO_SPECTRUM_CALL") != "1"):
+            # nothing cached yet: ytilde and |ytilde|^2 from ONE C call (fgp_data_spectrum) instead of nine torch launches
+            yt, ysq = _lib.data_spectrum(self._FAMILY, self._y[0].reshape(-1, n).contiguous(), B)
+            self._ytilde, self._ytilde_n, self._ysq = yt.reshape(tuple(self.shape_batch) + (n,)), n, ysq
+            return ysq
+        ytilde = self.get_ytilde(0)
         if self._ysq is None or self._ysq.shape[0] != B:
             sb = tuple(self.shape_batch)
             lead = _prod(sb[:len(sb) - len(pshape)])
@@ -1180,9 +1221,6 @@ class AbstractFastGP(torch.nn.Module):
         if isinstance(cv_weights, torch.Tensor):
             cv_weights = cv_weights.to(self.device)
         fused = (not autograd_route) and optimizer is None and _FusedFitLoop.eligible(self) and os.environ.get("FGP_B200_GENERIC_FIT") != "1"
-        if optimizer is None:
-            optimizer = self.get_default_optimizer(lr)
-        assert isinstance(optimizer, torch.optim.Optimizer)
         logtol = np.log(1 + stop_crit_improvement_threshold)
         store_loss_hist = store_hists or store_loss_hist
         store_scale_hist = store_hists or (store_scale_hist and self.raw_scale.requires_grad)
@@ -1192,6 +1230,9 @@ class AbstractFastGP(torch.nn.Module):
         if fused:
             return self._fit_fused(iterations, 1e-1 if lr is None else lr, logtol, stop_crit_wait_iterations, store_loss_hist, store_scale_hist,
                                    store_lengthscales_hist, store_noise_hist, store_task_kernel_hist, verbose, verbose_indent)
+        if optimizer is None:
+            optimizer = self.get_default_optimizer(lr)
+        assert isinstance(optimizer, torch.optim.Optimizer)
         if store_loss_hist:
             loss_hist = torch.empty(iterations + 1)
         if store_scale_hist:
@@ -1348,11 +1389,11 @@ class AbstractFastGP(torch.nn.Module):
         loop.finish()  # best iterate -> this GP's parameter storages (bumps the cache epoch)
         i = last
         for pname in ("raw_scale", "raw_lengthscales", "raw_noise", "raw_factor_task_kernel", "raw_noise_task_kernel"):
-            p = getattr(self, pname)
-            setattr(self, pname, torch.nn.Parameter(p.data, requires_grad=p.requires_grad))
+            p = self._parameters[pname]  # fresh Parameter objects as after the reference's fit (abstract_gp.py:297-298), straight into the registry
+            self._parameters[pname] = torch.nn.Parameter(p.data, requires_grad=p.requires_grad)
         data = {"iterations": i}
         if store_loss_hist:
-            data["loss_hist"] = -loop.loss_hist[:(i + 1), 0].cpu()
+            data["loss_hist"] = -(loop.loss_hist[:(i + 1)].cpu()[:, 0])  # one copy of the contiguous rows; the slice and the sign on the host
         if store_scale_hist:
             data["scale_hist"] = loop.scale_hist[:(i + 1)].reshape((i + 1,) + tuple(self.raw_scale.shape)).cpu()
         if store_lengthscales_hist:

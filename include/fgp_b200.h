@@ -166,6 +166,12 @@ size_t fgp_fit_state_doubles(int n_raw_params, int B);
 int fgp_fit_init(const fgp_fit_layout* layout, const fgp_fit_options* opt, fgp_stream_t stream); /* one launch, nothing synchronises */
 int fgp_fit_step(const fgp_fit_layout* layout, const double* mll_out_dev, fgp_stream_t stream);
 int fgp_fit_finish(const fgp_fit_layout* layout, fgp_stream_t stream); /* best iterate -> parameters */
+/* The same two calls for a layout whose raw_* point at POOLED staging buffers (captured CUDA graphs are tied to their addresses):
+ * fgp_fit_init_from first copies the caller's parameter storages (same shapes as the layout's) into the layout's, fgp_fit_finish_to also
+ * writes the best iterate out to them -- one launch each instead of three device-to-device copies around the loop (abstract_gp.py:297-298). */
+int fgp_fit_init_from(const fgp_fit_layout* layout, const fgp_fit_options* opt, const double* raw_scale_src, const double* raw_ls_src,
+                      const double* raw_noise_src, fgp_stream_t stream);
+int fgp_fit_finish_to(const fgp_fit_layout* layout, double* raw_scale_dst, double* raw_ls_dst, double* raw_noise_dst, fgp_stream_t stream);
 /* One whole fit() iteration in one call: the fused eigen-solve of K4 on layout->scale_B / ls_B / noise_B, whose last
  * CTA reduces the partial sums and runs the fit step in its tail (no separate finalize / fit_step launches).
  * x_dev: points (lattice float64 / net int64 (n,d)); z_host / C_dev: lattice generating vector / net generating matrices
@@ -271,6 +277,14 @@ int fgp_deriv_kernel_parts(int family, const void* x_dev, int64_t n, int d, cons
 int fgp_deriv_cross_kernel(int family, const double* xs_dev, int64_t m, const void* x_dev, int64_t n, int d, int nterms,
                            const int* ord_dev, const double* par_dev, const double* ind_dev, const double* w_dev, int t,
                            double scale, const double* ls_host, double* k_dev, fgp_stream_t stream);
+
+/* K3b: the spectrum of the data in one call (abstract_fast_gp.py:197-212 `ft` applied to y, util.py:164-183 _YtildeCache, and the |ytilde|^2
+ * that util.py:364-370 contracts against 1/lam): y (rows, n) float64, rows = lead * B, row l*B + b belongs to hyperparameter set b.
+ * ytilde (rows, n) = orthonormal FFT-BRO (family 0: interleaved complex128) / FWHT (family 1: float64) of y, mean-stabilised like the
+ * reference (transform y - mean, add mean sqrt(n) back at frequency 0); ysq (B, n) = sum over lead of |ytilde|^2.  work: *_workspace_bytes. */
+size_t fgp_data_spectrum_workspace_bytes(int64_t rows, int64_t n);
+int fgp_data_spectrum(int family, const double* y_dev, int64_t rows, int64_t B, int64_t n, const void* table_dev, double* ytilde_dev,
+                      double* ysq_dev, double* work_dev, fgp_stream_t stream);
 
 /* Per-frequency block systems of the multi-task / derivative-informed eigen-solve (replaces the Schur-complement recursion of
  * util.py:301-323 and the block solve of :354-363): nm independent R x R matrices L[k] (row-major (nm,R,R); interleaved complex when cplx != 0,

@@ -45,15 +45,16 @@ def wrap(obj, name):
         r = fn(*a, **k)
         if SYNC[0]:
             torch.cuda.synchronize()
-        marks.append((name, (time.perf_counter() - t0) * 1e6))
+        marks.append((name, (time.perf_counter() - t0) * 1e6, t0))
         return r
     setattr(obj, name, w)
 
 
 for nm in ("begin", "replay", "snapshot", "wait_snapshot", "finish", "close", "__init__"):
     wrap(F._FusedFitLoop, nm)
-for nm in ("get_ytilde", "_get_ysq"):
+for nm in ("get_ytilde", "_get_ysq", "_fit_fused", "_new_fused_loop"):
     wrap(F.AbstractFastGP, nm)
+wrap(F._FusedFitLoop, "eligible")
 wrap(F._FitContext, "acquire")
 
 for sync in (False, True):
@@ -67,8 +68,10 @@ for sync in (False, True):
         g.fit(iterations=K, verbose=0, stop_crit_wait_iterations=K + 1)
         torch.cuda.synchronize()
         tot = (time.perf_counter() - t0) * 1e6
+    if not sync:
+        print("timeline (us after fit() was entered: start, duration) of the last call:", [(nm, round((ts - t0) * 1e6), round(us)) for nm, us, ts in sorted(marks, key=lambda m: m[2])])
     agg = {}
-    for nm, us in marks:
+    for nm, us, _ in marks:
         agg.setdefault(nm, [0, 0.0])
         agg[nm][0] += 1
         agg[nm][1] += us

@@ -78,6 +78,33 @@ def test_fftbr_matches_oracle(L, P, m):
     assert rel(L.ifftbr(L.fftbr(zz)), z) < 1e-13
 
 
+@pytest.mark.parametrize("family", [0, 1])
+@pytest.mark.parametrize("m,rows,B", [(1, 1, 1), (6, 4, 2), (12, 6, 3), (12, 5, 1), (17, 2, 2), (20, 1, 1)])
+def test_data_spectrum_matches_oracle_transform(L, P, family, m, rows, B):
+    """fgp_data_spectrum (ytilde and |ytilde|^2 per hyperparameter set in one call) against the oracle's transform applied the way the
+    reference's `ft` does it (abstract_fast_gp.py:197-212: y - mean, transform, mean sqrt(n) back at frequency 0); the data carry a mean
+    1000 times their spread, which is what the stabilisation is for."""
+    n = 1 << m
+    g = torch.Generator().manual_seed(7 * m + rows)
+    y = 1000.0 + torch.randn(rows, n, generator=g)
+    yt, ysq = L.data_spectrum(family, y.to(dev), B)
+    ym = y.mean(-1, keepdim=True)
+    if m <= 14:
+        ref = (P.fftbr_torch if family == 0 else P.fwht_torch)(y - ym)
+    elif family == 0:
+        ref = torch.fft.fft((y - ym)[..., bitrev_perm(m)].to(torch.complex128), norm="ortho")
+    else:
+        ref = L.fwht((y - ym).to(dev)).cpu()  # itself oracle-checked at these sizes (test_fwht_matches_oracle / parseval tests)
+    ref = ref.clone()
+    ref[..., 0] += ym[..., 0] * np.sqrt(n)
+    assert yt.shape == (rows, n) and yt.dtype == (torch.complex128 if family == 0 else torch.float64)
+    assert rel(yt[..., :1], ref[..., :1]) < 1e-13  # the zero frequency, ~1000 sqrt(n)
+    if n > 1:
+        assert rel(yt[..., 1:], ref[..., 1:]) < 1e-12  # the O(1) rest, judged on its own scale
+    sq = (ref.abs() ** 2).reshape(rows // B, B, n).sum(0)
+    assert ysq.shape == (B, n) and rel(ysq[..., :1], sq[..., :1]) < 1e-12 and rel(ysq[..., 1:], sq[..., 1:]) < 1e-11
+
+
 def bitrev_perm(m):
     n = 1 << m
     i = np.arange(n, dtype=np.uint64)

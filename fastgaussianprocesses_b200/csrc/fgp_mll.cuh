@@ -661,10 +661,42 @@ __device__ __forceinline__ void passA_tile(const MllArgs& a, const Hyp& H, unsig
     double2* sm = (double2*)smraw;
     double2* W = (double2*)a.W + (int64_t)b * a.n + g0;
     const FftTables T = a.T;
-    tile_fill_c<false>(SmemC{sm, LP}, l1, lntr, [&](int tr, int idx) -> double2 {
-      return make_double2(point_k1<DT, NET, A2, GEN>(a, H, g0 + ((int64_t)tr << l1) + idx) - c, 0.0);
-    });
+    // Half-spectrum mode: the block is REAL (one block per tile): transform it as ONE complex transform of HALF its length.  In the
+    // bit-reversed input order the even natural samples are the first half of the block and the odd ones the second half, so
+    // z[p] = x[p] + i x[p + L1/2]; with Z = ft(z):  E_k = (Z_k + conj Z_{h-k}) / 2,  O_k = (Z_k - conj Z_{h-k}) / (2i)  are the transforms of
+    // the two halves and  X_k = E_k + w^k O_k  (k = 0 .. h, w = exp(-2 pi i / L1)) is the last radix-2 stage of the full transform.  Pass B
+    // reads the columns q <= L1/2 only.  Half the butterflies and half the shared-memory traffic of the complex transform of (x, 0).
+    const bool rf = a.hs != 0;
+    const int lh = l1 - 1, h = 1 << lh;
+    {
+      // ONE rolled loop (one inlined copy of the kernel evaluation) fills either layout: (x, 0) per element, or component e >> lh of slot e & (h-1)
+      const int total = 1 << (lntr + l1);
+#pragma unroll kFillUnroll
+      for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const double v = point_k1<DT, NET, A2, GEN>(a, H, g0 + e) - c;
+        if (rf)
+          ((double*)&sm[padidx<kPSC>(e & (h - 1))])[e >> lh] = v;
+        else
+          sm[(e >> l1) * LP + padidx<kPSC>(e & ((1 << l1) - 1))] = make_double2(v, 0.0);
+      }
+    }
     __syncthreads();
+    if (rf) {
+      const SmemC S{sm, LP};
+      block_fft_fwd_io<false>(sm, lh, 0, LP, T.stage, SmemTag{}, SmemTag{});
+      __syncthreads();
+      const uint32_t res = brev_bits((uint32_t)(blk0 & ((1 << l2) - 1)), l2);  // residue class of this block row
+      for (int k = threadIdx.x; k <= h; k += blockDim.x) {
+        const double2 zk = S(0, k & (h - 1)), zm = S(0, (h - k) & (h - 1));
+        const double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+        const double2 O = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
+        const double2 X = cadd(E, cmul(twiddle_n(T, (uint32_t)k << l2), O));
+        W[k] = cmul(X, twiddle_n(T, res * (uint32_t)k));
+      }
+      // the last pass-B tile also loads the (weight-0) columns just above L1/2: keep them finite
+      for (int k = h + 1 + threadIdx.x; k < h + (1 << a.lntrB) && k < (1 << l1); k += blockDim.x) W[k] = make_double2(0.0, 0.0);
+      return;
+    }
     block_fft_fwd_io<false>(sm, l1, lntr, LP, T.stage, SmemTag{}, [&](int tr, int idx, double2 v) {
       const uint32_t bb = (uint32_t)((blk0 + tr) & ((1 << l2) - 1));
       W[((int64_t)tr << l1) + idx] = cmul(v, twiddle_n(T, brev_bits(bb, l2) * (uint32_t)idx));
@@ -812,18 +844,34 @@ __device__ __forceinline__ void passC_tile(const MllArgs& a, const Hyp& H, unsig
   } else {
     double2* sm = (double2*)smraw;
     const double2* W = (const double2*)a.W + (int64_t)b * a.n + g0;
-    if (hs) {  // columns above L1/2 were not computed: W[b][L1-q] = conj(W[b][q])
-      const int L1 = 1 << l1, half1 = L1 >> 1;
-      block_fft_inv_io<false>(sm, l1, lntr, LP, a.T.stage, [&](int, int idx) -> double2 {
-        const double2 v = __ldcg(W + (idx > half1 ? L1 - idx : idx));
-        return make_double2(v.x, idx > half1 ? -v.y : v.y);
-      }, SmemTag{});
+    // Half-spectrum mode: the back-transformed row is Hermitian in q (columns above L1/2 were never computed), its inverse transform REAL:
+    // the inverse of pass A's split.  E'_k = X_k + conj X_{h-k},  O'_k = conj(w^k) (X_k - conj X_{h-k}),  Z'_k = E'_k + i O'_k  (k < h = L1/2),
+    // ONE inverse complex transform of length h, and x[p] = Re z[p], x[p + h] = Im z[p].
+    const int lh = l1 - 1, h = 1 << lh;
+    if (hs) {
+      const SmemC S{sm, LP};
+      const FftTables T = a.T;
+      const int l2 = a.l2;
+      for (int k = threadIdx.x; k < h; k += blockDim.x) {
+        const double2 xk = __ldcg(W + k), xm = __ldcg(W + (h - k));
+        const double2 o = cmulc(twiddle_n(T, (uint32_t)k << l2), make_double2(xk.x - xm.x, xk.y + xm.y));
+        S(0, k, make_double2((xk.x + xm.x) - o.y, (xk.y - xm.y) + o.x));
+      }
+      __syncthreads();
+      block_fft_inv_io<false>(sm, lh, 0, LP, T.stage, SmemTag{}, SmemTag{});
     } else {
       block_fft_inv_io<false>(sm, l1, lntr, LP, a.T.stage, [&](int tr, int idx) -> double2 { return __ldcg(W + ((int64_t)tr << l1) + idx); }, SmemTag{});
     }
     __syncthreads();
-    tile_drain_c<false>(SmemC{sm, LP}, l1, lntr,
-                        [&](int tr, int idx, double2 w) { point_grad<DT, NET, A2, GEN>(a, H, g0 + ((int64_t)tr << l1) + idx, w.x, acc); });
+    {
+      // ONE rolled loop (one inlined copy of the gradient contraction) drains either layout
+      const int total = 1 << (lntr + l1);
+#pragma unroll kFillUnroll
+      for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const double* slot = hs ? (const double*)&sm[padidx<kPSC>(e & (h - 1))] + (e >> lh) : (const double*)&sm[(e >> l1) * LP + padidx<kPSC>(e & ((1 << l1) - 1))];
+        point_grad<DT, NET, A2, GEN>(a, H, g0 + e, *slot, acc);
+      }
+    }
     if (hs && tile != 0 && tile != (1 << (a.l2 - 1))) {  // class r stands for r and L2 - r
 #pragma unroll
       for (int j = 0; j <= DM; ++j) acc[j] *= 2.0;

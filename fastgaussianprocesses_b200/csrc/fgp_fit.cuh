@@ -81,11 +81,32 @@ __device__ __forceinline__ double raw_grad(const FitLayout& c, const double* out
   return s;
 }
 
+// Values of raw element e = threadIdx.x that the fused kernels request BEFORE the completion ticket (one hyperparameter set, P <= blockDim.x):
+// the fit step then runs without a single load on its serial path (it was three dependent L2 round trips: Rprop state and raw value, the
+// effective values for the chain rule, the raw values again for the new effective ones -- 3.8 us per iteration in the -DFGP_TIMING stamps).
+struct FitPrefetch {
+  double raw, prev, step;
+};
+__device__ __forceinline__ double* fit_raw_ptr(const FitLayout& c, int e) {
+  const int n_ls = c.n_ls_b * c.n_ls_d;
+  return e < c.n_scale ? c.raw_scale + e : (e < c.n_scale + n_ls ? c.raw_ls + (e - c.n_scale) : c.raw_noise + (e - c.n_scale - n_ls));
+}
+__device__ __forceinline__ FitPrefetch fit_prefetch(const FitLayout& c) {
+  FitPrefetch f{0.0, 0.0, 0.0};
+  const int e = threadIdx.x;
+  if (e < c.P) {
+    f.raw = __ldcg(fit_raw_ptr(c, e));
+    f.prev = __ldcg(c.state + ST_HEADER + e);
+    f.step = __ldcg(c.state + ST_HEADER + c.P + e);
+  }
+  return f;
+}
+
 // One fit() iteration's bookkeeping, executed by ONE CTA (any size >= 32 threads).  `out` is read with cache-global
 // loads so the function can run in the tail of the kernel that produced it.  hdr: ST_HEADER doubles of shared memory.
 // hdr_loaded: the caller already copied the state header into hdr (and synchronised); s_out: see raw_grad.
 __device__ __forceinline__ void fit_step_device(const FitLayout& c, const double* out, double* red, double* hdr, int* flags, bool hdr_loaded = false,
-                                                const double* s_out = nullptr) {
+                                                const double* s_out = nullptr, const FitPrefetch* pf = nullptr) {
   double* st = hdr;
   if (!hdr_loaded) {
     for (int e = threadIdx.x; e < ST_HEADER; e += blockDim.x) hdr[e] = __ldcg(c.state + e);
@@ -144,6 +165,59 @@ __device__ __forceinline__ void fit_step_device(const FitLayout& c, const double
   double* step = prev + P;
   double* best = step + P;
   const int n_ls = c.n_ls_b * c.n_ls_d;
+  if (pf) {
+    // one set (B == 1, so n_scale == n_noise == n_ls_b == 1), s_out in shared memory, element e = threadIdx.x of the raw parameters in
+    // registers: same arithmetic as the general path below, no loads
+    const int e = threadIdx.x;
+    if (e >= P) return;
+    const int g = e < c.n_scale ? 0 : (e < c.n_scale + n_ls ? 1 : 2);
+    const int le = g == 0 ? e : (g == 1 ? e - c.n_scale : e - c.n_scale - n_ls);
+    const double ex = exp(pf->raw);  // exp(raw): the history row, and with tau the effective value of this iterate
+    if (i < (int)st[ST_HIST_CAP]) {
+      double* h = g == 0 ? c.scale_hist : (g == 1 ? c.ls_hist : c.noise_hist);
+      const int width = g == 0 ? c.n_scale : (g == 1 ? n_ls : c.n_noise);
+      if (h) h[(int64_t)i * width + le] = ex;
+    }
+    if (s_newbest) best[e] = pf->raw;
+    if (s_break) return;
+    if (!(g == 0 ? c.req_scale : (g == 1 ? c.req_ls : c.req_noise))) return;
+    double grad;
+    if (g == 0) {
+      grad = s_out[3] * (c.tau * ex);
+    } else if (g == 2) {
+      grad = s_out[2] * (c.tau * ex);
+    } else if (c.n_ls_d == 1) {
+      grad = 0.0;
+      for (int j = 0; j < c.d; ++j) grad += s_out[4 + j] * ex;
+    } else {
+      grad = 0.0;
+      grad += s_out[4 + le] * ex;
+    }
+    const double etam = st[ST_ETAM], etap = st[ST_ETAP], smin = st[ST_SMIN], smax = st[ST_SMAX];
+    const double sp = grad * pf->prev;
+    double factor = 1.0;
+    if (sp > 0.0) factor = etap;
+    if (sp < 0.0) factor = etam;
+    double ss = pf->step * factor;
+    ss = ss < smin ? smin : (ss > smax ? smax : ss);
+    step[e] = ss;
+    if (sp < 0.0) grad = 0.0;
+    const double sg = grad > 0.0 ? 1.0 : (grad < 0.0 ? -1.0 : 0.0);
+    const double nr = pf->raw - sg * ss;
+    *fit_raw_ptr(c, e) = nr;
+    prev[e] = grad;
+    const double en = exp(nr);  // the effective values the next iteration reads (write_effective)
+    if (g == 0) {
+      c.scale_B[0] = c.tau * en;
+    } else if (g == 2) {
+      c.noise_B[0] = c.tau * en;
+    } else if (c.n_ls_d == 1) {
+      for (int j = 0; j < c.d; ++j) c.ls_B[j] = en;
+    } else {
+      c.ls_B[le] = en;
+    }
+    return;
+  }
   // history rows of the effective hyperparameters at this iterate (abstract_gp.py:285-288)
   if (i < (int)st[ST_HIST_CAP]) {
     if (c.scale_hist)

@@ -146,31 +146,42 @@ static inline size_t dnb2_table_bytes(int d, int tile_log) { return (size_t)(64 
 
 template <bool NET>
 __device__ __forceinline__ void load_hyp(Hyp& H, const MllArgs& a, int b) {
-  if (threadIdx.x == 0) {
-    H.scale = __ldcg(a.scale + b);
-    H.noise = __ldcg(a.noise + b);
+  // Warp 0 alone, ONE L2 round trip (this runs on the critical path of every CTA of passes A and C: the stamps of a -DFGP_TIMING build
+  // showed 2.0 us for the prologue when one thread walked the lengthscales in a loop of dependent loads): lane j takes dimension j
+  // (d <= FGP_MAX_D = 32), lane 0 also scale and noise; the prefactor scale * prod_j A_j is a butterfly product over the lanes.
+  if (threadIdx.x >= 32) return;
+  const int j = threadIdx.x;
+  const bool on = j < a.d;
+  const double l = on ? __ldcg(a.ls + (int64_t)b * a.d + j) : 0.0;
+  double sc = 0.0, nz = 0.0;
+  if (j == 0) {
+    sc = __ldcg(a.scale + b);
+    nz = __ldcg(a.noise + b);
   }
-  if (!NET && !a.x) {  // generator mode: constants of the six-slot alpha = 2 form (unused by the other variants)
-    if (threadIdx.x == 0) {
-      double pref = __ldcg(a.scale + b);
-      for (int j = 0; j < a.d; ++j) pref *= fma(__ldcg(a.ls + (int64_t)b * a.d + j), a.P.q[j][0], 1.0);
-      H.pref = pref;
-    }
-    for (int j = threadIdx.x; j < a.d; j += blockDim.x) {
-      const double l = __ldcg(a.ls + (int64_t)b * a.d + j);
-      const double sg = sqrt(sqrt(-l * a.P.q[j][2] / fma(l, a.P.q[j][0], 1.0)));
-      H.sig[j] = sg;
-      H.sig32[j] = sg * 0x1.0p-32;
-    }
-  }
-  for (int j = threadIdx.x; j < a.d; j += blockDim.x) {
-    H.ls[j] = __ldcg(a.ls + (int64_t)b * a.d + j);
+  if (on) {
+    H.ls[j] = l;
     if (a.x) {
       if (NET)
         H.xb0[j] = (uint64_t)((const int64_t*)a.x)[j];
       else
         H.x0[j] = ((const double*)a.x)[j];
     }
+  }
+  if (!NET && !a.x) {  // generator mode: constants of the six-slot alpha = 2 form (unused by the other variants)
+    const double A = on ? fma(l, a.P.q[j][0], 1.0) : 1.0;
+    if (on) {
+      const double sg = sqrt(sqrt(-l * a.P.q[j][2] / A));
+      H.sig[j] = sg;
+      H.sig32[j] = sg * 0x1.0p-32;
+    }
+    double p = A;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) p *= __shfl_xor_sync(0xffffffffu, p, o);
+    if (j == 0) H.pref = sc * p;
+  }
+  if (j == 0) {
+    H.scale = sc;
+    H.noise = nz;
   }
 }
 
@@ -412,6 +423,18 @@ __device__ __forceinline__ void reduce_store(double* v, int nv, double* red, dou
 
 // inside a fused fit loop, iterations enqueued after the stop decision cost only their launches
 __device__ __forceinline__ bool fit_stopped(const MllArgs& a) { return a.has_fit && __ldcg(a.fit.state + ST_STOPPED) != 0.0; }
+#ifdef FGP_TIMING
+#define FGP_TSTAMP(slot)                                                                          \
+  do {                                                                                            \
+    if (threadIdx.x == 0 && blockIdx.x < 1024 && a.stamps) {                                      \
+      long long _t;                                                                               \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                      \
+      a.stamps[blockIdx.x * 48 + (slot)] = _t;                                                    \
+    }                                                                                             \
+  } while (0)
+#else
+#define FGP_TSTAMP(slot) do { } while (0)
+#endif
 // the same flag as a value: issue the load at kernel entry, test it after the hyperparameter loads are in flight (one L2 round
 // trip per kernel instead of two on the critical path of a ~17 us kernel)
 __device__ __forceinline__ double fit_stop_flag(const MllArgs& a) { return a.has_fit ? __ldcg(a.fit.state + ST_STOPPED) : 0.0; }
@@ -425,23 +448,50 @@ __device__ __forceinline__ void finalize_set(const MllArgs& a, int b, double* re
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   double s[3] = {0.0, 0.0, 0.0};
   {
+    // loads first, sums after: in a rolled `s += load` loop every load waits for the previous one's use (in-order issue) -- nine dependent
+    // L2 round trips per lane in the gradient loop below were 2.7 us of the 8 us serial tail of an iteration (-DFGP_TIMING stamps)
     const double* p = a.partB + (int64_t)b * a.ctasB * 3;
-    for (int c = threadIdx.x; c < a.ctasB; c += blockDim.x) {
-      s[0] += __ldcg(p + c * 3 + 0);
-      s[1] += __ldcg(p + c * 3 + 1);
-      s[2] += __ldcg(p + c * 3 + 2);
+    for (int c0 = threadIdx.x; c0 < a.ctasB; c0 += 2 * blockDim.x) {
+      double t[2][3];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = c0 + i * blockDim.x;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) t[i][k] = c < a.ctasB ? __ldcg(p + c * 3 + k) : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s[k] += t[i][k];
+      }
     }
   }
   // warp w reduces gradient components w, w + nwarp, ... over all pass-C CTAs, four components' loads in flight at a time; the
   // first four are requested before the block reduction above is waited for
   const double* p = a.partC + (int64_t)b * a.ctasA * (d + 1);
   auto load4 = [&](int j0, double* v) {
+    // components j0 + k nwarp, k = 0..3, two at a time: the loads of BOTH are requested before either sum (warp 0 owns components 0 and 8 at
+    // d = 8: one L2 round trip instead of two); each sum runs over the CTAs in ascending order, so the result does not depend on the split
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int j = j0 + k * nwarp;
+    for (int k = 0; k < 4; k += 2) {
+      const int ja = j0 + k * nwarp, jb = ja + nwarp;
       v[k] = 0.0;
-      if (j <= d)
-        for (int c = lane; c < a.ctasA; c += 32) v[k] += __ldcg(p + (int64_t)c * (d + 1) + j);
+      v[k + 1] = 0.0;
+      if (ja > d) continue;  // uniform over the warp
+      for (int c0 = lane; c0 < a.ctasA; c0 += 32 * 10) {  // 10 (+10) loads in flight per lane
+        double ta[10], tb[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const int c = c0 + 32 * i;
+          ta[i] = c < a.ctasA ? __ldcg(p + (int64_t)c * (d + 1) + ja) : 0.0;
+          tb[i] = (c < a.ctasA && jb <= d) ? __ldcg(p + (int64_t)c * (d + 1) + jb) : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          v[k] += ta[i];
+          v[k + 1] += tb[i];
+        }
+      }
     }
   };
   double inv_scale = 1.0;
@@ -491,6 +541,10 @@ __device__ __forceinline__ void mll_fit_tail(const MllArgs& a, int b, int ctas_b
   __shared__ int s_flags[2];
   __shared__ double s_out[FGP_MAX_D + 4];
   const double pre_hdr = threadIdx.x < ST_HEADER ? __ldcg(a.fit.state + threadIdx.x) : 0.0;
+  // one set: the fit step's own inputs too (nobody writes them during this kernel) -- see FitPrefetch
+  const bool use_pf = two_pass && B == 1 && a.fit.P <= (int)blockDim.x;
+  FitPrefetch pf{0.0, 0.0, 0.0};
+  if (use_pf) pf = fit_prefetch(a.fit);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -498,16 +552,19 @@ __device__ __forceinline__ void mll_fit_tail(const MllArgs& a, int b, int ctas_b
   }
   __syncthreads();
   if (!s_last) return;
+  FGP_TSTAMP(32);
   const bool local = two_pass && B == 1;  // this CTA finalizes the only set: the fit step reads the sums from shared memory
   if (two_pass) {
     __threadfence();
     finalize_set(a, b, red, local ? s_out : nullptr);
   }
+  FGP_TSTAMP(33);
   if (threadIdx.x < ST_HEADER) s_hdr[threadIdx.x] = pre_hdr;
   if (B == 1) {
     if (threadIdx.x == 0) a.fit.tickets[1 + b] = 0u;
     __syncthreads();
-    fit_step_device(a.fit, a.out, red, s_hdr, s_flags, true, local ? s_out : nullptr);
+    fit_step_device(a.fit, a.out, red, s_hdr, s_flags, true, local ? s_out : nullptr, use_pf ? &pf : nullptr);
+    FGP_TSTAMP(34);
     return;
   }
   __threadfence();
@@ -613,7 +670,7 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_single_kern
 // ------------------------------------------------------------------------------------------------------------
 #ifdef FGP_TIMING
 // tools-only build (-DFGP_TIMING, FGP_LIB_DIR): clock stamps of the persistent kernel, read back by fgp_debug_stamps()
-constexpr int kStampSlots = 16, kStampCtas = 1024;
+constexpr int kStampSlots = 48, kStampCtas = 1024;  // 0-7 globaltimer, 8-15 clock64 (persistent kernel); 16-31 globaltimer of the per-pass kernels
 long long* debug_stamp_buffer();  // fgp_mll_passb.cu: device buffer, allocated on first use
 #define FGP_STAMP(slot)                                                                           \
   do {                                                                                            \
@@ -624,8 +681,17 @@ long long* debug_stamp_buffer();  // fgp_mll_passb.cu: device buffer, allocated 
       a.stamps[blockIdx.x * kStampSlots + 8 + (slot)] = clock64();                                \
     }                                                                                             \
   } while (0)
+#define FGP_PSTAMP(slot)                                                                          \
+  do {                                                                                            \
+    if (threadIdx.x == 0 && blockIdx.x < kStampCtas && a.stamps) {                                \
+      long long _t;                                                                               \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                      \
+      a.stamps[blockIdx.x * kStampSlots + (slot)] = _t;                                           \
+    }                                                                                             \
+  } while (0)
 #else
 #define FGP_STAMP(slot) do { } while (0)
+#define FGP_PSTAMP(slot) do { } while (0)
 #endif
 
 // hyperparameters (and the net generator tables) of set b for a tile starting at point g0
@@ -681,16 +747,19 @@ __device__ __forceinline__ void passA_tile(const MllArgs& a, const Hyp& H, unsig
       }
     }
     __syncthreads();
+    FGP_PSTAMP(18);
     if (rf) {
       const SmemC S{sm, LP};
       block_fft_fwd_io<false>(sm, lh, 0, LP, T.stage, SmemTag{}, SmemTag{});
       __syncthreads();
+      FGP_PSTAMP(19);
       const uint32_t res = brev_bits((uint32_t)(blk0 & ((1 << l2) - 1)), l2);  // residue class of this block row
       for (int k = threadIdx.x; k <= h; k += blockDim.x) {
         const double2 zk = S(0, k & (h - 1)), zm = S(0, (h - k) & (h - 1));
         const double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
         const double2 O = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
-        const double2 X = cadd(E, cmul(twiddle_n(T, (uint32_t)k << l2), O));
+        const double2 wk = k < h ? __ldg(T.stage + h + k) : make_double2(-1.0, 0.0);  // exp(-2 pi i k / L1): one table entry
+        const double2 X = cadd(E, cmul(wk, O));
         W[k] = cmul(X, twiddle_n(T, res * (uint32_t)k));
       }
       // the last pass-B tile also loads the (weight-0) columns just above L1/2: keep them finite
@@ -751,6 +820,7 @@ __device__ __forceinline__ void passB_tile(const MllArgs& a, unsigned char* smra
         return make_double2(v.x, mir ? -v.y : v.y);
       }, SmemTag{});
       __syncthreads();
+      FGP_PSTAMP(22);
       // a thread stays in one column (the block size is a multiple of the columns per tile), so its weight cw is a constant and the
       // log-determinant terms of its eigenvalues can be taken as one log of their product
       double mant = 1.0, t0 = 0.0, t2 = 0.0;
@@ -792,6 +862,7 @@ __device__ __forceinline__ void passB_tile(const MllArgs& a, unsigned char* smra
       }
       if (want_grad) {
         __syncthreads();
+        FGP_PSTAMP(23);
         block_fft_inv_io<true>(sm, l2, lntr, LP, T.stage, SmemTag{}, [&](int tr, int r, double2 v) {
           const uint32_t res = brev_bits((uint32_t)r, l2);
           if (res > half2) return;  // pass C never reads the mirrored block rows
@@ -854,15 +925,17 @@ __device__ __forceinline__ void passC_tile(const MllArgs& a, const Hyp& H, unsig
       const int l2 = a.l2;
       for (int k = threadIdx.x; k < h; k += blockDim.x) {
         const double2 xk = __ldcg(W + k), xm = __ldcg(W + (h - k));
-        const double2 o = cmulc(twiddle_n(T, (uint32_t)k << l2), make_double2(xk.x - xm.x, xk.y + xm.y));
+        const double2 o = cmulc(__ldg(T.stage + h + k), make_double2(xk.x - xm.x, xk.y + xm.y));
         S(0, k, make_double2((xk.x + xm.x) - o.y, (xk.y - xm.y) + o.x));
       }
       __syncthreads();
+      FGP_PSTAMP(27);
       block_fft_inv_io<false>(sm, lh, 0, LP, T.stage, SmemTag{}, SmemTag{});
     } else {
       block_fft_inv_io<false>(sm, l1, lntr, LP, a.T.stage, [&](int tr, int idx) -> double2 { return __ldcg(W + ((int64_t)tr << l1) + idx); }, SmemTag{});
     }
     __syncthreads();
+    FGP_PSTAMP(28);
     {
       // ONE rolled loop (one inlined copy of the gradient contraction) drains either layout
       const int total = 1 << (lntr + l1);
@@ -877,6 +950,7 @@ __device__ __forceinline__ void passC_tile(const MllArgs& a, const Hyp& H, unsig
       for (int j = 0; j <= DM; ++j) acc[j] *= 2.0;
     }
   }
+  FGP_PSTAMP(29);
   reduce_store<DM + 1>(acc, d + 1, red, a.partC + ((int64_t)b * a.ctasA + tile) * (d + 1));
 }
 
@@ -889,10 +963,14 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passA_kerne
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
   pdl_prologue();
-  if (fit_stop_flag(a) != 0.0) return;  // uniform over the CTA, before any barrier
+  FGP_PSTAMP(16);
+  const double stop_flag = fit_stop_flag(a);  // tested after the prologue: its load shares the prologue's L2 round trip
   const int tile = blockIdx.x, b = blockIdx.y;
   tile_prologue<NET, GEN>(a, H, smraw, b, tileA_block0<NET>(a, tile) << a.l1, a.l1 + a.lntrA);
+  if (stop_flag != 0.0) return;  // uniform over the CTA
+  FGP_PSTAMP(17);
   passA_tile<DT, NET, A2, GEN>(a, H, smraw, tile, b);
+  FGP_PSTAMP(20);
 }
 
 template <int DT, bool NET, bool A2, bool GEN>
@@ -901,11 +979,16 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kerne
   __shared__ Hyp H;
   __shared__ double red[kRed];
   pdl_prologue();
-  if (fit_stop_flag(a) != 0.0) return;  // uniform over the CTA, before any barrier
+  FGP_PSTAMP(25);
+  const double stop_flag = fit_stop_flag(a);  // tested after the prologue: its load shares the prologue's L2 round trip
   const int tile = blockIdx.x, b = blockIdx.y;
   tile_prologue<NET, GEN>(a, H, smraw, b, tileA_block0<NET>(a, tile) << a.l1, a.l1 + a.lntrA);
+  if (stop_flag != 0.0) return;  // uniform over the CTA
+  FGP_PSTAMP(26);
   passC_tile<DT, NET, A2, GEN>(a, H, smraw, red, tile, b);
+  FGP_PSTAMP(30);
   if (a.has_fit) mll_fit_tail(a, b, a.ctasA, gridDim.y, true, red);
+  FGP_PSTAMP(31);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1060,8 +1143,14 @@ static int launch_mll_coop(const MllArgs& a0, const PassGeom& g, int B, size_t s
 }
 
 template <int DT, bool NET, bool A2, bool GEN>
-static int launch_mll(const MllArgs& a, const PassGeom& g, int B, cudaStream_t st) {
+static int launch_mll(const MllArgs& a0, const PassGeom& g, int B, cudaStream_t st) {
   int rc;
+#ifdef FGP_TIMING
+  MllArgs a = a0;
+  a.stamps = debug_stamp_buffer();
+#else
+  const MllArgs& a = a0;
+#endif
   const size_t smemAC = (size_t)a.tab_off + ((GEN && NET) ? dnb2_table_bytes(a.d, g.l2 ? g.l1 + g.lntrA : g.l1) : 0);
   if (g.l2 == 0) {
     if ((rc = set_smem_attr(mll_single_kernel<DT, NET, A2, GEN>, smemAC))) return rc;

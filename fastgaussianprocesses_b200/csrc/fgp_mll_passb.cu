@@ -8,9 +8,11 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passB_kerne
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ double red[kRed];
   pdl_prologue();
+  FGP_PSTAMP(21);
   if (fit_stop_flag(a) != 0.0) return;  // uniform over the CTA, before any barrier
   const int tile = blockIdx.x, b = blockIdx.y;
   passB_tile<NET>(a, smraw, red, tile, b);
+  FGP_PSTAMP(24);
   if (a.has_fit && !a.want_grad) mll_fit_tail(a, b, a.ctasB, gridDim.y, true, red);
 }
 

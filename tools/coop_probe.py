@@ -105,7 +105,7 @@ def main():
     if stamps_fn is not None and st.multi:
         st.step()
         torch.cuda.synchronize()
-        buf = np.zeros((1024, 16), dtype=np.int64)
+        buf = np.zeros((1024, 48), dtype=np.int64)
         stamps_fn.argtypes = [ctypes.c_void_p, ctypes.c_int]
         stamps_fn(buf.ctypes.data, 1024)
         live = buf[buf[:, 0] != 0]

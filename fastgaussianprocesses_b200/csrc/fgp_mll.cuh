@@ -447,17 +447,31 @@ __device__ __forceinline__ void finalize_set(const MllArgs& a, int b, double* re
   double* out = a.out + (int64_t)b * (d + 4);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   double s[3] = {0.0, 0.0, 0.0};
-  {
-    // loads first, sums after: in a rolled `s += load` loop every load waits for the previous one's use (in-order issue) -- nine dependent
-    // L2 round trips per lane in the gradient loop below were 2.7 us of the 8 us serial tail of an iteration (-DFGP_TIMING stamps)
-    const double* p = a.partB + (int64_t)b * a.ctasB * 3;
-    for (int c0 = threadIdx.x; c0 < a.ctasB; c0 += 2 * blockDim.x) {
+  // Loads first, sums after: in a rolled `s += load` loop every load waits for the previous one's use (in-order issue) -- nine dependent
+  // L2 round trips per lane in the gradient loop below were 2.7 us of the 8 us serial tail of an iteration (-DFGP_TIMING stamps).
+  // The first two pass-B partials of this thread are only REQUESTED here; they are added after the gradient partials below have been requested
+  // as well, so that both groups share one round trip
+  const double* pB = a.partB + (int64_t)b * a.ctasB * 3;
+  double tB[2][3];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tB[i][k] = c < a.ctasB ? __ldcg(pB + c * 3 + k) : 0.0;
+  }
+  auto sumB = [&]() {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s[k] += tB[i][k];
+    }
+    for (int c0 = threadIdx.x + 2 * blockDim.x; c0 < a.ctasB; c0 += 2 * blockDim.x) {
       double t[2][3];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int c = c0 + i * blockDim.x;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) t[i][k] = c < a.ctasB ? __ldcg(p + c * 3 + k) : 0.0;
+        for (int k = 0; k < 3; ++k) t[i][k] = c < a.ctasB ? __ldcg(pB + c * 3 + k) : 0.0;
       }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -465,7 +479,7 @@ __device__ __forceinline__ void finalize_set(const MllArgs& a, int b, double* re
         for (int k = 0; k < 3; ++k) s[k] += t[i][k];
       }
     }
-  }
+  };
   // warp w reduces gradient components w, w + nwarp, ... over all pass-C CTAs, four components' loads in flight at a time; the
   // first four are requested before the block reduction above is waited for
   const double* p = a.partC + (int64_t)b * a.ctasA * (d + 1);
@@ -513,6 +527,7 @@ __device__ __forceinline__ void finalize_set(const MllArgs& a, int b, double* re
     inv_scale = 1.0 / __ldcg(a.scale + b);
     load4(warp, v0);
   }
+  sumB();
   block_sum<3>(s, red);
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -547,17 +562,16 @@ __device__ __forceinline__ void mll_fit_tail(const MllArgs& a, int b, int ctas_b
   if (use_pf) pf = fit_prefetch(a.fit);
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    s_last = atomicAdd(&a.fit.tickets[1 + b], 1u) == (unsigned)(ctas_b - 1);
+    __threadfence();  // release: this CTA's partial sums before its ticket
+    const bool last = atomicAdd(&a.fit.tickets[1 + b], 1u) == (unsigned)(ctas_b - 1);
+    if (last) __threadfence();  // acquire, by the observing thread alone: the barrier below orders the other threads' (cache-global) loads after it
+    s_last = last;
   }
   __syncthreads();
   if (!s_last) return;
   FGP_TSTAMP(32);
   const bool local = two_pass && B == 1;  // this CTA finalizes the only set: the fit step reads the sums from shared memory
-  if (two_pass) {
-    __threadfence();
-    finalize_set(a, b, red, local ? s_out : nullptr);
-  }
+  if (two_pass) finalize_set(a, b, red, local ? s_out : nullptr);
   FGP_TSTAMP(33);
   if (threadIdx.x < ST_HEADER) s_hdr[threadIdx.x] = pre_hdr;
   if (B == 1) {

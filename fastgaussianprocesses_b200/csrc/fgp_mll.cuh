@@ -121,19 +121,35 @@ __device__ __forceinline__ uint64_t dnb2_fold(const uint64_t* __restrict__ Cj, u
   }
   return r;
 }
-// build the generator tables of a tile of 2^tile_log points starting at tile_base (a multiple of the tile size)
+// build the generator tables of a tile of 2^tile_log points starting at tile_base (a multiple of the tile size).
+// The generating-matrix columns (d * mmax words) are staged in shared memory by ONE parallel load; the folds then run on shared memory with
+// predicated XORs (no data-dependent loop of dependent global loads: that was 4 us of prologue per CTA at n = 2^20, up to 20 serial L2
+// round trips for the high bits of the tile base -- -DFGP_TIMING stamps, profiles/README.md).
 __device__ __forceinline__ void dnb2_build_tables(Hyp& H, const MllArgs& a, uint64_t* tab, int64_t tile_base, int tile_log) {
-  const int d = a.d;
+  const int d = a.d, mmax = a.mmax;
   const int nb = tile_log > 6 ? 1 << (tile_log - 6) : 1;
   uint64_t* TA = tab;
   uint64_t* TB = tab + 64 * d;
+  uint64_t* sC = TB + nb * d;  // (d, mmax) copy of the generating matrices
+  for (int e = threadIdx.x; e < d * mmax; e += blockDim.x) sC[e] = __ldg(a.C + e);
+  __syncthreads();
   for (int e = threadIdx.x; e < 64 * d; e += blockDim.x) {
     const int j = e >> 6, v = e & 63;
-    TA[e] = dnb2_fold(a.C + (int64_t)j * a.mmax, (uint64_t)v);
+    const uint64_t* Cj = sC + j * mmax;
+    uint64_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (k < mmax) r ^= ((v >> k) & 1) ? Cj[k] : 0ull;
+    TA[e] = r;
   }
   for (int e = threadIdx.x; e < nb * d; e += blockDim.x) {
     const int j = e / nb, h = e - j * nb;
-    TB[e] = dnb2_fold(a.C + (int64_t)j * a.mmax, (uint64_t)tile_base | ((uint64_t)h << 6));
+    const uint64_t* Cj = sC + j * mmax;
+    const uint64_t v = ((uint64_t)tile_base | ((uint64_t)h << 6)) >> 6;  // bits 6 and up of the point index
+    uint64_t r = 0;
+#pragma unroll 8
+    for (int k = 6; k < mmax; ++k) r ^= ((v >> (k - 6)) & 1ull) ? Cj[k] : 0ull;
+    TB[e] = r;
   }
   if (threadIdx.x == 0) {
     H.TA = TA;
@@ -142,7 +158,9 @@ __device__ __forceinline__ void dnb2_build_tables(Hyp& H, const MllArgs& a, uint
     H.nbB = nb;
   }
 }
-static inline size_t dnb2_table_bytes(int d, int tile_log) { return (size_t)(64 + (tile_log > 6 ? 1 << (tile_log - 6) : 1)) * d * sizeof(uint64_t); }
+static inline size_t dnb2_table_bytes(int d, int tile_log, int mmax) {
+  return (size_t)(64 + (tile_log > 6 ? 1 << (tile_log - 6) : 1) + mmax) * d * sizeof(uint64_t);
+}
 
 template <bool NET>
 __device__ __forceinline__ void load_hyp(Hyp& H, const MllArgs& a, int b) {
@@ -218,11 +236,14 @@ __device__ __forceinline__ void point_parts(const MllArgs& a, const Hyp& H, int6
     const uint64_t* ta = H.TA + (e & 63);
     const uint64_t* tb = H.TB + (e >> 6);
     const int nb = H.nbB;
+    const bool t52 = a.t <= 52;
 #pragma unroll
     for (int j = 0; j < DM; ++j) {
       if (j >= d) break;
       const uint64_t delta = ta[j * 64] ^ tb[j * nb];
-      p[j] = A2 ? dnb2_part_a2(delta, a.t, a.tscale) : dnb2_part(delta, a.alpha.v[j], a.t);
+      // t <= 52 (this package's nets): the integer converts exactly through the 2^52 magic number and the exponent field gives floor(log2):
+      // 18 instead of 55 instructions per (point, dimension), bit-identical to the general form (fgp_common.cuh)
+      p[j] = A2 ? (t52 ? dnb2_part_a2_t52(delta, a.t, a.tscale) : dnb2_part_a2(delta, a.t, a.tscale)) : dnb2_part(delta, a.alpha.v[j], a.t);
     }
     return;
   }
@@ -400,6 +421,23 @@ __device__ __forceinline__ double spectral_r(double lam, double ysq, double wn, 
   const double inv = 1.0 / lam;
   s[0] = fma(ysq, inv, s[0]);
   s[1] += log(fabs(lam));
+  const double g = inv * (wl - wn * ysq * inv);
+  s[2] += g;
+  return g;
+}
+
+// the real epilogue with the running-product logarithm of spectral_c_prod (zero / denormal eigenvalues take the plain log)
+__device__ __forceinline__ double spectral_r_prod(double lam, double ysq, double wn, double wl, double* s, double& mant, int& ex) {
+  const double inv = 1.0 / lam;
+  s[0] = fma(ysq, inv, s[0]);
+  const long long bits = __double_as_longlong(fabs(lam));
+  const int e = (int)((bits >> 52) & 0x7ff);
+  if (e == 0 || e == 0x7ff) {
+    s[1] += log(fabs(lam));
+  } else {
+    ex += e - 1022;
+    mant *= __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3fe0000000000000LL);
+  }
   const double g = inv * (wl - wn * ysq * inv);
   s[2] += g;
   return g;
@@ -735,6 +773,8 @@ __device__ __forceinline__ void passA_tile(const MllArgs& a, const Hyp& H, unsig
     tile_fill_r<false>(SmemR{sm, LP}, l1, lntr,
                        [&](int tr, int idx) -> double { return point_k1<DT, NET, A2, GEN>(a, H, g0 + ((int64_t)tr << l1) + idx) - c; });
     __syncthreads();
+    FGP_PSTAMP(18);
+    FGP_PSTAMP(19);
     // any schedule whose last round is strided (coalesced stores)
     block_wht_io<false>(sm, l1, lntr, LP, wht_sched_up(l1), SmemTag{}, [&](int tr, int idx, double v) { W[((int64_t)tr << l1) + idx] = v; });
   } else {
@@ -805,15 +845,25 @@ __device__ __forceinline__ void passB_tile(const MllArgs& a, unsigned char* smra
     double* lamo = a.lam ? a.lam + boff + q0 : nullptr;
     block_wht_io<true>(sm, l2, lntr, LP, wht_sched_up(l2), [&](int tr, int r) -> double { return __ldcg(W + ((int64_t)r << l1) + tr); }, SmemTag{});
     __syncthreads();
+    FGP_PSTAMP(22);
+    double mant = 1.0;  // one logarithm per 64 eigenvalues of a thread instead of one each (a third of this epilogue's FP64 work)
+    int ex = 0, cnt = 0;
     tile_map_r<true>(SmemR{sm, LP}, l2, lntr, [&](int tr, int r, double v) -> double {
       const int64_t k = ((int64_t)r << l1) + tr;
       double lam = v + noise;
       if (k + q0 == 0) lam += dc;
       if (lamo) lamo[k] = lam;
-      return spectral_r(lam, ysq[k], wn, wl, s);
+      const double g = spectral_r_prod(lam, ysq[k], wn, wl, s, mant, ex);
+      if (++cnt == 64) {  // 0.5^64 is far from underflow
+        s[1] += logprod_flush(mant, ex);
+        cnt = 0;
+      }
+      return g;
     });
+    s[1] += logprod_flush(mant, ex);
     if (want_grad) {
       __syncthreads();
+      FGP_PSTAMP(23);
       block_wht_io<true>(sm, l2, lntr, LP, wht_sched_up(l2), SmemTag{}, [&](int tr, int r, double v) { W[((int64_t)r << l1) + tr] = v; });
     }
   } else {
@@ -924,6 +974,8 @@ __device__ __forceinline__ void passC_tile(const MllArgs& a, const Hyp& H, unsig
     // top stages first: a thread's 16 loads are 2^(l1-4) apart, consecutive threads read consecutive addresses
     block_wht_io<false>(sm, l1, lntr, LP, wht_sched_coalesced(l1), [&](int tr, int idx) -> double { return __ldcg(W + ((int64_t)tr << l1) + idx); }, SmemTag{});
     __syncthreads();
+    FGP_PSTAMP(27);
+    FGP_PSTAMP(28);
     tile_drain_r<false>(SmemR{sm, LP}, l1, lntr,
                         [&](int tr, int idx, double w) { point_grad<DT, NET, A2, GEN>(a, H, g0 + ((int64_t)tr << l1) + idx, w, acc); });
   } else {
@@ -1165,7 +1217,7 @@ static int launch_mll(const MllArgs& a0, const PassGeom& g, int B, cudaStream_t 
 #else
   const MllArgs& a = a0;
 #endif
-  const size_t smemAC = (size_t)a.tab_off + ((GEN && NET) ? dnb2_table_bytes(a.d, g.l2 ? g.l1 + g.lntrA : g.l1) : 0);
+  const size_t smemAC = (size_t)a.tab_off + ((GEN && NET) ? dnb2_table_bytes(a.d, g.l2 ? g.l1 + g.lntrA : g.l1, a.mmax) : 0);
   if (g.l2 == 0) {
     if ((rc = set_smem_attr(mll_single_kernel<DT, NET, A2, GEN>, smemAC))) return rc;
     launch_chain(mll_single_kernel<DT, NET, A2, GEN>, dim3(B), dim3(g.threadsA), smemAC, st, a);

@@ -426,6 +426,28 @@ __device__ __forceinline__ double spectral_r(double lam, double ysq, double wn, 
   return g;
 }
 
+// The same for a pass whose shared-memory tile is dead by now: all nv values at once through `scratch` (>= nv * warps doubles of the tile) -- two
+// barriers instead of two per group of four (pass C reduces d + 1 = 9 values per CTA: 1.6 us of its critical path in the phase stamps).
+// Fixed order: lanes by the shuffle tree, warps ascending.
+template <int NV>
+__device__ __forceinline__ void reduce_store_all(double* v, int nv, double* scratch, double* dst) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  __syncthreads();  // every reader of the tile is done
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    if (k >= nv) break;
+    const double r = warp_sum(v[k]);
+    if (lane == 0) scratch[k * nwarp + warp] = r;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nv; k += blockDim.x) {
+    double r = 0.0;
+    for (int w = 0; w < nwarp; ++w) r += scratch[k * nwarp + w];
+    dst[k] = r;
+    __threadfence();  // the fit tail's completion ticket is taken by thread 0 after a barrier: each writer releases its own store
+  }
+}
+
 // the real epilogue with the running-product logarithm of spectral_c_prod (zero / denormal eigenvalues take the plain log)
 __device__ __forceinline__ double spectral_r_prod(double lam, double ysq, double wn, double wl, double* s, double& mant, int& ex) {
   const double inv = 1.0 / lam;
@@ -1017,7 +1039,7 @@ __device__ __forceinline__ void passC_tile(const MllArgs& a, const Hyp& H, unsig
     }
   }
   FGP_PSTAMP(29);
-  reduce_store<DM + 1>(acc, d + 1, red, a.partC + ((int64_t)b * a.ctasA + tile) * (d + 1));
+  reduce_store_all<DM + 1>(acc, d + 1, (double*)smraw, a.partC + ((int64_t)b * a.ctasA + tile) * (d + 1));
 }
 
 // ------------------------------------------------------------------------------------------------------------

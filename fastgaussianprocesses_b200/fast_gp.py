@@ -21,6 +21,7 @@ one hyperparameter set per batch element, and the adaptive nugget (util.py:286-2
 import functools
 import math
 import os
+import weakref
 from fractions import Fraction
 from typing import List, Tuple, Union
 
@@ -843,9 +844,12 @@ class AbstractFastGP(torch.nn.Module):
         self._epoch += 1
         # single-task fast path: enqueue ytilde = ft(y) and |ytilde|^2 right away.  They are what fit() and coeffs need first, and here
         # their host-side launch work overlaps the (asynchronous) host-to-device copy of y instead of delaying the first fit iteration.
+        self._data_epoch = getattr(self, "_data_epoch", 0) + 1
         if self._mt is None and not self._DENSE and self._nint > 0 and os.environ.get("FGP_B200_NO_PREFETCH") != "1":
             with torch.no_grad():
                 self._get_ysq(self._pshape())
+                if self._nint > 1 and os.environ.get("FGP_B200_NO_PREARM") != "1":
+                    self._prearm_fit()
 
     # ------------------------------------------------------------------------------------------------ properties
     @property
@@ -1322,10 +1326,43 @@ class AbstractFastGP(torch.nn.Module):
         old = getattr(self, "_fused_loop", None)
         if old is not None:
             old.close(finish=False)
+        hist_flags = tuple(bool(f) for f in hist_flags)
+        pre = getattr(self, "_prearmed_loop", None)
+        self._prearmed_loop = None
+        if pre is not None:
+            # the loop add_y_next armed while the data was in flight: taken if it still fits (same data, same parameter layout, same history
+            # rows, enough history capacity); begin() copies the parameter values in either way
+            c = pre.ctx
+            if (c is not None and pre.data_epoch == self._data_epoch and c.hist_flags == hist_flags and c.hist_capacity >= max(hist_capacity, 1)
+                    and pre.param_shapes == tuple(tuple(p.shape) for p in (self.raw_scale, self.raw_lengthscales, self.raw_noise))
+                    and pre.param_req == tuple(bool(p.requires_grad) for p in (self.raw_scale, self.raw_lengthscales, self.raw_noise))
+                    and pre.tau == self._tau_host()):
+                pre.fgp = self  # a strong reference for the duration of the fit (the armed loop only held a weak one)
+                self._fused_loop = pre
+                return pre
+            pre.close(finish=False)
         self.get_ytilde(0)
         loop = _FusedFitLoop(self, hist_flags, max(hist_capacity, 1))
         self._fused_loop = loop
         return loop
+
+    def _prearm_fit(self):
+        """Called at the end of add_y_next (one task, default transforms): acquire the pooled fit context and copy |ytilde|^2 into it NOW,
+        while the host-to-device copy of y and the transform are still running -- ~75 us of host work that fit() would otherwise do with
+        the GPU idle.  Costs nothing on the device but the 8n-byte copy fit() needs anyway; undone by the next add_y_next."""
+        pre = getattr(self, "_prearmed_loop", None)
+        self._prearmed_loop = None
+        if pre is not None:
+            pre.close(finish=False)
+        if getattr(self, "_fused_loop", None) is not None or not _FusedFitLoop.eligible(self) or os.environ.get("FGP_B200_GENERIC_FIT") == "1":
+            return
+        loop = _FusedFitLoop(self, (False, False, False), 1)
+        loop.data_epoch = self._data_epoch
+        loop.param_shapes = tuple(tuple(p.shape) for p in (self.raw_scale, self.raw_lengthscales, self.raw_noise))
+        loop.param_req = tuple(bool(p.requires_grad) for p in (self.raw_scale, self.raw_lengthscales, self.raw_noise))
+        loop.tau = self._tau_host()
+        loop.fgp = weakref.proxy(self)  # no reference cycle: when the GP goes away the loop goes with it and hands its context back
+        self._prearmed_loop = loop
 
     def fit_stepper(self):
         """The fused device-side fit loop armed for an open-ended run: `.step()` = one MLL+gradient+Rprop iteration on the device

@@ -75,7 +75,9 @@ class _XXbSeq(object):
     """Growing cache of the points of one sequence, generated on the GPU (util.py:16-38)."""
 
     def __init__(self, fgp, seq):
-        self.fgp = fgp
+        # a weak back-reference: the GP keeps these objects in a numpy object array (as the reference does), which the cycle collector
+        # does not traverse -- a strong one would make every GP object, its device data and its armed fit context immortal
+        self.fgp = weakref.proxy(fgp)
         self.seq = seq
         self.n = 0
         self.x = torch.empty((0, seq.d), device=fgp.device)
@@ -680,6 +682,9 @@ class AbstractFastGP(torch.nn.Module):
         self._ytilde = None
         self._ytilde_n = -1
         self._ysq = None
+        self._data_epoch = 0        # bumped by add_y_next
+        self._fused_loop = None     # the device-side fit loop while a fit / fit_stepper is open
+        self._prearmed_loop = None  # the loop add_y_next armed for the next fit (fast_gp.py:_prearm_fit)
         if self.num_tasks == 1:
             self._tau_host()
         # the injected transforms of the reference (abstract_fast_gp.py:26-27)

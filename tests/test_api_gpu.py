@@ -2,6 +2,8 @@
 UNMODIFIED reference (tests/golden/make_golden.py).  The test bodies follow the reference's own doctests
 (fast_gp_lattice.py:24-121, fast_gp_digital_net_b2.py:24-116): get_x_next -> add_y_next -> posterior -> fit -> doubling.
 Tolerances: points bit-exact; 1e-10 relative (norm-wise) unless a looser one is stated with its reason."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -284,6 +286,48 @@ def test_repeated_fit_and_growth_reuse_the_device_loop():
     assert gp._fit_route[1] != ctx and d3["iterations"] == 5
     xt = torch.rand(9, 2, generator=torch.Generator().manual_seed(1))
     assert torch.isfinite(gp.post_mean(xt)).all() and (gp.post_var(xt) >= 0).all()
+
+
+def test_add_y_next_arms_the_fit_context_and_hands_it_back():
+    """add_y_next acquires the pooled fit context while y is in flight (fast_gp.py:_prearm_fit); fit() takes it if it still fits, a changed
+    parameter layout falls back to a fresh loop, and a GP that goes away returns the context to the pool."""
+    import gc
+    import fastgaussianprocesses_b200 as fgp
+    from fastgaussianprocesses_b200.fast_gp import _FitContext
+    f = lambda x: torch.cos(2 * np.pi * x).sum(1)
+    mk = lambda seed: fgp.FastGPLattice(fgp.Lattice(2, seed=seed), device=dev, noise=1e-6)
+    gp = mk(3)
+    gp.add_y_next(f(gp.get_x_next(128)))
+    pre = gp._prearmed_loop
+    assert pre is not None and pre.ctx is not None
+    ctx_id = id(pre.ctx)
+    d1 = gp.fit(iterations=4, verbose=0, store_loss_hist=True, stop_crit_wait_iterations=100)
+    assert gp._fit_route[1] == ctx_id and gp._prearmed_loop is None and d1["iterations"] == 4
+    # the same problem without arming: identical trajectory
+    os.environ["FGP_B200_NO_PREARM"] = "1"
+    try:
+        gq = mk(3)
+        gq.add_y_next(f(gq.get_x_next(128)))
+        assert gq._prearmed_loop is None
+        d1q = gq.fit(iterations=4, verbose=0, store_loss_hist=True, stop_crit_wait_iterations=100)
+    finally:
+        del os.environ["FGP_B200_NO_PREARM"]
+    assert torch.equal(d1["loss_hist"], d1q["loss_hist"]) and torch.equal(gp.lengthscales.detach(), gq.lengthscales.detach())
+    # armed, then the parameter layout changes: fit() drops the armed loop and still does its job
+    gp2 = mk(4)
+    gp2.add_y_next(f(gp2.get_x_next(128)))
+    gp2.raw_noise.requires_grad_(False)
+    noise0 = gp2.noise.detach().clone()
+    d2 = gp2.fit(iterations=3, verbose=0, stop_crit_wait_iterations=100)
+    assert d2["iterations"] == 3 and gp2._prearmed_loop is None and torch.equal(gp2.noise.detach(), noise0)
+    # an armed GP that is never fitted hands its context back when it goes away
+    gp3 = mk(5)
+    gp3.add_y_next(f(gp3.get_x_next(128)))
+    c3 = gp3._prearmed_loop.ctx
+    assert all(c3 is not c for c in _FitContext.POOL.get(c3.key, []))
+    del gp3, pre
+    gc.collect()
+    assert any(c3 is c for c in _FitContext.POOL.get(c3.key, []))
 
 
 def test_sharded_posterior_single_process_is_identity():

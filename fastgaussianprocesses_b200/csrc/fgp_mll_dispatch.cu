@@ -39,7 +39,7 @@ static int mll_common(bool net, const uint64_t* z_host, const uint64_t* C_dev, i
     if (rc) return rc;
     a.T = make_tables(table);
   }
-  const PassGeom g = make_geom(n, !net, false, true);
+  const PassGeom g = make_geom(n, !net, false, true, B);
   a.ysq = ysq;
   a.scale = scale;
   a.ls = ls;
@@ -108,7 +108,7 @@ size_t fgp_mll_workspace_bytes(int family, int64_t n, int d, int B) {
   using namespace fgp;
   if (!is_pow2(n) || B < 1 || d < 1) return 0;
   const bool net = family != 0;
-  const PassGeom g = make_geom(n, !net, false, true);
+  const PassGeom g = make_geom(n, !net, false, true, B);
   if (g.l2 == 0) return 256;
   return align256((size_t)B * n * (net ? sizeof(double) : sizeof(double2))) + align256((size_t)B * g.ctasB * 3 * sizeof(double)) +
          align256((size_t)B * g.ctasA * (d + 1) * sizeof(double)) + 256 /* control words of the persistent kernel */;

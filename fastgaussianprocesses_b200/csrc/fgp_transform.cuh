@@ -610,7 +610,10 @@ static inline int env_int(const char* name, int dflt) {
 // of 4: 2^24 159 -> 146 us, 2^26 1149 -> 753 us on B200); the fused MLL kernels keep 64 KiB tiles (they carry generator tables).
 // mll: the fused eigen-solve kernels (fgp_mll.cuh): 2^11-point tiles and 4-column strips up to n = 2^20 -- two tiles per SM in
 // flight in every pass (measured at n = 2^20, d = 8 on B200: 47.4 us per iteration against 49.5 us with 2^12 / 8, 58.4 against 62.4 cold)
-static inline PassGeom make_geom(int64_t n, bool cplx, bool standalone = false, bool mll = false) {
+// batch (mll only): hyperparameter sets evaluated by one call.  From about two single-GP waves of work on (batch * n >= 2^21, n >= 2^18) the
+// passes are throughput-bound and the 2^12-point tiles / 8-column strips win again (measured, tools/tune_batched.py: 64 x 2^18 447 -> 392 us per
+// batched iteration, 16 x 2^20 462 -> 410, 8 x 2^18 72 -> 65; 4 x 2^18 45 -> 47, 64 x 2^16 138 -> 152: not below)
+static inline PassGeom make_geom(int64_t n, bool cplx, bool standalone = false, bool mll = false, int64_t batch = 1) {
   PassGeom g;
   const size_t elem = cplx ? sizeof(double2) : sizeof(double);
   g.m = ilog2(n);
@@ -619,7 +622,8 @@ static inline PassGeom make_geom(int64_t n, bool cplx, bool standalone = false, 
   static const int capC = env_int("FGP_CAP_C", 0), capR = env_int("FGP_CAP_R", 0), colsEnv = env_int("FGP_COLS_LOG2", -1);
   static const int hardC = env_int("FGP_HARD_C", 0), hardR = env_int("FGP_HARD_R", 13);
   // complex: 2^11-point tiles and 4-column strips while one iteration's CTAs fit one wave (n <= 2^18), 2^12 / 8 above
-  const int small_c = mll ? 20 : 18;  // complex tiles: 2^11 points / 4 columns up to here
+  const bool fat = mll && ilog2(n) >= 18 && batch * n >= (int64_t(1) << 21);
+  const int small_c = mll ? (fat ? 0 : 20) : 18;  // complex tiles: 2^11 points / 4 columns up to here
   int cap = cplx ? (capC ? capC : (g.m <= small_c ? 11 : 12)) : (capR ? capR : (g.m <= 22 ? 12 : ((standalone && g.m >= 25) ? 14 : 13)));
   // largest tile: 64 KiB of elements; the 2^24-point FFT takes 128 KiB pass-B tiles (2 columns instead of 1)
   static const int hardREnv = env_int("FGP_HARD_R", 0);

@@ -86,6 +86,16 @@ __device__ __forceinline__ double2 cmulc(double2 a, double2 b) {  // conj(a) * b
   return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.x, b.y, -a.y * b.x));
 }
 
+// L2 prefetches (no register destination, nothing to wait for).  A fit iteration is a chain of dependent phases, each one memory
+// round trip long: data that a LATER phase reads from HBM (|y~|^2 in the spectral epilogue of pass B, the twiddle tables) is requested
+// at kernel entry so that the phase finds it in L2.  l2_prefetch_bulk is the TMA form (cp.async.bulk.prefetch.L2: one instruction for a
+// contiguous range, 16-byte aligned, a multiple of 16 bytes); l2_prefetch_line takes one 128-byte line.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_line(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(p)));
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -861,6 +861,9 @@ __device__ __forceinline__ void passB_tile(const MllArgs& a, unsigned char* smra
   const double wn = a.weights ? a.weights[2 * b] : 0.5, wl = a.weights ? a.weights[2 * b + 1] : 0.5;
   const int want_grad = a.want_grad;
   double s[3] = {0.0, 0.0, 0.0};
+  // |y~|^2 of this tile (one 64- or 128-byte segment per row) is only read by the spectral epilogue, after the column transform: when it is
+  // not in L2 that phase waits for HBM (2.5 -> 5.5 us in the stamps of an L2-flushed iteration).  Request the lines now.
+  for (int r = threadIdx.x; r < (1 << l2); r += blockDim.x) l2_prefetch_line(ysq + ((int64_t)r << l1));
   if (NET) {
     double* sm = (double*)smraw;
     double* W = (double*)a.W + boff + q0;
@@ -980,8 +983,28 @@ __device__ __forceinline__ void passB_tile(const MllArgs& a, unsigned char* smra
 }
 
 // pass C: contiguous blocks of the back-transformed dL/dlam -> inverse block transform -> contraction with dk1/dtheta
+// Half-spectrum pass C, 2^11-point tiles, 256 threads: the tile's loads do not depend on the hyperparameters, so the per-pass kernel issues
+// them BEFORE the tile prologue (one L2 round trip in flight behind the other instead of two in a row: the stamps showed 1.6 + 1.4 us).
+constexpr int kPreC = 4;
+struct PreC {
+  double2 xk[kPreC], xm[kPreC];
+  bool on = false;
+};
+template <bool NET>
+__device__ __forceinline__ void passC_preload(const MllArgs& a, int tile, int b, PreC& P) {
+  if (NET || !a.hs || (1 << (a.l1 - 1)) != kPreC * (int)blockDim.x) return;
+  const int h = 1 << (a.l1 - 1);
+  const double2* W = (const double2*)a.W + (int64_t)b * a.n + (tileA_block0<NET>(a, tile) << a.l1);
+#pragma unroll
+  for (int i = 0; i < kPreC; ++i) {
+    const int k = threadIdx.x + i * (int)blockDim.x;
+    P.xk[i] = __ldcg(W + k);
+    P.xm[i] = __ldcg(W + (h - k));
+  }
+  P.on = true;
+}
 template <int DT, bool NET, bool A2, bool GEN>
-__device__ __forceinline__ void passC_tile(const MllArgs& a, const Hyp& H, unsigned char* smraw, double* red, int tile, int b) {
+__device__ __forceinline__ void passC_tile(const MllArgs& a, const Hyp& H, unsigned char* smraw, double* red, int tile, int b, const PreC& P = PreC()) {
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
   const int d = DT > 0 ? DT : a.d;
   const int l1 = a.l1, lntr = a.lntrA, LP = a.LPA;
@@ -1011,10 +1034,20 @@ __device__ __forceinline__ void passC_tile(const MllArgs& a, const Hyp& H, unsig
       const SmemC S{sm, LP};
       const FftTables T = a.T;
       const int l2 = a.l2;
-      for (int k = threadIdx.x; k < h; k += blockDim.x) {
-        const double2 xk = __ldcg(W + k), xm = __ldcg(W + (h - k));
-        const double2 o = cmulc(__ldg(T.stage + h + k), make_double2(xk.x - xm.x, xk.y + xm.y));
-        S(0, k, make_double2((xk.x + xm.x) - o.y, (xk.y - xm.y) + o.x));
+      if (P.on) {
+#pragma unroll
+        for (int i = 0; i < kPreC; ++i) {
+          const int k = threadIdx.x + i * (int)blockDim.x;
+          const double2 xk = P.xk[i], xm = P.xm[i];
+          const double2 o = cmulc(__ldg(T.stage + h + k), make_double2(xk.x - xm.x, xk.y + xm.y));
+          S(0, k, make_double2((xk.x + xm.x) - o.y, (xk.y - xm.y) + o.x));
+        }
+      } else {
+        for (int k = threadIdx.x; k < h; k += blockDim.x) {
+          const double2 xk = __ldcg(W + k), xm = __ldcg(W + (h - k));
+          const double2 o = cmulc(__ldg(T.stage + h + k), make_double2(xk.x - xm.x, xk.y + xm.y));
+          S(0, k, make_double2((xk.x + xm.x) - o.y, (xk.y - xm.y) + o.x));
+        }
       }
       __syncthreads();
       FGP_PSTAMP(27);
@@ -1054,6 +1087,10 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passA_kerne
   FGP_PSTAMP(16);
   const double stop_flag = fit_stop_flag(a);  // tested after the prologue: its load shares the prologue's L2 round trip
   const int tile = blockIdx.x, b = blockIdx.y;
+  if (!NET && threadIdx.x == 0) {  // twiddle tables (192 KiB, first used 4 us from now): one bulk L2 prefetch of 1 KiB per CTA
+    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x, total = 3u * kTabLen * (unsigned)sizeof(double2);
+    if (cta * 1024u < total) l2_prefetch_bulk((const char*)a.T.stage + cta * 1024u, 1024u);
+  }
   tile_prologue<NET, GEN>(a, H, smraw, b, tileA_block0<NET>(a, tile) << a.l1, a.l1 + a.lntrA);
   if (stop_flag != 0.0) return;  // uniform over the CTA
   FGP_PSTAMP(17);
@@ -1070,10 +1107,12 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kerne
   FGP_PSTAMP(25);
   const double stop_flag = fit_stop_flag(a);  // tested after the prologue: its load shares the prologue's L2 round trip
   const int tile = blockIdx.x, b = blockIdx.y;
+  PreC P;
+  passC_preload<NET>(a, tile, b, P);  // W is valid memory whatever the stop flag says
   tile_prologue<NET, GEN>(a, H, smraw, b, tileA_block0<NET>(a, tile) << a.l1, a.l1 + a.lntrA);
   if (stop_flag != 0.0) return;  // uniform over the CTA
   FGP_PSTAMP(26);
-  passC_tile<DT, NET, A2, GEN>(a, H, smraw, red, tile, b);
+  passC_tile<DT, NET, A2, GEN>(a, H, smraw, red, tile, b, P);
   FGP_PSTAMP(30);
   if (a.has_fit) mll_fit_tail(a, b, a.ctasA, gridDim.y, true, red);
   FGP_PSTAMP(31);

@@ -1,6 +1,7 @@
 """Phase stamps (%globaltimer) of the three per-pass kernels of one fit iteration, from a -DFGP_TIMING build:
     FGP_LIB_DIR=$PWD/fastgaussianprocesses_b200/lib_rt FGP_BUILD_DEFS=-DFGP_TIMING python -m fastgaussianprocesses_b200.build
-    FGP_B200_LIB=$PWD/fastgaussianprocesses_b200/lib_rt/libfgp_b200.so python tools/pass_stamps.py [log2n] [d] [lattice|net]
+    FGP_B200_LIB=$PWD/fastgaussianprocesses_b200/lib_rt/libfgp_b200.so python tools/pass_stamps.py [log2n] [d] [lattice|net] [cold]
+"cold": 256 MiB are written before every stamped iteration (the L2 flush of bench.py's `value`).
 Prints, in microseconds since the first pass-A CTA started: per stamp the min / mean / max over CTAs, and the per-phase durations."""
 import ctypes, json, os, sys
 import numpy as np, torch
@@ -12,6 +13,8 @@ log2n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 d = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 dev = torch.device("cuda:0")
 fam = sys.argv[3] if len(sys.argv) > 3 else "lattice"
+cold = len(sys.argv) > 4 and sys.argv[4] == "cold"
+flush = torch.empty(256 * 1024 * 1024 // 8, device=dev) if cold else None
 gp = fgp.FastGPLattice(fgp.Lattice(d, seed=7), device=dev) if fam == "lattice" else fgp.FastGPDigitalNetB2(fgp.DigitalNetB2(d, seed=7), device=dev)
 x = gp.get_x_next(1 << log2n)
 gp.add_y_next(torch.cos(2 * np.pi * x).sum(1))
@@ -26,6 +29,9 @@ names = {16: "A entry", 17: "A prologue done", 18: "A k1 in smem", 19: "A block 
          25: "C entry", 26: "C prologue done", 27: "C packed in smem", 28: "C inverse fft done", 29: "C contraction done", 30: "C partials stored", 31: "C exit (fit tail)"}
 runs = []
 for rep in range(5):
+    if cold:
+        flush.zero_()
+        torch.cuda.synchronize()
     st.step()
     torch.cuda.synchronize()
     buf = np.zeros((1024, 48), dtype=np.int64)
@@ -38,7 +44,7 @@ for rep in range(5):
         tl = tail[np.argmax(tail[:, 34])]
         tail_us = {"ticket won": (tl[32] - t0) * 1e-3, "partials reduced": (tl[33] - t0) * 1e-3, "fit step done": (tl[34] - t0) * 1e-3, "that CTA's partials stored": (tl[30] - t0) * 1e-3}
 rel = runs[-1]
-out = {"family": fam, "log2n": log2n, "d": d, "ctas": int(rel.shape[0]), "stamps_us": {}}
+out = {"family": fam, "log2n": log2n, "d": d, "l2": "flushed" if cold else "warm", "ctas": int(rel.shape[0]), "stamps_us": {}}
 for k in range(16, 32):
     col = rel[:, k - 16]
     col = col[col > -1e6]

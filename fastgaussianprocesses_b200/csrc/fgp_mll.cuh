@@ -162,8 +162,13 @@ static inline size_t dnb2_table_bytes(int d, int tile_log, int mmax) {
   return (size_t)(64 + (tile_log > 6 ? 1 << (tile_log - 6) : 1) + mmax) * d * sizeof(uint64_t);
 }
 
-template <bool NET>
-__device__ __forceinline__ void load_hyp(Hyp& H, const MllArgs& a, int b) {
+struct NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+// hook(): independent loads of the caller (pass C's tile), issued by warp 0 right AFTER its hyperparameter loads are in flight and before it
+// waits for them, so that the hyperparameters -- the critical path of the prologue -- are not queued behind them
+template <bool NET, typename Hook = NoHook>
+__device__ __forceinline__ void load_hyp(Hyp& H, const MllArgs& a, int b, Hook hook = Hook()) {
   // Warp 0 alone, ONE L2 round trip (this runs on the critical path of every CTA of passes A and C: the stamps of a -DFGP_TIMING build
   // showed 2.0 us for the prologue when one thread walked the lengthscales in a loop of dependent loads): lane j takes dimension j
   // (d <= FGP_MAX_D = 32), lane 0 also scale and noise; the prefactor scale * prod_j A_j is a butterfly product over the lanes.
@@ -176,6 +181,7 @@ __device__ __forceinline__ void load_hyp(Hyp& H, const MllArgs& a, int b) {
     sc = __ldcg(a.scale + b);
     nz = __ldcg(a.noise + b);
   }
+  hook();
   if (on) {
     H.ls[j] = l;
     if (a.x) {
@@ -769,10 +775,11 @@ long long* debug_stamp_buffer();  // fgp_mll_passb.cu: device buffer, allocated 
 #endif
 
 // hyperparameters (and the net generator tables) of set b for a tile starting at point g0
-template <bool NET, bool GEN>
-__device__ __forceinline__ void tile_prologue(const MllArgs& a, Hyp& H, unsigned char* smraw, int b, int64_t g0, int tile_log) {
+template <bool NET, bool GEN, typename Hook = NoHook>
+__device__ __forceinline__ void tile_prologue(const MllArgs& a, Hyp& H, unsigned char* smraw, int b, int64_t g0, int tile_log, Hook hook = Hook()) {
+  if (threadIdx.x >= 32) hook();
   __syncthreads();  // the previous tile's readers of H and of the shared-memory tile are done
-  load_hyp<NET>(H, a, b);
+  load_hyp<NET>(H, a, b, hook);
   if (GEN && NET) dnb2_build_tables(H, a, (uint64_t*)(smraw + a.tab_off), g0, tile_log);
   __syncthreads();
 }
@@ -1108,8 +1115,8 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kerne
   const double stop_flag = fit_stop_flag(a);  // tested after the prologue: its load shares the prologue's L2 round trip
   const int tile = blockIdx.x, b = blockIdx.y;
   PreC P;
-  passC_preload<NET>(a, tile, b, P);  // W is valid memory whatever the stop flag says
-  tile_prologue<NET, GEN>(a, H, smraw, b, tileA_block0<NET>(a, tile) << a.l1, a.l1 + a.lntrA);
+  // W is valid memory whatever the stop flag says
+  tile_prologue<NET, GEN>(a, H, smraw, b, tileA_block0<NET>(a, tile) << a.l1, a.l1 + a.lntrA, [&]() { passC_preload<NET>(a, tile, b, P); });
   if (stop_flag != 0.0) return;  // uniform over the CTA
   FGP_PSTAMP(26);
   passC_tile<DT, NET, A2, GEN>(a, H, smraw, red, tile, b, P);

@@ -63,6 +63,7 @@ struct MllArgs {
   // workspace (zero between launches: the last CTA to leave resets them) and the number of fit iterations of one launch
   unsigned int* bar;
   int iters;
+  int pdl;  // programmatic dependent launch mode of the per-pass kernels (pdl_mode())
 #ifdef FGP_TIMING
   long long* stamps;  // tools-only build: phase stamps of the persistent kernel
 #endif
@@ -73,7 +74,7 @@ struct MllArgs {
 // in the stream, each about one wave long, so the launch latency and CTA ramp-up of a kernel are a visible share of it.
 // With the attribute the next kernel's CTAs become resident as soon as every CTA of the current one has started
 // (pdl_prologue triggers at once); they wait in cudaGridDependencySynchronize() for its memory before touching anything.
-bool pdl_enabled();  // fgp_mll_passb.cu: off by default (measured slower), FGP_PDL=1 turns it on
+int pdl_mode();  // fgp_mll_passb.cu: 0 = off (default), FGP_PDL=1: every CTA triggers at entry, FGP_PDL=2: the trigger is the CTA's exit
 template <typename K>
 static cudaError_t launch_chain(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const MllArgs& a) {
   cudaLaunchConfig_t cfg;
@@ -86,12 +87,12 @@ static cudaError_t launch_chain(K kernel, dim3 grid, dim3 block, size_t smem, cu
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = a.pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, a);
 }
-__device__ __forceinline__ void pdl_prologue() {
-  cudaTriggerProgrammaticLaunchCompletion();
-  cudaGridDependencySynchronize();
+__device__ __forceinline__ void pdl_prologue(const MllArgs& a) {
+  if (a.pdl == 1) cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();  // returns at once in a launch without the attribute
 }
 
 struct Hyp {  // per-CTA hyperparameters and first point, staged in shared memory
@@ -673,7 +674,7 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_single_kern
   __shared__ Hyp H;
   __shared__ double red[kRed];
   constexpr int DM = DT > 0 ? DT : FGP_MAX_D;
-  pdl_prologue();
+  pdl_prologue(a);
   const double stop_flag = fit_stop_flag(a);
   const int b = blockIdx.x;
   const int n = (int)a.n;
@@ -1090,7 +1091,7 @@ template <int DT, bool NET, bool A2, bool GEN>
 __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passA_kernel(const __grid_constant__ MllArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
-  pdl_prologue();
+  pdl_prologue(a);
   FGP_PSTAMP(16);
   const double stop_flag = fit_stop_flag(a);  // tested after the prologue: its load shares the prologue's L2 round trip
   const int tile = blockIdx.x, b = blockIdx.y;
@@ -1110,7 +1111,7 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kerne
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ Hyp H;
   __shared__ double red[kRed];
-  pdl_prologue();
+  pdl_prologue(a);
   FGP_PSTAMP(25);
   const double stop_flag = fit_stop_flag(a);  // tested after the prologue: its load shares the prologue's L2 round trip
   const int tile = blockIdx.x, b = blockIdx.y;
@@ -1121,6 +1122,9 @@ __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passC_kerne
   FGP_PSTAMP(26);
   passC_tile<DT, NET, A2, GEN>(a, H, smraw, red, tile, b, P);
   FGP_PSTAMP(30);
+  // PDL mode 2: this CTA's tile is done; what is left is the serial tail of ONE CTA (ticket, partial sums, fit step: ~4.7 us).  Trigger now, so
+  // that the next iteration's pass-A CTAs are launched and resident (waiting in cudaGridDependencySynchronize) while the tail runs.
+  if (a.pdl == 2) cudaTriggerProgrammaticLaunchCompletion();
   if (a.has_fit) mll_fit_tail(a, b, a.ctasA, gridDim.y, true, red);
   FGP_PSTAMP(31);
 }

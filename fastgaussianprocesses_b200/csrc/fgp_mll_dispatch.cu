@@ -55,6 +55,7 @@ static int mll_common(bool net, const uint64_t* z_host, const uint64_t* C_dev, i
     a.has_fit = 1;
   }
   a.iters = iters;
+  a.pdl = pdl_mode();
   a.l1 = g.l1;
   a.l2 = g.l2;
   a.lntrA = g.l2 ? g.lntrA : 0;  // the single-pass kernel runs one transform per CTA

@@ -7,7 +7,7 @@ template <bool NET>
 __global__ void __launch_bounds__(FGP_LB_THREADS, FGP_LB_BLOCKS) mll_passB_kernel(const __grid_constant__ MllArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ double red[kRed];
-  pdl_prologue();
+  pdl_prologue(a);
   FGP_PSTAMP(21);
   if (fit_stop_flag(a) != 0.0) return;  // uniform over the CTA, before any barrier
   const int tile = blockIdx.x, b = blockIdx.y;
@@ -22,11 +22,11 @@ __global__ void __launch_bounds__(256) mll_finalize_kernel(const __grid_constant
   finalize_set(a, blockIdx.x, red);
 }
 
-bool pdl_enabled() {
-  // measured on B200 (profiles/README.md, snapshot j): 57.1 us per lattice fit iteration with the attribute, 51.4 without -- the
-  // early-resident CTAs of the next kernel cost more than the hidden launch latency gains.  Off unless FGP_PDL=1.
-  static const bool on = env_int("FGP_PDL", 0) != 0;
-  return on;
+int pdl_mode() {
+  // measured on B200 (profiles/README.md, snapshot j): 57.1 us per lattice fit iteration with every CTA triggering at entry (mode 1), 51.4
+  // without the attribute -- the early-resident CTAs of the next kernel cost more than the hidden launch latency gains.  Mode 2 leaves the
+  // trigger to the CTA's exit: the next kernel's CTAs only move into slots that are free for good.  Off unless FGP_PDL is set; read per call.
+  return env_int("FGP_PDL", 0);
 }
 
 // The persistent cooperative kernel is OPT-IN (FGP_COOP=1).  Measured on B200 (profiles/README.md, round 2): its phases walk the same

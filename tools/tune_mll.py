@@ -27,8 +27,17 @@ for _ in range(K):
 e1.record()
 torch.cuda.synchronize()
 warm = e0.elapsed_time(e1) / K * 1e3
+G = st.GRAPH_ITERS  # chunk graphs of fit(): G iterations per launch, the C -> A edges inside the graph
+st.replay(G)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(10):
+    st.replay(G)
+e1.record()
+torch.cuda.synchronize()
+warm_chunk = e0.elapsed_time(e1) / (10 * G) * 1e3
 flush = torch.empty(256 * 1024 * 1024 // 8, device=dev)
 kern = st.kernel_times(reps=10, flush=flush)
 kern_w = st.kernel_times(reps=10, flush=None)
-print(json.dumps({"cfg": {k: v for k, v in os.environ.items() if k.startswith("FGP_")}, "fam": fam, "log2n": log2n, "d": d, "warm_us_per_iter": round(warm, 2),
+print(json.dumps({"cfg": {k: v for k, v in os.environ.items() if k.startswith("FGP_")}, "fam": fam, "log2n": log2n, "d": d, "warm_us_per_iter": round(warm, 2), "warm_us_per_iter_chunk_graph": round(warm_chunk, 2),
                   "cold_kernels_us": {k["name"]: round(k["ms"] * 1e3, 1) for k in kern}, "eager_warm_kernels_us": {k["name"]: round(k["ms"] * 1e3, 1) for k in kern_w}}))

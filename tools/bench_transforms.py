@@ -20,4 +20,10 @@ for m in (16, 20, 22, 24):
 xb = torch.randn(64, 1 << 20, device=dev)
 t, _ = timeit(lambda: L.fwht(xb), reps=5, warm=2)
 res["fwht_batch64_2^20"] = {"ms": round(t * 1e3, 3), "alg16n_GBs": round(16 * xb.numel() / t / 1e9)}
+x26 = torch.randn(1 << 26, device=dev)
+t, _ = timeit(lambda: L.fwht(x26), reps=5, warm=2)
+res["fwht_2^26"] = {"us": round(t * 1e6, 1), "alg16n_GBs": round(16 * x26.numel() / t / 1e9)}
+xf = torch.randn(64, 1 << 20, device=dev)
+t, _ = timeit(lambda: L.fftbr(xf), reps=5, warm=2)
+res["fft_r2c_batch64_2^20"] = {"ms": round(t * 1e3, 3), "alg24n_GBs": round(24 * xf.numel() / t / 1e9)}
 print(json.dumps(res))

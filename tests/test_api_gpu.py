@@ -469,3 +469,34 @@ def test_persistent_kernel_fit_matches_the_three_launch_route(monkeypatch, famil
     for key in ("loss_hist", "scale_hist", "lengthscales_hist"):
         assert rel(d1[key], d0[key]) < 1e-12, key
     assert rel(s1, s0) < 1e-12 and rel(l1, l0) < 1e-12
+
+
+@pytest.mark.parametrize("family,d,m", [("lattice", 5, 17), ("dnb2", 5, 15)])
+def test_programmatic_dependent_launch_route_is_bit_identical(monkeypatch, family, d, m):
+    """FGP_PDL=2 launches the three per-pass kernels with the programmatic-stream-serialization attribute (the next kernel's CTAs become
+    resident as the current ones exit, pass C triggers before its serial fit tail) -- same kernels, same arithmetic: the fit trajectory must
+    be bit-identical, launched eagerly and replayed from a CUDA graph captured with the attribute."""
+    import fastgaussianprocesses_b200 as fgp
+    n = 1 << m
+
+    def run(pdl, graph):
+        monkeypatch.setenv("FGP_PDL", str(pdl))
+        if graph:
+            monkeypatch.delenv("FGP_B200_NO_GRAPH", raising=False)
+        else:
+            monkeypatch.setenv("FGP_B200_NO_GRAPH", "1")
+        gp = (fgp.FastGPLattice(fgp.Lattice(d, seed=23), device=dev, noise=1e-6) if family == "lattice"
+              else fgp.FastGPDigitalNetB2(fgp.DigitalNetB2(d, seed=23), device=dev, noise=1e-6))
+        x = gp.get_x_next(n)
+        gp.add_y_next(torch.cos(2 * np.pi * x).sum(1) + torch.sin(2 * np.pi * x[:, 0]) * x[:, -1])
+        data = gp.fit(iterations=18, verbose=0, store_hists=True, stop_crit_wait_iterations=100)
+        return data, gp.raw_lengthscales.detach().clone()
+
+    d2g, l2g = run(2, True)   # first use of this shape: the pooled context captures its graphs with the attribute
+    d2, l2 = run(2, False)
+    d0, l0 = run(0, False)
+    for a, la in ((d2g, l2g), (d2, l2)):
+        assert a["iterations"] == d0["iterations"]
+        for key in ("loss_hist", "scale_hist", "lengthscales_hist"):
+            assert torch.equal(torch.as_tensor(a[key]), torch.as_tensor(d0[key])), key
+        assert torch.equal(la, l0)
